@@ -1,0 +1,68 @@
+"""ctypes binding of libgegp.so (the C ABI declared in include/gegp.h).
+
+There is NO CPU fallback: if the CUDA library has not been built, importing the compute path raises.
+Build it with ``python -c "import __graft_entry__ as g; g.build()"`` (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgegp.so")
+
+# mirrors of the #defines in include/gegp.h
+ABI_VERSION = 1
+MODE_BASE, MODE_PRECON, MODE_PRECON_COV = 0, 1, 2
+OUT_LML, OUT_SIGMA2, OUT_BETA, OUT_LOGDET, OUT_INFO, OUT_QUAD, OUT_DVARK, OUT_DVARF, OUT_DVARG, OUT_GRAD = range(10)
+OP_LML, OP_LML_GRAD, OP_PREDICT = 0, 1, 2
+
+EXPORTS = (
+    "gegp_abi_version", "gegp_workspace_bytes", "gegp_ld", "gegp_build_cov", "gegp_cross_cov", "gegp_potrf",
+    "gegp_trsm_rows", "gegp_lml_eval", "gegp_predict_setup", "gegp_predict",
+)
+
+
+def out_len(d: int) -> int:
+    return OUT_GRAD + d
+
+
+_lib = None
+
+
+def load():
+    """Load libgegp.so once and declare every prototype. Raises if the library is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA extension is not built and there is no CPU fallback. "
+            "Run __graft_entry__.build() (needs nvcc).")
+    lib = C.CDLL(LIB_PATH)
+    vp, dp, ip = C.c_void_p, C.c_void_p, C.c_void_p   # device pointers travel as integers
+    i, i64, dbl, sz = C.c_int, C.c_int64, C.c_double, C.c_size_t
+    lib.gegp_abi_version.restype = i
+    lib.gegp_abi_version.argtypes = []
+    lib.gegp_workspace_bytes.restype = sz
+    lib.gegp_workspace_bytes.argtypes = [i, i, i, i, i]
+    lib.gegp_ld.restype = i64
+    lib.gegp_ld.argtypes = [i]
+    lib.gegp_build_cov.restype = i
+    lib.gegp_build_cov.argtypes = [i, i, i, dp, ip, dp, dp, i, dbl, dbl, dp, i64, dp, i, vp]
+    lib.gegp_cross_cov.restype = i
+    lib.gegp_cross_cov.argtypes = [i, i, i, dp, ip, dp, i, dp, dp, dp, i64, vp]
+    lib.gegp_potrf.restype = i
+    lib.gegp_potrf.argtypes = [i, i, dp, i64, ip, vp]
+    lib.gegp_trsm_rows.restype = i
+    lib.gegp_trsm_rows.argtypes = [i, dp, i64, dp, i64, i, vp]
+    lib.gegp_lml_eval.restype = i
+    lib.gegp_lml_eval.argtypes = [i, dp, dp, i, i, i, dp, ip, dp, dp, i, dbl, i, dbl, i, dp, dp, vp, sz, vp]
+    lib.gegp_predict_setup.restype = i
+    lib.gegp_predict_setup.argtypes = [i, i, i, dp, ip, dp, dp, i, dbl, dp, dbl, dp, i64, dp, dp, ip, vp]
+    lib.gegp_predict.restype = i
+    lib.gegp_predict.argtypes = [i, i, i, dp, ip, dp, dp, i64, dp, i, dbl, dbl, dp, i, dp, dp, dp, ip, vp, sz, vp]
+    if lib.gegp_abi_version() != ABI_VERSION:
+        raise RuntimeError("libgegp.so ABI version mismatch; rebuild the extension")
+    _lib = lib
+    return lib

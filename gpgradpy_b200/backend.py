@@ -1,0 +1,206 @@
+"""Thin PyTorch-side plumbing over the C ABI: device buffers, streams and workspace management.
+
+Every function here hands raw device pointers to libgegp.so; no arithmetic of the hot path is done in
+Python/PyTorch, and there is no CPU fallback (a missing CUDA device or library raises).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+F64 = torch.float64
+
+
+def device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("gpgradpy_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_dev(a, dtype=F64):
+    """Host array / tensor -> contiguous device tensor (no copy if already there)."""
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device(), dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device())
+
+
+def _p(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed with code {rc} (negative: bad argument index / -1000-cudaError)")
+
+
+def ld_of(N: int) -> int:
+    return int(L.load().gegp_ld(N))
+
+
+def slot_from_mask(mask, n):
+    """bvec_use_grad (bool[n]) -> (slot int32[n] device tensor or None, n_g)."""
+    if mask is None:
+        return None, n
+    m = np.asarray(mask, dtype=bool)
+    assert m.size == n
+    slot = np.where(m, np.cumsum(m) - 1, -1).astype(np.int32)
+    ng = int(m.sum())
+    if ng == n:
+        return None, n
+    return torch.as_tensor(slot).to(device()), ng
+
+
+_ws_cache: dict = {}
+
+
+def workspace(nbytes: int) -> torch.Tensor:
+    """Grow-only byte workspace per device (torch caching allocator owns the memory)."""
+    key = torch.cuda.current_device()
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _ws_cache.pop(key, None)
+        buf = None
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device())
+        _ws_cache[key] = buf
+    return buf
+
+
+def free_workspace():
+    _ws_cache.clear()
+
+
+def build_cov(X, theta, *, n_g=None, slot=None, noise=None, mode=L.MODE_BASE, eta=0.0, varK=1.0, uplo=0, out=None):
+    """gegp_build_cov -> (K [N, N] strided view over an [N, ld] buffer, p [2N] or None)."""
+    lib = L.load()
+    X = to_dev(X)
+    n, d = X.shape
+    n_g = n if n_g is None else n_g
+    N = n + n_g * d
+    theta = to_dev(theta)
+    noise = to_dev(noise)
+    ld = ld_of(N)
+    if out is None:
+        out = torch.empty((N, ld), dtype=F64, device=device())
+    p = torch.empty(2 * N, dtype=F64, device=device()) if mode == L.MODE_PRECON else None
+    rc = lib.gegp_build_cov(n, n_g, d, _p(X), _p(slot), _p(theta), _p(noise), mode, float(eta), float(varK), _p(out),
+                            out.stride(0), _p(p), int(uplo), _stream())
+    _check(rc, "gegp_build_cov")
+    return out[:, :N], p
+
+
+def cross_cov(X, Xs, theta, *, n_g=None, slot=None, pinv=None):
+    lib = L.load()
+    X, Xs, theta, pinv = to_dev(X), to_dev(Xs), to_dev(theta), to_dev(pinv)
+    n, d = X.shape
+    n_g = n if n_g is None else n_g
+    N = n + n_g * d
+    nx = Xs.shape[0]
+    ld = ld_of(N)
+    out = torch.empty((nx, ld), dtype=F64, device=device())
+    rc = lib.gegp_cross_cov(n, n_g, d, _p(X), _p(slot), _p(Xs), nx, _p(theta), _p(pinv), _p(out), ld, _stream())
+    _check(rc, "gegp_cross_cov")
+    return out[:, :N]
+
+
+def potrf(A: torch.Tensor, N: int, n_extra: int = 0):
+    """In-place trapezoid Cholesky of A[(N+n_extra), ld]; returns the device info int tensor."""
+    lib = L.load()
+    assert A.is_cuda and A.dtype == F64 and A.stride(1) == 1 and A.shape[0] >= N + n_extra
+    info = torch.zeros(1, dtype=torch.int32, device=A.device)
+    rc = lib.gegp_potrf(N, n_extra, _p(A), A.stride(0), _p(info), _stream())
+    _check(rc, "gegp_potrf")
+    return info
+
+
+def trsm_rows(Lfac: torch.Tensor, N: int, B: torch.Tensor):
+    lib = L.load()
+    rc = lib.gegp_trsm_rows(N, _p(Lfac), Lfac.stride(0), _p(B), B.stride(0), B.shape[0], _stream())
+    _check(rc, "gegp_trsm_rows")
+    return B
+
+
+def lml_eval(X, y, theta_batch, *, n_g=None, slot=None, mode=L.MODE_PRECON, eta=0.0, noise=None, varK_batch=None,
+             pnlt_grad=0.0, want_grad=True, want_alpha=False, max_ws_bytes=None):
+    """gegp_lml_eval for B candidate rows -> (out [B, 9+d] device tensor, alpha [B, N] or None)."""
+    lib = L.load()
+    X, y = to_dev(X), to_dev(y)
+    n, d = X.shape
+    n_g = n if n_g is None else n_g
+    N = n + n_g * d
+    th = to_dev(theta_batch).reshape(-1, d)
+    B = th.shape[0]
+    noisy = noise is not None
+    noise = to_dev(noise)
+    vk = to_dev(varK_batch).reshape(-1) if noisy else None
+    if noisy:
+        assert vk.numel() == B
+    out = torch.empty((B, L.out_len(d)), dtype=F64, device=device())
+    alpha = torch.empty((B, N), dtype=F64, device=device()) if want_alpha else None
+    op = L.OP_LML_GRAD if want_grad else L.OP_LML
+    per1 = int(lib.gegp_workspace_bytes(op, n, n_g, d, 1))
+    if max_ws_bytes is None:
+        free, _total = torch.cuda.mem_get_info()
+        cached = _ws_cache.get(torch.cuda.current_device())
+        max_ws_bytes = int(0.6 * (free + (cached.numel() if cached is not None else 0)))
+    chunk = max(1, min(B, (max_ws_bytes - 4096 - 4 * B) // per1))
+    nbytes = int(lib.gegp_workspace_bytes(op, n, n_g, d, chunk)) + 4 * B + 256
+    ws = workspace(nbytes)
+    rc = lib.gegp_lml_eval(B, _p(th), _p(vk), n, n_g, d, _p(X), _p(slot), _p(y), _p(noise), int(mode), float(eta),
+                           int(noisy), float(pnlt_grad), int(bool(want_grad)), _p(out), _p(alpha), _p(ws), ws.numel(),
+                           _stream())
+    _check(rc, "gegp_lml_eval")
+    return out, alpha
+
+
+class PredictState:
+    """Factor + solved residual row kept on the device between setup_eval_model and eval_model."""
+
+    def __init__(self, A, p, info, alpha, n, n_g, d, N, X, slot, theta, mode, beta):
+        self.A, self.p, self.info, self.alpha = A, p, info, alpha
+        self.n, self.n_g, self.d, self.N = n, n_g, d, N
+        self.X, self.slot, self.theta, self.mode, self.beta = X, slot, theta, mode, beta
+
+
+def predict_setup(X, y, theta, beta, *, n_g=None, slot=None, noise=None, mode=L.MODE_PRECON, eta=0.0,
+                  want_alpha=True) -> PredictState:
+    lib = L.load()
+    X, y, theta, noise = to_dev(X), to_dev(y), to_dev(theta), to_dev(noise)
+    n, d = X.shape
+    n_g = n if n_g is None else n_g
+    N = n + n_g * d
+    ld = ld_of(N)
+    A = torch.empty((N + 1, ld), dtype=F64, device=device())
+    p = torch.empty(2 * N, dtype=F64, device=device())
+    info = torch.zeros(1, dtype=torch.int32, device=device())
+    alpha = torch.empty(N, dtype=F64, device=device()) if want_alpha else None
+    rc = lib.gegp_predict_setup(n, n_g, d, _p(X), _p(slot), _p(theta), _p(noise), int(mode), float(eta), _p(y),
+                                float(beta), _p(A), ld, _p(p), _p(alpha), _p(info), _stream())
+    _check(rc, "gegp_predict_setup")
+    return PredictState(A, p, info, alpha, n, n_g, d, N, X, slot, theta, mode, float(beta))
+
+
+def predict(st: PredictState, Xs, varK: float, *, chunk_bytes: int = 1 << 30):
+    """gegp_predict -> (mu, sig, sig2, n_negative) device tensors."""
+    lib = L.load()
+    Xs = to_dev(Xs)
+    nx = Xs.shape[0]
+    mu = torch.empty(nx, dtype=F64, device=device())
+    sig = torch.empty(nx, dtype=F64, device=device())
+    sig2 = torch.empty(nx, dtype=F64, device=device())
+    nneg = torch.zeros(1, dtype=torch.int32, device=device())
+    row_bytes = ld_of(st.N) * 8
+    cx = max(1, min(nx, chunk_bytes // row_bytes))
+    ws = workspace(cx * row_bytes)
+    rc = lib.gegp_predict(st.n, st.n_g, st.d, _p(st.X), _p(st.slot), _p(st.theta), _p(st.A), st.A.stride(0), _p(st.p),
+                          int(st.mode), st.beta, float(varK), _p(Xs), nx, _p(mu), _p(sig), _p(sig2), _p(nneg), _p(ws),
+                          cx * row_bytes, _stream())
+    _check(rc, "gegp_predict")
+    return mu, sig, sig2, nneg

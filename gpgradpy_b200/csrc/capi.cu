@@ -1,0 +1,267 @@
+// extern "C" entry points of libgegp.so (see include/gegp.h for the contract and the reference mapping).
+#include "kernels.h"
+#include "linalg.h"
+#include <algorithm>
+
+using namespace gegp;
+
+namespace {
+
+inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
+
+struct LmlLayout {
+  int64_t ld;          // leading dimension of every N-column matrix
+  size_t A, P, W, U, Kinv, Part;  // per-candidate element (double) offsets
+  size_t per_cand_doubles;
+};
+
+LmlLayout lml_layout(int n, int d, int N, bool grad) {
+  LmlLayout L{};
+  L.ld = gegp_ld(N);
+  size_t off = 0;
+  L.A = off;    off += (size_t)(N + 2) * L.ld;
+  L.P = off;    off += (size_t)2 * L.ld;
+  L.W = off;    off += (size_t)L.ld;
+  if (grad) {
+    L.U = off;    off += (size_t)N * L.ld;
+    L.Kinv = off; off += (size_t)N * L.ld;
+    L.Part = off; off += round_up((int64_t)lml_grad_partial_doubles(n, d), 2);
+  }
+  L.per_cand_doubles = off;
+  return L;
+}
+
+// the workspace starts with one int per candidate (Cholesky info), padded to 256 bytes
+size_t info_header_bytes(int B) { return (size_t)round_up((int64_t)B * (int64_t)sizeof(int), 256); }
+
+bool bad_geom(int n, int n_g, int d) { return n <= 0 || d <= 0 || n_g < 0 || n_g > n; }
+
+}  // namespace
+
+extern "C" {
+
+int gegp_abi_version(void) { return GEGP_ABI_VERSION; }
+
+int64_t gegp_ld(int N) { return round_up(N, 16); }
+
+size_t gegp_workspace_bytes(int op, int n, int n_g, int d, int arg) {
+  if (bad_geom(n, n_g, d) || arg <= 0) return 0;
+  const int N = n + n_g * d;
+  if (op == GEGP_OP_LML || op == GEGP_OP_LML_GRAD) {
+    LmlLayout L = lml_layout(n, d, N, op == GEGP_OP_LML_GRAD);
+    return info_header_bytes(arg) + L.per_cand_doubles * sizeof(double) * (size_t)arg;
+  }
+  if (op == GEGP_OP_PREDICT) return (size_t)arg * gegp_ld(N) * sizeof(double);
+  return 0;
+}
+
+int gegp_build_cov(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+                   const double* noise, int mode, double eta, double varK, double* K_out, int64_t ldk, double* p_out,
+                   int uplo, void* stream) {
+  if (bad_geom(n, n_g, d)) return -1;
+  if (!X) return -4;
+  if (!theta) return -6;
+  if (mode < GEGP_MODE_BASE || mode > GEGP_MODE_PRECON_COV) return -8;
+  if (!K_out) return -11;
+  const int N = n + n_g * d;
+  if (ldk < N) return -12;
+  if (mode == GEGP_MODE_PRECON && !p_out) return -13;
+  if (n_g != n && !grad_slot) return -5;  // gradient-free GP (n_g == 0): pass a slot array of -1
+  Ctx ctx{(cudaStream_t)stream, 1};
+  Geom gm{n, n_g, d, N, X, (n_g == n) ? nullptr : grad_slot};
+  NoiseSpec ns{noise, 0, nullptr, varK, 0};
+  int rc = 0;
+  if (p_out) {
+    rc = launch_prep_p(ctx, gm, theta, 0, ns, mode, p_out, p_out + N, 0);
+    if (rc) return rc;
+  }
+  return launch_build_cov(ctx, gm, theta, 0, ns, p_out ? p_out + N : nullptr, 0, mode, eta, K_out, ldk, 0, uplo ? 1 : 0);
+}
+
+int gegp_cross_cov(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* Xs, int nx,
+                   const double* theta, const double* pinv, double* Kx, int64_t ld, void* stream) {
+  if (bad_geom(n, n_g, d)) return -1;
+  if (!X) return -4;
+  if (!Xs || nx < 0) return -6;
+  if (!theta) return -8;
+  if (!Kx) return -10;
+  const int N = n + n_g * d;
+  if (ld < N) return -11;
+  if (n_g != n && !grad_slot) return -5;
+  if (nx == 0) return 0;
+  Ctx ctx{(cudaStream_t)stream, 1};
+  Geom gm{n, n_g, d, N, X, (n_g == n) ? nullptr : grad_slot};
+  return launch_cross_cov(ctx, gm, theta, pinv, Xs, nx, Kx, ld);
+}
+
+int gegp_potrf(int N, int n_extra, double* A, int64_t lda, int* info_dev, void* stream) {
+  if (N <= 0) return -1;
+  if (n_extra < 0) return -2;
+  if (!A) return -3;
+  if (lda < N || (lda & 1)) return -4;
+  if (!info_dev) return -5;
+  Ctx ctx{(cudaStream_t)stream, 1};
+  return chol_trap(ctx, A, lda, 0, N + n_extra, N, 0, info_dev);
+}
+
+int gegp_trsm_rows(int N, const double* L, int64_t ldl, double* B, int64_t ldb, int r, void* stream) {
+  if (N <= 0) return -1;
+  if (!L) return -2;
+  if (ldl < N || (ldl & 1)) return -3;
+  if (!B) return -4;
+  if (ldb < N || (ldb & 1)) return -5;
+  if (r < 0) return -6;
+  Ctx ctx{(cudaStream_t)stream, 1};
+  return trsm_right_rec(ctx, L, ldl, 0, B, ldb, 0, r, N);
+}
+
+int gegp_lml_eval(int B, const double* theta_batch, const double* varK_batch, int n, int n_g, int d, const double* X,
+                  const int32_t* grad_slot, const double* y, const double* noise, int mode, double eta, int noisy,
+                  double pnlt_grad, int want_grad, double* out, double* alpha_out, void* work, size_t work_bytes,
+                  void* stream) {
+  if (B <= 0) return -1;
+  if (!theta_batch) return -2;
+  if (noisy && !varK_batch) return -3;
+  if (bad_geom(n, n_g, d) || n_g == 0) return -4;
+  if (!X) return -7;
+  if (n_g != n && !grad_slot) return -8;
+  if (!y) return -9;
+  if (noisy && !noise) return -10;
+  if (mode != GEGP_MODE_BASE && mode != GEGP_MODE_PRECON) return -11;
+  if (!out) return -16;
+  if (!work || (reinterpret_cast<uintptr_t>(work) & 15)) return -18;
+  const int N = n + n_g * d;
+  const LmlLayout L = lml_layout(n, d, N, want_grad != 0);
+  const size_t per = L.per_cand_doubles * sizeof(double);
+  const size_t header = info_header_bytes(B);
+  if (work_bytes < header + per) return -19;
+  const int chunk = (int)std::min<size_t>((size_t)B, (work_bytes - header) / per);
+  cudaStream_t st = (cudaStream_t)stream;
+  int* info = reinterpret_cast<int*>(work);
+  double* wk = reinterpret_cast<double*>(reinterpret_cast<char*>(work) + header);
+  const int64_t sC = (int64_t)L.per_cand_doubles;  // candidate stride of every workspace array
+  const int outlen = GEGP_OUT_LEN(d);
+  Geom gm{n, n_g, d, N, X, (n_g == n) ? nullptr : grad_slot};
+
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = std::min(chunk, B - b0);
+    Ctx ctx{st, nb};
+    const double* theta = theta_batch + (int64_t)b0 * d;
+    const double* varK = noisy ? varK_batch + b0 : nullptr;
+    double* A = wk + L.A;
+    double* P = wk + L.P;
+    double* pinv = P + L.ld;
+    double* W = wk + L.W;
+    double* outb = out + (int64_t)b0 * outlen;
+    {
+      cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int) * nb, st);
+      if (e != cudaSuccess) return -1000 - (int)e;
+    }
+    NoiseSpec ns{noisy ? noise : nullptr, 0, varK, 1.0, 1};
+    int rc = launch_prep_p(ctx, gm, theta, d, ns, mode, P, pinv, sC);
+    if (rc) return rc;
+    rc = launch_build_cov(ctx, gm, theta, d, ns, pinv, sC, mode, eta, A, L.ld, sC, 1);
+    if (rc) return rc;
+    rc = launch_append_rhs(ctx, N, n, y, pinv, sC, A + (int64_t)N * L.ld, L.ld, sC);
+    if (rc) return rc;
+    rc = chol_trap(ctx, A, L.ld, sC, N + 2, N, 0, info);
+    if (rc) return rc;
+    rc = launch_lml_finalize(ctx, N, A, L.ld, sC, pinv, sC, noisy, varK, W, sC, outb, outlen, info);
+    if (rc) return rc;
+    if (want_grad || alpha_out) {
+      rc = trsv_lower_trans(ctx, A, L.ld, sC, W, L.ld, sC, N, 1);  // W <- L^-T w  (preconditioned alpha)
+      if (rc) return rc;
+      if (alpha_out) {
+        rc = launch_scale_vec(ctx, N, W, sC, pinv, sC, alpha_out + (int64_t)b0 * N, N);
+        if (rc) return rc;
+      }
+    }
+    if (want_grad) {
+      double* U = wk + L.U;
+      double* Kinv = wk + L.Kinv;
+      rc = chol_inverse(ctx, A, L.ld, sC, U, L.ld, sC, Kinv, L.ld, sC, N);
+      if (rc) return rc;
+      rc = launch_lml_grad(ctx, gm, theta, d, Kinv, L.ld, sC, W, sC, pinv, sC, mode, eta, noisy, varK, pnlt_grad,
+                           wk + L.Part, sC, outb, outlen);
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
+int gegp_predict_setup(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+                       const double* noise, int mode, double eta, const double* y, double beta, double* A, int64_t lda,
+                       double* p_out, double* alpha_out, int* info_dev, void* stream) {
+  if (bad_geom(n, n_g, d) || n_g == 0) return -1;
+  if (!X) return -4;
+  if (n_g != n && !grad_slot) return -5;
+  if (!theta) return -6;
+  if (mode != GEGP_MODE_BASE && mode != GEGP_MODE_PRECON) return -8;
+  if (!y) return -10;
+  if (!A) return -12;
+  const int N = n + n_g * d;
+  if (lda < N || (lda & 1)) return -13;
+  if (!p_out) return -14;
+  if (!info_dev) return -16;
+  Ctx ctx{(cudaStream_t)stream, 1};
+  Geom gm{n, n_g, d, N, X, (n_g == n) ? nullptr : grad_slot};
+  NoiseSpec ns{noise, 0, nullptr, 1.0, 0};
+  double* pinv = p_out + N;
+  int rc = launch_prep_p(ctx, gm, theta, 0, ns, mode, p_out, pinv, 0);
+  if (rc) return rc;
+  rc = launch_build_cov(ctx, gm, theta, 0, ns, pinv, 0, mode, eta, A, lda, 0, 1);
+  if (rc) return rc;
+  double* row = A + (int64_t)N * lda;
+  rc = launch_append_res(ctx, N, n, y, beta, pinv, row);
+  if (rc) return rc;
+  rc = chol_trap(ctx, A, lda, 0, N + 1, N, 0, info_dev);
+  if (rc) return rc;
+  if (alpha_out) {
+    cudaError_t e = cudaMemcpyAsync(alpha_out, row, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream);
+    if (e != cudaSuccess) return -1000 - (int)e;
+    rc = trsv_lower_trans(ctx, A, lda, 0, alpha_out, N, 0, N, 1);
+    if (rc) return rc;
+    rc = launch_scale_vec(ctx, N, alpha_out, 0, pinv, 0, alpha_out, 0);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int gegp_predict(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta, const double* A,
+                 int64_t lda, const double* p, int mode, double beta, double varK, const double* Xs, int nx, double* mu,
+                 double* sig, double* sig2_out, int* n_negative_dev, void* work, size_t work_bytes, void* stream) {
+  if (bad_geom(n, n_g, d) || n_g == 0) return -1;
+  if (!X) return -4;
+  if (n_g != n && !grad_slot) return -5;
+  if (!theta) return -6;
+  if (!A) return -7;
+  const int N = n + n_g * d;
+  if (lda < N || (lda & 1)) return -8;
+  if (!p) return -9;
+  if (!Xs || nx < 0) return -13;
+  if (!mu) return -15;
+  if (!sig) return -16;
+  if (!work || (reinterpret_cast<uintptr_t>(work) & 15)) return -19;
+  (void)mode;
+  const int64_t ldz = gegp_ld(N);
+  const int chunk = (int)std::min<size_t>((size_t)nx, work_bytes / (ldz * sizeof(double)));
+  if (nx > 0 && chunk < 1) return -20;
+  Ctx ctx{(cudaStream_t)stream, 1};
+  Geom gm{n, n_g, d, N, X, (n_g == n) ? nullptr : grad_slot};
+  const double* pinv = p + N;
+  const double* w = A + (int64_t)N * lda;
+  double* Z = reinterpret_cast<double*>(work);
+  for (int x0 = 0; x0 < nx; x0 += chunk) {
+    const int cx = std::min(chunk, nx - x0);
+    int rc = launch_cross_cov(ctx, gm, theta, pinv, Xs + (int64_t)x0 * d, cx, Z, ldz);
+    if (rc) return rc;
+    rc = trsm_right_rec(ctx, A, lda, 0, Z, ldz, 0, cx, N);
+    if (rc) return rc;
+    rc = launch_predict_rows(ctx, N, Z, ldz, cx, w, beta, varK, mu + x0, sig + x0, sig2_out ? sig2_out + x0 : nullptr,
+                             n_negative_dev);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // extern "C"

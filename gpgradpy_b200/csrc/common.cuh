@@ -1,0 +1,64 @@
+// Common device helpers for the gradient-enhanced GP kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+namespace gegp {
+
+constexpr int LEAF = 128;  // blocking quantum of the recursive factorisation / inverse
+
+// Launch context: every kernel of one C-ABI call goes to this stream; `batch` independent problems
+// (multi-start candidates) are laid out with a fixed element stride and mapped to blockIdx.z.
+struct Ctx {
+  cudaStream_t stream;
+  int batch;
+};
+
+#define GEGP_CHECK_LAUNCH()                                                                      \
+  do {                                                                                           \
+    cudaError_t e__ = cudaGetLastError();                                                        \
+    if (e__ != cudaSuccess) {                                                                    \
+      fprintf(stderr, "[gegp] launch error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__,   \
+              __LINE__);                                                                         \
+      return -1000 - (int)e__;                                                                   \
+    }                                                                                            \
+  } while (0)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// D(8x8) += A(8x4) * B(4x8), fp64 tensor-core MMA (SASS: DMMA.8x8x4).
+// a: row = lane>>2, k = lane&3 ; b: k = lane&3, n = lane>>2 ; c: row = lane>>2, cols = 2*(lane&3)+{0,1}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum; result valid in every thread. `sh` must hold >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double t = 0;
+  for (int i = 0; i < nw; i++) t += sh[i];  // fixed order: deterministic
+  return t;
+}
+
+}  // namespace gegp

@@ -1,0 +1,208 @@
+// fp64 tensor-core GEMM engine:  C = alpha * A * op(B) + beta * C   (row-major, DMMA.8x8x4).
+//
+// Every O(N^3) step of the gradient-enhanced GP hot path (Cholesky trailing updates, triangular
+// solves against many right-hand sides, the explicit inverse for the trace terms) is expressed on this
+// kernel.  CTA tile BM x BN x 16, multi-stage cp.async pipeline into padded shared memory whose row
+// strides (20 / BN+4 doubles) make every DMMA fragment load bank-conflict free, warp tile WM x WN built
+// from m8n8k4 fp64 MMAs.  Triangular operands are exploited by clipping the k range per output tile.
+#include "linalg.h"
+
+namespace gegp {
+
+constexpr int BK = 16;
+constexpr int KPAD = BK + 4;  // 20 doubles: 4 consecutive rows land on 4 disjoint 8-bank groups
+
+template <int BM, int BN, int WM, int WN, int STAGES, bool B_KCONT>
+struct GemmCfg {
+  static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
+  static constexpr int THREADS = WARPS_M * WARPS_N * 32;
+  static constexpr int MI = WM / 8, NI = WN / 8;
+  static constexpr int A_STAGE = BM * KPAD;
+  static constexpr int B_LD = B_KCONT ? KPAD : (BN + 4);
+  static constexpr int B_STAGE = B_KCONT ? BN * KPAD : BK * (BN + 4);
+  static constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+};
+
+template <int BM, int BN, int WM, int WN, int STAGES, bool B_KCONT>
+__global__ void __launch_bounds__(GemmCfg<BM, BN, WM, WN, STAGES, B_KCONT>::THREADS)
+gemm_f64_kernel(const GemmArgs g) {
+  using Cfg = GemmCfg<BM, BN, WM, WN, STAGES, B_KCONT>;
+  constexpr int T = Cfg::THREADS;
+  extern __shared__ __align__(16) double smem[];
+  double* sA = smem;
+  double* sB = smem + STAGES * Cfg::A_STAGE;
+
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (g.cmode != C_FULL && n0 >= m0 + BM) return;  // tile entirely above the diagonal
+
+  const int zo = blockIdx.z / g.inner, zi = blockIdx.z - zo * g.inner;
+  const double* __restrict__ A = g.A + zo * g.sAo + zi * g.sAi;
+  const double* __restrict__ B = g.B + zo * g.sBo + zi * g.sBi;
+  double* __restrict__ C = g.C + zo * g.sCo + zi * g.sCi;
+
+  int kb = 0, ke = g.K;
+  if (g.klo_mode == KLO_M0) kb = m0;
+  else if (g.klo_mode == KLO_N0) kb = n0;
+  else if (g.klo_mode == KLO_MAXMN) kb = max(m0, n0);
+  if (g.khi_mode == KHI_M0) ke = min(ke, m0 + BM);
+  else if (g.khi_mode == KHI_N0) ke = min(ke, n0 + BN);
+  kb = (kb / BK) * BK;
+  const int ktiles = ke > kb ? (ke - kb + BK - 1) / BK : 0;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm0 = (warp / Cfg::WARPS_N) * WM, wn0 = (warp % Cfg::WARPS_N) * WN;
+  const int lr = lane >> 2, lk = lane & 3;
+
+  auto load_tile = [&](int stage, int kt) {
+    const int k0 = kb + kt * BK;
+    double* a_s = sA + stage * Cfg::A_STAGE;
+    double* b_s = sB + stage * Cfg::B_STAGE;
+    // A: BM rows x 8 chunks of 16 bytes
+#pragma unroll
+    for (int c = tid; c < BM * (BK / 2); c += T) {
+      const int r = c / (BK / 2), ck = c % (BK / 2);
+      const int gr = m0 + r, gk = k0 + 2 * ck;
+      int bytes = (gr < g.M) ? min(16, max(0, (ke - gk) * 8)) : 0;
+      const double* src = bytes ? (A + (int64_t)gr * g.lda + gk) : A;
+      cp_async16(a_s + r * KPAD + 2 * ck, src, bytes);
+    }
+    if (B_KCONT) {
+#pragma unroll
+      for (int c = tid; c < BN * (BK / 2); c += T) {
+        const int r = c / (BK / 2), ck = c % (BK / 2);
+        const int gr = n0 + r, gk = k0 + 2 * ck;
+        int bytes = (gr < g.N) ? min(16, max(0, (ke - gk) * 8)) : 0;
+        const double* src = bytes ? (B + (int64_t)gr * g.ldb + gk) : B;
+        cp_async16(b_s + r * KPAD + 2 * ck, src, bytes);
+      }
+    } else {
+#pragma unroll
+      for (int c = tid; c < BK * (BN / 2); c += T) {
+        const int kk = c / (BN / 2), cn = c % (BN / 2);
+        const int gk = k0 + kk, gn = n0 + 2 * cn;
+        int bytes = (gk < ke) ? min(16, max(0, (g.N - gn) * 8)) : 0;
+        const double* src = bytes ? (B + (int64_t)gk * g.ldb + gn) : B;
+        cp_async16(b_s + kk * (BN + 4) + 2 * cn, src, bytes);
+      }
+    }
+  };
+
+  double acc[Cfg::MI][Cfg::NI][2];
+#pragma unroll
+  for (int i = 0; i < Cfg::MI; i++)
+#pragma unroll
+    for (int j = 0; j < Cfg::NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) {
+    if (s < ktiles) load_tile(s, s);
+    cp_async_commit();
+  }
+
+  for (int kt = 0; kt < ktiles; kt++) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nk = kt + STAGES - 1;
+      if (nk < ktiles) load_tile(nk % STAGES, nk);
+      cp_async_commit();
+    }
+    const double* a_s = sA + (kt % STAGES) * Cfg::A_STAGE;
+    const double* b_s = sB + (kt % STAGES) * Cfg::B_STAGE;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double af[Cfg::MI], bf[Cfg::NI];
+#pragma unroll
+      for (int i = 0; i < Cfg::MI; i++) af[i] = a_s[(wm0 + i * 8 + lr) * KPAD + kk + lk];
+#pragma unroll
+      for (int j = 0; j < Cfg::NI; j++) {
+        if (B_KCONT) bf[j] = b_s[(wn0 + j * 8 + lr) * KPAD + kk + lk];
+        else bf[j] = b_s[(kk + lk) * (BN + 4) + wn0 + j * 8 + lr];
+      }
+#pragma unroll
+      for (int i = 0; i < Cfg::MI; i++)
+#pragma unroll
+        for (int j = 0; j < Cfg::NI; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue
+  const bool vec_ok = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll
+  for (int i = 0; i < Cfg::MI; i++) {
+    const int row = m0 + wm0 + i * 8 + lr;
+    if (row >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < Cfg::NI; j++) {
+      const int col = n0 + wn0 + j * 8 + 2 * lk;
+      if (col >= g.N) continue;
+      double* cp = C + (int64_t)row * g.ldc + col;
+      double v0 = g.alpha * acc[i][j][0], v1 = g.alpha * acc[i][j][1];
+      const bool has1 = (col + 1 < g.N);
+      bool st0 = true, st1 = has1;
+      if (g.cmode != C_FULL) { st0 = (col <= row); st1 = has1 && (col + 1 <= row); }
+      if (g.beta != 0.0) {
+        if (st0) v0 += g.beta * cp[0];
+        if (st1) v1 += g.beta * cp[1];
+      }
+      if (st0 && st1 && vec_ok) {
+        *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
+      } else {
+        if (st0) cp[0] = v0;
+        if (st1) cp[1] = v1;
+      }
+      if (g.cmode == C_LOWER_MIRROR) {
+        if (st0 && col < row) C[(int64_t)col * g.ldc + row] = v0;
+        if (st1 && col + 1 < row) C[(int64_t)(col + 1) * g.ldc + row] = v1;
+      }
+    }
+  }
+}
+
+template <int BM, int BN, int WM, int WN, int STAGES, bool B_KCONT>
+static int launch_cfg(const Ctx& ctx, const GemmArgs& g) {
+  using Cfg = GemmCfg<BM, BN, WM, WN, STAGES, B_KCONT>;
+  auto kern = gemm_f64_kernel<BM, BN, WM, WN, STAGES, B_KCONT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    attr_set = true;
+  }
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.outer * g.inner);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM, ctx.stream>>>(g);
+  GEGP_CHECK_LAUNCH();
+  return 0;
+}
+
+GemmArgs gemm_args(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                   int M, int N, int K, double alpha, double beta, bool b_kcont) {
+  GemmArgs g{};
+  g.A = A; g.B = B; g.C = C; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.b_kcont = b_kcont;
+  g.klo_mode = KLO_ZERO; g.khi_mode = KHI_K; g.cmode = C_FULL;
+  g.inner = 1; g.outer = 1;
+  g.sAo = g.sBo = g.sCo = g.sAi = g.sBi = g.sCi = 0;
+  return g;
+}
+
+int gemm_f64(const Ctx& ctx, GemmArgs g) {
+  if (g.M <= 0 || g.N <= 0 || g.outer * g.inner <= 0) return 0;
+  if (g.K <= 0 && g.beta == 1.0) return 0;
+  // operands must allow 16-byte cp.async: even leading dimensions and 16-byte aligned bases
+  if ((g.lda & 1) || (g.ldb & 1) || (reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15) ||
+      (g.sAo & 1) || (g.sAi & 1) || (g.sBo & 1) || (g.sBi & 1))
+    return -900;
+  // Large tile when it still fills the machine, small tile otherwise (batched small problems).
+  const long tiles_big = (long)((g.M + 127) / 128) * ((g.N + 127) / 128) * g.outer * g.inner;
+  const bool big = (g.cmode == C_FULL ? tiles_big : tiles_big / 2) >= 120 && g.M >= 128 && g.N >= 128;
+  if (g.b_kcont) {
+    if (big) return launch_cfg<128, 128, 64, 32, 4, true>(ctx, g);
+    return launch_cfg<64, 64, 32, 32, 4, true>(ctx, g);
+  } else {
+    if (big) return launch_cfg<128, 128, 64, 32, 4, false>(ctx, g);
+    return launch_cfg<64, 64, 32, 32, 4, false>(ctx, g);
+  }
+}
+
+}  // namespace gegp

@@ -1,0 +1,60 @@
+// Internal dense fp64 linear-algebra engine (row-major, lower-triangular convention).
+// All routines are asynchronous on ctx.stream and batched over ctx.batch problems (blockIdx.z).
+#pragma once
+#include "common.cuh"
+
+namespace gegp {
+
+enum KLo { KLO_ZERO = 0, KLO_M0 = 1, KLO_N0 = 2, KLO_MAXMN = 3 };
+enum KHi { KHI_K = 0, KHI_M0 = 1, KHI_N0 = 2 };
+enum CMode { C_FULL = 0, C_LOWER = 1, C_LOWER_MIRROR = 2 };
+
+struct GemmArgs {
+  const double* A;  // element (m,k) at A[m*lda + k]
+  const double* B;  // b_kcont: element (n,k) at B[n*ldb + k]; else element (k,n) at B[k*ldb + n]
+  double* C;        // element (m,n) at C[m*ldc + n]
+  int64_t lda, ldb, ldc;
+  int M, N, K;
+  double alpha, beta;     // C = alpha * A*op(B) + beta * C
+  bool b_kcont;
+  int klo_mode, khi_mode; // triangular-operand clipping of the k range per output tile
+  int cmode;
+  // batching: z = zo*inner + zi ; pointer offset = zo*s?o + zi*s?i (elements)
+  int inner;
+  int64_t sAo, sBo, sCo, sAi, sBi, sCi;
+  int outer;
+};
+
+GemmArgs gemm_args(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                   int M, int N, int K, double alpha, double beta, bool b_kcont);
+
+// C = alpha*A*op(B) + beta*C on fp64 tensor cores (DMMA). Returns 0 or a negative launch error.
+int gemm_f64(const Ctx& ctx, GemmArgs g);
+
+// --- leaves (<= LEAF wide) ---
+// In-place Cholesky of the k x k lower block at A (k <= LEAF); first non-positive pivot is recorded in
+// info[z] (1-based global index row0+i+1) if info[z] was 0.
+int leaf_potf2(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int k, int row0, int* info);
+// B (r x k) <- B * L^-T with L the k x k lower block (substitution, no explicit inverse).
+int leaf_trsm_right(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* B, int64_t ldb,
+                    int64_t strideB, int r, int k);
+// U_blk = (L_blk^-1)^T for every LEAF diagonal block of the N x N lower factor L, written into the
+// (pre-zeroed) N x N buffer U.
+int leaf_trtri_t(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* U, int64_t ldu,
+                 int64_t strideU, int N);
+
+// --- blocked algorithms ---
+// Trapezoid Cholesky: A is m x k (m >= k), lower. Factors the leading k x k block in place (L) and
+// overwrites rows k..m-1 with A21 * L^-T (so appended right-hand-side rows come out forward-solved).
+int chol_trap(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, int k, int row0, int* info);
+// B (r x k) <- B * L^-T for an already factored k x k lower L.
+int trsm_right_rec(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* B, int64_t ldb,
+                   int64_t strideB, int r, int k);
+// Kinv (full symmetric N x N) = L^-T L^-1. U (N x N) is scratch holding L^-T; Kinv doubles as scratch.
+int chol_inverse(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* U, int64_t ldu,
+                 int64_t strideU, double* Kinv, int64_t ldk, int64_t strideK, int N);
+// x <- L^-T x (back substitution), nrhs vectors x[r*ldx + i], blocked by LEAF.
+int trsv_lower_trans(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* x, int64_t ldx,
+                     int64_t strideX, int N, int nrhs);
+
+}  // namespace gegp

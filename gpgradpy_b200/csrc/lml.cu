@@ -1,0 +1,325 @@
+// K3: log marginal likelihood and its hyper-parameter gradient from the Cholesky factor, with dK/dtheta
+// generated on the fly (never materialised), and the K4 posterior row reductions.
+//
+// Reference: calc_lkd_w_Kern_mtd_adjoint (optz/CalcLkd.py:149-181), calc_lkd_all_w_noise (:185-251),
+// calc_model_max_lkd_poly (eval/GpMeanFun.py:98-108), sq_exp_calc_KernGrad_grad_th
+// (kernel/KernelSqExp.py:471-568), calc_KernGrad_hp / calc_Kcov_grad_hp (optz/GpHparaGrad.py:13-155),
+// eval_model (eval/GpEvalModel.py:154-168).
+#include "kernels.h"
+
+namespace gegp {
+
+// ------------------------------------------------------------------------------------------------
+// finalize: rows N and N+1 of the factored trapezoid hold z_y = L^-1 P^-1 y and z_h = L^-1 P^-1 H.
+//   beta = (z_h.z_y)/(z_h.z_h) ; w = z_y - beta z_h ; quad = w.w = res^T K^-1 res
+//   logdet = 2 sum log(L_ii * p_i)
+//   noise-free: sigma2 = max(1e-32, quad/N), LML = -(N ln sigma2 + logdet)/2
+//   noisy     : LML = -(logdet + quad)/2
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+lml_finalize_kernel(int N, const double* __restrict__ A_all, int64_t lda, int64_t strideA,
+                    const double* __restrict__ pinv_all, int64_t strideP, int noisy, const double* __restrict__ varK,
+                    double* __restrict__ w_all, int64_t strideW, double* __restrict__ out_all, int64_t strideOut,
+                    const int* __restrict__ info) {
+  __shared__ double sh[32];
+  const int z = blockIdx.x;
+  const double* A = A_all + z * strideA;
+  const double* pinv = pinv_all + z * strideP;
+  const double* zy = A + (int64_t)N * lda;
+  const double* zh = zy + lda;
+  double hh = 0, hy = 0, ld = 0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double h = zh[i];
+    hh += h * h;
+    hy += h * zy[i];
+    ld += log(A[(int64_t)i * lda + i]) - log(pinv[i]);
+  }
+  hh = block_sum(hh, sh);
+  hy = block_sum(hy, sh);
+  ld = block_sum(ld, sh);
+  const double beta = hy / hh;
+  double quad = 0;
+  double* w = w_all + z * strideW;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double wi = zy[i] - beta * zh[i];
+    w[i] = wi;
+    quad += wi * wi;
+  }
+  quad = block_sum(quad, sh);
+  if (threadIdx.x == 0) {
+    double* out = out_all + z * strideOut;
+    const double logdet = 2.0 * ld;
+    double s2, lml;
+    if (noisy) {
+      s2 = varK[z];
+      lml = -(logdet + quad) / 2.0;
+    } else {
+      s2 = fmax(1e-32, quad / N);
+      lml = -(N * log(s2) + logdet) / 2.0;
+    }
+    out[GEGP_OUT_LML] = lml;
+    out[GEGP_OUT_SIGMA2] = s2;
+    out[GEGP_OUT_BETA] = beta;
+    out[GEGP_OUT_LOGDET] = logdet;
+    out[GEGP_OUT_INFO] = (double)info[z];
+    out[GEGP_OUT_QUAD] = quad;
+    out[GEGP_OUT_DVARK] = 0.0;
+    out[GEGP_OUT_DVARF] = 0.0;
+    out[GEGP_OUT_DVARG] = 0.0;
+  }
+}
+
+int launch_lml_finalize(const Ctx& ctx, int N, const double* A, int64_t lda, int64_t strideA, const double* pinv,
+                        int64_t strideP, int noisy, const double* varK, double* w, int64_t strideW, double* out,
+                        int64_t strideOut, const int* info) {
+  lml_finalize_kernel<<<ctx.batch, 1024, 0, ctx.stream>>>(N, A, lda, strideA, pinv, strideP, noisy, varK, w, strideW, out,
+                                                          strideOut, info);
+  GEGP_CHECK_LAUNCH();
+  return 0;
+}
+
+// alpha_t <- alpha_t .* pinv  (un-preconditioned alpha = K^-1 res) into a separate output
+__global__ void scale_vec_kernel(int N, const double* __restrict__ a, int64_t strideA, const double* __restrict__ pinv,
+                                 int64_t strideP, double* __restrict__ out, int64_t strideOut) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) out[blockIdx.z * strideOut + i] = a[blockIdx.z * strideA + i] * pinv[blockIdx.z * strideP + i];
+}
+
+int launch_scale_vec(const Ctx& ctx, int N, const double* a, int64_t strideA, const double* pinv, int64_t strideP,
+                     double* out, int64_t strideOut) {
+  scale_vec_kernel<<<dim3((N + 255) / 256, 1, ctx.batch), 256, 0, ctx.stream>>>(N, a, strideA, pinv, strideP, out,
+                                                                             strideOut);
+  GEGP_CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gradient contraction:  g_m = sum_{rows,cols} (dK/dtheta_m) .* W ,  W = P^-1 (c1 a a^T - Kinv/2) P^-1
+// (a = preconditioned alpha, Kinv = inverse of the factored matrix).  One CTA per (point a, 128 points b);
+// each thread owns one pair and walks the (d+1) x (d+1) block of W that belongs to it, reading Kinv
+// coalesced along b.  Using the symmetry of W and K, only rows i of the pair block are needed:
+//   S   = W00 - 4 sum_i u_i W_i0 + 2 sum_i th_i W_ii - 4 sum_i u_i (W u)_i          (u_i = th_i r_i)
+//   t_m = -4 r_m W_m0 + 2 W_mm - 8 r_m (W u)_m
+//   g_m = sum_pairs k (t_m - r_m^2 S) ;  sum(K .* W) = sum_pairs k S
+// Per-CTA partial sums are written to `partial` and reduced in a fixed order by the finalize kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int GB = 128;
+
+__global__ void __launch_bounds__(GB)
+lml_grad_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideTheta, const double* __restrict__ Kinv_all,
+                int64_t ldk, int64_t strideK, const double* __restrict__ alpha_all, int64_t strideAlpha,
+                const double* __restrict__ pinv_all, int64_t strideP, const double* __restrict__ out_all,
+                int64_t strideOut, int noisy, double pnlt_grad, double* __restrict__ partial_all,
+                int64_t stridePartial) {
+  extern __shared__ double sm[];
+  const int d = gm.d, n = gm.n, ng = gm.ng, N = gm.N;
+  double* vs = sm;              // [d][GB]  v_j = pinv[col_j] * u_j
+  double* gs = vs + d * GB;     // [d+1][GB] per-thread t_m, then g_m ; row d = k*S
+  double* xa = gs + (d + 1) * GB;  // [d]
+  double* th = xa + d;             // [d]
+
+  const int tid = threadIdx.x, z = blockIdx.z;
+  const int a = blockIdx.y, b = blockIdx.x * GB + tid;
+  const double* theta = theta_all + z * strideTheta;
+  const double* Kinv = Kinv_all + z * strideK;
+  const double* alpha = alpha_all + z * strideAlpha;
+  const double* pinv = pinv_all + z * strideP;
+  const double* outz = out_all + z * strideOut;
+  const int np = 2 * d + 2;
+  double* part = partial_all + z * stridePartial + ((int64_t)a * gridDim.x + blockIdx.x) * np;
+
+  for (int e = tid; e < d; e += GB) { xa[e] = gm.X[(int64_t)a * d + e]; th[e] = theta[e]; }
+  __syncthreads();
+
+  const double c1 = noisy ? 0.5 : (pnlt_grad / N + 1.0 / (2.0 * outz[GEGP_OUT_SIGMA2]));
+  const double c2 = 0.5;
+  const int sa = gm.slot ? gm.slot[a] : a;
+  const bool valid = (b < n);
+  const int sb = valid ? (gm.slot ? gm.slot[b] : b) : -1;
+  const bool same = valid && (a == b);
+
+  double kk = 0.0, S = 0.0, Ab = 0.0;
+  double dv = 0.0;
+  if (valid) {
+    double e = 0.0;
+    for (int j = 0; j < d; j++) {
+      const double r = xa[j] - gm.X[(int64_t)b * d + j];
+      const double u = th[j] * r;
+      e -= u * r;
+      double v = 0.0;
+      if (sb >= 0) {
+        const int col = n + j * ng + sb;
+        v = pinv[col] * u;
+        Ab += v * alpha[col];
+      }
+      vs[j * GB + tid] = v;
+    }
+    kk = exp(e);
+    const double pa0 = pinv[a], pb0 = pinv[b];
+    const double W00 = pa0 * pb0 * (c1 * alpha[a] * alpha[b] - c2 * Kinv[(int64_t)a * ldk + b]);
+    S = W00;
+    if (same) dv = W00;
+  } else {
+    for (int j = 0; j < d; j++) vs[j * GB + tid] = 0.0;
+  }
+  // diagonal sums are produced by the single thread with b == a
+  if (same) {
+    part[d + 1] = dv;
+    if (sa < 0) for (int i = 0; i < d; i++) part[d + 2 + i] = 0.0;
+  }
+
+  for (int i = 0; i < d; i++) {
+    double t = 0.0;
+    if (valid && sa >= 0) {
+      const int row = n + i * ng + sa;
+      const double pr = pinv[row], ar = alpha[row];
+      const double* krow = Kinv + (int64_t)row * ldk;
+      const double rb = gm.X[(int64_t)b * d + i];
+      const double ri = xa[i] - rb, ui = th[i] * ri;
+      const double Wi0 = pr * pinv[b] * (c1 * ar * alpha[b] - c2 * krow[b]);
+      double rowdot = 0.0, Wii = 0.0;
+      if (sb >= 0) {
+        double dot = 0.0, kii = 0.0;
+        for (int j = 0; j < d; j++) {
+          const double kv = krow[n + j * ng + sb];
+          dot += vs[j * GB + tid] * kv;
+          if (j == i) kii = kv;
+        }
+        rowdot = pr * (c1 * ar * Ab - c2 * dot);
+        const int coli = n + i * ng + sb;
+        Wii = pr * pinv[coli] * (c1 * ar * alpha[coli] - c2 * kii);
+      }
+      S += -4.0 * ui * Wi0 + 2.0 * th[i] * Wii - 4.0 * ui * rowdot;
+      t = -4.0 * ri * Wi0 + 2.0 * Wii - 8.0 * ri * rowdot;
+      if (same) part[d + 2 + i] = Wii;
+    }
+    gs[i * GB + tid] = t;
+  }
+  // g_m = k (t_m - r_m^2 S)
+  for (int m = 0; m < d; m++) {
+    double g = 0.0;
+    if (valid) {
+      const double r = xa[m] - gm.X[(int64_t)b * d + m];
+      g = kk * (gs[m * GB + tid] - r * r * S);
+    }
+    gs[m * GB + tid] = g;
+  }
+  gs[d * GB + tid] = valid ? kk * S : 0.0;
+  __syncthreads();
+  // reduce d+1 rows of GB values: warp w handles rows w, w+4, ...
+  const int lane = tid & 31, w = tid >> 5;
+  for (int m = w; m <= d; m += GB / 32) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < GB / 32; q++) s += gs[m * GB + lane + 32 * q];
+    s = warp_sum(s);
+    if (lane == 0) part[m] = s;
+  }
+  // CTAs that do not contain the diagonal pair contribute zeros to the diagonal sums
+  const bool has_diag = (a / GB == (int)blockIdx.x);
+  if (!has_diag && tid < d + 1) part[d + 1 + tid] = 0.0;
+}
+
+// Sum the per-CTA partials in a fixed order and assemble the gradient entries of `out`.
+//   noise-free: dLML/dtheta_m = G_m + [precon] 2 eta DG_m
+//   noisy     : dLML/dtheta_m = varK (G_m + [precon] 2 eta DG_m)
+//               dLML/dvarK    = SK + eta (DV + sum_m 2 th_m DG_m) [precon]  |  SK + eta (DV + sum DG_m) [base]
+//               dLML/dvar_f   = (1 + eta) DV [precon] | DV [base] ; dLML/dvar_g likewise with sum_m DG_m
+__global__ void __launch_bounds__(256)
+lml_grad_finalize_kernel(int d, int64_t nparts, const double* __restrict__ partial_all, int64_t stridePartial,
+                         const double* __restrict__ theta_all, int64_t strideTheta, int mode, double eta, int noisy,
+                         const double* __restrict__ varK, double* __restrict__ out_all, int64_t strideOut) {
+  __shared__ double sh[32];
+  extern __shared__ double tot[];  // [2d+2]
+  const int z = blockIdx.x, np = 2 * d + 2;
+  const double* part = partial_all + z * stridePartial;
+  for (int c = 0; c < np; c++) {
+    double s = 0.0;
+    for (int64_t p = threadIdx.x; p < nparts; p += blockDim.x) s += part[p * np + c];
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) tot[c] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double* th = theta_all + z * strideTheta;
+    double* out = out_all + z * strideOut;
+    const bool precon = (mode == GEGP_MODE_PRECON);
+    const double vk = noisy ? varK[z] : 1.0;
+    const double SK = tot[d], DV = tot[d + 1];
+    double sdg = 0.0, sdg_th = 0.0;
+    for (int m = 0; m < d; m++) {
+      const double DG = tot[d + 2 + m];
+      sdg += DG;
+      sdg_th += 2.0 * th[m] * DG;
+      out[GEGP_OUT_GRAD + m] = vk * (tot[m] + (precon ? 2.0 * eta * DG : 0.0));
+    }
+    if (noisy) {
+      out[GEGP_OUT_DVARK] = SK + eta * (precon ? (DV + sdg_th) : (DV + sdg));
+      out[GEGP_OUT_DVARF] = (precon ? 1.0 + eta : 1.0) * DV;
+      out[GEGP_OUT_DVARG] = (precon ? 1.0 + eta : 1.0) * sdg;
+    }
+  }
+}
+
+size_t lml_grad_partial_doubles(int n, int d) {
+  return (size_t)n * ((n + GB - 1) / GB) * (2 * d + 2);
+}
+
+int launch_lml_grad(const Ctx& ctx, const Geom& gm, const double* theta, int64_t strideTheta, const double* Kinv,
+                    int64_t ldk, int64_t strideK, const double* alpha_t, int64_t strideAlpha, const double* pinv,
+                    int64_t strideP, int mode, double eta, int noisy, const double* varK, double pnlt_grad,
+                    double* partial, int64_t stridePartial, double* out, int64_t strideOut) {
+  const int d = gm.d;
+  const size_t smem = (size_t)(d * GB + (d + 1) * GB + 2 * d) * sizeof(double);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaFuncSetAttribute(lml_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smem_set = smem;
+  }
+  dim3 grid((gm.n + GB - 1) / GB, gm.n, ctx.batch);
+  lml_grad_kernel<<<grid, GB, smem, ctx.stream>>>(gm, theta, strideTheta, Kinv, ldk, strideK, alpha_t, strideAlpha, pinv,
+                                                  strideP, out, strideOut, noisy, pnlt_grad, partial, stridePartial);
+  GEGP_CHECK_LAUNCH();
+  const int64_t nparts = (int64_t)grid.x * grid.y;
+  lml_grad_finalize_kernel<<<ctx.batch, 256, (2 * d + 2) * sizeof(double), ctx.stream>>>(
+      d, nparts, partial, stridePartial, theta, strideTheta, mode, eta, noisy, varK, out, strideOut);
+  GEGP_CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// predict rows: Z[x,:] = L^-1 P^-1 k*(x) ; mu = beta + Z_x . w ; sig2 = 1 - |Z_x|^2
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+predict_rows_kernel(int N, const double* __restrict__ Z, int64_t ldz, int nx, const double* __restrict__ w,
+                    double beta, double varK, double* __restrict__ mu, double* __restrict__ sig,
+                    double* __restrict__ sig2, int* __restrict__ n_negative) {
+  __shared__ double sh[32];
+  const int x = blockIdx.x;
+  const double* zr = Z + (int64_t)x * ldz;
+  double d1 = 0, d2 = 0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double v = zr[i];
+    d1 += v * w[i];
+    d2 += v * v;
+  }
+  d1 = block_sum(d1, sh);
+  d2 = block_sum(d2, sh);
+  if (threadIdx.x == 0) {
+    const double s2 = 1.0 - d2;
+    mu[x] = beta + d1;
+    if (sig2) sig2[x] = s2;
+    if (s2 < 0 && n_negative) atomicAdd(n_negative, 1);
+    sig[x] = sqrt(fmax(s2, 0.0)) * sqrt(varK);
+  }
+}
+
+int launch_predict_rows(const Ctx& ctx, int N, const double* Z, int64_t ldz, int nx, const double* w, double beta,
+                        double varK, double* mu, double* sig, double* sig2, int* n_negative) {
+  if (nx <= 0) return 0;
+  predict_rows_kernel<<<nx, 256, 0, ctx.stream>>>(N, Z, ldz, nx, w, beta, varK, mu, sig, sig2, n_negative);
+  GEGP_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace gegp

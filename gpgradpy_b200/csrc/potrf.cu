@@ -1,0 +1,120 @@
+// Blocked fp64 algorithms built on the DMMA GEMM engine: recursive trapezoid Cholesky, recursive
+// right-side triangular solve, and the explicit inverse K^-1 = L^-T L^-1 needed by the trace terms
+// of the LML gradient (reference: scipy cho_factor / cho_solve at kernel/Kernel.py:251,
+// optz/CalcLkd.py:154,174).
+#include "linalg.h"
+
+namespace gegp {
+
+static inline int split_point(int k) {
+  // split k into k1 + k2 with k1 a multiple of LEAF, k1 >= k2
+  int h = (k + 1) / 2;
+  int k1 = ((h + LEAF - 1) / LEAF) * LEAF;
+  if (k1 >= k) k1 = ((k - 1) / LEAF) * LEAF;
+  return k1;
+}
+
+static GemmArgs batched(const Ctx& ctx, GemmArgs g, int64_t sA, int64_t sB, int64_t sC) {
+  g.outer = ctx.batch; g.inner = 1;
+  g.sAo = sA; g.sBo = sB; g.sCo = sC;
+  return g;
+}
+
+int trsm_right_rec(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* B, int64_t ldb,
+                   int64_t strideB, int r, int k) {
+  if (r <= 0 || k <= 0) return 0;
+  if (k <= 64) return leaf_trsm_right(ctx, L, ldl, strideL, B, ldb, strideB, r, k);
+  // X = [X1 X2], L = [[L11 0],[L21 L22]]:  X1 = B1 L11^-T ; B2 -= X1 L21^T ; X2 = B2 L22^-T
+  int k1 = (k <= LEAF) ? 64 : split_point(k);
+  int rc = trsm_right_rec(ctx, L, ldl, strideL, B, ldb, strideB, r, k1);
+  if (rc) return rc;
+  GemmArgs g = gemm_args(B, ldb, L + (int64_t)k1 * ldl, ldl, B + k1, ldb, r, k - k1, k1, -1.0, 1.0, true);
+  rc = gemm_f64(ctx, batched(ctx, g, strideB, strideL, strideB));
+  if (rc) return rc;
+  return trsm_right_rec(ctx, L + (int64_t)k1 * ldl + k1, ldl, strideL, B + k1, ldb, strideB, r, k - k1);
+}
+
+int chol_trap(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, int k, int row0, int* info) {
+  if (k <= 0) return 0;
+  if (k <= LEAF) {
+    int rc = leaf_potf2(ctx, A, lda, strideA, k, row0, info);
+    if (rc) return rc;
+    return trsm_right_rec(ctx, A, lda, strideA, A + (int64_t)k * lda, lda, strideA, m - k, k);
+  }
+  const int k1 = split_point(k);
+  int rc = chol_trap(ctx, A, lda, strideA, m, k1, row0, info);
+  if (rc) return rc;
+  // trailing update: C = A[k1:, k1:k] -= A[k1:, :k1] * A[k1:k, :k1]^T  (lower part of the square region)
+  double* C = A + (int64_t)k1 * lda + k1;
+  const double* P = A + (int64_t)k1 * lda;
+  GemmArgs g = gemm_args(P, lda, P, lda, C, lda, m - k1, k - k1, k1, -1.0, 1.0, true);
+  g.cmode = C_LOWER;
+  rc = gemm_f64(ctx, batched(ctx, g, strideA, strideA, strideA));
+  if (rc) return rc;
+  return chol_trap(ctx, C, lda, strideA, m - k1, k - k1, row0 + k1, info);
+}
+
+// U = L^-T (upper triangular) by levels: diagonal LEAF blocks first, then for block size bs = LEAF,
+// 2*LEAF, ... every pair (a = [s, s+bs), b = [s+bs, s+2bs)):  U_ab = -(U_aa * L_ba^T) * U_bb.
+// The product in parentheses is staged in T (the Kinv buffer, same coordinates).
+static int inverse_transposed(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* U, int64_t ldu,
+                              int64_t strideU, double* T, int64_t ldt, int64_t strideT, int N) {
+  int rc = leaf_trtri_t(ctx, L, ldl, strideL, U, ldu, strideU, N);
+  if (rc) return rc;
+  for (int bs = LEAF; bs < N; bs *= 2) {
+    const int npairs_full = N / (2 * bs);  // pairs whose b block is full
+    for (int pass = 0; pass < 2; pass++) {
+      // pass 0: all full pairs in one batched launch; pass 1: the ragged last pair (if any)
+      int s, bsz, inner;
+      if (pass == 0) { if (npairs_full == 0) continue; s = 0; bsz = bs; inner = npairs_full; }
+      else {
+        s = npairs_full * 2 * bs; bsz = N - s - bs; inner = 1;
+        if (bsz <= 0) continue;
+      }
+      const int64_t pstepL = (int64_t)2 * bs * (ldl + 1), pstepU = (int64_t)2 * bs * (ldu + 1),
+                    pstepT = (int64_t)2 * bs * (ldt + 1);
+      const double* Uaa = U + (int64_t)s * ldu + s;
+      const double* Lba = L + (int64_t)(s + bs) * ldl + s;
+      double* Tab = T + (int64_t)s * ldt + s + bs;
+      // T_ab (bs x bsz) = U_aa (bs x bs, upper: k >= i) * L_ba^T  -> NT, k clipped below by m0
+      GemmArgs g1 = gemm_args(Uaa, ldu, Lba, ldl, Tab, ldt, bs, bsz, bs, 1.0, 0.0, true);
+      g1.klo_mode = KLO_M0;
+      g1.outer = ctx.batch; g1.inner = inner;
+      g1.sAo = strideU; g1.sBo = strideL; g1.sCo = strideT; g1.sAi = pstepU; g1.sBi = pstepL; g1.sCi = pstepT;
+      rc = gemm_f64(ctx, g1);
+      if (rc) return rc;
+      // U_ab = -T_ab (bs x bsz) * U_bb (bsz x bsz upper, element (k,j) nonzero for k <= j) -> NN, k < n0+BN
+      const double* Ubb = U + (int64_t)(s + bs) * ldu + s + bs;
+      double* Uab = U + (int64_t)s * ldu + s + bs;
+      GemmArgs g2 = gemm_args(Tab, ldt, Ubb, ldu, Uab, ldu, bs, bsz, bsz, -1.0, 0.0, false);
+      g2.khi_mode = KHI_N0;
+      g2.outer = ctx.batch; g2.inner = inner;
+      g2.sAo = strideT; g2.sBo = strideU; g2.sCo = strideU; g2.sAi = pstepT; g2.sBi = pstepU; g2.sCi = pstepU;
+      rc = gemm_f64(ctx, g2);
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
+int chol_inverse(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* U, int64_t ldu,
+                 int64_t strideU, double* Kinv, int64_t ldk, int64_t strideK, int N) {
+  if (N <= 0) return 0;
+  // U must start as zero: its strictly lower triangle is read by the GEMMs as part of full tiles.
+  for (int b = 0; b < ctx.batch; b++) {
+    cudaError_t e = cudaMemset2DAsync(U + (int64_t)b * strideU, ldu * sizeof(double), 0, (size_t)N * sizeof(double), N,
+                                      ctx.stream);
+    if (e != cudaSuccess) return -1000 - (int)e;
+  }
+  int rc = inverse_transposed(ctx, L, ldl, strideL, U, ldu, strideU, Kinv, ldk, strideK, N);
+  if (rc) return rc;
+  // Kinv = U * U^T, U upper: sum over k >= max(i, j); lower tiles computed, mirrored to the upper half.
+  GemmArgs g = gemm_args(U, ldu, U, ldu, Kinv, ldk, N, N, N, 1.0, 0.0, true);
+  g.klo_mode = KLO_MAXMN;
+  g.cmode = C_LOWER_MIRROR;
+  g.outer = ctx.batch; g.inner = 1;
+  g.sAo = strideU; g.sBo = strideU; g.sCo = strideK;
+  return gemm_f64(ctx, g);
+}
+
+}  // namespace gegp

@@ -1,0 +1,122 @@
+/* gegp.h -- C ABI of the B200-native gradient-enhanced Gaussian-process hot path (libgegp.so).
+ *
+ * Drop-in boundary for marchildon/gpgradpy v1.3.2.  The reference has no FFI; the operator interface it
+ * exposes is the set of bound Python methods listed below, and each entry point here is what a ctypes
+ * binding behind that method calls (see INTEGRATION.md for the binding stubs):
+ *
+ *   gegp_build_cov      <- Kernel.calc_all_K_w_chofac   gpgradpy/src/kernel/Kernel.py:140-307
+ *                          KernelSqExpGradMod.sq_exp_calc_KernGrad  kernel/KernelSqExp.py:322-410
+ *                          CommonFun.calc_Rtensor       base/CommonFun.py:58-84
+ *   gegp_potrf          <- scipy cho_factor call sites  kernel/Kernel.py:251,291
+ *   gegp_lml_eval       <- CalcLkd.calc_lkd_all         optz/CalcLkd.py:270-346  (noise-free :30-95,149-181;
+ *                          noisy :185-251), GpHparaGrad.calc_KernGrad_hp / calc_Kcov_grad_hp
+ *                          optz/GpHparaGrad.py:13-155, GpMeanFunPoly.calc_model_max_lkd_poly
+ *                          eval/GpMeanFun.py:69-122; with B > 1 the candidate loops
+ *                          optz/GpHparaX0.py:39-45 and optz/OptzLkd.py:249-270
+ *   gegp_predict_setup  <- GpEvalModel.setup_eval_model eval/GpEvalModel.py:17-57
+ *   gegp_predict        <- GpEvalModel.eval_model       eval/GpEvalModel.py:59-198 (mu, sigma)
+ *   gegp_cross_cov      <- calc_KernGrad(X, X*) use at  eval/GpEvalModel.py:133-139
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp64 unless stated; matrices are row-major with an explicit
+ *     leading dimension (must be even; bases 16-byte aligned);
+ *   - N = n + n_g*d; row/column order is dimension-major: value of point a -> a, d/dx_i at gradient slot g ->
+ *     n + i*n_g + g (base/CommonFun.py:170, kernel/Kernel.py:353);
+ *   - grad_slot[n] (int32, device) maps a point to its gradient slot or -1; NULL means all points carry gradients;
+ *   - every call is asynchronous on `stream` (a cudaStream_t), never allocates, never throws;
+ *   - return value: 0 ok; < 0 bad argument (-(index of the argument)) or -1000-cudaError for a launch failure.
+ *     Numerical failure (matrix not positive definite) is reported LAPACK-style in a device int / the
+ *     GEGP_OUT_INFO slot: 0 ok, k > 0 leading minor of order k is not positive definite.
+ */
+#ifndef GEGP_H_
+#define GEGP_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GEGP_ABI_VERSION 1
+
+/* covariance assembly modes (kernel/Kernel.py:220-237 vs :268-277) */
+#define GEGP_MODE_BASE 0       /* varK * (K + diag(noise) + eta*I)                                  */
+#define GEGP_MODE_PRECON 1     /* varK * (P^-1 (K + diag(noise)) P^-1 + eta*I), P = diag sqrt(diag)    */
+#define GEGP_MODE_PRECON_COV 2 /* varK * (K + diag(noise) + eta*diag(K + noise))  (= P * PRECON * P)   */
+
+/* layout of the per-candidate result vector of gegp_lml_eval (doubles) */
+#define GEGP_OUT_LML 0     /* log marginal likelihood (no N/2 ln 2pi term, optz/CalcLkd.py:168,226)      */
+#define GEGP_OUT_SIGMA2 1  /* noise-free: closed-form varK = res^T K^-1 res / N (floor 1e-32); noisy: varK */
+#define GEGP_OUT_BETA 2    /* GLS constant mean                                                         */
+#define GEGP_OUT_LOGDET 3  /* ln det of the (un-preconditioned) factored matrix                          */
+#define GEGP_OUT_INFO 4    /* 0 or the order of the first non-positive leading minor                     */
+#define GEGP_OUT_QUAD 5    /* res^T K^-1 res                                                            */
+#define GEGP_OUT_DVARK 6   /* noisy only: dLML/dvarK                                                    */
+#define GEGP_OUT_DVARF 7   /* noisy only: dLML/dvar_fval                                                */
+#define GEGP_OUT_DVARG 8   /* noisy only: dLML/dvar_fgrad                                               */
+#define GEGP_OUT_GRAD 9    /* dLML/dtheta[0..d-1] (w.r.t. theta, not log10 theta)                        */
+#define GEGP_OUT_LEN(d) (GEGP_OUT_GRAD + (d))
+
+/* operations for gegp_workspace_bytes */
+#define GEGP_OP_LML 0       /* gegp_lml_eval without gradient : arg = B */
+#define GEGP_OP_LML_GRAD 1  /* gegp_lml_eval with gradient    : arg = B */
+#define GEGP_OP_PREDICT 2   /* gegp_predict                   : arg = nx chunk */
+
+int gegp_abi_version(void);
+
+size_t gegp_workspace_bytes(int op, int n, int n_g, int d, int arg);
+
+/* leading dimension this library uses for an N-column work matrix (multiple of 16 doubles) */
+int64_t gegp_ld(int N);
+
+/* K1: fused covariance builder.  theta[d]; noise[N] (already divided by varK where the reference divides,
+ * kernel/Kernel.py:218) or NULL; p_out[2N] receives p and 1/p (required for GEGP_MODE_PRECON, else may be NULL);
+ * uplo 0: full matrix, 1: lower triangle only (strict upper part is left untouched). */
+int gegp_build_cov(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+                   const double* noise, int mode, double eta, double varK, double* K_out, int64_t ldk,
+                   double* p_out, int uplo, void* stream);
+
+/* Cross covariance, transposed: Kx[x, c] = cov(test point x, training datum c) * (pinv ? pinv[c] : 1);
+ * Kx is [nx, ld]. */
+int gegp_cross_cov(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* Xs, int nx,
+                   const double* theta, const double* pinv, double* Kx, int64_t ld, void* stream);
+
+/* K2: blocked Cholesky on the fp64 tensor cores.  A is (N + n_extra) x lda, lower triangle of the leading
+ * N x N block holds the SPD matrix; on exit it holds L (lower) and the n_extra appended rows R are
+ * overwritten with R * L^-T (forward-solved right-hand sides).  info_dev: device int, must be 0 on entry. */
+int gegp_potrf(int N, int n_extra, double* A, int64_t lda, int* info_dev, void* stream);
+
+/* B (r x ldb, r rows of length N) <- B * L^-T against an existing factor. */
+int gegp_trsm_rows(int N, const double* L, int64_t ldl, double* B, int64_t ldb, int r, void* stream);
+
+/* K3/K5: LML (+ hyper-parameter gradient) for B candidate theta rows, fused build -> factor -> reduce.
+ * theta_batch[B, d]; y[N] data vector (values then Fortran-flattened gradients); noise[N] or NULL
+ * (NOT divided by varK; used only when noisy != 0); noisy = 0: varK := 1 inside K and sigma^2 in closed form
+ * (kernel/Kernel.py:128-138, optz/CalcLkd.py:149-181); noisy = 1: varK_batch[B] given, LML of
+ * optz/CalcLkd.py:185-251.  mode is GEGP_MODE_BASE or GEGP_MODE_PRECON.  pnlt_grad is the varK-penalty
+ * derivative term of optz/CalcLkd.py:175 (0 when lkd_varK_pnlt_use is False).
+ * out[B, GEGP_OUT_LEN(d)].  alpha_out[B, N] (K^-1 (y - H beta), un-preconditioned) or NULL. */
+int gegp_lml_eval(int B, const double* theta_batch, const double* varK_batch, int n, int n_g, int d,
+                  const double* X, const int32_t* grad_slot, const double* y, const double* noise, int mode,
+                  double eta, int noisy, double pnlt_grad, int want_grad, double* out, double* alpha_out,
+                  void* work, size_t work_bytes, void* stream);
+
+/* K4 setup: build (varK := 1, kernel/Kernel.py:196-197) + factor + forward-solve of P^-1 (y - H beta).
+ * A is (N + 1) x lda; p_out[2N]; on exit row N of A holds w = L^-1 P^-1 (y - H beta).
+ * alpha_out[N] (optional) receives K^-1 (y - H beta) (eval/GpEvalModel.py:57). */
+int gegp_predict_setup(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+                       const double* noise, int mode, double eta, const double* y, double beta, double* A,
+                       int64_t lda, double* p_out, double* alpha_out, int* info_dev, void* stream);
+
+/* K4: posterior mean and standard deviation at nx test points (eval/GpEvalModel.py:154-168):
+ * mu = beta + k*^T K^-1 (y - H beta), sig = sqrt(varK) sqrt(max(0, 1 - k*^T K^-1 k*)); sig2_out (optional)
+ * receives the unclipped 1 - k*^T K^-1 k*, n_negative_dev counts entries < 0 (the reference asserts on them). */
+int gegp_predict(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+                 const double* A, int64_t lda, const double* p, int mode, double beta, double varK,
+                 const double* Xs, int nx, double* mu, double* sig, double* sig2_out, int* n_negative_dev,
+                 void* work, size_t work_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEGP_H_ */

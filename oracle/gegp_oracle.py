@@ -1,0 +1,497 @@
+"""CPU oracle for the gradient-enhanced GP hot path  --  TEST INFRASTRUCTURE ONLY.
+
+This module is a NumPy/SciPy restatement of the reference algorithm (marchildon/gpgradpy
+v1.3.2).  It exists to CHECK the CUDA path (tests/, __graft_entry__.smoke(), bench.py's
+cpu_baseline / --impl reference leg).  Nothing under gpgradpy_b200/ may import it.
+
+Parity pin: the reference ships NO golden vectors (its unit tests are finite-difference
+self-consistency checks).  This oracle is pinned by running the reference
+itself in the build container: oracle/make_golden.py imports /root/reference, evaluates the
+same inputs and writes tests/golden/*.npz; tests/test_oracle_golden.py compares this file
+against those fixtures on CPU.
+
+Conventions:
+  * data / matrix order is dimension-major: [f(x_0..x_{n-1}) | d/dx_0 at grad points | d/dx_1 ...]
+    (gradients flattened Fortran-order; base/CommonFun.py:170, kernel/Kernel.py:353)
+  * r = x_row - x_col (base/CommonFun.py:82)
+  * noise-free LML uses varK = 1 inside K and the closed form sigma^2 (optz/CalcLkd.py:157-159)
+"""
+from __future__ import annotations
+
+import dataclasses
+import numpy as np
+from scipy import linalg
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic inputs (plt/plt_cond.py:54-85 for the test function)
+# ----------------------------------------------------------------------------------------------
+
+def rosenbrock(x, a=10.0):
+    """d-dimensional Rosenbrock value, restated from plt/plt_cond.py:54-64."""
+    x = np.asarray(x, dtype=float)
+    return np.sum(a * (x[:, 1:] - x[:, :-1] ** 2) ** 2 + (1.0 - x[:, :-1]) ** 2, axis=1)
+
+
+def rosenbrock_grad(x, a=10.0):
+    """Gradient of the above, restated from plt/plt_cond.py:66-85."""
+    x = np.asarray(x, dtype=float)
+    g = np.zeros_like(x)
+    g[:, :-1] += -2.0 * (1.0 - x[:, :-1]) - 4.0 * a * x[:, :-1] * (x[:, 1:] - x[:, :-1] ** 2)
+    g[:, 1:] += 2.0 * a * (x[:, 1:] - x[:, :-1] ** 2)
+    return g
+
+
+def synthetic_problem(n, d, seed=0, lo=-2.0, hi=2.0):
+    """X ~ U[lo,hi]^d, Rosenbrock a=10 value and gradient."""
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(lo, hi, (n, d))
+    return x, rosenbrock(x), rosenbrock_grad(x)
+
+
+def bench_theta(d):
+    """theta_i = 0.05*linspace(0.5,1.5,d)*(10/d)  (SURVEY.md 8d)."""
+    return 0.05 * np.linspace(0.5, 1.5, d) * (10.0 / d)
+
+
+# ----------------------------------------------------------------------------------------------
+# kernel matrices
+# ----------------------------------------------------------------------------------------------
+
+def calc_rtensor(X, Y):
+    """R[i,a,b] = X[a,i] - Y[b,i]   (base/CommonFun.py:58-84)."""
+    return (X[:, None, :] - Y[None, :, :]).transpose(2, 0, 1).copy()
+
+
+def kern_base(X, Y, theta):
+    """k = exp(-sum_i theta_i r_i^2), accumulated i = 0..d-1 (kernel/KernelSqExp.py:18-46)."""
+    R = calc_rtensor(X, Y)
+    e = np.zeros(R.shape[1:])
+    for i in range(R.shape[0]):
+        e -= theta[i] * R[i] ** 2
+    return np.exp(e)
+
+
+def _sel(n, mask):
+    return np.arange(n) if mask is None else np.flatnonzero(np.asarray(mask, dtype=bool))
+
+
+def kern_grad(X, Y, theta, mask1=None, mask2=None):
+    """Gradient-enhanced kernel matrix (kernel/KernelSqExp.py:322-410).
+
+    Blocks: K00 = k; K_i0 = -2 th_i r_i k (:392); K_0j = +2 th_j r_j k (:393);
+    K_ii = (2 th_i - 4 th_i^2 r_i^2) k (:396); K_ij = -4 th_i th_j r_i r_j k (:406-408).
+    Gradient rows/cols are restricted to the masked points (:349-377).
+    """
+    theta = np.asarray(theta, dtype=float)
+    n1, d = X.shape
+    n2 = Y.shape[0]
+    s1, s2 = _sel(n1, mask1), _sel(n2, mask2)
+    g1, g2 = s1.size, s2.size
+    R = calc_rtensor(X, Y)
+    k = kern_base(X, Y, theta)
+    K = np.zeros((n1 + g1 * d, n2 + g2 * d))
+    K[:n1, :n2] = k
+    for i in range(d):
+        ri = slice(n1 + i * g1, n1 + (i + 1) * g1)
+        ci = slice(n2 + i * g2, n2 + (i + 1) * g2)
+        K[ri, :n2] = -2.0 * theta[i] * R[i][s1, :] * k[s1, :]
+        K[:n1, ci] = 2.0 * theta[i] * R[i][:, s2] * k[:, s2]
+        Rgg_i = R[i][np.ix_(s1, s2)]
+        kgg = k[np.ix_(s1, s2)]
+        K[ri, ci] = (2.0 * theta[i] - 4.0 * theta[i] ** 2 * Rgg_i ** 2) * kgg
+        for j in range(i + 1, d):
+            rj = slice(n1 + j * g1, n1 + (j + 1) * g1)
+            cj = slice(n2 + j * g2, n2 + (j + 1) * g2)
+            term = -4.0 * theta[i] * theta[j] * (Rgg_i * R[j][np.ix_(s1, s2)] * kgg)
+            K[ri, cj] += term
+            K[rj, ci] += term
+    return K
+
+
+def kern_grad_dtheta(X, theta, mask=None):
+    """d K / d theta_m for all m -> [d, N, N]  (kernel/KernelSqExp.py:471-568).
+
+    Restated from the closed form:
+      dK00 = -r_m^2 k ; dK_i0 = -r_m^2 K_i0 - 2 d_im r_m k ; dK_0j = transpose sign ;
+      dK_ij = -r_m^2 K_ij + (2 d_ij d_im - 4 (d_im th_j + d_jm th_i) r_i r_j) k.
+    With a mask this is the derivative of K_full[sel, sel] (the semantics the builder has);
+    the reference's jit is only right for None/prefix masks.
+    """
+    theta = np.asarray(theta, dtype=float)
+    n, d = X.shape
+    s = _sel(n, mask)
+    g = s.size
+    N = n + g * d
+    R = calc_rtensor(X, X)
+    k = kern_base(X, X, theta)
+    K = kern_grad(X, X, theta, mask, mask)
+    out = np.zeros((d, N, N))
+
+    def blk(i):
+        return slice(n + i * g, n + (i + 1) * g)
+
+    for m in range(d):
+        r2 = R[m] ** 2
+        D = out[m]
+        D[:n, :n] = -r2 * k
+        for i in range(d):
+            D[blk(i), :n] = -r2[s, :] * K[blk(i), :n]
+            D[:n, blk(i)] = -r2[:, s] * K[:n, blk(i)]
+            for j in range(d):
+                D[blk(i), blk(j)] = -r2[np.ix_(s, s)] * K[blk(i), blk(j)]
+        D[blk(m), :n] += -2.0 * R[m][s, :] * k[s, :]
+        D[:n, blk(m)] += 2.0 * R[m][:, s] * k[:, s]
+        kgg = k[np.ix_(s, s)]
+        D[blk(m), blk(m)] += 2.0 * kgg
+        for j in range(d):
+            t = -4.0 * theta[j] * R[m][np.ix_(s, s)] * R[j][np.ix_(s, s)] * kgg
+            D[blk(m), blk(j)] += t
+            D[blk(j), blk(m)] += t
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# nugget (base/GpWellCond.py)
+# ----------------------------------------------------------------------------------------------
+
+def vreq_rescale_origin(n, d):
+    """base/GpWellCond.py:26-40."""
+    if n == 1:
+        return 1.0
+    ds = 2.0 * np.sqrt(d)
+    v = (2.0 + np.sqrt(4.0 + 2.0 * np.exp(2.0) * np.log((n - 1) * (1.0 + ds) / 2.0))) / np.exp(1.0)
+    return min(v, ds)
+
+
+def nugget(n, d, mode, cond_max_target=1e10, use_grad=True, eta_set_mtd="Kbase_eta", eta_dflt=1e-8):
+    """(eta_Kbase, eta_Kgrad) per conditioning mode  (base/GpWellCond.py:116-154, :78-99, :109-114)."""
+    if eta_set_mtd == "dflt_eta":
+        return eta_dflt, eta_dflt
+    eta_base = n / (cond_max_target - 1.0)
+    if not use_grad:
+        return eta_base, np.nan
+    if n == 1:
+        return eta_base, eta_base
+    if mode == "precon":
+        u = 0.5 * (n - 1) * (1.0 + np.sqrt(1.0 + 4.0 * d)) * np.exp(-(1.0 + 2.0 * d - np.sqrt(1.0 + 4.0 * d)) / (4.0 * d))
+        return eta_base, (1.0 + u) / (cond_max_target - 1.0)
+    if "rescale" in mode:
+        vmin = vreq_rescale_origin(n, d)
+        vf = 2.0 * np.sqrt(d) / vmin
+        return eta_base, (1.0 + (n - 1) * vf * np.exp(1.0 / vf - 1.0)) / (cond_max_target - 1.0)
+    if eta_set_mtd == "Kbase_eta_w_dim":
+        return eta_base, eta_base * (d + 1)
+    return eta_base, eta_base
+
+
+# ----------------------------------------------------------------------------------------------
+# data packing, mean function
+# ----------------------------------------------------------------------------------------------
+
+def make_data_vec(fval, grad=None):
+    """[fval, grad.reshape(order='F')]  (base/CommonFun.py:152-173)."""
+    if grad is None:
+        return np.atleast_1d(fval).astype(float)
+    return np.hstack((fval, grad.reshape(grad.size, order="F")))
+
+
+def aug_vand(n, n_g, d):
+    """Constant-mean augmented Vandermonde column H = [1_n ; 0]  (eval/GpMeanFun.py:172-191)."""
+    H = np.zeros((n + n_g * d, 1))
+    H[:n, 0] = 1.0
+    return H
+
+
+# ----------------------------------------------------------------------------------------------
+# covariance assembly + factorisation  (kernel/Kernel.py:140-307)
+# ----------------------------------------------------------------------------------------------
+
+@dataclasses.dataclass
+class KAll:
+    Kern: np.ndarray
+    Kcor: np.ndarray | None
+    Kcov: np.ndarray
+    chofac: tuple | None       # (factor, lower) exactly as the reference returns it
+    eta: float
+    pvec: np.ndarray | None
+    Ltilde: np.ndarray | None  # precon: chol(varK (Kcor + eta I)), lower
+    idx_eta_argmax: int | None = None
+
+
+def all_K_w_chofac(X, theta, mode="precon", eta=None, noise_vec=None, varK=1.0, mask=None,
+                   cond_max_target=1e10, eta_is_const=True, calc_chofac=True):
+    """Faithful restatement of calc_all_K_w_chofac (kernel/Kernel.py:213-302) with use_grad=True.
+
+    precon (:220-266): p = sqrt(diag(K + noise/varK)); Kcor = P^-1 (K+noise/varK) P^-1;
+    Kt = varK (Kcor + eta I); Kcov = P Kt P; factor returned as (P Lt, lower=True).
+    otherwise (:268-302): Kcov = varK (K + noise/varK + eta I); cho_factor default (upper).
+    """
+    K = kern_grad(X, X, theta, mask, mask)
+    N = K.shape[0]
+    if noise_vec is None:
+        noise_vec = np.zeros(N)
+    Kw = K + np.diag(noise_vec / varK)
+    idx = None
+    if mode == "precon":
+        p = np.sqrt(np.diag(Kw))
+        pinv = 1.0 / p
+        Kcor = (pinv[:, None] * Kw) * pinv[None, :]      # (P_inv @ Kw) @ P_inv, same rounding
+        if not eta_is_const:
+            rs = np.sum(np.abs(Kcor), axis=1)
+            idx = int(np.argmax(rs))
+            eta = rs[idx] / (cond_max_target - 1.0)
+        Kt = varK * (Kcor + eta * np.eye(N))
+        Kcov = (p[:, None] * Kt) * p[None, :]
+        fac = Lt = None
+        if calc_chofac:
+            try:
+                Lt = linalg.cholesky(Kt, lower=True)
+                fac = (p[:, None] * Lt, True)
+            except linalg.LinAlgError:
+                fac = Lt = None
+        return KAll(K, Kcor, Kcov, fac, eta, p, Lt, idx)
+    if not eta_is_const:
+        rs = np.sum(np.abs(K), axis=1)
+        idx = int(np.argmax(rs))
+        eta = rs[idx] / (cond_max_target - 1.0)
+    Kcov = varK * (Kw + eta * np.eye(N))
+    fac = None
+    if calc_chofac:
+        try:
+            fac = linalg.cho_factor(Kcov)
+        except linalg.LinAlgError:
+            fac = None
+    return KAll(K, None, Kcov, fac, eta, None, None, idx)
+
+
+def kerngrad_hp(X, theta, mode, eta, mask=None):
+    """d(K + eta-term)/d theta stack, noise-free  (optz/GpHparaGrad.py:13-56).
+
+    precon adds 2*eta on the diagonal of gradient block m (:40-50): d(eta p^2)/d theta_m.
+    """
+    n, d = X.shape
+    g = _sel(n, mask).size
+    D = kern_grad_dtheta(X, theta, mask)
+    if mode == "precon":
+        for m in range(d):
+            idx = np.arange(n + m * g, n + (m + 1) * g)
+            D[m, idx, idx] += 2.0 * eta
+    return D
+
+
+# ----------------------------------------------------------------------------------------------
+# LML and gradient
+# ----------------------------------------------------------------------------------------------
+
+@dataclasses.dataclass
+class Lkd:
+    ln_lkd: float | None = None
+    ln_lkd_grad: np.ndarray | None = None
+    hp_varK: float | None = None
+    hp_beta: np.ndarray | None = None
+    ln_det: float | None = None
+    alpha: np.ndarray | None = None
+    chofac_good: bool = True
+    eta: float | None = None
+
+
+def gls_beta(chofac, H, y):
+    """beta = (H^T K^-1 H)^-1 H^T K^-1 y  (eval/GpMeanFun.py:98-108)."""
+    invK_H = linalg.cho_solve(chofac, H)
+    term1 = np.linalg.solve(H.T @ invK_H, invK_H.T)
+    return term1 @ y
+
+
+def lkd_wo_noise(X, fval, grad, theta, mode="precon", eta=None, mask=None, calc_grad=True,
+                 pnlt_grad=0.0, pnlt_val=0.0):
+    """Noise-free LML + d/dtheta, adjoint form.  Follows calc_lkd_all (optz/CalcLkd.py:322-339),
+    calc_lkd_all_wo_noise (:30-95) and calc_lkd_w_Kern_mtd_adjoint (:149-181) with varK := 1 inside
+    K (kernel/Kernel.py:128-138).  Materialises everything exactly as the reference does."""
+    n, d = X.shape
+    if eta is None:
+        eta = nugget(n, d, mode)[1]
+    ka = all_K_w_chofac(X, theta, mode, eta, None, 1.0, mask)
+    if ka.chofac is None:
+        return Lkd(chofac_good=False, eta=eta)
+    g = _sel(n, mask).size
+    y = make_data_vec(fval, grad)
+    N = y.size
+    H = aug_vand(n, g, d)
+    beta = gls_beta(ka.chofac, H, y)
+    res = y - H @ beta
+    alpha = linalg.cho_solve(ka.chofac, res)
+    varK = max(1e-32, float(res @ alpha) / N)
+    ln_det = 2.0 * np.sum(np.log(np.diag(ka.chofac[0])))
+    lml = -(N * np.log(varK) + ln_det) / 2.0 - pnlt_val
+    out = Lkd(lml, None, varK, beta, ln_det, alpha, True, eta)
+    if calc_grad:
+        D = kerngrad_hp(X, theta, mode, eta, mask)
+        adj_varK = np.outer(alpha, -alpha / N)
+        Kinv = linalg.cho_solve(ka.chofac, np.eye(N))
+        adj = -adj_varK * (pnlt_grad + N / (2.0 * varK)) - 0.5 * Kinv
+        out.ln_lkd_grad = np.einsum("ijk,jk", D, adj)
+    return out
+
+
+def lkd_wo_noise_lean(X, fval, grad, theta, mode="precon", eta=None, calc_grad=True, tile=256):
+    """Same quantities as lkd_wo_noise for sizes where the reference cannot run (its dK/dtheta
+    tensor is d*N*N*8 bytes).  In-place LAPACK potrf/potri; dK/dtheta contracted tile by tile.
+    All gradients used (mask=None).  Must agree with lkd_wo_noise (checked in tests)."""
+    n, d = X.shape
+    theta = np.asarray(theta, dtype=float)
+    if eta is None:
+        eta = nugget(n, d, mode)[1]
+    K = kern_grad(X, X, theta)
+    N = K.shape[0]
+    if mode == "precon":
+        p = np.sqrt(np.diag(K)).copy()
+        K /= p[:, None]
+        K /= p[None, :]
+    else:
+        p = np.ones(N)
+    K[np.diag_indices(N)] += eta
+    y = make_data_vec(fval, grad)
+    H = aug_vand(n, n, d)[:, 0]
+    c, info = linalg.lapack.dpotrf(K, lower=1, overwrite_a=1, clean=0)
+    if info != 0:
+        return Lkd(chofac_good=False, eta=eta)
+    rhs = np.stack((y / p, H / p), axis=1)
+    sol, _ = linalg.lapack.dpotrs(c, rhs, lower=1)
+    beta = float(rhs[:, 1] @ sol[:, 0]) / float(rhs[:, 1] @ sol[:, 1])
+    alpha_t = sol[:, 0] - beta * sol[:, 1]
+    res_t = rhs[:, 0] - beta * rhs[:, 1]
+    varK = max(1e-32, float(res_t @ alpha_t) / N)
+    ln_det = 2.0 * np.sum(np.log(np.diag(c) * p))
+    lml = -(N * np.log(varK) + ln_det) / 2.0
+    out = Lkd(lml, None, varK, np.array([beta]), ln_det, alpha_t / p, True, eta)
+    if not calc_grad:
+        return out
+    Kinv, info = linalg.lapack.dpotri(c, lower=1, overwrite_c=1)
+    il = np.tril_indices(N, -1)
+    Kinv.T[il] = Kinv[il]
+    # W = alpha alpha^T/(2 varK) - K^-1/2 in un-preconditioned coordinates
+    W = np.outer(alpha_t, alpha_t) / (2.0 * varK) - 0.5 * Kinv
+    W /= p[:, None]
+    W /= p[None, :]
+    gradv = np.zeros(d)
+    for a0 in range(0, n, tile):
+        a1 = min(n, a0 + tile)
+        rows = np.concatenate([np.arange(a0, a1)] + [n + i * n + np.arange(a0, a1) for i in range(d)])
+        Xa = X[a0:a1]
+        R = Xa[:, None, :] - X[None, :, :]                    # [ta, n, d]
+        k = np.exp(-np.einsum("abi,i->ab", R ** 2, theta))
+        Wt = W[rows].reshape(d + 1, a1 - a0, d + 1, n)        # [i, a, j, b]
+        u = R * theta[None, None, :]
+        W00 = Wt[0, :, 0, :]
+        Wi0 = Wt[1:, :, 0, :]                                  # [i, a, b]
+        W0j = Wt[0, :, 1:, :].transpose(1, 0, 2)               # [j, a, b]
+        Wij = Wt[1:, :, 1:, :]                                 # [i, a, j, b]
+        Wii = np.einsum("iaib->iab", Wij)
+        uT = u.transpose(2, 0, 1)                              # [i, a, b]
+        rT = R.transpose(2, 0, 1)
+        Wu = np.einsum("iajb,jab->iab", Wij, uT)               # sum_j W_ij u_j
+        WTu = np.einsum("iajb,iab->jab", Wij, uT)              # sum_i W_ij u_i
+        S = W00 + 2.0 * np.sum(uT * (W0j - Wi0), axis=0) + 2.0 * np.einsum("i,iab->ab", theta, Wii) \
+            - 4.0 * np.sum(uT * Wu, axis=0)
+        T = 2.0 * rT * (W0j - Wi0) + 2.0 * Wii - 4.0 * rT * (Wu + WTu)
+        gradv += np.einsum("ab,mab->m", k, T - rT ** 2 * S[None])
+    if mode == "precon":
+        dW = np.diag(W)
+        for m in range(d):
+            gradv[m] += 2.0 * eta * np.sum(dW[n + m * n: n + (m + 1) * n])
+    out.ln_lkd_grad = gradv
+    return out
+
+
+def kcov_grad_hp_noisy(X, theta, Kern, mode, eta, varK, has_var_fval, has_var_fgrad, mask=None):
+    """dKcov/d[theta.., varK, var_fval?, var_fgrad?]  (optz/GpHparaGrad.py:58-155)."""
+    n, d = X.shape
+    g = _sel(n, mask).size
+    N = n + g * d
+    stack = []
+    Dth = varK * kern_grad_dtheta(X, theta, mask)
+    if mode == "precon":
+        for i in range(d):
+            Dth[i] += np.diag(np.diag(Dth[i])) * eta            # :105-109
+    stack.extend(list(Dth))
+    if mode == "precon":
+        stack.append(Kern + eta * np.diag(np.diag(Kern)))        # :132-133
+    else:
+        stack.append(Kern + eta * np.eye(N))
+    sc = (1.0 + eta) if mode == "precon" else 1.0
+    if has_var_fval:
+        stack.append(sc * np.diag(np.hstack((np.ones(n), np.zeros(g * d)))))
+    if has_var_fgrad:
+        stack.append(sc * np.diag(np.hstack((np.zeros(n), np.ones(g * d)))))
+    return np.array(stack)
+
+
+def lkd_w_noise(X, fval, grad, theta, varK, noise_vec, mode="precon", eta=None, mask=None,
+                calc_grad=True, has_var_fval=False, has_var_fgrad=False):
+    """Noisy-data LML + gradient wrt [theta, varK, (var_fval), (var_fgrad)], adjoint form
+    (optz/CalcLkd.py:185-251, :299-320).  LML = -(ln det Kcov + res^T alpha)/2."""
+    n, d = X.shape
+    if eta is None:
+        eta = nugget(n, d, mode)[1]
+    ka = all_K_w_chofac(X, theta, mode, eta, noise_vec, varK, mask)
+    if ka.chofac is None:
+        return Lkd(chofac_good=False, eta=eta)
+    g = _sel(n, mask).size
+    y = make_data_vec(fval, grad)
+    N = y.size
+    H = aug_vand(n, g, d)
+    beta = gls_beta(ka.chofac, H, y)
+    res = y - H @ beta
+    alpha = linalg.cho_solve(ka.chofac, res)
+    ln_det = 2.0 * np.sum(np.log(np.diag(ka.chofac[0])))
+    lml = -(ln_det + float(res @ alpha)) / 2.0
+    out = Lkd(lml, None, varK, beta, ln_det, alpha, True, eta)
+    if calc_grad:
+        D = kcov_grad_hp_noisy(X, theta, ka.Kern, mode, eta, varK, has_var_fval, has_var_fgrad, mask)
+        adj = 0.5 * (np.outer(alpha, alpha) - linalg.cho_solve(ka.chofac, np.eye(N)))
+        out.ln_lkd_grad = np.einsum("ijk,jk", D, adj)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# posterior  (eval/GpEvalModel.py:17-57, 59-198)
+# ----------------------------------------------------------------------------------------------
+
+def eval_model(X, fval, grad, theta, varK, beta, Xs, mode="precon", eta=None, noise_vec=None, mask=None):
+    """mu = beta + K*^T K^-1 (y - H beta); sig = sqrt(varK) sqrt(max(0, 1 - diag(K*^T K^-1 K*)))
+    with the factor built for varK := 1 (kernel/Kernel.py:196-197)."""
+    n, d = X.shape
+    if eta is None:
+        eta = nugget(n, d, mode)[1]
+    ka = all_K_w_chofac(X, theta, mode, eta, noise_vec, 1.0, mask)
+    g = _sel(n, mask).size
+    y = make_data_vec(fval, grad)
+    H = aug_vand(n, g, d)
+    fdiff = y - H @ np.atleast_1d(beta)
+    a = linalg.cho_solve(ka.chofac, fdiff)
+    Kyx = kern_grad(X, Xs, theta, mask, None)[:, : Xs.shape[0]]
+    KinvK = linalg.cho_solve(ka.chofac, Kyx)
+    sig2 = 1.0 - np.einsum("ij,ij->j", Kyx, KinvK)
+    n_neg = int(np.sum(sig2 < 0))
+    sig = np.sqrt(np.maximum(sig2, 0.0)) * np.sqrt(varK)
+    mu = float(np.atleast_1d(beta)[0]) + Kyx.T @ a
+    return mu, sig, sig2, n_neg
+
+
+# ----------------------------------------------------------------------------------------------
+# rescaling (base/Rescaling.py:72-125, 199-214)
+# ----------------------------------------------------------------------------------------------
+
+def rescale_origin(X, fval, grad, dist_set):
+    """x_s = (x - x[last]) c with c = dist_set / min pairwise distance; f_s = (f - f[last]) s with
+    s = 100/(max f - min f); grad_s = grad s / c."""
+    from scipy.spatial.distance import pdist
+    n = X.shape[0]
+    c = 1.0 if n == 1 else dist_set / max(1e-14, float(np.min(pdist(X))))
+    xs = (X - X[-1][None, :]) * c
+    rng_f = max(1e-20, float(np.max(fval) - np.min(fval)))
+    s = 1.0 if n == 1 else 100.0 / rng_f
+    fs = (fval - fval[-1]) * s
+    gs = grad * (s / c)
+    return xs, fs, gs, c, s, fval[-1]
