@@ -19,7 +19,7 @@ OP_LML, OP_LML_GRAD, OP_PREDICT = 0, 1, 2
 
 EXPORTS = (
     "gegp_abi_version", "gegp_workspace_bytes", "gegp_ld", "gegp_build_cov", "gegp_cross_cov", "gegp_potrf",
-    "gegp_trsm_rows", "gegp_lml_eval", "gegp_predict_setup", "gegp_predict",
+    "gegp_trsm_rows", "gegp_lml_eval", "gegp_predict_setup", "gegp_predict", "gegp_profile_begin", "gegp_profile_end",
 )
 
 
@@ -62,7 +62,24 @@ def load():
     lib.gegp_predict_setup.argtypes = [i, i, i, dp, ip, dp, dp, i, dbl, dp, dbl, dp, i64, dp, dp, ip, vp]
     lib.gegp_predict.restype = i
     lib.gegp_predict.argtypes = [i, i, i, dp, ip, dp, dp, i64, dp, i, dbl, dbl, dp, i, dp, dp, dp, ip, vp, sz, vp]
+    lib.gegp_profile_begin.restype = None
+    lib.gegp_profile_begin.argtypes = [i]
+    lib.gegp_profile_end.restype = i
+    lib.gegp_profile_end.argtypes = [C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(dbl), C.POINTER(dbl)]
     if lib.gegp_abi_version() != ABI_VERSION:
         raise RuntimeError("libgegp.so ABI version mismatch; rebuild the extension")
     _lib = lib
     return lib
+
+
+def profile_begin(time_gemm: bool = False):
+    load().gegp_profile_begin(int(time_gemm))
+
+
+def profile_end():
+    """-> dict(launches, gemm_launches, gemm_ms, gemm_flops); synchronises the device when GEMM timing was on."""
+    a, b, c, d = C.c_long(0), C.c_long(0), C.c_double(0), C.c_double(0)
+    rc = load().gegp_profile_end(C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+    if rc != 0:
+        raise RuntimeError("gegp_profile_end failed")
+    return dict(launches=a.value, gemm_launches=b.value, gemm_ms=c.value, gemm_flops=d.value)

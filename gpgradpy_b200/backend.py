@@ -28,6 +28,15 @@ def to_dev(a, dtype=F64):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device())
 
 
+def pinned_like(buf, a):
+    """Copy the host array `a` into a page-locked fp64 staging tensor (re-using `buf` when the shape matches)."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if buf is None or tuple(buf.shape) != a.shape:
+        buf = torch.empty(a.shape, dtype=F64, pin_memory=True)
+    buf.copy_(torch.from_numpy(a))
+    return buf
+
+
 def _p(t) -> int:
     return 0 if t is None else t.data_ptr()
 

@@ -239,7 +239,7 @@ int launch_build_cov(const Ctx& ctx, const Geom& gm, const double* theta, int64_
   const size_t smem = (size_t)(TA * gm.d + gm.d * TB + 2 * gm.d) * sizeof(double) + (TA + TB) * sizeof(int);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
-    cudaFuncSetAttribute(build_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    GEGP_SET_SMEM(build_cov_kernel, smem);
     smem_set = smem;
   }
   dim3 grid((gm.n + TB - 1) / TB, (gm.n + TA - 1) / TA, ctx.batch);

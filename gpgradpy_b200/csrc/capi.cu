@@ -3,7 +3,33 @@
 #include "linalg.h"
 #include <algorithm>
 
+#include <vector>
+
 using namespace gegp;
+
+namespace gegp {
+static Prof g_prof;
+static std::vector<cudaEvent_t> g_ev;   // begin/end pairs around every GEMM launch while profiling
+static size_t g_ev_used = 0;
+Prof& prof() { return g_prof; }
+static cudaEvent_t next_event() {
+  if (g_ev_used == g_ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    g_ev.push_back(e);
+  }
+  return g_ev[g_ev_used++];
+}
+void prof_gemm_begin(cudaStream_t s) {
+  if (g_prof.on) cudaEventRecord(next_event(), s);
+}
+void prof_gemm_end(cudaStream_t s, double flops) {
+  if (!g_prof.on) return;
+  cudaEventRecord(next_event(), s);
+  g_prof.gemm_flops += flops;
+  g_prof.gemm_launches++;
+}
+}  // namespace gegp
 
 namespace {
 
@@ -41,6 +67,31 @@ bool bad_geom(int n, int n_g, int d) { return n <= 0 || d <= 0 || n_g < 0 || n_g
 extern "C" {
 
 int gegp_abi_version(void) { return GEGP_ABI_VERSION; }
+
+void gegp_profile_begin(int time_gemm) {
+  g_prof = Prof{};
+  g_prof.on = (time_gemm != 0);
+  g_ev_used = 0;
+}
+
+int gegp_profile_end(long* launches, long* gemm_launches, double* gemm_ms, double* gemm_flops) {
+  double ms = 0.0;
+  if (g_prof.on) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    for (size_t i = 0; i + 1 < g_ev_used; i += 2) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, g_ev[i], g_ev[i + 1]);
+      ms += t;
+    }
+  }
+  if (launches) *launches = g_prof.launches;
+  if (gemm_launches) *gemm_launches = g_prof.gemm_launches;
+  if (gemm_ms) *gemm_ms = ms;
+  if (gemm_flops) *gemm_flops = g_prof.gemm_flops;
+  g_prof.on = false;
+  g_ev_used = 0;
+  return 0;
+}
 
 int64_t gegp_ld(int N) { return round_up(N, 16); }
 
@@ -122,7 +173,7 @@ int gegp_lml_eval(int B, const double* theta_batch, const double* varK_batch, in
   if (B <= 0) return -1;
   if (!theta_batch) return -2;
   if (noisy && !varK_batch) return -3;
-  if (bad_geom(n, n_g, d) || n_g == 0) return -4;
+  if (bad_geom(n, n_g, d)) return -4;
   if (!X) return -7;
   if (n_g != n && !grad_slot) return -8;
   if (!y) return -9;
@@ -192,7 +243,7 @@ int gegp_lml_eval(int B, const double* theta_batch, const double* varK_batch, in
 int gegp_predict_setup(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
                        const double* noise, int mode, double eta, const double* y, double beta, double* A, int64_t lda,
                        double* p_out, double* alpha_out, int* info_dev, void* stream) {
-  if (bad_geom(n, n_g, d) || n_g == 0) return -1;
+  if (bad_geom(n, n_g, d)) return -1;
   if (!X) return -4;
   if (n_g != n && !grad_slot) return -5;
   if (!theta) return -6;
@@ -230,7 +281,7 @@ int gegp_predict_setup(int n, int n_g, int d, const double* X, const int32_t* gr
 int gegp_predict(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta, const double* A,
                  int64_t lda, const double* p, int mode, double beta, double varK, const double* Xs, int nx, double* mu,
                  double* sig, double* sig2_out, int* n_negative_dev, void* work, size_t work_bytes, void* stream) {
-  if (bad_geom(n, n_g, d) || n_g == 0) return -1;
+  if (bad_geom(n, n_g, d)) return -1;
   if (!X) return -4;
   if (n_g != n && !grad_slot) return -5;
   if (!theta) return -6;

@@ -4,6 +4,19 @@
 #include <cstdint>
 #include <cstdio>
 
+// ---- optional instrumentation (bench.py roofline pass; off by default, no cost when off) ----
+namespace gegp {
+struct Prof {
+  bool on = false;
+  long launches = 0;        // every kernel launch of the library since the last reset
+  double gemm_flops = 0.0;  // useful flops of the DMMA GEMM launches (2*M*N*K with triangular clipping)
+  long gemm_launches = 0;
+};
+Prof& prof();
+void prof_gemm_begin(cudaStream_t s);
+void prof_gemm_end(cudaStream_t s, double flops);
+}  // namespace gegp
+
 namespace gegp {
 
 constexpr int LEAF = 128;  // blocking quantum of the recursive factorisation / inverse
@@ -17,10 +30,21 @@ struct Ctx {
 
 #define GEGP_CHECK_LAUNCH()                                                                      \
   do {                                                                                           \
+    ::gegp::prof().launches++;                                                                   \
     cudaError_t e__ = cudaGetLastError();                                                        \
     if (e__ != cudaSuccess) {                                                                    \
       fprintf(stderr, "[gegp] launch error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__,   \
               __LINE__);                                                                         \
+      return -1000 - (int)e__;                                                                   \
+    }                                                                                            \
+  } while (0)
+
+#define GEGP_SET_SMEM(kern, bytes)                                                               \
+  do {                                                                                           \
+    cudaError_t e__ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+    if (e__ != cudaSuccess) {                                                                    \
+      fprintf(stderr, "[gegp] cannot set %d bytes of dynamic shared memory: %s (%s:%d)\n", (int)(bytes), \
+              cudaGetErrorString(e__), __FILE__, __LINE__);                                      \
       return -1000 - (int)e__;                                                                   \
     }                                                                                            \
   } while (0)
@@ -62,3 +86,4 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 }
 
 }  // namespace gegp
+

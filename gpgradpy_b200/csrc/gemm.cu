@@ -166,11 +166,20 @@ static int launch_cfg(const Ctx& ctx, const GemmArgs& g) {
   auto kern = gemm_f64_kernel<BM, BN, WM, WN, STAGES, B_KCONT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    GEGP_SET_SMEM(kern, Cfg::SMEM);
     attr_set = true;
   }
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.outer * g.inner);
+  prof_gemm_begin(ctx.stream);
   kern<<<grid, Cfg::THREADS, Cfg::SMEM, ctx.stream>>>(g);
+  if (prof().on) {
+    // useful flops: triangular output halves the tile count, triangular operands halve the k range
+    double f = 2.0 * g.M * (double)g.N * g.K * g.outer * g.inner;
+    if (g.cmode != C_FULL) f *= 0.5 * (g.M >= g.N ? (2.0 - (double)g.N / g.M) : 1.0);
+    if (g.klo_mode == KLO_MAXMN) f *= 2.0 / 3.0;
+    else if (g.klo_mode != KLO_ZERO || g.khi_mode != KHI_K) f *= 0.5;
+    prof_gemm_end(ctx.stream, f);
+  }
   GEGP_CHECK_LAUNCH();
   return 0;
 }

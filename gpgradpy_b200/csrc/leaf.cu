@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(256) potf2_kernel(double* A, int64_t lda, int6
   __syncthreads();
   const int tr = tid >> 4, tc = tid & 15;
   for (int j = 0; j < k; j++) {
+    __syncthreads();  // trailing update of step j-1 is complete
     const double piv = s[j * PLD + j];
     if (!(piv > 0.0)) {  // also catches NaN
       if (tid == 0 && bad == 0) bad = j + 1;
@@ -61,7 +62,7 @@ int leaf_potf2(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int k, i
   if (k > PNB) return -901;
   static bool attr = false;
   const int smem = PNB * PLD * (int)sizeof(double);
-  if (!attr) { cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  if (!attr) { GEGP_SET_SMEM(potf2_kernel, smem); attr = true; }
   potf2_kernel<<<dim3(1, 1, ctx.batch), 256, smem, ctx.stream>>>(A, lda, strideA, k, row0, info);
   GEGP_CHECK_LAUNCH();
   return 0;
@@ -136,7 +137,7 @@ int leaf_trsm_right(const Ctx& ctx, const double* L, int64_t ldl, int64_t stride
   if (k > TKB) return -902;
   static bool attr = false;
   const int smem = (TKB * TKB + TROWS * TXLD) * (int)sizeof(double);
-  if (!attr) { cudaFuncSetAttribute(trsm_right_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  if (!attr) { GEGP_SET_SMEM(trsm_right_leaf_kernel, smem); attr = true; }
   trsm_right_leaf_kernel<<<dim3((r + TROWS - 1) / TROWS, 1, ctx.batch), TROWS, smem, ctx.stream>>>(L, ldl, strideL, B,
                                                                                              ldb, strideB, r, k);
   GEGP_CHECK_LAUNCH();
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(PNB) trtri_t_kernel(const double* L, int64_t l
                                                        int64_t ldu, int64_t strideU, int N) {
   extern __shared__ double sm[];
   double* Ls = sm;               // PNB x PLD, row-major lower block
-  double* Ms = sm + PNB * PLD;   // Ms[r*PNB + j] = (L^-1)[r][j]
+  double* Ms = sm + PNB * PLD;   // packed lower: Ms[r*(r+1)/2 + j] = (L^-1)[r][j], j <= r
   L += (int64_t)blockIdx.z * strideL;
   U += (int64_t)blockIdx.z * strideU;
   const int b0 = blockIdx.x * PNB;
@@ -171,19 +172,19 @@ __global__ void __launch_bounds__(PNB) trtri_t_kernel(const double* L, int64_t l
       double a0 = 0, a1 = 0;
       int kk = j;
       for (; kk + 1 < r; kk += 2) {
-        a0 += Ls[r * PLD + kk] * Ms[kk * PNB + j];
-        a1 += Ls[r * PLD + kk + 1] * Ms[(kk + 1) * PNB + j];
+        a0 += Ls[r * PLD + kk] * Ms[kk * (kk + 1) / 2 + j];
+        a1 += Ls[r * PLD + kk + 1] * Ms[(kk + 1) * (kk + 2) / 2 + j];
       }
-      if (kk < r) a0 += Ls[r * PLD + kk] * Ms[kk * PNB + j];
+      if (kk < r) a0 += Ls[r * PLD + kk] * Ms[kk * (kk + 1) / 2 + j];
       acc -= a0 + a1;
     }
-    Ms[r * PNB + j] = (r >= j) ? acc / Ls[r * PLD + r] : 0.0;
+    if (r >= j) Ms[r * (r + 1) / 2 + j] = acc / Ls[r * PLD + r];
   }
   __syncthreads();
   // U[b0+j][b0+r] = Minv[r][j], r >= j  (upper triangular); coalesced along r
   for (int e = tid; e < k * k; e += PNB) {
     const int jj = e / k, r = e % k;
-    if (r >= jj) U[(int64_t)(b0 + jj) * ldu + b0 + r] = Ms[r * PNB + jj];
+    if (r >= jj) U[(int64_t)(b0 + jj) * ldu + b0 + r] = Ms[r * (r + 1) / 2 + jj];
   }
 }
 
@@ -191,8 +192,8 @@ int leaf_trtri_t(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, 
                  int64_t strideU, int N) {
   if (N <= 0) return 0;
   static bool attr = false;
-  const int smem = (PNB * PLD + PNB * PNB) * (int)sizeof(double);
-  if (!attr) { cudaFuncSetAttribute(trtri_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  const int smem = (PNB * PLD + PNB * (PNB + 1) / 2) * (int)sizeof(double);
+  if (!attr) { GEGP_SET_SMEM(trtri_t_kernel, smem); attr = true; }
   trtri_t_kernel<<<dim3((N + PNB - 1) / PNB, 1, ctx.batch), PNB, smem, ctx.stream>>>(L, ldl, strideL, U, ldu, strideU, N);
   GEGP_CHECK_LAUNCH();
   return 0;
@@ -285,7 +286,7 @@ int trsv_lower_trans(const Ctx& ctx, const double* L, int64_t ldl, int64_t strid
   const int nblk = (N + VNB - 1) / VNB;
   static bool attr = false;
   const int smem = VNB * PLD * (int)sizeof(double);
-  if (!attr) { cudaFuncSetAttribute(trsv_lt_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  if (!attr) { GEGP_SET_SMEM(trsv_lt_step_kernel, smem); attr = true; }
   // step j = nblk: only the diagonal solve of the last block; then j = nblk-1 .. 1
   for (int j = nblk; j >= 1; j--) {
     trsv_lt_step_kernel<<<dim3(j, 1, ctx.batch), 256, smem, ctx.stream>>>(L, ldl, strideL, x, ldx, strideX, N, nrhs, j);

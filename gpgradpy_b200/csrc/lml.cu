@@ -273,7 +273,7 @@ int launch_lml_grad(const Ctx& ctx, const Geom& gm, const double* theta, int64_t
   const size_t smem = (size_t)(d * GB + (d + 1) * GB + 2 * d) * sizeof(double);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
-    cudaFuncSetAttribute(lml_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    GEGP_SET_SMEM(lml_grad_kernel, smem);
     smem_set = smem;
   }
   dim3 grid((gm.n + GB - 1) / GB, gm.n, ctx.batch);

@@ -1,0 +1,834 @@
+"""`GaussianProcess`: host-side mirror of GpGradPy's GP class with the hot path on the B200.
+
+Same constructor, option attributes, method names, argument meaning and return contracts as the reference
+class (gpgradpy/src/GaussianProcess.py:24-457 and its mixins) for the Gaussian ("SqExp") kernel with a
+constant mean, gradient-free or gradient-enhanced data and the base / rescaling / preconditioned modes.
+Everything O(N^2) or O(N^3) is done by libgegp.so (hand-written sm_100a kernels behind include/gegp.h):
+
+  calc_all_K_w_chofac   -> gegp_build_cov + gegp_potrf        (kernel/Kernel.py:140-307)
+  calc_lkd_all          -> gegp_lml_eval                      (optz/CalcLkd.py:270-346)
+  select_hp_optz_x0     -> gegp_lml_eval, B candidates, sharded across ranks (optz/GpHparaX0.py:16-65)
+  setup_eval_model      -> gegp_predict_setup                 (eval/GpEvalModel.py:17-57)
+  eval_model            -> gegp_predict                       (eval/GpEvalModel.py:59-198; mu and sigma)
+
+Host Python keeps what the reference keeps in Python: log10 <-> theta transforms and the chain factor
+(optz/OptzLkd.py:65-70), SLSQP (optz/OptzLkd.py:265), bounds and Latin-hypercube starts, nugget
+formulas, rescaling, history arrays.  There is no CPU fallback for the device work.
+"""
+from __future__ import annotations
+
+import copy
+import time
+
+import numpy as np
+from scipy.optimize import Bounds, NonlinearConstraint, minimize
+from scipy.stats import qmc
+
+from . import _lib as L
+from . import backend as bk
+from . import hpara as H
+from . import parallel
+from .hpara import HparaOptzInfo, HparaOptzVal, LkdInfo
+from .rescaling import Rescaling
+
+
+class DeviceMatrix:
+    """A matrix that lives on the GPU and turns into a NumPy array on demand (np.asarray / indexing)."""
+
+    def __init__(self, t, symmetrize_from_lower=False):
+        self._t, self._sym, self._np = t, symmetrize_from_lower, None
+
+    @property
+    def tensor(self):
+        return self._t
+
+    @property
+    def shape(self):
+        return tuple(self._t.shape)
+
+    def numpy(self):
+        if self._np is None:
+            a = self._t.cpu().numpy().copy()
+            self._np = a
+        return self._np
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, idx):
+        return self.numpy()[idx]
+
+
+class GaussianProcess:
+    # ---- options (names and defaults of gpgradpy/src/GaussianProcess.py:27-113) ----
+    print_txt_data = False
+    save_data_npz = False
+    save_data_txt = False
+
+    optz_mtd = "SLSQP"
+    optz_n_x0 = 5
+    optz_iter_max = 250
+    optz_tol_obj = 1e-12
+    optz_tol_x = 1e-12
+    optz_log_hp_theta = True
+    optz_log_hp_var = True
+    optz_log_hp_kernel = True
+
+    lkd_use_adj_mtd = True
+    lkd_optz_start_avail = ["hp_best", "lhs"]
+    lkd_optz_start_mtd = "hp_best"
+    lkd_hp_best_n_eval = 40
+    lkd_varK_pnlt_use = False
+    lkd_varK_pnlt_lb_var = 0.1
+    lkd_varK_pnlt_c1 = 1.0
+    lkd_varK_pnlt_c2 = 10.0
+
+    hp_const_n_eval = 1
+    hp_lhs_bound_factor = 1e3
+    hp_box_bound_factor = 1e5
+    hp_median_n_idx = 5
+    hp_theta_init = 1e-2
+    hp_varK_init = 1.0
+    hp_kernel_init = np.nan
+    hp_var_fval_init = 0.0
+    hp_var_fgrad_init = 0.0
+    hp_theta_range = [1e-18, 1e24]
+    hp_varK_range = [1e-24, 1e14]
+    hp_kernel_range = [np.nan, np.nan]
+    hp_var_fval_range = [1e-8, 1e8]
+    hp_var_fgrad_range = [1e-8, 1e8]
+
+    wellcond_mtd_avail = ["base", "precon", "rescale_origin", "rescale_eta_vary", "dflt_vmin", "dflt_vmax"]
+    cond_eta_set_mtd = "Kbase_eta"
+    cond_eta_is_const = True
+    cond_eta_dflt = 1e-8
+    cond_max_target = 1e10
+    cond_max = 1e10
+    cond_max_abs = 1e16
+    cond_norm = 2
+    cond_dist_min_dflt = 1
+    cond_dist_max_dflt = 1
+    cond_vreq_max_iter = 3
+    vmin_rescale_eta_vary = 1.0
+    cond_vreq_iter_tol = 1e-1
+
+    b_optz_hp_kernel = True
+    b_use_data_scl = None
+    b_has_noisy_data = None
+    b_optz_var_fval = None
+    b_optz_var_fgrad = None
+    bvec_use_grad = None
+    _vmin_req_grad = np.nan
+    _time_chofac = 0
+    _save_data = False
+    _last_hp_vec = None
+    hp_vals = None
+    kernel_has_hp = False
+    hp_kernel_default = None
+    dist_group = None  # torch.distributed group used to shard candidate batches (None: default group / single rank)
+
+    HparaOptzVal = HparaOptzVal
+    HparaOptzInfo = HparaOptzInfo
+    LkdInfo = LkdInfo
+
+    def __init__(self, dim, use_grad, kernel_type="SqExp", wellcond_mtd="precon", mean_fun_type="poly_ord_0",
+                 path_data_surr="baye_data_surr", surr_name="obj_"):
+        assert isinstance(dim, int), "dim must be an integer"
+        assert isinstance(use_grad, bool), "use_grad must be of type bool"
+        assert isinstance(kernel_type, str), "kernel_type must be of type str"
+        if kernel_type != "SqExp":
+            raise Exception("Kernel type is not available (the B200 path implements the Gaussian kernel 'SqExp')")
+        if mean_fun_type != "poly_ord_0":
+            raise Exception(f"mean_fun_type = {mean_fun_type} not available")
+        self.dim, self.use_grad, self.kernel_type = dim, use_grad, kernel_type
+        self.mean_fun_type, self.n_beta_coeff, self.beta_var_npara = mean_fun_type, 1, 1
+        self.set_wellcond_mtd(wellcond_mtd)
+        self.path_data_surr, self.surr_name = path_data_surr, surr_name
+        self.hp_kernel = None
+        self._pred = None
+
+    # ------------------------------------------------------------------ configuration
+    def set_wellcond_mtd(self, wellcond_mtd):
+        """gpgradpy/src/GaussianProcess.py:192-217."""
+        assert wellcond_mtd in self.wellcond_mtd_avail, f"Requested method not available, wellcond_mtd : {wellcond_mtd}"
+        if wellcond_mtd == "rescale_eta_vary":
+            self.cond_eta_is_const = False
+        if not self.use_grad:
+            wellcond_mtd = "base"
+        self.wellcond_mtd = wellcond_mtd
+        self.b_use_cond_cstr = wellcond_mtd != "precon"
+        if self.b_use_cond_cstr:
+            self.condnum_nlc = NonlinearConstraint(self.return_cond_val, -np.inf, self.cond_max,
+                                                   jac=self.return_cond_grad)
+        self.b_use_data_scl = ("rescale" in wellcond_mtd) or ("dflt_v" in wellcond_mtd)
+
+    @property
+    def _mode(self):
+        return L.MODE_PRECON if self.wellcond_mtd == "precon" else L.MODE_BASE
+
+    # ------------------------------------------------------------------ small kernel-level helpers kept for API parity
+    @staticmethod
+    def theta2gamma(theta):
+        return np.sqrt(2 * np.asarray(theta))          # kernel/KernelSqExp.py:581-583
+
+    @staticmethod
+    def gamma2theta(gamma):
+        return 0.5 * np.asarray(gamma) ** 2            # kernel/KernelSqExp.py:586-588
+
+    @staticmethod
+    def make_data_vec(fval, fgrad=None):
+        """base/CommonFun.py:152-173."""
+        if fgrad is None:
+            return np.atleast_1d(fval)
+        return np.hstack((fval, fgrad.reshape(fgrad.size, order="F")))
+
+    def calc_nugget_Kbase(self, n_eval, cond_max=None):
+        return H.nugget_Kbase(n_eval, self.cond_max_target if cond_max is None else cond_max)
+
+    def calc_mtd_rescale_origin_vreq(self, n_eval, dim=None):
+        return H.vreq_rescale_origin(n_eval, self.dim if dim is None else dim)
+
+    def calc_nugget_Kfull_vreq(self, n_eval, vmin=None):
+        return H.nugget_Kfull_vreq(n_eval, self.dim, self.cond_max_target, vmin)
+
+    def calc_nugget(self, n_eval):
+        """(eta_Kbase, eta_Kgrad) -- base/GpWellCond.py:116-154."""
+        if self.cond_eta_set_mtd == "dflt_eta":
+            return self.cond_eta_dflt, self.cond_eta_dflt
+        eta_Kbase = self.calc_nugget_Kbase(n_eval)
+        if not self.use_grad:
+            return eta_Kbase, np.nan
+        if n_eval == 1:
+            return eta_Kbase, eta_Kbase
+        if self.wellcond_mtd == "precon":
+            return eta_Kbase, H.nugget_precon_sqexp(n_eval, self.dim, self.cond_max_target)
+        if "rescale" in self.wellcond_mtd:
+            return eta_Kbase, self.calc_nugget_Kfull_vreq(n_eval)
+        if self.cond_eta_set_mtd == "Kbase_eta":
+            return eta_Kbase, eta_Kbase
+        if self.cond_eta_set_mtd == "Kbase_eta_w_dim":
+            return eta_Kbase, eta_Kbase * (self.dim + 1)
+        raise Exception(f"Uknown method for cond_eta_set_mtd = {self.cond_eta_set_mtd}")
+
+    # ------------------------------------------------------------------ hyper-parameter plumbing (base/GpHpara.py)
+    def make_hp_class(self, beta=None, theta=None, kernel=None, varK=None, var_fval=None, var_fgrad=None):
+        return HparaOptzVal(beta, theta, kernel, varK, var_fval, var_fgrad)
+
+    def set_custom_hp(self, beta=None, theta=None, kernel=None, varK=None, var_fval=None, var_fgrad=None):
+        if varK is not None:
+            assert varK > 0, f"varK must be positive but it is {varK}"
+        self.hp_vals = self.make_hp_class(beta, theta, kernel, varK, var_fval, var_fgrad)
+
+    def hp_vec2dataclass(self, hp_optz_info, hp_vec):
+        """base/GpHpara.py:56-103 (10** for the log-optimised entries)."""
+        v = np.array(hp_vec, dtype=float, copy=True)
+        b = hp_optz_info.bvec_log_optz
+        v[b] = 10 ** v[b]
+        theta = v[hp_optz_info.idx_theta] if hp_optz_info.has_theta else None
+        varK = float(v[hp_optz_info.idx_varK]) if hp_optz_info.has_varK else None
+        var_fval = float(v[hp_optz_info.idx_var_fval]) if hp_optz_info.has_var_fval else None
+        var_fgrad = float(v[hp_optz_info.idx_var_fgrad]) if hp_optz_info.has_var_fgrad else None
+        return self.make_hp_class(None, theta, None, varK, var_fval, var_fgrad)
+
+    def set_hp_optz_info(self, has_theta, has_kernel=False, has_varK=False, has_var_fval=False, has_var_fgrad=False):
+        """optz/GpHparaOptz.py:44-138."""
+        assert not has_kernel, "the Gaussian kernel has no extra hyper-parameter"
+        n_hp = has_theta * self.dim + has_varK + has_var_fval + has_var_fgrad
+        blog = np.zeros(n_hp, dtype=bool)
+        cnt = 0
+        empty = np.array([], dtype=int)
+        idx_theta = empty
+        if has_theta:
+            idx_theta = np.arange(cnt, cnt + self.dim, dtype=int)
+            cnt += self.dim
+            blog[idx_theta] = self.optz_log_hp_theta
+        idx_varK = idx_vf = idx_vg = empty
+        if has_varK:
+            idx_varK, cnt = cnt, cnt + 1
+            blog[idx_varK] = self.optz_log_hp_var
+        if has_var_fval:
+            idx_vf, cnt = cnt, cnt + 1
+            blog[idx_vf] = self.optz_log_hp_var
+        if has_var_fgrad:
+            idx_vg, cnt = cnt, cnt + 1
+            blog[idx_vg] = self.optz_log_hp_var
+        return HparaOptzInfo(n_hp=n_hp, has_theta=has_theta, idx_theta=idx_theta, has_kernel=False, idx_kernel=empty,
+                             has_varK=has_varK, idx_varK=idx_varK, has_var_fval=has_var_fval, idx_var_fval=idx_vf,
+                             has_var_fgrad=has_var_fgrad, idx_var_fgrad=idx_vg, bvec_log_optz=blog)
+
+    def setup_hp_idx4optz(self):
+        self.hp_info_optz_lkd = self.set_hp_optz_info(True, False, self.b_has_noisy_data, self.b_optz_var_fval,
+                                                      self.b_optz_var_fgrad)
+
+    # ------------------------------------------------------------------ data
+    def set_data(self, x_eval, fval, std_fval, grad=None, std_grad=None, bvec_use_grad=None):
+        """gpgradpy/src/GaussianProcess.py:219-363 (validation, noise flags, nugget, scaling, device upload)."""
+        x_eval = np.asarray(x_eval, dtype=float)
+        fval = np.atleast_1d(np.asarray(fval, dtype=float)).ravel()
+        n_eval = fval.size
+        if self.use_grad:
+            if bvec_use_grad is None:
+                n_grad = n_eval
+            else:
+                bvec_use_grad = np.asarray(bvec_use_grad, dtype=bool)
+                n_grad = int(np.sum(bvec_use_grad))
+                assert bvec_use_grad.size == n_eval, \
+                    f"Length of bvec_use_grad is {bvec_use_grad.size} but it should be n_eval = {n_eval}"
+                assert grad.shape[0] == n_grad, f"No. of rows of grad is {grad.shape[0]} but it should be n_grad = {n_grad}"
+        else:
+            assert bvec_use_grad is None, "bvec_use_grad must be None if grads are not used for the GP"
+            n_grad = 0
+        self.n_eval, self.n_grad, self.n_data = n_eval, n_grad, n_eval + n_grad * self.dim
+        assert x_eval.ndim == 2, f"x_eval must be a 2 array but x_eval.ndim = {x_eval.ndim}"
+        assert x_eval.shape == (n_eval, self.dim), "No. of points do not match with x_eval and fval"
+
+        if (std_fval is None) or np.any(np.isnan(std_fval)):
+            self.known_eps_fval = False
+        else:
+            self.known_eps_fval = True
+            std_fval = np.atleast_1d(np.asarray(std_fval, dtype=float)).ravel()
+            assert n_eval == std_fval.size, f"Size of std_fval is {std_fval.size} while it should be {n_eval}"
+        if grad is None:
+            assert self.use_grad is False, "No grad info provided but use_grad was set to True"
+            self.has_grad_info, self.known_eps_fgrad = False, False
+        else:
+            assert self.use_grad, "Grad info provided but use_grad was set to False"
+            grad = np.asarray(grad, dtype=float)
+            self.has_grad_info = True
+            assert grad.ndim == 2 and grad.shape == (n_grad, self.dim), "Shape of grad does not match x_eval"
+            if (std_grad is None) or np.any(np.isnan(std_grad)):
+                self.known_eps_fgrad = False
+            else:
+                std_grad = np.asarray(std_grad, dtype=float)
+                self.known_eps_fgrad = True
+                assert grad.shape == std_grad.shape, "Shape of grad does not match std_grad"
+
+        self._x_eval_in, self._fval_in, self._grad_in = x_eval, fval, grad
+        self._std_fval_in = std_fval if self.known_eps_fval else None
+        self._std_grad_in = std_grad if self.known_eps_fgrad else None
+        self.bvec_use_grad = bvec_use_grad
+
+        if self.known_eps_fval:
+            self.b_optz_var_fval, self.b_fval_zero = False, bool(np.max(std_fval) < 1e-10)
+        else:
+            self.b_optz_var_fval, self.b_fval_zero = True, False
+        if self.use_grad is False:
+            self.b_optz_var_fgrad, self.b_fgrad_zero = False, True
+        elif self.known_eps_fgrad:
+            self.b_optz_var_fgrad, self.b_fgrad_zero = False, bool(np.max(std_grad) < 1e-10)
+        else:
+            self.b_optz_var_fgrad, self.b_fgrad_zero = True, False
+        self.b_has_noisy_data = not (self.b_fval_zero and self.b_fgrad_zero)
+
+        self._eta_Kbase, self._eta_Kgrad = self.calc_nugget(n_eval)
+        self._etaK = self._eta_Kgrad if self.use_grad else self._eta_Kbase
+        self._vmin_init = np.nan if n_eval == 1 else float(np.min(_pdist(x_eval)))
+        self.setup_hp_idx4optz()
+
+        if self.b_use_data_scl:
+            if self.wellcond_mtd == "rescale_origin":
+                dist_set = self.calc_mtd_rescale_origin_vreq(n_eval, self.dim)
+                self._vmin_req_grad, mtd = dist_set, "set_vmin"
+            elif self.wellcond_mtd == "rescale_eta_vary":
+                dist_set, mtd = self.vmin_rescale_eta_vary, "set_vmin"
+            elif self.wellcond_mtd == "dflt_vmin":
+                dist_set, mtd = self.cond_dist_min_dflt, "set_vmin"
+            elif self.wellcond_mtd == "dflt_vmax":
+                dist_set, mtd = self.cond_dist_max_dflt, "set_vmax"
+            else:
+                raise Exception(f"Unknown method wellcond_mtd = {self.wellcond_mtd}")
+            self.DataScl = Rescaling(x_eval, x_scl_method=mtd, dist_set=dist_set)
+            self.DataScl.set_obj_data(fval, std_fval, grad, std_grad)
+        self._dev_ready = False
+        self._pred = None
+        self._last_hp_vec = None
+
+    def _ensure_device(self):
+        """Put the (scaled) training data on the device (lazily): X[n,d], y[N], gradient-slot map."""
+        if getattr(self, "_dev_ready", False):
+            return
+        x_scl = self.get_scl_x_w_dist()[0]
+        fval, _, grad, _ = self.get_scl_eval_data()
+        self._slot_dev, ng = bk.slot_from_mask(self.bvec_use_grad if self.use_grad else np.zeros(self.n_eval, bool),
+                                               self.n_eval)
+        assert ng == self.n_grad
+        self._y_host = self.make_data_vec(fval, grad if self.use_grad else None)
+        # host -> device through pinned staging buffers (kept, so a refresh re-uses them)
+        self._x_pin = bk.pinned_like(getattr(self, "_x_pin", None), x_scl)
+        self._y_pin = bk.pinned_like(getattr(self, "_y_pin", None), self._y_host)
+        self._X_dev = self._x_pin.to(bk.device(), non_blocking=True)
+        self._y_dev = self._y_pin.to(bk.device(), non_blocking=True)
+        self._dev_ready = True
+
+    # ---- scaled / unscaled accessors (GaussianProcess.py:399-457)
+    def get_scl_x_w_dist(self):
+        """(x_scl, Rtensor).  The CUDA builder reads X directly, so no [d,n,n] distance tensor is kept: Rtensor is None."""
+        if self.b_use_data_scl:
+            return self.DataScl.get_scl_x_w_dist()
+        return self._x_eval_in, None
+
+    def x_init_2_scl(self, x):
+        return self.DataScl.x_init_2_scl(x) if self.b_use_data_scl else x
+
+    def x_scl_2_init(self, x):
+        return self.DataScl.x_scl_2_init(x) if self.b_use_data_scl else x
+
+    def get_init_eval_data(self):
+        return self._fval_in, self._std_fval_in, self._grad_in, self._std_grad_in
+
+    def get_scl_eval_data(self):
+        f, sf, g, sg = self.data_init_2_scl(*self.get_init_eval_data())[:4]
+        return f, (sf if self.known_eps_fval else None), g, (sg if self.known_eps_fgrad else None)
+
+    def data_init_2_scl(self, *a):
+        a = tuple(a) + (None,) * (6 - len(a))
+        return self.DataScl.obj_init_2_scl(*a) if self.b_use_data_scl else a
+
+    def data_scl_2_init(self, *a):
+        a = tuple(a) + (None,) * (6 - len(a))
+        return self.DataScl.obj_scl_2_init(*a) if self.b_use_data_scl else a
+
+    # ------------------------------------------------------------------ noise
+    def calc_noise_vec(self, hp_vals):
+        """kernel/Kernel.py:309-357."""
+        if self.b_fval_zero and self.b_fgrad_zero:
+            std_fval, std_fgrad = np.zeros(self.n_eval), np.zeros((self.n_grad, self.dim))
+        else:
+            std_fval, _, std_fgrad = self.get_scl_eval_data()[1:]
+        if not self.use_grad:
+            return std_fval ** 2 if self.known_eps_fval else np.full(self.n_eval, hp_vals.var_fval)
+        v = np.zeros(self.n_data)
+        v[: self.n_eval] = std_fval ** 2 if self.known_eps_fval else hp_vals.var_fval
+        v[self.n_eval:] = (std_fgrad ** 2).reshape(std_fgrad.size, order="F") if self.known_eps_fgrad else hp_vals.var_fgrad
+        return v
+
+    # ------------------------------------------------------------------ covariance assembly + factorisation
+    def calc_Kern_w_chofac(self, Rtensor, hp_vals, noise_vec=None, calc_chofac=True, calc_cond=False):
+        assert self.b_has_noisy_data is False, "This function should not be called if there is noisy data"
+        return self.calc_all_K_w_chofac(Rtensor, hp_vals, noise_vec, calc_chofac, calc_cond, varK=1)
+
+    def calc_all_K_w_chofac(self, Rtensor, hp_vals, noise_vec=None, calc_chofac=True, calc_cond=False, varK=None,
+                            b_normlz_w_varK=False):
+        """Same 7-tuple as kernel/Kernel.py:140-307; the matrices are device-resident DeviceMatrix objects that
+        convert to NumPy on demand.  `Rtensor` is accepted for signature compatibility and ignored."""
+        import torch
+        self._ensure_device()
+        theta = np.asarray(hp_vals.theta, dtype=float)
+        if varK is None:
+            assert hp_vals.varK is not None, f"varK is not provided and hp_vals.varK is None, hp_vals = {hp_vals}"
+            varK = hp_vals.varK
+        if b_normlz_w_varK:
+            varK = 1.0
+        else:
+            assert varK > 0, f"varK must be positive but varK = {varK}"
+        assert np.sum(np.isnan(theta)) == 0, f"There are nan values theta = {theta}"
+        if noise_vec is None:
+            noise_vec = self.calc_noise_vec(hp_vals)
+        noise = None if not np.any(noise_vec) else bk.to_dev(np.asarray(noise_vec, dtype=float) / varK)
+        X, slot, ng, N = self._X_dev, self._slot_dev, self.n_grad, self.n_data
+        kw = dict(n_g=ng, slot=slot)
+        Kern, _ = bk.build_cov(X, theta, mode=L.MODE_BASE, eta=0.0, **kw)
+        idx_etaK_argmax = None
+        precon = self.wellcond_mtd == "precon"
+        if precon:
+            assert self.use_grad is True, "self.wellcond_mtd should be base if use_grad is False"
+        if self.cond_eta_is_const:
+            etaK = self._etaK
+        else:  # variable nugget from Gershgorin row sums (kernel/Kernel.py:229-234, 269-274)
+            M = bk.build_cov(X, theta, noise=noise, mode=L.MODE_PRECON, eta=0.0, **kw)[0] if precon else Kern
+            rs = torch.sum(torch.abs(M), dim=1)
+            idx_etaK_argmax = int(torch.argmax(rs).item())
+            etaK = float(rs[idx_etaK_argmax].item()) / (self.cond_max_target - 1)
+        if precon:
+            Kt, p = bk.build_cov(X, theta, noise=noise, mode=L.MODE_PRECON, eta=etaK, varK=varK, **kw)
+            Kcor = DeviceMatrix(Kt / varK - etaK * torch.eye(N, dtype=Kt.dtype, device=Kt.device))
+            Kcov = DeviceMatrix(bk.build_cov(X, theta, noise=noise, mode=L.MODE_PRECON_COV, eta=etaK, varK=varK, **kw)[0])
+            fac_src, pvec = Kt, p[:N]
+        else:
+            Kc, _ = bk.build_cov(X, theta, noise=noise, mode=L.MODE_BASE, eta=etaK, varK=varK, **kw)
+            Kcor, Kcov, fac_src, pvec = None, DeviceMatrix(Kc), Kc, None
+        condK = None
+        if calc_cond:   # host NumPy, exactly like the reference (np.linalg.cond); not part of the CUDA hot path
+            condK = float(np.linalg.cond(fac_src.cpu().numpy(), p=self.cond_norm))
+            if (not precon) and condK > self.cond_max_abs:
+                calc_chofac = False
+        Kcov_chofac = None
+        t0 = time.time()
+        if calc_chofac:
+            ld = bk.ld_of(N)
+            A = torch.empty((N, ld), dtype=fac_src.dtype, device=fac_src.device)
+            A[:, :N] = fac_src
+            info = bk.potrf(A, N, 0)
+            if int(info.item()) == 0:
+                Lt = torch.tril(A[:, :N])
+                if precon:
+                    Kcov_chofac = (DeviceMatrix(pvec[:, None] * Lt), True)       # (P @ L, lower=True)  :252
+                else:
+                    Kcov_chofac = (DeviceMatrix(Lt.T.contiguous()), False)        # scipy default: upper     :291
+        self._time_chofac += time.time() - t0
+        return DeviceMatrix(Kern), Kcor, Kcov, Kcov_chofac, condK, etaK, idx_etaK_argmax
+
+    # ------------------------------------------------------------------ likelihood
+    def calc_lkd_varK_pnlt(self, varK, fval_vec):
+        """optz/CalcLkd.py:118-133."""
+        if not self.lkd_varK_pnlt_use:
+            return 0, 0
+        var_fval = max(np.var(fval_vec), self.lkd_varK_pnlt_lb_var)
+        mx = max(varK - self.lkd_varK_pnlt_c2 * var_fval, 0)
+        return self.lkd_varK_pnlt_c1 * var_fval * mx ** 2, 2 * self.lkd_varK_pnlt_c1 * var_fval * mx
+
+    def _eval_rows(self, theta_rows, *, want_grad, varK_rows=None, noise_vec=None, pnlt_grad=0.0):
+        """Device evaluation of B candidate rows -> torch [B, 9+d] (see GEGP_OUT_* in include/gegp.h)."""
+        self._ensure_device()
+        out, _ = bk.lml_eval(self._X_dev, self._y_dev, theta_rows, n_g=self.n_grad, slot=self._slot_dev,
+                             mode=self._mode, eta=self._etaK, noise=noise_vec, varK_batch=varK_rows,
+                             pnlt_grad=pnlt_grad, want_grad=want_grad)
+        return out
+
+    def calc_lkd_all(self, hp_vals, calc_lkd=True, calc_cond=False, calc_grad=False, lkd_use_adj_mtd=None):
+        """(LkdInfo, b_chofac_good) -- optz/CalcLkd.py:270-346, adjoint form only (the reference default)."""
+        assert self.cond_eta_is_const, "variable-nugget LML is not on the CUDA path yet (SURVEY 8f item 3)"
+        theta = np.asarray(hp_vals.theta, dtype=float)
+        d = self.dim
+        cond = None
+        if calc_cond:
+            cond = self.calc_all_K_w_chofac(None, hp_vals, calc_chofac=False, calc_cond=True,
+                                            varK=None if self.b_has_noisy_data else 1)[4]
+        if self.b_has_noisy_data:
+            noise = self.calc_noise_vec(hp_vals)
+            o = self._eval_rows(theta[None, :], want_grad=calc_grad, varK_rows=np.array([hp_vals.varK]),
+                                noise_vec=noise).cpu().numpy()[0]
+            if o[L.OUT_INFO] != 0:
+                return LkdInfo(cond=self._cond_on_failure(hp_vals)), False
+            info = LkdInfo(hp_beta=np.array([o[L.OUT_BETA]]), ln_det_Kmat=o[L.OUT_LOGDET], ln_lkd=o[L.OUT_LML],
+                           data_vec=self._y_host, cond=cond)
+            if calc_grad:
+                hi = self.hp_info_optz_lkd
+                g = np.zeros(hi.n_hp)
+                g[hi.idx_theta] = o[L.OUT_GRAD:L.OUT_GRAD + d]
+                if hi.has_varK:
+                    g[hi.idx_varK] = o[L.OUT_DVARK]
+                if hi.has_var_fval:
+                    g[hi.idx_var_fval] = o[L.OUT_DVARF]
+                if hi.has_var_fgrad:
+                    g[hi.idx_var_fgrad] = o[L.OUT_DVARG]
+                info.ln_lkd_grad = g
+            return info, True
+        pn_val = pn_grad = 0.0
+        if self.lkd_varK_pnlt_use:   # the penalty slope depends on sigma^2: one value-only pass first
+            o0 = self._eval_rows(theta[None, :], want_grad=False).cpu().numpy()[0]
+            pn_val, pn_grad = self.calc_lkd_varK_pnlt(o0[L.OUT_SIGMA2], self.get_scl_eval_data()[0])
+        o = self._eval_rows(theta[None, :], want_grad=calc_grad, pnlt_grad=pn_grad).cpu().numpy()[0]
+        if o[L.OUT_INFO] != 0:
+            return LkdInfo(cond=self._cond_on_failure(hp_vals)), False
+        info = LkdInfo(hp_beta=np.array([o[L.OUT_BETA]]), hp_varK=o[L.OUT_SIGMA2], ln_det_Kmat=o[L.OUT_LOGDET],
+                       cond=cond)
+        if calc_lkd:
+            info.ln_lkd = o[L.OUT_LML] - pn_val
+            if calc_grad:
+                info.ln_lkd_grad = o[L.OUT_GRAD:L.OUT_GRAD + d].copy()
+        return info, True
+
+    def _cond_on_failure(self, hp_vals):
+        """Failed Cholesky: the reference substitutes -cond for the objective (optz/OptzLkd.py:75-77)."""
+        try:
+            return self.calc_all_K_w_chofac(None, hp_vals, calc_chofac=False, calc_cond=True,
+                                            varK=None if self.b_has_noisy_data else 1)[4]
+        except Exception:
+            return np.inf
+
+    def calc_lkd_batch(self, hp_vec_rows, calc_grad=False):
+        """LML (and d/dtheta) of many noise-free candidate rows at once, sharded over the process group.
+
+        hp_vec_rows: [B, n_hp] in optimiser coordinates (log10 where bvec_log_optz).  Returns a NumPy table
+        [B, 9+d] laid out as GEGP_OUT_* -- identical on every rank.  This is the batched form of the loops at
+        optz/GpHparaX0.py:39-45 and optz/OptzLkd.py:249-270."""
+        import torch
+        assert not self.b_has_noisy_data
+        rows = np.atleast_2d(np.asarray(hp_vec_rows, dtype=float))
+        hi = self.hp_info_optz_lkd
+        th = rows[:, hi.idx_theta].copy()
+        if self.optz_log_hp_theta:
+            th = 10 ** th
+        cand = bk.to_dev(th)
+        table = parallel.sharded_eval(lambda c: self._eval_rows(c, want_grad=calc_grad), cand, self.dist_group)
+        return table.cpu().numpy()
+
+    # ------------------------------------------------------------------ optimiser callbacks (optz/OptzLkd.py:16-113)
+    def calc_store_likelihood(self, hp_vec, always_calc_cond=False, calc_grad=True):
+        hp_vec = np.atleast_1d(hp_vec).ravel()
+        # value and gradient come from ONE fused evaluation; the cache makes the second callback free
+        # (the reference never refreshes _last_hp_vec, optz/OptzLkd.py:48 vs :263, and evaluates twice).
+        if not np.array_equal(hp_vec, self._last_hp_vec):
+            hp_vals = self.hp_vec2dataclass(self.hp_info_optz_lkd, hp_vec)
+            calc_cond = self.b_use_cond_cstr or always_calc_cond
+            lkd_info, good = self.calc_lkd_all(hp_vals, calc_lkd=True, calc_cond=calc_cond, calc_grad=calc_grad)
+            cond_val, cond_grad = lkd_info.cond, lkd_info.cond_grad
+            if good:
+                val, grad = lkd_info.ln_lkd, lkd_info.ln_lkd_grad
+                if calc_grad:
+                    b = self.hp_info_optz_lkd.bvec_log_optz
+                    grad = grad.copy()
+                    grad[b] *= 10 ** hp_vec[b] * np.log(10)
+            else:
+                val, grad = -cond_val, np.zeros(hp_vec.size)
+            self._lkd_val, self._lkd_grad, self._cond_val, self._cond_grad = val, grad, cond_val, cond_grad
+            if calc_grad:
+                self._last_hp_vec = hp_vec.copy()
+        return self._lkd_val, self._lkd_grad, self._cond_val, self._cond_grad
+
+    def return_optz_val(self, hp_vec):
+        return -self.calc_store_likelihood(hp_vec)[0]
+
+    def return_optz_grad(self, hp_vec):
+        return -self.calc_store_likelihood(hp_vec)[1]
+
+    def return_cond_val(self, hp_vec):
+        return self.calc_store_likelihood(hp_vec)[2]
+
+    def return_cond_grad(self, hp_vec):
+        raise NotImplementedError("condition-number gradient (optz/GpHparaCon.py:161-235) is outside the CUDA hot path; "
+                                  "use wellcond_mtd='precon' for fits")
+
+    # ------------------------------------------------------------------ start points (optz/GpHparaX0.py)
+    def get_hp_x0_lhs_median(self, i_optz, hp_optz_info, n_x0):
+        """LHS in log10 space around the median of past hyper-parameters (optz/GpHparaX0.py:67-183)."""
+        lo_i, hi_i = int(max(0, i_optz - self.hp_median_n_idx)), i_optz
+        lf, bf = self.hp_lhs_bound_factor, self.hp_box_bound_factor
+        n_hp = hp_optz_info.n_hp
+        lhs_lb, lhs_ub, box_lb, box_ub = (np.full(n_hp, np.nan) for _ in range(4))
+
+        def fill(idx, hist, rng):
+            med = np.clip(np.median(hist, axis=0), rng[0], rng[1])
+            lhs_lb[idx], lhs_ub[idx] = np.maximum(med / lf, rng[0]), np.minimum(med * lf, rng[1])
+            box_lb[idx], box_ub[idx] = np.maximum(med / bf, rng[0]), np.minimum(med * bf, rng[1])
+
+        if hp_optz_info.has_theta:
+            fill(hp_optz_info.idx_theta, self.hp_theta_all[lo_i:hi_i, :], self.hp_theta_range)
+        if hp_optz_info.has_varK:
+            fill(hp_optz_info.idx_varK, self.hp_varK_all[lo_i:hi_i], self.hp_varK_range)
+        if hp_optz_info.has_var_fval:
+            fill(hp_optz_info.idx_var_fval, np.maximum(self.hp_var_fval_all[lo_i:hi_i], self.hp_var_fval_range[0]),
+                 self.hp_var_fval_range)
+        if hp_optz_info.has_var_fgrad:
+            fill(hp_optz_info.idx_var_fgrad, np.maximum(self.hp_var_fgrad_all[lo_i:hi_i], self.hp_var_fgrad_range[0]),
+                 self.hp_var_fgrad_range)
+        b = hp_optz_info.bvec_log_optz
+        for arr in (lhs_lb, lhs_ub, box_lb, box_ub):
+            arr[b] = np.log10(arr[b])
+        if np.any(lhs_lb > lhs_ub) or np.any(np.isnan(lhs_lb)):
+            raise Exception("Invalid bounds for lhs")
+        if np.any(box_lb > box_ub):
+            raise Exception("Invalid bounds for box")
+        bounds = Bounds(box_lb, box_ub, keep_feasible=True)
+        if n_hp == 1:
+            hp_x0 = np.linspace(lhs_lb[0], lhs_ub[0], n_x0 + 2)[1:-1, None]
+        else:
+            hp_x0 = self._lhs(np.array([lhs_lb, lhs_ub]).T, n_x0)
+        return hp_x0, bounds
+
+    @staticmethod
+    def _lhs(limits, n, seed=1):
+        """Latin hypercube with random_state=1 like the reference; `smt` when importable, else scipy.stats.qmc."""
+        try:
+            from smt.sampling_methods import LHS  # noqa: WPS433 (optional dependency of the reference)
+            return LHS(xlimits=limits, random_state=seed)(n)
+        except Exception:
+            unit = qmc.LatinHypercube(d=limits.shape[0], seed=seed).random(n)
+            return limits[:, 0][None, :] + unit * (limits[:, 1] - limits[:, 0])[None, :]
+
+    def select_hp_optz_x0(self, i_optz, hp_optz_info):
+        """optz/GpHparaX0.py:16-65; the 40-candidate scan runs as ONE batched device call (sharded over ranks)."""
+        t0 = time.time()
+        if self.lkd_optz_start_mtd == "lhs":
+            n_x0 = self.optz_n_x0
+        elif self.lkd_optz_start_mtd == "hp_best":
+            n_x0 = self.lkd_hp_best_n_eval
+        else:
+            raise Exception(f"Unknown lkd_optz_start_mtd: {self.lkd_optz_start_mtd}")
+        hp_x0, bounds = self.get_hp_x0_lhs_median(i_optz, hp_optz_info, n_x0)
+        if self.lkd_optz_start_mtd == "hp_best":
+            if self.b_has_noisy_data or self.wellcond_mtd != "precon":
+                lml = np.full(n_x0, np.nan)
+                cond_all = np.full(n_x0, np.nan)
+                calc_cond = self.wellcond_mtd != "precon"
+                for i in range(n_x0):
+                    info, good = self.calc_lkd_all(self.hp_vec2dataclass(hp_optz_info, hp_x0[i, :]), calc_cond=calc_cond)
+                    if good:
+                        lml[i], cond_all[i] = info.ln_lkd, (info.cond if info.cond is not None else np.nan)
+                if calc_cond:
+                    bad = cond_all > 1.2 * self.cond_max
+                    if np.sum(bad) == bad.size:
+                        bad[np.nanargmin(cond_all)] = False
+                    lml[bad] = np.nan
+            else:
+                tab = self.calc_lkd_batch(hp_x0, calc_grad=False)
+                lml = np.where(tab[:, L.OUT_INFO] == 0, tab[:, L.OUT_LML], np.nan)
+            hp_x0 = hp_x0[np.nanargmax(lml), :][None, :]
+        return hp_x0, bounds, time.time() - t0
+
+    # ------------------------------------------------------------------ fit (optz/GpHparaOptz.py, optz/OptzLkd.py:185-333)
+    def get_init_hp_vals(self):
+        fval = self.get_scl_eval_data()[0]
+        beta = np.array([np.mean(fval)])
+        vf = None if self.known_eps_fval else self.hp_var_fval_init
+        vg = None if ((self.use_grad is False) or self.known_eps_fgrad) else self.hp_var_fgrad_init
+        return self.make_hp_class(beta, self.hp_theta_init * np.ones(self.dim), None, self.hp_varK_init, vf, vg)
+
+    def optz_closed_form_hp(self, hp_vals):
+        info, _ = self.calc_lkd_all(hp_vals, calc_lkd=False, calc_cond=False, calc_grad=False)
+        hp_vals.beta = info.hp_beta
+        if self.b_has_noisy_data is False:
+            hp_vals.varK = info.hp_varK
+        return hp_vals
+
+    def optz_hp_max_lkd(self, hp_x0_all, optz_bound):
+        assert self.optz_mtd == "SLSQP", "the reference recommends SLSQP; trust-constr is not wired here"
+        opt = {"ftol": self.optz_tol_obj, "eps": self.optz_tol_x, "maxiter": self.optz_iter_max, "disp": False}
+        if hp_x0_all.ndim == 1:
+            hp_x0_all = hp_x0_all[None, :]
+        n_optz = hp_x0_all.shape[0]
+        ok = np.zeros(n_optz, bool)
+        nit = np.full(n_optz, np.nan)
+        obj = np.full(n_optz, np.nan)
+        sol = np.full((n_optz, self.hp_info_optz_lkd.n_hp), np.nan)
+        if self.b_use_cond_cstr:
+            raise NotImplementedError("fits with the condition-number constraint (base / rescale modes) are the next "
+                                      "row of SURVEY 8f; the CUDA fit path is wellcond_mtd='precon'")
+        for i in range(n_optz):
+            self._last_hp_vec = None
+            res = minimize(self.return_optz_val, hp_x0_all[i, :], method="SLSQP", jac=self.return_optz_grad,
+                           bounds=optz_bound, options=opt)
+            sol[i, :], obj[i], ok[i], nit[i] = res.x, res.fun, res.success, res.nit
+        best = sol[np.nanargmin(obj), :]
+        info = {"hp_optz_success": float(np.mean(ok)), "hp_optz_iter_mean": float(np.mean(nit)),
+                "hp_optz_iter_max": float(np.max(nit)), "hp_optz_con_good": 1.0, "optz_n_cho_fail": 0,
+                "optz_n_cond2big": 0, "optz_max_init_cond": np.nan}
+        return best, np.nan, info
+
+    def optz_hp(self, i_optz):
+        if self.n_eval <= self.hp_const_n_eval:
+            hp_vals, info, cond_val = self.get_init_hp_vals(), None, np.nan
+            t_optz = t_cho = t_x0 = 0
+        else:
+            self._time_chofac = 0
+            hp_x0, bound, t_x0 = self.select_hp_optz_x0(i_optz, self.hp_info_optz_lkd)
+            t0 = time.time()
+            hp_optz, cond_val, info = self.optz_hp_max_lkd(hp_x0, bound)
+            t_optz, t_cho = time.time() - t0, self._time_chofac
+            hp_vals = self.optz_closed_form_hp(self.hp_vec2dataclass(self.hp_info_optz_lkd, hp_optz))
+        self.store_new_para_surr(i_optz, hp_vals, info, cond_val, t_optz, t_cho, t_x0)
+
+    # ------------------------------------------------------------------ history (base/GpParaDef.py)
+    def init_optz_surr(self, n_optz_max):
+        self._save_data, self.n_optz_max = True, n_optz_max
+        full = lambda *s: np.full(s, np.nan)  # noqa: E731
+        self.hp_beta_all, self.hp_varK_all = full(n_optz_max, self.n_beta_coeff), full(n_optz_max)
+        self.hp_var_fval_all, self.hp_var_fgrad_all = full(n_optz_max), full(n_optz_max)
+        self.hp_kernel_all, self.hp_theta_all = full(n_optz_max), full(n_optz_max, self.dim)
+        self.min_nugget_all, self.Kcov_cond_all = full(n_optz_max), full(n_optz_max)
+        self.eta_Kbase_all, self.eta_Kgrad_all = full(n_optz_max), full(n_optz_max)
+        self.vmin_init_all, self.vmin_req_grad_all = full(n_optz_max), full(n_optz_max)
+        self.xvec_rescaling_all = full(n_optz_max, self.dim)
+        self.hp_optz_success, self.hp_optz_iter_mean, self.hp_optz_iter_max = full(n_optz_max), full(n_optz_max), full(n_optz_max)
+        self.time_pick_hp0_all, self.time_hp_optz_all, self.time_chofac_all = full(n_optz_max), full(n_optz_max), full(n_optz_max)
+
+    def store_new_para_surr(self, i_optz, hp_vals, surr_optz_info=None, cond_val=np.nan, time_hp_optz=np.nan,
+                            time_chofac=np.nan, time_pick_hp0=np.nan):
+        self.hp_vals = hp_vals
+        if self._save_data is False:
+            return
+        i = i_optz
+        self.time_hp_optz_all[i], self.time_chofac_all[i], self.time_pick_hp0_all[i] = time_hp_optz, time_chofac, time_pick_hp0
+        self.hp_beta_all[i, :], self.hp_theta_all[i, :] = hp_vals.beta, hp_vals.theta
+        self.hp_varK_all[i] = hp_vals.varK
+        self.hp_var_fval_all[i] = np.nan if hp_vals.var_fval is None else hp_vals.var_fval
+        self.hp_var_fgrad_all[i] = np.nan if hp_vals.var_fgrad is None else hp_vals.var_fgrad
+        self.min_nugget_all[i] = self._eta_Kgrad if self.use_grad else self._eta_Kbase
+        self.Kcov_cond_all[i] = cond_val
+        self.eta_Kbase_all[i], self.eta_Kgrad_all[i] = self._eta_Kbase, self._eta_Kgrad
+        self.vmin_init_all[i], self.vmin_req_grad_all[i] = self._vmin_init, self._vmin_req_grad
+        if self.b_use_data_scl:
+            self.xvec_rescaling_all[i] = self.DataScl.xvec_scale
+        if surr_optz_info is not None:
+            self.hp_optz_success[i] = surr_optz_info["hp_optz_success"]
+            self.hp_optz_iter_mean[i] = surr_optz_info["hp_optz_iter_mean"]
+            self.hp_optz_iter_max[i] = surr_optz_info["hp_optz_iter_max"]
+
+    def set_hp_from_idx(self, i_optz):
+        vf = None if np.isnan(self.hp_var_fval_all[i_optz]) else self.hp_var_fval_all[i_optz]
+        vg = None if np.isnan(self.hp_var_fgrad_all[i_optz]) else self.hp_var_fgrad_all[i_optz]
+        self.hp_vals = self.make_hp_class(self.hp_beta_all[i_optz, :], self.hp_theta_all[i_optz, :], None,
+                                          self.hp_varK_all[i_optz], vf, vg)
+
+    def set_hpara(self, method2set_hp, i_optz, hp_vals=None, calc_cond=False):
+        """gpgradpy/src/GaussianProcess.py:365-395."""
+        assert type(method2set_hp) is str, "method2set_hp must be a string"
+        if method2set_hp == "stored":
+            assert i_optz >= 0
+            self.set_hp_from_idx(i_optz)
+        elif method2set_hp == "optz":
+            self.optz_hp(i_optz)
+        elif method2set_hp == "current":
+            assert i_optz > 0
+            assert self.hp_vals is not None, "Cannot use current hp_vals if they have not been set yet"
+        elif method2set_hp == "set":
+            assert hp_vals is not None, 'If method2set_hp == "set", then the class hp_vals must be provided'
+            self.hp_vals = hp_vals
+        else:
+            raise Exception(f"Unknown method to set GP hp: method2set_hp = {method2set_hp}")
+        self.setup_eval_model(calc_cond=calc_cond)
+
+    # ------------------------------------------------------------------ posterior (eval/GpEvalModel.py)
+    def setup_eval_model(self, calc_cond=False):
+        """Factor K (varK := 1) once and keep it on the device with w = L^-1 P^-1 (y - H beta)."""
+        self._ensure_device()
+        self._hp_vals_model_setup = copy.copy(self.hp_vals)
+        hp = self.hp_vals
+        noise = self.calc_noise_vec(hp)   # NOT divided by varK: the reference sets varK = 1 first (kernel/Kernel.py:196-197,218)
+        noise = None if not np.any(noise) else noise
+        beta = float(np.atleast_1d(hp.beta)[0])
+        self._pred = bk.predict_setup(self._X_dev, self._y_dev, np.asarray(hp.theta, dtype=float), beta,
+                                      n_g=self.n_grad, slot=self._slot_dev, noise=noise, mode=self._mode,
+                                      eta=self._etaK)
+        self.data_vec = self._y_host
+        self.etaK_eval = self._etaK
+        self.condK = None
+        if calc_cond:
+            self.condK = self.calc_all_K_w_chofac(None, hp, b_normlz_w_varK=True, calc_chofac=False, calc_cond=True)[4]
+        good = int(self._pred.info.item()) == 0
+        self.KernEta_chofac = self._pred if good else None
+        self.invKernEta_fdiff = DeviceMatrix(self._pred.alpha) if good else None
+
+    def eval_model(self, x2model_in, calc_grad=False, calc_hess=False, squeeze_nx=False):
+        """(mu, sig, None, None, None, None) -- eval/GpEvalModel.py:59-198 for calc_grad = calc_hess = False."""
+        assert self.KernEta_chofac is not None, "To evaluate the surr the Cholesky decomposition is required"
+        if calc_grad or calc_hess:
+            raise NotImplementedError("surrogate x-derivatives (eval/GpEvalModel.py:170-180) are outside the CUDA hot path")
+        x = np.asarray(x2model_in, dtype=float)
+        if x.ndim == 1:
+            x = x[None, :]
+        elif x.ndim != 2:
+            raise Exception(f"x2model_in should be a 2d array but it has shape {x.shape}")
+        if squeeze_nx:
+            assert x.shape[0] == 1, "If squeeze_nx is True, then x_acq must only have one point"
+        if not (self.hp_vals == self._hp_vals_model_setup):
+            raise Exception("Cannot change hp_vals between calling setup_eval_model() and eval_model()")
+        if self.b_use_data_scl:
+            x = self.DataScl.x_init_2_scl(x)
+        mu, sig, sig2, nneg = bk.predict(self._pred, x, float(self.hp_vals.varK))
+        mu, sig = mu.cpu().numpy(), sig.cpu().numpy()
+        n_bad = int(nneg.item())
+        assert n_bad == 0, ("The variance of the surr should be non-negative but min(sig2_wo_sigK) = "
+                            f"{float(sig2.min().item())}")
+        if self.b_use_data_scl:
+            mu, sig = self.data_scl_2_init(mu, sig)[:2]
+        if squeeze_nx:
+            mu, sig = mu[0], sig[0]
+        return mu, sig, None, None, None, None
+
+
+def _pdist(x):
+    from scipy.spatial.distance import pdist
+    return pdist(x)

@@ -116,6 +116,11 @@ int gegp_predict(int n, int n_g, int d, const double* X, const int32_t* grad_slo
                  const double* Xs, int nx, double* mu, double* sig, double* sig2_out, int* n_negative_dev,
                  void* work, size_t work_bytes, void* stream);
 
+/* Instrumentation for bench.py (not on the product path): count kernel launches, and (time_gemm != 0)
+ * bracket every DMMA GEMM launch with CUDA events on its stream.  gegp_profile_end synchronises the device. */
+void gegp_profile_begin(int time_gemm);
+int gegp_profile_end(long* launches, long* gemm_launches, double* gemm_ms, double* gemm_flops);
+
 #ifdef __cplusplus
 }
 #endif

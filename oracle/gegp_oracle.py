@@ -46,6 +46,8 @@ def synthetic_problem(n, d, seed=0, lo=-2.0, hi=2.0):
     """X ~ U[lo,hi]^d, Rosenbrock a=10 value and gradient."""
     rng = np.random.default_rng(seed)
     x = rng.uniform(lo, hi, (n, d))
+    if d == 1:  # Rosenbrock is empty in 1-D: use f = sin(3x) + x^2 instead
+        return x, np.sin(3.0 * x[:, 0]) + x[:, 0] ** 2, 3.0 * np.cos(3.0 * x) + 2.0 * x
     return x, rosenbrock(x), rosenbrock_grad(x)
 
 

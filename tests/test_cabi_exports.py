@@ -1,0 +1,63 @@
+"""CPU: libgegp.so loads and exports every symbol include/gegp.h declares; host-only entry points behave."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "gegp.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gegp_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_declares_the_contract():
+    names = _declared_functions()
+    for must in ("gegp_build_cov", "gegp_cross_cov", "gegp_potrf", "gegp_trsm_rows", "gegp_lml_eval",
+                 "gegp_predict_setup", "gegp_predict", "gegp_workspace_bytes"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from gpgradpy_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build() first"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in _declared_functions():
+        assert hasattr(lib, name), f"{name} declared in include/gegp.h but not exported"
+    assert set(_lib.EXPORTS) == set(_declared_functions())
+
+
+def test_host_only_entry_points():
+    from gpgradpy_b200 import _lib
+    lib = _lib.load()
+    assert lib.gegp_abi_version() == _lib.ABI_VERSION
+    assert lib.gegp_ld(5500) == 5504 and lib.gegp_ld(21000) == 21008 and lib.gegp_ld(16) == 16
+    n, d = 500, 10
+    N = n * (d + 1)
+    w0 = lib.gegp_workspace_bytes(_lib.OP_LML, n, n, d, 1)
+    w1 = lib.gegp_workspace_bytes(_lib.OP_LML_GRAD, n, n, d, 1)
+    assert w0 >= (N + 2) * 5504 * 8 and w1 >= w0 + 2 * N * 5504 * 8
+    assert lib.gegp_workspace_bytes(_lib.OP_LML, 0, 0, d, 1) == 0          # bad geometry
+    assert lib.gegp_workspace_bytes(_lib.OP_PREDICT, n, n, d, 100) == 100 * 5504 * 8
+
+
+def test_argument_checks_return_negative_codes_without_touching_the_gpu():
+    from gpgradpy_b200 import _lib
+    lib = _lib.load()
+    assert lib.gegp_build_cov(0, 0, 3, 0, 0, 0, 0, 0, 0.0, 1.0, 0, 0, 0, 0, 0) == -1      # n <= 0
+    assert lib.gegp_build_cov(4, 4, 3, 0, 0, 0, 0, 0, 0.0, 1.0, 0, 0, 0, 0, 0) == -4      # X is NULL
+    assert lib.gegp_potrf(0, 0, 0, 0, 0, 0) == -1
+    assert lib.gegp_potrf(8, 0, 0, 8, 0, 0) == -3
+    assert lib.gegp_lml_eval(0, 0, 0, 4, 4, 3, 0, 0, 0, 0, 1, 0.0, 0, 0.0, 0, 0, 0, 0, 0, 0) == -1
+    assert lib.gegp_trsm_rows(8, 0, 8, 0, 8, 1, 0) == -2
+
+
+def test_no_cpu_fallback_when_library_is_missing(monkeypatch):
+    from gpgradpy_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libgegp.so")
+    with pytest.raises(RuntimeError):
+        _lib.load()

@@ -1,0 +1,140 @@
+"""GPU: the GaussianProcess API (the drop-in boundary) against the reference outputs in tests/golden.
+
+These read like the reference's own use: GP.set_data -> GP.calc_lkd_all / calc_all_K_w_chofac ->
+GP.set_hpara -> GP.eval_model (gpgradpy/plt/plt_cond.py:154-207, eval/GpEvalModel.py)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def _gp(g, mode, mask=None, std_f=0.0, std_g=0.0):
+    from gpgradpy_b200.gp import GaussianProcess
+    x = g["x"]
+    n, d = x.shape
+    GP = GaussianProcess(d, True, "SqExp", mode)
+    GP.set_data(x, g["fval"], std_f * np.ones(n), g["grad"], std_g * np.ones(g["grad"].shape), mask)
+    return GP
+
+
+@pytest.mark.parametrize("name,mode", [("d4_n37_precon", "precon"), ("d3_n30_base", "base"),
+                                       ("d3_n25_rescale_origin", "rescale_origin"), ("c1_d2_n20_precon", "precon")])
+def test_calc_lkd_all_and_K_tuple(golden_dir, name, mode):
+    g = _load(golden_dir, name)
+    GP = _gp(g, mode)
+    hp = GP.make_hp_class(theta=g["theta"])
+    info, ok = GP.calc_lkd_all(hp, calc_grad=True)
+    assert ok
+    tol = 1e-6 if name.startswith("c1_") else 1e-8
+    assert abs(info.ln_lkd - g["ln_lkd"]) < 1e-8 * abs(g["ln_lkd"])
+    assert abs(info.hp_varK - g["hp_varK"]) < tol * g["hp_varK"]
+    assert np.max(np.abs(info.ln_lkd_grad - g["ln_lkd_grad"])) < tol * np.max(np.abs(g["ln_lkd_grad"]))
+    assert info.hp_beta.shape == (1,)
+    # 7-tuple of calc_all_K_w_chofac (kernel/Kernel.py:307)
+    Kern, Kcor, Kcov, fac, condK, etaK, idx = GP.calc_all_K_w_chofac(GP.get_scl_x_w_dist()[1], hp, varK=1)
+    assert etaK == float(g["eta"]) and condK is None and idx is None
+    assert np.allclose(np.asarray(Kern), g["Kern"], rtol=1e-11, atol=1e-13 * np.abs(g["Kern"]).max())
+    assert np.allclose(np.asarray(Kcov), g["Kcov"], rtol=1e-11, atol=1e-13 * np.abs(g["Kcov"]).max())
+    if mode == "precon":
+        assert np.allclose(np.asarray(Kcor), g["Kcor"], rtol=1e-11, atol=1e-13)
+        assert fac[1] is True
+        Lg = np.tril(np.asarray(fac[0]))
+    else:
+        assert Kcor is None and fac[1] is False
+        Lg = np.triu(np.asarray(fac[0])).T
+    assert np.max(np.abs(Lg @ Lg.T - g["Kcov"])) < 1e-12 * np.max(np.abs(g["Kcov"]))
+    assert np.max(np.abs(Lg - g["chol_lower"])) < 1e-6 * np.max(np.abs(g["chol_lower"]))
+
+
+@pytest.mark.parametrize("name,mode", [("d4_n37_precon", "precon"), ("d3_n30_base", "base"),
+                                       ("d3_n25_rescale_origin", "rescale_origin")])
+def test_set_hpara_and_eval_model(golden_dir, name, mode):
+    g = _load(golden_dir, name)
+    GP = _gp(g, mode)
+    hp = GP.make_hp_class(theta=g["theta"], varK=float(g["hp_varK"]), beta=g["hp_beta"])
+    GP.set_hpara("set", 1, hp)
+    mu, sig, a, b, c, e = GP.eval_model(g["x_test"])
+    assert a is None and b is None and c is None and e is None
+    assert np.max(np.abs(mu - g["mu"])) < 1e-8 * np.max(np.abs(g["mu"]))
+    scale = np.max(g["sig"])
+    assert np.max(np.abs(sig - g["sig"])) < 1e-6 * scale
+    m1, s1 = GP.eval_model(g["x_test"][0], squeeze_nx=True)[:2]
+    assert np.isscalar(m1) or np.ndim(m1) == 0
+    assert abs(m1 - mu[0]) < 1e-12 * max(1.0, abs(mu[0]))
+    GP.hp_vals = GP.make_hp_class(theta=2 * g["theta"], varK=1.0, beta=g["hp_beta"])
+    with pytest.raises(Exception):
+        GP.eval_model(g["x_test"])          # hp changed after setup_eval_model (eval/GpEvalModel.py:105-111)
+
+
+def test_noisy_path(golden_dir):
+    g = _load(golden_dir, "d3_n24_noisy_precon")
+    GP = _gp(g, "precon", std_f=float(g["std_f"]), std_g=float(g["std_g"]))
+    assert GP.b_has_noisy_data and GP.hp_info_optz_lkd.has_varK
+    hp = GP.make_hp_class(theta=g["theta"], varK=float(g["varK"]))
+    info, ok = GP.calc_lkd_all(hp, calc_grad=True)
+    assert ok and abs(info.ln_lkd - g["ln_lkd"]) < 1e-8 * abs(g["ln_lkd"])
+    ref = g["ln_lkd_grad"]
+    assert np.max(np.abs(info.ln_lkd_grad - ref) / np.maximum(np.abs(ref), 1e-3 * np.abs(ref).max())) < 1e-8
+    hp2 = GP.make_hp_class(theta=g["theta"], varK=float(g["varK"]), beta=g["hp_beta"])
+    GP.set_hpara("set", 1, hp2)
+    mu, sig = GP.eval_model(g["x_test"])[:2]
+    assert np.max(np.abs(mu - g["mu"])) < 1e-8 * np.max(np.abs(g["mu"]))
+    assert np.max(np.abs(sig - g["sig"])) < 1e-6 * np.max(g["sig"])
+
+
+def test_masked_gradients(golden_dir):
+    g = _load(golden_dir, "d3_n18_mask_prefix")
+    GP = _gp(g, "precon", mask=g["mask"])
+    info, ok = GP.calc_lkd_all(GP.make_hp_class(theta=g["theta"]), calc_grad=True)
+    assert ok and abs(info.ln_lkd - g["ln_lkd"]) < 1e-8 * abs(g["ln_lkd"])
+    assert np.max(np.abs(info.ln_lkd_grad - g["ln_lkd_grad"])) < 1e-8 * np.max(np.abs(g["ln_lkd_grad"]))
+
+
+def test_fit_precon_small():
+    """set_hpara('optz'): history protocol of SURVEY appendix B.12, then the optimum must beat the start,
+    have a small projected gradient, and agree with the CPU oracle at the optimum."""
+    from gpgradpy_b200.gp import GaussianProcess
+    from oracle import gegp_oracle as O
+    x, f, g = O.synthetic_problem(24, 2, 1)
+    GP = GaussianProcess(2, True, "SqExp", "precon")
+    GP.init_optz_surr(3)
+    GP.set_data(x[:1], f[:1], np.zeros(1), g[:1], np.zeros((1, 2)))
+    GP.set_hpara("optz", 0)                      # one point: stores theta = 1e-2, no optimisation
+    assert np.allclose(GP.hp_theta_all[0], 1e-2)
+    GP.set_data(x, f, np.zeros(24), g, np.zeros((24, 2)))
+    GP.set_hpara("optz", 1)
+    th = GP.hp_vals.theta
+    assert th.shape == (2,) and np.all(th > 0) and GP.hp_vals.varK > 0
+    eta = GP._etaK
+    ref = O.lkd_wo_noise(x, f, g, th, "precon", eta)
+    info, ok = GP.calc_lkd_all(GP.hp_vals, calc_grad=True)
+    assert ok and abs(info.ln_lkd - ref.ln_lkd) < 1e-8 * abs(ref.ln_lkd)
+    assert abs(GP.hp_vals.varK - ref.hp_varK) < 1e-7 * ref.hp_varK
+    lml_start = O.lkd_wo_noise(x, f, g, 1e-2 * np.ones(2), "precon", eta, calc_grad=False).ln_lkd
+    assert info.ln_lkd >= lml_start
+    glog = info.ln_lkd_grad * th * np.log(10)
+    assert np.max(np.abs(glog)) < 1e-2 * max(1.0, abs(info.ln_lkd))
+    mu, sig = GP.eval_model(x[:5] + 1e-4)[:2]
+    assert np.max(np.abs(mu - f[:5])) < 1e-2 * np.max(np.abs(f)) + 1e-6
+
+
+def test_gradient_free_gp():
+    """use_grad=False (mode forced to 'base'): LML + gradient against the oracle with an all-False mask."""
+    from gpgradpy_b200.gp import GaussianProcess
+    from oracle import gegp_oracle as O
+    x, f, g = O.synthetic_problem(30, 3, 2)
+    GP = GaussianProcess(3, False, "SqExp", "precon")
+    GP.set_data(x, f, np.zeros(30))
+    th = O.bench_theta(3)
+    info, ok = GP.calc_lkd_all(GP.make_hp_class(theta=th), calc_grad=True)
+    mask = np.zeros(30, bool)
+    ref = O.lkd_wo_noise(x, f, np.zeros((0, 3)), th, "base", GP._etaK, mask=mask)
+    assert ok and abs(info.ln_lkd - ref.ln_lkd) < 1e-8 * abs(ref.ln_lkd)
+    assert np.max(np.abs(info.ln_lkd_grad - ref.ln_lkd_grad)) < 1e-7 * np.max(np.abs(ref.ln_lkd_grad))

@@ -1,0 +1,131 @@
+"""CPU: host-side mirror of the reference API (no device work): nuggets, hp packing, bounds, rescaling, sharding."""
+import os
+
+import numpy as np
+import pytest
+
+from gpgradpy_b200 import hpara as H
+from gpgradpy_b200.gp import GaussianProcess
+from gpgradpy_b200.parallel import shard_bounds
+from oracle import gegp_oracle as O
+
+
+def _load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def _gp(x, f, g, mode, **kw):
+    n, d = x.shape
+    GP = GaussianProcess(d, True, "SqExp", mode)
+    GP.set_data(x, f, np.zeros(n), g, np.zeros(g.shape), **kw)
+    return GP
+
+
+@pytest.mark.parametrize("name,mode", [("c1_d2_n20_precon", "precon"), ("c1_d2_n20_base", "base"),
+                                       ("d3_n25_rescale_origin", "rescale_origin"), ("c2_d10_n500_precon", "precon")])
+def test_nugget_matches_reference(golden_dir, name, mode):
+    g = _load(golden_dir, name)
+    GP = _gp(g["x"], g["fval"], g["grad"], mode)
+    assert abs(GP._etaK - float(g["eta"])) <= 1e-15 * float(g["eta"])
+    n, d = g["x"].shape
+    assert abs(GP._etaK - O.nugget(n, d, mode)[1]) <= 1e-15 * GP._etaK
+
+
+def test_rescale_origin_matches_reference(golden_dir):
+    g = _load(golden_dir, "d3_n25_rescale_origin")
+    GP = _gp(g["x"], g["fval"], g["grad"], "rescale_origin")
+    xs = GP.get_scl_x_w_dist()[0]
+    fs, _, gs, _ = GP.get_scl_eval_data()
+    assert np.array_equal(xs, g["x_scl"]) and np.allclose(fs, g["fval_scl"], rtol=1e-15, atol=0)
+    assert np.allclose(gs, g["grad_scl"], rtol=1e-15, atol=0)
+    # round trip of the prediction scaling
+    mu, sig = GP.data_scl_2_init(fs, np.abs(fs))[:2]
+    assert np.allclose(mu, g["fval"], rtol=1e-13, atol=1e-12)
+
+
+def test_flags_and_data_vector():
+    x, f, g = O.synthetic_problem(7, 3, 0)
+    GP = _gp(x, f, g, "precon")
+    assert GP.n_data == 7 * 4 and GP.b_has_noisy_data is False and GP.b_use_cond_cstr is False
+    assert np.array_equal(GP.make_data_vec(f, g), O.make_data_vec(f, g))
+    hi = GP.hp_info_optz_lkd
+    assert hi.n_hp == 3 and hi.has_theta and not hi.has_varK and hi.bvec_log_optz.all()
+    hp = GP.hp_vec2dataclass(hi, np.array([-1.0, 0.0, 0.5]))
+    assert np.allclose(hp.theta, [0.1, 1.0, 10 ** 0.5])
+    # noisy data with unknown noise variance adds varK / var_fval / var_fgrad to the optimised vector
+    GP2 = GaussianProcess(3, True, "SqExp", "precon")
+    GP2.set_data(x, f, None, g, None)
+    hi2 = GP2.hp_info_optz_lkd
+    assert GP2.b_has_noisy_data and hi2.n_hp == 6 and hi2.idx_varK == 3 and hi2.idx_var_fval == 4 and hi2.idx_var_fgrad == 5
+    nv = GP2.calc_noise_vec(GP2.make_hp_class(var_fval=0.25, var_fgrad=2.0))
+    assert nv.shape == (28,) and np.all(nv[:7] == 0.25) and np.all(nv[7:] == 2.0)
+    # known noise: gradient std is flattened Fortran-order (kernel/Kernel.py:353)
+    GP3 = GaussianProcess(3, True, "SqExp", "base")
+    sg = np.arange(21, dtype=float).reshape(7, 3) + 1
+    GP3.set_data(x, f, 0.1 * np.ones(7), g, sg)
+    nv3 = GP3.calc_noise_vec(GP3.make_hp_class())
+    assert np.allclose(nv3[7:], (sg ** 2).reshape(-1, order="F")) and np.allclose(nv3[:7], 0.01)
+
+
+def test_mode_table():
+    for mode, scl, cstr in [("precon", False, False), ("base", False, True), ("rescale_origin", True, True),
+                            ("dflt_vmin", True, True)]:
+        GP = GaussianProcess(2, True, "SqExp", mode)
+        assert GP.b_use_data_scl == scl and GP.b_use_cond_cstr == cstr
+    assert GaussianProcess(2, False, "SqExp", "precon").wellcond_mtd == "base"   # GaussianProcess.py:202-203
+    with pytest.raises(AssertionError):
+        GaussianProcess(2, True, "SqExp", "req_vmin")                              # stale name of the reference tests
+    with pytest.raises(Exception):
+        GaussianProcess(2, True, "Ma5f2")
+
+
+def test_lhs_bounds_follow_history():
+    x, f, g = O.synthetic_problem(9, 2, 0)
+    GP = _gp(x, f, g, "precon")
+    GP.init_optz_surr(4)
+    GP.hp_theta_all[0, :] = [1e-2, 1e-2]
+    GP.hp_theta_all[1, :] = [1.0, 4.0]
+    x0, bounds = GP.get_hp_x0_lhs_median(2, GP.hp_info_optz_lkd, 40)
+    med = np.log10(np.median(GP.hp_theta_all[:2], axis=0))
+    assert x0.shape == (40, 2)
+    assert np.allclose(bounds.lb, med - 5) and np.allclose(bounds.ub, med + 5)
+    assert np.all(x0 >= med - 3 - 1e-12) and np.all(x0 <= med + 3 + 1e-12)
+    # one sample per stratum in every dimension (Latin hypercube)
+    strata = np.floor((x0 - (med - 3)) / 6.0 * 40).astype(int)
+    assert all(len(set(strata[:, j])) == 40 for j in range(2))
+
+
+def test_shard_bounds_partition():
+    for B in (1, 7, 40, 1024):
+        for size in (1, 2, 3, 8):
+            if size > B:
+                continue
+            parts = [shard_bounds(B, r, size) for r in range(size)]
+            assert parts[0][0] == 0 and parts[-1][1] == B
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(size - 1))
+            lens = [hi - lo for lo, hi in parts]
+            assert max(lens) - min(lens) <= 1
+
+
+def test_chain_rule_cache_and_failure_contract(monkeypatch):
+    """calc_store_likelihood: log10 chain factor (optz/OptzLkd.py:65-70), one evaluation per point, -cond on failure."""
+    x, f, g = O.synthetic_problem(9, 2, 0)
+    GP = _gp(x, f, g, "precon")
+    calls = []
+
+    def fake(hp_vals, calc_lkd=True, calc_cond=False, calc_grad=False, lkd_use_adj_mtd=None):
+        calls.append(hp_vals.theta.copy())
+        return H.LkdInfo(ln_lkd=-3.0, ln_lkd_grad=np.array([2.0, -1.0]), cond=7.0), True
+
+    monkeypatch.setattr(GP, "calc_lkd_all", fake)
+    v = np.array([-1.0, 0.5])
+    assert GP.return_optz_val(v) == 3.0
+    gr = GP.return_optz_grad(v)
+    assert len(calls) == 1                                   # second callback served from the cache
+    assert np.allclose(gr, -np.array([2.0, -1.0]) * 10 ** v * np.log(10))
+    GP.return_optz_val(v + 1e-3)
+    assert len(calls) == 2
+    monkeypatch.setattr(GP, "calc_lkd_all", lambda *a, **k: (H.LkdInfo(cond=123.0), False))
+    GP._last_hp_vec = None
+    assert GP.return_optz_val(v) == 123.0                    # objective = -(-cond)
