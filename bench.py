@@ -247,12 +247,13 @@ def run_b200(args):
         gemm_ms = pr["gemm_ms"] / reps
         ld = bk.ld_of(N_)
         buf = torch.empty((N_ + 2, ld), dtype=torch.float64, device="cuda")
+        dinv_ = bk.dinv_buffer(N_)
         ms_full = ev_ms(lambda: bk.build_cov(Xd, thd[0], mode=L.MODE_PRECON, eta=eta_, out=buf[:N_]), reps)
         ms_low = ev_ms(lambda: bk.build_cov(Xd, thd[0], mode=L.MODE_PRECON, eta=eta_, out=buf[:N_], uplo=1), reps)
 
         def fac():
             bk.build_cov(Xd, thd[0], mode=L.MODE_PRECON, eta=eta_, out=buf[:N_], uplo=1)
-            bk.potrf(buf, N_, 0)
+            bk.potrf(buf, N_, 0, dinv_)
         ms_chol = ev_ms(fac, reps) - ms_low
         del buf
         return {"n": n_, "d": d_, "N": N_, "lml_grad_ms": ms_grad, "lml_only_ms": ms_val,

@@ -12,14 +12,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgegp.so")
 
 # mirrors of the #defines in include/gegp.h
-ABI_VERSION = 1
+ABI_VERSION = 2
 MODE_BASE, MODE_PRECON, MODE_PRECON_COV = 0, 1, 2
 OUT_LML, OUT_SIGMA2, OUT_BETA, OUT_LOGDET, OUT_INFO, OUT_QUAD, OUT_DVARK, OUT_DVARF, OUT_DVARG, OUT_GRAD = range(10)
 OP_LML, OP_LML_GRAD, OP_PREDICT = 0, 1, 2
 
 EXPORTS = (
     "gegp_abi_version", "gegp_workspace_bytes", "gegp_ld", "gegp_build_cov", "gegp_cross_cov", "gegp_potrf",
-    "gegp_trsm_rows", "gegp_lml_eval", "gegp_predict_setup", "gegp_predict", "gegp_profile_begin", "gegp_profile_end",
+    "gegp_trsm_rows", "gegp_dinv_doubles", "gegp_potri", "gegp_dgemm", "gegp_lml_eval", "gegp_predict_setup", "gegp_predict", "gegp_profile_begin", "gegp_profile_end",
 )
 
 
@@ -53,15 +53,21 @@ def load():
     lib.gegp_cross_cov.restype = i
     lib.gegp_cross_cov.argtypes = [i, i, i, dp, ip, dp, i, dp, dp, dp, i64, vp]
     lib.gegp_potrf.restype = i
-    lib.gegp_potrf.argtypes = [i, i, dp, i64, ip, vp]
+    lib.gegp_potrf.argtypes = [i, i, dp, i64, dp, ip, vp]
+    lib.gegp_dinv_doubles.restype = i64
+    lib.gegp_dinv_doubles.argtypes = [i]
     lib.gegp_trsm_rows.restype = i
-    lib.gegp_trsm_rows.argtypes = [i, dp, i64, dp, i64, i, vp]
+    lib.gegp_trsm_rows.argtypes = [i, dp, i64, dp, dp, i64, i, vp]
+    lib.gegp_potri.restype = i
+    lib.gegp_potri.argtypes = [i, dp, i64, dp, dp, i64, dp, i64, vp]
+    lib.gegp_dgemm.restype = i
+    lib.gegp_dgemm.argtypes = [i, i, i, i, dbl, dp, i64, dp, i64, dbl, dp, i64, vp]
     lib.gegp_lml_eval.restype = i
     lib.gegp_lml_eval.argtypes = [i, dp, dp, i, i, i, dp, ip, dp, dp, i, dbl, i, dbl, i, dp, dp, vp, sz, vp]
     lib.gegp_predict_setup.restype = i
-    lib.gegp_predict_setup.argtypes = [i, i, i, dp, ip, dp, dp, i, dbl, dp, dbl, dp, i64, dp, dp, ip, vp]
+    lib.gegp_predict_setup.argtypes = [i, i, i, dp, ip, dp, dp, i, dbl, dp, dbl, dp, i64, dp, dp, dp, ip, vp]
     lib.gegp_predict.restype = i
-    lib.gegp_predict.argtypes = [i, i, i, dp, ip, dp, dp, i64, dp, i, dbl, dbl, dp, i, dp, dp, dp, ip, vp, sz, vp]
+    lib.gegp_predict.argtypes = [i, i, i, dp, ip, dp, dp, i64, dp, dp, i, dbl, dbl, dp, i, dp, dp, dp, ip, vp, sz, vp]
     lib.gegp_profile_begin.restype = None
     lib.gegp_profile_begin.argtypes = [i]
     lib.gegp_profile_end.restype = i

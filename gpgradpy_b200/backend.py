@@ -119,21 +119,54 @@ def cross_cov(X, Xs, theta, *, n_g=None, slot=None, pinv=None):
     return out[:, :N]
 
 
-def potrf(A: torch.Tensor, N: int, n_extra: int = 0):
-    """In-place trapezoid Cholesky of A[(N+n_extra), ld]; returns the device info int tensor."""
+def dinv_buffer(N: int) -> torch.Tensor:
+    """Device buffer for the inverse-transposed diagonal blocks that belong to a factor of order N."""
+    return torch.empty(int(L.load().gegp_dinv_doubles(N)), dtype=F64, device=device())
+
+
+def potrf(A: torch.Tensor, N: int, n_extra: int = 0, dinv: torch.Tensor | None = None):
+    """In-place trapezoid Cholesky of A[(N+n_extra), ld]; returns (device info int tensor, dinv blocks)."""
     lib = L.load()
     assert A.is_cuda and A.dtype == F64 and A.stride(1) == 1 and A.shape[0] >= N + n_extra
     info = torch.zeros(1, dtype=torch.int32, device=A.device)
-    rc = lib.gegp_potrf(N, n_extra, _p(A), A.stride(0), _p(info), _stream())
+    if dinv is None:
+        dinv = dinv_buffer(N)
+    rc = lib.gegp_potrf(N, n_extra, _p(A), A.stride(0), _p(dinv), _p(info), _stream())
     _check(rc, "gegp_potrf")
-    return info
+    return info, dinv
 
 
-def trsm_rows(Lfac: torch.Tensor, N: int, B: torch.Tensor):
+def trsm_rows(Lfac: torch.Tensor, dinv: torch.Tensor, N: int, B: torch.Tensor):
     lib = L.load()
-    rc = lib.gegp_trsm_rows(N, _p(Lfac), Lfac.stride(0), _p(B), B.stride(0), B.shape[0], _stream())
+    rc = lib.gegp_trsm_rows(N, _p(Lfac), Lfac.stride(0), _p(dinv), _p(B), B.stride(0), B.shape[0], _stream())
     _check(rc, "gegp_trsm_rows")
     return B
+
+
+def potri(Lfac: torch.Tensor, dinv: torch.Tensor, N: int, U: torch.Tensor | None = None,
+          Kinv: torch.Tensor | None = None):
+    """Explicit inverse from the factor -> (U = L^-T in its upper triangle, Kinv full symmetric), [N, ld] buffers."""
+    lib = L.load()
+    ld = ld_of(N)
+    if U is None:
+        U = torch.empty((N, ld), dtype=F64, device=device())
+    if Kinv is None:
+        Kinv = torch.empty((N, ld), dtype=F64, device=device())
+    rc = lib.gegp_potri(N, _p(Lfac), Lfac.stride(0), _p(dinv), _p(U), U.stride(0), _p(Kinv), Kinv.stride(0), _stream())
+    _check(rc, "gegp_potri")
+    return U, Kinv
+
+
+def dgemm(A: torch.Tensor, B: torch.Tensor, C: torch.Tensor, *, transb: bool, alpha=1.0, beta=0.0):
+    """C = alpha * A @ (B.T if transb else B) + beta * C on the DMMA engine (row-major 2-D device tensors)."""
+    lib = L.load()
+    M, K = A.shape
+    N = B.shape[0] if transb else B.shape[1]
+    assert (B.shape[1] if transb else B.shape[0]) == K and tuple(C.shape) == (M, N)
+    rc = lib.gegp_dgemm(int(transb), M, N, K, float(alpha), _p(A), A.stride(0), _p(B), B.stride(0), float(beta), _p(C),
+                        C.stride(0), _stream())
+    _check(rc, "gegp_dgemm")
+    return C
 
 
 def lml_eval(X, y, theta_batch, *, n_g=None, slot=None, mode=L.MODE_PRECON, eta=0.0, noise=None, varK_batch=None,
@@ -172,8 +205,8 @@ def lml_eval(X, y, theta_batch, *, n_g=None, slot=None, mode=L.MODE_PRECON, eta=
 class PredictState:
     """Factor + solved residual row kept on the device between setup_eval_model and eval_model."""
 
-    def __init__(self, A, p, info, alpha, n, n_g, d, N, X, slot, theta, mode, beta):
-        self.A, self.p, self.info, self.alpha = A, p, info, alpha
+    def __init__(self, A, dinv, p, info, alpha, n, n_g, d, N, X, slot, theta, mode, beta):
+        self.A, self.dinv, self.p, self.info, self.alpha = A, dinv, p, info, alpha
         self.n, self.n_g, self.d, self.N = n, n_g, d, N
         self.X, self.slot, self.theta, self.mode, self.beta = X, slot, theta, mode, beta
 
@@ -187,13 +220,14 @@ def predict_setup(X, y, theta, beta, *, n_g=None, slot=None, noise=None, mode=L.
     N = n + n_g * d
     ld = ld_of(N)
     A = torch.empty((N + 1, ld), dtype=F64, device=device())
+    dinv = dinv_buffer(N)
     p = torch.empty(2 * N, dtype=F64, device=device())
     info = torch.zeros(1, dtype=torch.int32, device=device())
     alpha = torch.empty(N, dtype=F64, device=device()) if want_alpha else None
     rc = lib.gegp_predict_setup(n, n_g, d, _p(X), _p(slot), _p(theta), _p(noise), int(mode), float(eta), _p(y),
-                                float(beta), _p(A), ld, _p(p), _p(alpha), _p(info), _stream())
+                                float(beta), _p(A), ld, _p(dinv), _p(p), _p(alpha), _p(info), _stream())
     _check(rc, "gegp_predict_setup")
-    return PredictState(A, p, info, alpha, n, n_g, d, N, X, slot, theta, mode, float(beta))
+    return PredictState(A, dinv, p, info, alpha, n, n_g, d, N, X, slot, theta, mode, float(beta))
 
 
 def predict(st: PredictState, Xs, varK: float, *, chunk_bytes: int = 1 << 30):
@@ -208,8 +242,8 @@ def predict(st: PredictState, Xs, varK: float, *, chunk_bytes: int = 1 << 30):
     row_bytes = ld_of(st.N) * 8
     cx = max(1, min(nx, chunk_bytes // row_bytes))
     ws = workspace(cx * row_bytes)
-    rc = lib.gegp_predict(st.n, st.n_g, st.d, _p(st.X), _p(st.slot), _p(st.theta), _p(st.A), st.A.stride(0), _p(st.p),
-                          int(st.mode), st.beta, float(varK), _p(Xs), nx, _p(mu), _p(sig), _p(sig2), _p(nneg), _p(ws),
+    rc = lib.gegp_predict(st.n, st.n_g, st.d, _p(st.X), _p(st.slot), _p(st.theta), _p(st.A), st.A.stride(0), _p(st.dinv),
+                          _p(st.p), int(st.mode), st.beta, float(varK), _p(Xs), nx, _p(mu), _p(sig), _p(sig2), _p(nneg), _p(ws),
                           cx * row_bytes, _stream())
     _check(rc, "gegp_predict")
     return mu, sig, sig2, nneg

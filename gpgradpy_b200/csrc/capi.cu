@@ -37,7 +37,7 @@ inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
 
 struct LmlLayout {
   int64_t ld;          // leading dimension of every N-column matrix
-  size_t A, P, W, U, Kinv, Part;  // per-candidate element (double) offsets
+  size_t A, P, W, D, U, Kinv, Part;  // per-candidate element (double) offsets
   size_t per_cand_doubles;
 };
 
@@ -47,7 +47,8 @@ LmlLayout lml_layout(int n, int d, int N, bool grad) {
   size_t off = 0;
   L.A = off;    off += (size_t)(N + 2) * L.ld;
   L.P = off;    off += (size_t)2 * L.ld;
-  L.W = off;    off += (size_t)L.ld;
+  L.W = off;    off += (size_t)2 * L.ld;   // w = L^-1 P^-1 res, then the preconditioned alpha = L^-T w
+  L.D = off;    off += (size_t)dinv_doubles(N);
   if (grad) {
     L.U = off;    off += (size_t)N * L.ld;
     L.Kinv = off; off += (size_t)N * L.ld;
@@ -145,25 +146,56 @@ int gegp_cross_cov(int n, int n_g, int d, const double* X, const int32_t* grad_s
   return launch_cross_cov(ctx, gm, theta, pinv, Xs, nx, Kx, ld);
 }
 
-int gegp_potrf(int N, int n_extra, double* A, int64_t lda, int* info_dev, void* stream) {
+int64_t gegp_dinv_doubles(int N) { return N > 0 ? dinv_doubles(N) : 0; }
+
+int gegp_potrf(int N, int n_extra, double* A, int64_t lda, double* dinv, int* info_dev, void* stream) {
   if (N <= 0) return -1;
   if (n_extra < 0) return -2;
-  if (!A) return -3;
+  if (!A || (reinterpret_cast<uintptr_t>(A) & 15)) return -3;
   if (lda < N || (lda & 1)) return -4;
-  if (!info_dev) return -5;
+  if (!dinv || (reinterpret_cast<uintptr_t>(dinv) & 15)) return -5;
+  if (!info_dev) return -6;
   Ctx ctx{(cudaStream_t)stream, 1};
-  return chol_trap(ctx, A, lda, 0, N + n_extra, N, 0, info_dev);
+  return chol_trap(ctx, A, lda, 0, N + n_extra, N, 0, info_dev, dinv, 0);
 }
 
-int gegp_trsm_rows(int N, const double* L, int64_t ldl, double* B, int64_t ldb, int r, void* stream) {
+int gegp_trsm_rows(int N, const double* L, int64_t ldl, const double* dinv, double* B, int64_t ldb, int r,
+                   void* stream) {
   if (N <= 0) return -1;
   if (!L) return -2;
   if (ldl < N || (ldl & 1)) return -3;
-  if (!B) return -4;
-  if (ldb < N || (ldb & 1)) return -5;
-  if (r < 0) return -6;
+  if (!dinv) return -4;
+  if (!B || (reinterpret_cast<uintptr_t>(B) & 15)) return -5;
+  if (ldb < N || (ldb & 1)) return -6;
+  if (r < 0) return -7;
   Ctx ctx{(cudaStream_t)stream, 1};
-  return trsm_right_rec(ctx, L, ldl, 0, B, ldb, 0, r, N);
+  return trsm_right_rec(ctx, L, ldl, 0, dinv, 0, 0, B, ldb, 0, r, N);
+}
+
+int gegp_potri(int N, const double* L, int64_t ldl, const double* dinv, double* U, int64_t ldu, double* Kinv,
+               int64_t ldk, void* stream) {
+  if (N <= 0) return -1;
+  if (!L) return -2;
+  if (ldl < N || (ldl & 1)) return -3;
+  if (!dinv) return -4;
+  if (!U || (reinterpret_cast<uintptr_t>(U) & 15)) return -5;
+  if (ldu < N || (ldu & 1)) return -6;
+  if (!Kinv || (reinterpret_cast<uintptr_t>(Kinv) & 15)) return -7;
+  if (ldk < N || (ldk & 1)) return -8;
+  Ctx ctx{(cudaStream_t)stream, 1};
+  return chol_inverse(ctx, L, ldl, 0, dinv, 0, U, ldu, 0, Kinv, ldk, 0, N);
+}
+
+int gegp_dgemm(int transb, int M, int N, int K, double alpha, const double* A, int64_t lda, const double* B,
+               int64_t ldb, double beta, double* C, int64_t ldc, void* stream) {
+  if (M < 0) return -2;
+  if (N < 0) return -3;
+  if (K < 0) return -4;
+  if (!A || lda < K) return -6;
+  if (!B || ldb < (transb ? K : N)) return -8;
+  if (!C || ldc < N) return -11;
+  Ctx ctx{(cudaStream_t)stream, 1};
+  return gemm_f64(ctx, gemm_args(A, lda, B, ldb, C, ldc, M, N, K, alpha, beta, transb != 0));
 }
 
 int gegp_lml_eval(int B, const double* theta_batch, const double* varK_batch, int n, int n_g, int d, const double* X,
@@ -215,25 +247,29 @@ int gegp_lml_eval(int B, const double* theta_batch, const double* varK_batch, in
     if (rc) return rc;
     rc = launch_append_rhs(ctx, N, n, y, pinv, sC, A + (int64_t)N * L.ld, L.ld, sC);
     if (rc) return rc;
-    rc = chol_trap(ctx, A, L.ld, sC, N + 2, N, 0, info);
+    double* D = wk + L.D;
+    rc = chol_trap(ctx, A, L.ld, sC, N + 2, N, 0, info, D, sC);
     if (rc) return rc;
     rc = launch_lml_finalize(ctx, N, A, L.ld, sC, pinv, sC, noisy, varK, W, sC, outb, outlen, info);
     if (rc) return rc;
-    if (want_grad || alpha_out) {
-      rc = trsv_lower_trans(ctx, A, L.ld, sC, W, L.ld, sC, N, 1);  // W <- L^-T w  (preconditioned alpha)
-      if (rc) return rc;
-      if (alpha_out) {
-        rc = launch_scale_vec(ctx, N, W, sC, pinv, sC, alpha_out + (int64_t)b0 * N, N);
-        if (rc) return rc;
-      }
-    }
+    double* alpha_t = W;  // preconditioned alpha = L^-T w
     if (want_grad) {
       double* U = wk + L.U;
       double* Kinv = wk + L.Kinv;
-      rc = chol_inverse(ctx, A, L.ld, sC, U, L.ld, sC, Kinv, L.ld, sC, N);
+      rc = chol_inverse(ctx, A, L.ld, sC, D, sC, U, L.ld, sC, Kinv, L.ld, sC, N);
       if (rc) return rc;
-      rc = launch_lml_grad(ctx, gm, theta, d, Kinv, L.ld, sC, W, sC, pinv, sC, mode, eta, noisy, varK, pnlt_grad,
+      alpha_t = W + L.ld;
+      rc = trmv_upper(ctx, U, L.ld, sC, W, sC, alpha_t, sC, N);  // U = L^-T is already there: no substitution
+      if (rc) return rc;
+      rc = launch_lml_grad(ctx, gm, theta, d, Kinv, L.ld, sC, alpha_t, sC, pinv, sC, mode, eta, noisy, varK, pnlt_grad,
                            wk + L.Part, sC, outb, outlen);
+      if (rc) return rc;
+    } else if (alpha_out) {
+      rc = trsv_lower_trans(ctx, A, L.ld, sC, D, sC, W, L.ld, sC, N, 1);
+      if (rc) return rc;
+    }
+    if (alpha_out) {
+      rc = launch_scale_vec(ctx, N, alpha_t, sC, pinv, sC, alpha_out + (int64_t)b0 * N, N);
       if (rc) return rc;
     }
   }
@@ -242,7 +278,7 @@ int gegp_lml_eval(int B, const double* theta_batch, const double* varK_batch, in
 
 int gegp_predict_setup(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
                        const double* noise, int mode, double eta, const double* y, double beta, double* A, int64_t lda,
-                       double* p_out, double* alpha_out, int* info_dev, void* stream) {
+                       double* dinv, double* p_out, double* alpha_out, int* info_dev, void* stream) {
   if (bad_geom(n, n_g, d)) return -1;
   if (!X) return -4;
   if (n_g != n && !grad_slot) return -5;
@@ -252,8 +288,9 @@ int gegp_predict_setup(int n, int n_g, int d, const double* X, const int32_t* gr
   if (!A) return -12;
   const int N = n + n_g * d;
   if (lda < N || (lda & 1)) return -13;
-  if (!p_out) return -14;
-  if (!info_dev) return -16;
+  if (!dinv) return -14;
+  if (!p_out) return -15;
+  if (!info_dev) return -17;
   Ctx ctx{(cudaStream_t)stream, 1};
   Geom gm{n, n_g, d, N, X, (n_g == n) ? nullptr : grad_slot};
   NoiseSpec ns{noise, 0, nullptr, 1.0, 0};
@@ -265,12 +302,12 @@ int gegp_predict_setup(int n, int n_g, int d, const double* X, const int32_t* gr
   double* row = A + (int64_t)N * lda;
   rc = launch_append_res(ctx, N, n, y, beta, pinv, row);
   if (rc) return rc;
-  rc = chol_trap(ctx, A, lda, 0, N + 1, N, 0, info_dev);
+  rc = chol_trap(ctx, A, lda, 0, N + 1, N, 0, info_dev, dinv, 0);
   if (rc) return rc;
   if (alpha_out) {
     cudaError_t e = cudaMemcpyAsync(alpha_out, row, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream);
     if (e != cudaSuccess) return -1000 - (int)e;
-    rc = trsv_lower_trans(ctx, A, lda, 0, alpha_out, N, 0, N, 1);
+    rc = trsv_lower_trans(ctx, A, lda, 0, dinv, 0, alpha_out, N, 0, N, 1);
     if (rc) return rc;
     rc = launch_scale_vec(ctx, N, alpha_out, 0, pinv, 0, alpha_out, 0);
     if (rc) return rc;
@@ -279,7 +316,8 @@ int gegp_predict_setup(int n, int n_g, int d, const double* X, const int32_t* gr
 }
 
 int gegp_predict(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta, const double* A,
-                 int64_t lda, const double* p, int mode, double beta, double varK, const double* Xs, int nx, double* mu,
+                 int64_t lda, const double* dinv, const double* p, int mode, double beta, double varK, const double* Xs,
+                 int nx, double* mu,
                  double* sig, double* sig2_out, int* n_negative_dev, void* work, size_t work_bytes, void* stream) {
   if (bad_geom(n, n_g, d)) return -1;
   if (!X) return -4;
@@ -288,15 +326,16 @@ int gegp_predict(int n, int n_g, int d, const double* X, const int32_t* grad_slo
   if (!A) return -7;
   const int N = n + n_g * d;
   if (lda < N || (lda & 1)) return -8;
-  if (!p) return -9;
-  if (!Xs || nx < 0) return -13;
-  if (!mu) return -15;
-  if (!sig) return -16;
-  if (!work || (reinterpret_cast<uintptr_t>(work) & 15)) return -19;
+  if (!dinv) return -9;
+  if (!p) return -10;
+  if (!Xs || nx < 0) return -14;
+  if (!mu) return -16;
+  if (!sig) return -17;
+  if (!work || (reinterpret_cast<uintptr_t>(work) & 15)) return -20;
   (void)mode;
   const int64_t ldz = gegp_ld(N);
   const int chunk = (int)std::min<size_t>((size_t)nx, work_bytes / (ldz * sizeof(double)));
-  if (nx > 0 && chunk < 1) return -20;
+  if (nx > 0 && chunk < 1) return -21;
   Ctx ctx{(cudaStream_t)stream, 1};
   Geom gm{n, n_g, d, N, X, (n_g == n) ? nullptr : grad_slot};
   const double* pinv = p + N;
@@ -306,7 +345,7 @@ int gegp_predict(int n, int n_g, int d, const double* X, const int32_t* grad_slo
     const int cx = std::min(chunk, nx - x0);
     int rc = launch_cross_cov(ctx, gm, theta, pinv, Xs + (int64_t)x0 * d, cx, Z, ldz);
     if (rc) return rc;
-    rc = trsm_right_rec(ctx, A, lda, 0, Z, ldz, 0, cx, N);
+    rc = trsm_right_rec(ctx, A, lda, 0, dinv, 0, 0, Z, ldz, 0, cx, N);
     if (rc) return rc;
     rc = launch_predict_rows(ctx, N, Z, ldz, cx, w, beta, varK, mu + x0, sig + x0, sig2_out ? sig2_out + x0 : nullptr,
                              n_negative_dev);

@@ -176,7 +176,7 @@ static int launch_cfg(const Ctx& ctx, const GemmArgs& g) {
     // useful flops: triangular output halves the tile count, triangular operands halve the k range
     double f = 2.0 * g.M * (double)g.N * g.K * g.outer * g.inner;
     if (g.cmode != C_FULL) f *= 0.5 * (g.M >= g.N ? (2.0 - (double)g.N / g.M) : 1.0);
-    if (g.klo_mode == KLO_MAXMN) f *= 2.0 / 3.0;
+    if (g.klo_mode == KLO_MAXMN) f *= 1.0 / 3.0;  // sum_{i>=j} (N - i) / (N^2/2 * N)
     else if (g.klo_mode != KLO_ZERO || g.khi_mode != KHI_K) f *= 0.5;
     prof_gemm_end(ctx.stream, f);
   }
@@ -191,6 +191,7 @@ GemmArgs gemm_args(const double* A, int64_t lda, const double* B, int64_t ldb, d
   g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.b_kcont = b_kcont;
   g.klo_mode = KLO_ZERO; g.khi_mode = KHI_K; g.cmode = C_FULL;
   g.inner = 1; g.outer = 1;
+  g.row_owner = false;
   g.sAo = g.sBo = g.sCo = g.sAi = g.sBi = g.sCi = 0;
   return g;
 }
@@ -205,6 +206,11 @@ int gemm_f64(const Ctx& ctx, GemmArgs g) {
   // Large tile when it still fills the machine, small tile otherwise (batched small problems).
   const long tiles_big = (long)((g.M + 127) / 128) * ((g.N + 127) / 128) * g.outer * g.inner;
   const bool big = (g.cmode == C_FULL ? tiles_big : tiles_big / 2) >= 120 && g.M >= 128 && g.N >= 128;
+  if (g.row_owner) {
+    // in-place right multiply: one column tile must cover all of N so that a CTA only overwrites rows it alone reads
+    if (g.N > 128 || g.A != g.C || g.b_kcont) return -904;
+    return launch_cfg<128, 128, 64, 32, 4, false>(ctx, g);
+  }
   if (g.b_kcont) {
     if (big) return launch_cfg<128, 128, 64, 32, 4, true>(ctx, g);
     return launch_cfg<64, 64, 32, 32, 4, true>(ctx, g);

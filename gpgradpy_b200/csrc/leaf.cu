@@ -1,297 +1,621 @@
-// Latency-bound leaves of the blocked factorisation: diagonal-block Cholesky, substitution-based
-// triangular solves (no explicit inverses on the solve path), diagonal-block triangular inverse,
-// and the blocked back-substitution for a few right-hand sides.
+// Latency-bound leaves of the blocked factorisation.
+//
+// potf2_inv_kernel factors one LEAF x LEAF (128) diagonal block AND inverts the factor inside one CTA:
+// the block lives in shared memory, 32 x 32 diagonal sub-blocks are factored/inverted in the registers of
+// one warp (row per lane, warp shuffles), everything else (panel solves, trailing updates, assembly of the
+// 128 x 128 inverse from the 32 x 32 ones) runs on the fp64 tensor cores (DMMA.8x8x4) straight from
+// shared memory.  The inverse-transposed block U_bb = L_bb^-T is what the blocked algorithms multiply
+// with (panel solves become DMMA GEMMs; the explicit inverse K^-1 starts from these blocks), so there is
+// no substitution kernel on the O(N^3) path.
 #include "linalg.h"
 
 namespace gegp {
 
-// ------------------------------------------------------------------------------------------------
-// potf2: k x k (k <= 128) lower Cholesky in shared memory, one CTA per problem.
-// ------------------------------------------------------------------------------------------------
-constexpr int PNB = LEAF;       // 128
-constexpr int PLD = PNB + 1;    // odd stride: column reads hit distinct banks
+namespace {
 
-__global__ void __launch_bounds__(256) potf2_kernel(double* A, int64_t lda, int64_t strideA, int k, int row0,
-                                                     int* info) {
-  extern __shared__ double s[];  // PNB x PLD
-  __shared__ int bad;
-  A += (int64_t)blockIdx.z * strideA;
-  const int tid = threadIdx.x;
-  if (tid == 0) bad = 0;
-  for (int e = tid; e < PNB * PNB; e += 256) {
-    const int r = e / PNB, c = e % PNB;
-    double v = (r == c) ? 1.0 : 0.0;
-    if (r < k && c <= r) v = A[(int64_t)r * lda + c];
-    s[r * PLD + c] = v;
-  }
-  __syncthreads();
-  const int tr = tid >> 4, tc = tid & 15;
-  for (int j = 0; j < k; j++) {
-    __syncthreads();  // trailing update of step j-1 is complete
-    const double piv = s[j * PLD + j];
-    if (!(piv > 0.0)) {  // also catches NaN
-      if (tid == 0 && bad == 0) bad = j + 1;
-    }
+constexpr int NB = LEAF;        // 128
+constexpr int PLD = NB + 4;     // 132 == 4 (mod 16): every DMMA fragment load below is bank-conflict free
+constexpr int LT = 256;         // threads per CTA (8 warps)
+constexpr int NW = LT / 32;
+constexpr unsigned FULL = 0xffffffffu;
+
+// Shared-memory tile T[NB][PLD]:  L(r,c) = T[r][c] (c <= r) ;  U(i,j) = L^-T (i <= j) = T[i][j+1].
+// The one-column shift keeps both diagonals (L_ii and 1/L_ii).
+
+// Factor + invert the 32 x 32 diagonal sub-block at j0 with one warp: lane r owns row r of L and of M = L^-1.
+__device__ __forceinline__ int warp_potf2_inv32(double* __restrict__ s, int j0, int lane) {
+  double a[32], m[32];
+  const double* row = s + (j0 + lane) * PLD + j0;
+#pragma unroll
+  for (int c = 0; c < 32; c++) a[c] = (c <= lane) ? row[c] : 0.0;
+#pragma unroll
+  for (int c = 0; c < 32; c++) m[c] = (c == lane) ? 1.0 : 0.0;
+  int bad = 0;
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    const double piv = __shfl_sync(FULL, a[j], j);
+    if (!(piv > 0.0) && bad == 0) bad = j + 1;  // also catches NaN; uniform over the warp
     const double dj = sqrt(piv);
     const double inv = 1.0 / dj;
-    __syncthreads();  // everyone has read the pivot
-    for (int r = j + 1 + tid; r < k; r += 256) s[r * PLD + j] *= inv;
-    if (tid == 0) s[j * PLD + j] = dj;
-    __syncthreads();
-    // rank-1 update of the trailing lower triangle: s[r][c] -= s[r][j]*s[c][j], j < c <= r < k
-    const int p0 = (j + 1 - tr + 15) >> 4, q0 = (j + 1 - tc + 15) >> 4;
-    for (int p = max(p0, 0); tr + 16 * p < k; p++) {
-      const int r = tr + 16 * p;
-      const double lrj = s[r * PLD + j];
-      for (int q = max(q0, 0); tc + 16 * q <= r; q++) {
-        const int c = tc + 16 * q;
-        s[r * PLD + c] -= lrj * s[c * PLD + j];
+    a[j] = (lane == j) ? dj : a[j] * inv;       // column j of L (zero above the diagonal stays zero)
+    if (lane == j) {
+#pragma unroll
+      for (int c = 0; c <= j; c++) m[c] *= inv;  // row j of M is final
+    }
+    const double lrj = (lane > j) ? a[j] : 0.0;
+#pragma unroll
+    for (int c = j + 1; c < 32; c++) {
+      const double lcj = __shfl_sync(FULL, a[j], c);
+      a[c] -= lrj * lcj;                         // right-looking update of the rows below
+    }
+#pragma unroll
+    for (int c = 0; c <= j; c++) {
+      const double mjc = __shfl_sync(FULL, m[c], j);
+      m[c] -= lrj * mjc;                         // M[r][:] -= L[r][j] * M[j][:]
+    }
+  }
+  double* wrow = s + (j0 + lane) * PLD + j0;
+#pragma unroll
+  for (int c = 0; c < 32; c++)
+    if (c <= lane) wrow[c] = a[c];
+#pragma unroll
+  for (int i = 0; i < 32; i++)
+    if (i <= lane) s[(j0 + i) * PLD + j0 + lane + 1] = m[i];  // U(i, lane) = M[lane][i]
+  return bad;
+}
+
+// Rows [r_beg, kk) of the 32 columns at j0:  X = B * L_jj^-T, in place, strips of 8 rows per warp.
+// Computed with the inverse U_jj = L_jj^-T plus one refinement step, which makes it as accurate as a
+// substitution:  X1 = B U ;  R = B - X1 L_jj^T ;  X = X1 + R U.   `scr` is this warp's 8 x SLD scratch strip
+// (accumulator layout -> A-fragment layout goes through shared memory).
+constexpr int SLD = 36;  // == 4 (mod 16)
+
+__device__ __forceinline__ void panel_solve32(double* __restrict__ s, double* __restrict__ scr, int j0, int r_beg,
+                                              int kk, int warp, int lane) {
+  const int lr = lane >> 2, lk = lane & 3;
+  const int nstrips = (kk - r_beg) >> 3;
+  for (int st = warp; st < nstrips; st += NW) {
+    const int r0 = r_beg + st * 8;
+    double* brow = s + (r0 + lr) * PLD + j0;
+    double af[8];
+    double acc[4][2];
+    // X1 = B U
+#pragma unroll
+    for (int kq = 0; kq < 8; kq++) af[kq] = brow[4 * kq + lk];
+#pragma unroll
+    for (int ct = 0; ct < 4; ct++) {
+      acc[ct][0] = acc[ct][1] = 0.0;
+      const int c = ct * 8 + lr;
+#pragma unroll
+      for (int kq = 0; kq <= 2 * ct + 1; kq++) {
+        const int k = 4 * kq + lk;
+        const double b = (k <= c) ? s[(j0 + k) * PLD + j0 + c + 1] : 0.0;
+        dmma884(acc[ct][0], acc[ct][1], af[kq], b);
+      }
+    }
+#pragma unroll
+    for (int ct = 0; ct < 4; ct++) {
+      scr[lr * SLD + ct * 8 + 2 * lk] = acc[ct][0];
+      scr[lr * SLD + ct * 8 + 2 * lk + 1] = acc[ct][1];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int kq = 0; kq < 8; kq++) af[kq] = -scr[lr * SLD + 4 * kq + lk];   // -X1 as the A operand
+    __syncwarp();
+    // R = B - X1 L_jj^T   (b[k][n] = L_jj(n, k), zero for k > n)
+    double rr[4][2];
+#pragma unroll
+    for (int ct = 0; ct < 4; ct++) {
+      rr[ct][0] = brow[ct * 8 + 2 * lk];
+      rr[ct][1] = brow[ct * 8 + 2 * lk + 1];
+      const int nn = ct * 8 + lr;
+#pragma unroll
+      for (int kq = 0; kq <= 2 * ct + 1; kq++) {
+        const int k = 4 * kq + lk;
+        const double b = (k <= nn) ? s[(j0 + nn) * PLD + j0 + k] : 0.0;
+        dmma884(rr[ct][0], rr[ct][1], af[kq], b);
+      }
+    }
+#pragma unroll
+    for (int ct = 0; ct < 4; ct++) {
+      scr[lr * SLD + ct * 8 + 2 * lk] = rr[ct][0];
+      scr[lr * SLD + ct * 8 + 2 * lk + 1] = rr[ct][1];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int kq = 0; kq < 8; kq++) af[kq] = scr[lr * SLD + 4 * kq + lk];    // R as the A operand
+    __syncwarp();
+    // X = X1 + R U
+#pragma unroll
+    for (int ct = 0; ct < 4; ct++) {
+      const int c = ct * 8 + lr;
+#pragma unroll
+      for (int kq = 0; kq <= 2 * ct + 1; kq++) {
+        const int k = 4 * kq + lk;
+        const double b = (k <= c) ? s[(j0 + k) * PLD + j0 + c + 1] : 0.0;
+        dmma884(acc[ct][0], acc[ct][1], af[kq], b);
+      }
+    }
+#pragma unroll
+    for (int ct = 0; ct < 4; ct++) {
+      brow[ct * 8 + 2 * lk] = acc[ct][0];
+      brow[ct * 8 + 2 * lk + 1] = acc[ct][1];
+    }
+    __syncwarp();
+  }
+}
+
+// Trailing update of the lower triangle of rows/cols [base, kk) with the 32-wide panel at j0:
+// C -= X X^T, 8 x 8 tiles, K = 32.
+__device__ __forceinline__ void trailing_update32(double* __restrict__ s, int j0, int base, int kk, int warp, int lane) {
+  const int lr = lane >> 2, lk = lane & 3;
+  const int nt = (kk - base) >> 3;
+  const int ntiles = nt * (nt + 1) / 2;
+  for (int t = warp; t < ntiles; t += NW) {
+    int rt = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+    while ((rt + 1) * (rt + 2) / 2 <= t) rt++;
+    while (rt * (rt + 1) / 2 > t) rt--;
+    const int ct = t - rt * (rt + 1) / 2;
+    const int r0 = base + rt * 8, c0 = base + ct * 8;
+    double* cp = s + (r0 + lr) * PLD + c0 + 2 * lk;
+    double acc0 = cp[0], acc1 = cp[1];
+#pragma unroll
+    for (int kq = 0; kq < 8; kq++) {
+      const double a = -s[(r0 + lr) * PLD + j0 + 4 * kq + lk];
+      const double b = s[(c0 + lr) * PLD + j0 + 4 * kq + lk];
+      dmma884(acc0, acc1, a, b);
+    }
+    const int r = r0 + lr, c = c0 + 2 * lk;
+    if (c <= r) cp[0] = acc0;        // entries right of the diagonal belong to U: never touched
+    if (c + 1 <= r) cp[1] = acc1;
+  }
+}
+
+// Inverse assembly for the block pair a = [a0, a0+sza), b = [b0, b0+szb), a before b:
+//   U_ab = -U_aa * L_ba^T * U_bb
+// phase 1:  P = U_aa * L_ba^T  -> stored where U_ab will live ;  phase 2:  U_ab = -P * U_bb (in place).
+__device__ __forceinline__ void pair_phase1(double* __restrict__ s, int a0, int sza, int b0, int szb, int w, int nw,
+                                            int lane) {
+  const int lr = lane >> 2, lk = lane & 3;
+  const int nit = sza >> 3, njt = szb >> 3;
+  for (int t = w; t < nit * njt; t += nw) {
+    const int it = t / njt, jt = t - it * njt;
+    const int i = it * 8 + lr;
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int kq = 2 * it; kq < (sza >> 2); kq++) {
+      const int k = 4 * kq + lk;
+      const double a = (k >= i) ? s[(a0 + i) * PLD + a0 + k + 1] : 0.0;       // U_aa(i,k)
+      const double b = s[(b0 + jt * 8 + lr) * PLD + a0 + k];                  // L(b0+j, a0+k)
+      dmma884(acc0, acc1, a, b);
+    }
+    double* o = s + (a0 + i) * PLD + b0 + jt * 8 + 2 * lk + 1;
+    o[0] = acc0;
+    o[1] = acc1;
+  }
+}
+
+template <int MAXKQ>
+__device__ __forceinline__ void pair_phase2(double* __restrict__ s, int a0, int sza, int b0, int szb, int w, int nw,
+                                            int lane) {
+  const int lr = lane >> 2, lk = lane & 3;
+  const int nst = sza >> 3, njt = szb >> 3, nkq = szb >> 2;
+  for (int st = w; st < nst; st += nw) {
+    const int i = a0 + st * 8 + lr;
+    double af[MAXKQ];
+#pragma unroll
+    for (int kq = 0; kq < MAXKQ; kq++) af[kq] = (kq < nkq) ? s[i * PLD + b0 + 4 * kq + lk + 1] : 0.0;
+    double acc[MAXKQ / 2][2];
+#pragma unroll
+    for (int jt = 0; jt < MAXKQ / 2; jt++) {
+      acc[jt][0] = acc[jt][1] = 0.0;
+      if (jt < njt) {
+        const int j = jt * 8 + lr;
+#pragma unroll
+        for (int kq = 0; kq <= 2 * jt + 1; kq++) {
+          const int k = 4 * kq + lk;
+          const double b = (k <= j) ? s[(b0 + k) * PLD + b0 + j + 1] : 0.0;   // U_bb(k,j)
+          dmma884(acc[jt][0], acc[jt][1], af[kq], b);
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int jt = 0; jt < MAXKQ / 2; jt++) {
+      if (jt < njt) {
+        double* o = s + i * PLD + b0 + jt * 8 + 2 * lk + 1;
+        o[0] = -acc[jt][0];
+        o[1] = -acc[jt][1];
       }
     }
   }
+}
+
+}  // namespace
+
+// One CTA per problem: A (k x k lower, k <= 128) -> L in place; Dinv (128 x 128, ld 128) <- L^-T (upper
+// triangular, explicit zeros elsewhere).  The first non-positive pivot is recorded in info[z]
+// (1-based global index row0 + i + 1) if info[z] was 0.
+__global__ void __launch_bounds__(LT, 1)
+potf2_inv_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int k, int row0, int* __restrict__ info,
+                 double* __restrict__ Dinv, int64_t strideD) {
+  extern __shared__ __align__(16) double s[];  // NB x PLD tile, then NW x 8 x SLD scratch strips
+  __shared__ int bad_sh;
+  A += (int64_t)blockIdx.z * strideA;
+  Dinv += (int64_t)blockIdx.z * strideD;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kk = (k + 31) & ~31;  // padded with an identity block up to a multiple of 32
+  if (tid == 0) bad_sh = 0;
+  for (int e = tid; e < kk * NB; e += LT) {
+    const int r = e >> 7, c = e & (NB - 1);
+    if (c >= kk) continue;
+    double v = (r == c) ? 1.0 : 0.0;
+    if (r < k && c <= r) v = A[(int64_t)r * lda + c];
+    if (c <= r) s[r * PLD + c] = v;
+  }
   __syncthreads();
-  for (int e = tid; e < k * k; e += 256) {
-    const int r = e / k, c = e % k;
+
+  for (int j0 = 0; j0 < kk; j0 += 32) {
+    if (warp == 0) {
+      const int bad = warp_potf2_inv32(s, j0, lane);
+      if (lane == 0 && bad && bad_sh == 0 && j0 + bad <= k) bad_sh = j0 + bad;
+    }
+    __syncthreads();
+    if (j0 + 32 < kk) {
+      panel_solve32(s, s + NB * PLD + warp * 8 * SLD, j0, j0 + 32, kk, warp, lane);
+      __syncthreads();
+      trailing_update32(s, j0, j0 + 32, kk, warp, lane);
+      __syncthreads();
+    }
+  }
+  // L is final: write it out while the inverse is assembled
+  for (int e = tid; e < k * NB; e += LT) {
+    const int r = e >> 7, c = e & (NB - 1);
     if (c <= r) A[(int64_t)r * lda + c] = s[r * PLD + c];
   }
-  if (tid == 0 && bad) atomicCAS(info + blockIdx.z, 0, row0 + bad);
+  if (tid == 0 && bad_sh) atomicCAS(info + blockIdx.z, 0, row0 + bad_sh);
+
+  // level 1: pairs of 32-blocks -> 64-blocks
+  if (kk >= 64) {
+    const int npairs = (kk >= 128) ? 2 : 1;
+    const int nw = NW / npairs, pr = warp / nw, w = warp - pr * nw;
+    pair_phase1(s, pr * 64, 32, pr * 64 + 32, 32, w, nw, lane);
+    __syncthreads();
+    pair_phase2<8>(s, pr * 64, 32, pr * 64 + 32, 32, w, nw, lane);
+    __syncthreads();
+  }
+  // level 2: [0,64) with [64,kk)
+  if (kk > 64) {
+    pair_phase1(s, 0, 64, 64, kk - 64, warp, NW, lane);
+    __syncthreads();
+    pair_phase2<16>(s, 0, 64, 64, kk - 64, warp, NW, lane);
+    __syncthreads();
+  }
+  for (int e = tid; e < NB * NB; e += LT) {
+    const int i = e >> 7, j = e & (NB - 1);
+    Dinv[e] = (i < kk && j < kk && j >= i) ? s[i * PLD + j + 1] : 0.0;
+  }
 }
 
-int leaf_potf2(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int k, int row0, int* info) {
+int leaf_potf2_inv(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int k, int row0, int* info, double* Dinv,
+                   int64_t strideD) {
   if (k <= 0) return 0;
-  if (k > PNB) return -901;
+  if (k > NB) return -901;
   static bool attr = false;
-  const int smem = PNB * PLD * (int)sizeof(double);
-  if (!attr) { GEGP_SET_SMEM(potf2_kernel, smem); attr = true; }
-  potf2_kernel<<<dim3(1, 1, ctx.batch), 256, smem, ctx.stream>>>(A, lda, strideA, k, row0, info);
+  const int smem = (NB * PLD + NW * 8 * SLD) * (int)sizeof(double);
+  if (!attr) { GEGP_SET_SMEM(potf2_inv_kernel, smem); attr = true; }
+  potf2_inv_kernel<<<dim3(1, 1, ctx.batch), LT, smem, ctx.stream>>>(A, lda, strideA, k, row0, info, Dinv, strideD);
   GEGP_CHECK_LAUNCH();
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// trsm (right, lower, transposed): B <- B * L^-T, k <= 64, by forward substitution per row.
-// One thread per row; the row lives in shared memory, 8 columns at a time in registers.
+// Leaf solve  B (r x k) <- B * L^-T  for one factored LEAF block (k <= 128), fused in one kernel.
+// Block substitution over the four 32-column blocks j:
+//     C_j = B_j - sum_{i<j} X_i L_ji^T                      (DMMA, X_i kept in registers as A fragments)
+//     X_j = C_j L_jj^-T  via  X1 = C_j U_jj ; R = C_j - X1 L_jj^T ; X_j = X1 + R U_jj
+// i.e. only the 32 x 32 diagonal inverses U_jj (the diagonal blocks of Dinv) are multiplied with, and each of
+// those products is followed by one refinement step, so the solve is as accurate as a substitution while
+// running entirely on the fp64 tensor cores.  A warp owns an 8-row strip; a CTA of 16 warps owns 128 rows and
+// stages the L block and the U_jj blocks in the same shifted shared-memory tile the factor kernel uses.
 // ------------------------------------------------------------------------------------------------
-constexpr int TKB = 64;         // max triangle width of the leaf
-constexpr int TROWS = 128;      // rows per CTA
-constexpr int TXLD = TKB + 1;
+constexpr int TW = 16;  // warps per CTA of the leaf solve
 
-__global__ void __launch_bounds__(TROWS) trsm_right_leaf_kernel(const double* L, int64_t ldl, int64_t strideL,
-                                                                 double* B, int64_t ldb, int64_t strideB, int r,
-                                                                 int k) {
-  extern __shared__ __align__(16) double tsm[];
-  double* Lt = tsm;               // Lt[kk*TKB + c] = L[c][kk]  (zero above the diagonal)
-  double* xs = tsm + TKB * TKB;   // TROWS x TXLD
+__device__ __forceinline__ void frag_c_to_a(double* __restrict__ scr, const double (&c)[4][2], double (&a)[8], int lr,
+                                            int lk, double sign) {
+  __syncwarp();
+#pragma unroll
+  for (int ct = 0; ct < 4; ct++) {
+    scr[lr * SLD + ct * 8 + 2 * lk] = c[ct][0];
+    scr[lr * SLD + ct * 8 + 2 * lk + 1] = c[ct][1];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int kq = 0; kq < 8; kq++) a[kq] = sign * scr[lr * SLD + 4 * kq + lk];
+}
+
+__global__ void __launch_bounds__(TW * 32, 1)
+leaf_trsm_kernel(const double* __restrict__ L, int64_t ldl, int64_t strideL, const double* __restrict__ Dinv,
+                 int64_t strideD, double* __restrict__ B, int64_t ldb, int64_t strideB, int r, int k) {
+  extern __shared__ __align__(16) double s[];  // NB x PLD tile, then TW x 8 x SLD scratch strips
   L += (int64_t)blockIdx.z * strideL;
+  Dinv += (int64_t)blockIdx.z * strideD;
   B += (int64_t)blockIdx.z * strideB;
-  const int tid = threadIdx.x;
-  const int row0 = blockIdx.x * TROWS;
-  for (int e = tid; e < TKB * TKB; e += TROWS) {
-    const int c = e / TKB, kk = e % TKB;  // read L row-major (coalesced), store transposed
-    double v = (c == kk) ? 1.0 : 0.0;
-    if (c < k && kk <= c) v = L[(int64_t)c * ldl + kk];
-    else if (c != kk) v = 0.0;
-    Lt[kk * TKB + c] = v;
-  }
-  const int nrows = min(TROWS, r - row0);
-  for (int e = tid; e < TROWS * TKB; e += TROWS) {
-    const int rr = e / TKB, c = e % TKB;
-    xs[rr * TXLD + c] = (rr < nrows && c < k) ? B[(int64_t)(row0 + rr) * ldb + c] : 0.0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lk = lane & 3;
+  const int kk = (k + 31) & ~31;
+  // stage L (lower, identity padded) and the 32 x 32 diagonal blocks of U (shifted one column right)
+  for (int e = tid; e < kk * NB; e += TW * 32) {
+    const int i = e >> 7, c = e & (NB - 1);
+    if (c >= kk) continue;
+    if (c <= i) {
+      double v = (i == c) ? 1.0 : 0.0;
+      if (i < k) v = L[(int64_t)i * ldl + c];
+      s[i * PLD + c] = v;
+    } else if ((c >> 5) == (i >> 5)) {
+      s[i * PLD + c + 1] = Dinv[i * NB + c];
+    }
+    if (c == i) s[i * PLD + c + 1] = Dinv[i * NB + c];
   }
   __syncthreads();
-  double* x = xs + tid * TXLD;
-  for (int c0 = 0; c0 < k; c0 += 8) {
-    double acc[8];
+  double* scr = s + NB * PLD + warp * 8 * SLD;
+  const int nb32 = kk >> 5;
+  const bool vec = ((k & 1) == 0);
+
+  for (int st = blockIdx.x * TW + warp; st * 8 < r; st += gridDim.x * TW) {
+    const int row = st * 8 + lr;
+    const bool rok = row < r;
+    double* brow = B + (int64_t)row * ldb;
+    double xneg[3][8];  // -X_i as A fragments, i = 0..2
 #pragma unroll
-    for (int c = 0; c < 8; c++) acc[c] = x[c0 + c];
-    for (int kk = 0; kk < c0; kk++) {
-      const double xk = x[kk];
-      const double2* lp = reinterpret_cast<const double2*>(Lt + kk * TKB + c0);
+    for (int j = 0; j < 4; j++) {
+      if (j < nb32) {
+        const int j0 = j * 32;
+        double acc[4][2];
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
-        const double2 l2 = lp[c];
-        acc[2 * c] -= l2.x * xk;
-        acc[2 * c + 1] -= l2.y * xk;
+        for (int ct = 0; ct < 4; ct++) {
+          const int c = j0 + ct * 8 + 2 * lk;
+          acc[ct][0] = acc[ct][1] = 0.0;
+          if (rok) {
+            if (vec) {
+              if (c < k) {
+                const double2 v = *reinterpret_cast<const double2*>(brow + c);
+                acc[ct][0] = v.x;
+                acc[ct][1] = v.y;
+              }
+            } else {
+              if (c < k) acc[ct][0] = brow[c];
+              if (c + 1 < k) acc[ct][1] = brow[c + 1];
+            }
+          }
+        }
+        // C_j = B_j - sum_{i<j} X_i L_ji^T
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          if (i < j) {
+#pragma unroll
+            for (int ct = 0; ct < 4; ct++) {
+              const double* lrow = s + (j0 + ct * 8 + lr) * PLD + i * 32 + lk;
+#pragma unroll
+              for (int kq = 0; kq < 8; kq++) dmma884(acc[ct][0], acc[ct][1], xneg[i][kq], lrow[4 * kq]);
+            }
+          }
+        }
+        // X1 = C_j U_jj
+        double af[8], x1[4][2];
+        frag_c_to_a(scr, acc, af, lr, lk, 1.0);
+#pragma unroll
+        for (int ct = 0; ct < 4; ct++) {
+          x1[ct][0] = x1[ct][1] = 0.0;
+          const int c = ct * 8 + lr;
+#pragma unroll
+          for (int kq = 0; kq <= 2 * ct + 1; kq++) {
+            const int kx = 4 * kq + lk;
+            const double b = (kx <= c) ? s[(j0 + kx) * PLD + j0 + c + 1] : 0.0;
+            dmma884(x1[ct][0], x1[ct][1], af[kq], b);
+          }
+        }
+        // R = C_j - X1 L_jj^T
+        frag_c_to_a(scr, x1, af, lr, lk, -1.0);
+#pragma unroll
+        for (int ct = 0; ct < 4; ct++) {
+          const int nn = ct * 8 + lr;
+#pragma unroll
+          for (int kq = 0; kq <= 2 * ct + 1; kq++) {
+            const int kx = 4 * kq + lk;
+            const double b = (kx <= nn) ? s[(j0 + nn) * PLD + j0 + kx] : 0.0;
+            dmma884(acc[ct][0], acc[ct][1], af[kq], b);
+          }
+        }
+        // X_j = X1 + R U_jj
+        frag_c_to_a(scr, acc, af, lr, lk, 1.0);
+#pragma unroll
+        for (int ct = 0; ct < 4; ct++) {
+          const int c = ct * 8 + lr;
+#pragma unroll
+          for (int kq = 0; kq <= 2 * ct + 1; kq++) {
+            const int kx = 4 * kq + lk;
+            const double b = (kx <= c) ? s[(j0 + kx) * PLD + j0 + c + 1] : 0.0;
+            dmma884(x1[ct][0], x1[ct][1], af[kq], b);
+          }
+        }
+        if (rok) {
+#pragma unroll
+          for (int ct = 0; ct < 4; ct++) {
+            const int c = j0 + ct * 8 + 2 * lk;
+            if (vec) {
+              if (c < k) *reinterpret_cast<double2*>(brow + c) = make_double2(x1[ct][0], x1[ct][1]);
+            } else {
+              if (c < k) brow[c] = x1[ct][0];
+              if (c + 1 < k) brow[c + 1] = x1[ct][1];
+            }
+          }
+        }
+        if (j < 3) frag_c_to_a(scr, x1, xneg[j], lr, lk, -1.0);
       }
     }
-#pragma unroll
-    for (int c = 0; c < 8; c++) {
-      double v = acc[c];
-#pragma unroll
-      for (int kk = 0; kk < c; kk++) v -= Lt[(c0 + kk) * TKB + c0 + c] * acc[kk];
-      v /= Lt[(c0 + c) * TKB + c0 + c];
-      acc[c] = v;
-      x[c0 + c] = v;
-    }
-  }
-  __syncthreads();
-  for (int e = tid; e < TROWS * TKB; e += TROWS) {
-    const int rr = e / TKB, c = e % TKB;
-    if (rr < nrows && c < k) B[(int64_t)(row0 + rr) * ldb + c] = xs[rr * TXLD + c];
   }
 }
 
-int leaf_trsm_right(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* B, int64_t ldb,
-                    int64_t strideB, int r, int k) {
+int leaf_trsm(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv, int64_t strideD,
+              double* B, int64_t ldb, int64_t strideB, int r, int k) {
   if (r <= 0 || k <= 0) return 0;
-  if (k > TKB) return -902;
+  if (k > NB) return -902;
   static bool attr = false;
-  const int smem = (TKB * TKB + TROWS * TXLD) * (int)sizeof(double);
-  if (!attr) { GEGP_SET_SMEM(trsm_right_leaf_kernel, smem); attr = true; }
-  trsm_right_leaf_kernel<<<dim3((r + TROWS - 1) / TROWS, 1, ctx.batch), TROWS, smem, ctx.stream>>>(L, ldl, strideL, B,
-                                                                                             ldb, strideB, r, k);
+  const int smem = (NB * PLD + TW * 8 * SLD) * (int)sizeof(double);
+  if (!attr) { GEGP_SET_SMEM(leaf_trsm_kernel, smem); attr = true; }
+  const int nctas = (r + TW * 8 - 1) / (TW * 8);
+  leaf_trsm_kernel<<<dim3(nctas, 1, ctx.batch), TW * 32, smem, ctx.stream>>>(L, ldl, strideL, Dinv, strideD, B, ldb,
+                                                                            strideB, r, k);
   GEGP_CHECK_LAUNCH();
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// trtri (transposed output): U_blk = (L_blk^-1)^T for every LEAF x LEAF diagonal block.
-// One CTA per block, one thread per column of L_blk^-1 (forward substitution on e_j).
+// U diagonal blocks <- Dinv blocks (start of the explicit inverse; the rest of U is produced by GEMMs).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PNB) trtri_t_kernel(const double* L, int64_t ldl, int64_t strideL, double* U,
-                                                       int64_t ldu, int64_t strideU, int N) {
-  extern __shared__ double sm[];
-  double* Ls = sm;               // PNB x PLD, row-major lower block
-  double* Ms = sm + PNB * PLD;   // packed lower: Ms[r*(r+1)/2 + j] = (L^-1)[r][j], j <= r
-  L += (int64_t)blockIdx.z * strideL;
+__global__ void __launch_bounds__(256)
+scatter_dinv_kernel(const double* __restrict__ Dinv, int64_t strideD, double* __restrict__ U, int64_t ldu,
+                    int64_t strideU, int N) {
+  Dinv += (int64_t)blockIdx.z * strideD + (int64_t)blockIdx.x * NB * NB;
   U += (int64_t)blockIdx.z * strideU;
-  const int b0 = blockIdx.x * PNB;
-  const int k = min(PNB, N - b0);
-  const int tid = threadIdx.x;
-  for (int e = tid; e < PNB * PNB; e += PNB) {
-    const int r = e / PNB, c = e % PNB;
-    double v = (r == c) ? 1.0 : 0.0;
-    if (r < k && c <= r) v = L[(int64_t)(b0 + r) * ldl + b0 + c];
-    Ls[r * PLD + c] = v;
-  }
-  __syncthreads();
-  const int j = tid;  // column of the inverse
-  for (int r = 0; r < k; r++) {
-    double acc = (r == j) ? 1.0 : 0.0;
-    if (r > j) {
-      double a0 = 0, a1 = 0;
-      int kk = j;
-      for (; kk + 1 < r; kk += 2) {
-        a0 += Ls[r * PLD + kk] * Ms[kk * (kk + 1) / 2 + j];
-        a1 += Ls[r * PLD + kk + 1] * Ms[(kk + 1) * (kk + 2) / 2 + j];
-      }
-      if (kk < r) a0 += Ls[r * PLD + kk] * Ms[kk * (kk + 1) / 2 + j];
-      acc -= a0 + a1;
-    }
-    if (r >= j) Ms[r * (r + 1) / 2 + j] = acc / Ls[r * PLD + r];
-  }
-  __syncthreads();
-  // U[b0+j][b0+r] = Minv[r][j], r >= j  (upper triangular); coalesced along r
-  for (int e = tid; e < k * k; e += PNB) {
-    const int jj = e / k, r = e % k;
-    if (r >= jj) U[(int64_t)(b0 + jj) * ldu + b0 + r] = Ms[r * (r + 1) / 2 + jj];
+  const int b0 = blockIdx.x * NB;
+  const int k = min(NB, N - b0);
+  for (int e = threadIdx.x; e < NB * NB; e += 256) {
+    const int i = e >> 7, j = e & (NB - 1);
+    if (i < k && j < k) U[(int64_t)(b0 + i) * ldu + b0 + j] = Dinv[e];
   }
 }
 
-int leaf_trtri_t(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* U, int64_t ldu,
-                 int64_t strideU, int N) {
+int leaf_scatter_dinv(const Ctx& ctx, const double* Dinv, int64_t strideD, double* U, int64_t ldu, int64_t strideU,
+                      int N) {
   if (N <= 0) return 0;
-  static bool attr = false;
-  const int smem = (PNB * PLD + PNB * (PNB + 1) / 2) * (int)sizeof(double);
-  if (!attr) { GEGP_SET_SMEM(trtri_t_kernel, smem); attr = true; }
-  trtri_t_kernel<<<dim3((N + PNB - 1) / PNB, 1, ctx.batch), PNB, smem, ctx.stream>>>(L, ldl, strideL, U, ldu, strideU, N);
+  scatter_dinv_kernel<<<dim3((N + NB - 1) / NB, 1, ctx.batch), 256, 0, ctx.stream>>>(Dinv, strideD, U, ldu, strideU, N);
   GEGP_CHECK_LAUNCH();
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// Back substitution x <- L^-T x for nrhs (<= 4) vectors, blocked by LEAF.
-// Step j (descending): every CTA c < j applies x_c -= L[j,c]^T x_j ; CTA c == j-1 then solves its
-// diagonal block so that x_{j-1} is final for the next step.  One launch per block row.
+// Back substitution x <- L^-T x for nrhs (<= 4) vectors, blocked by LEAF, diagonal blocks applied as
+// x_j <- U_jj x_j.  Step j (descending): every CTA c < j applies x_c -= L[j,c]^T x_j ; CTA c == j-1 then
+// multiplies its block with U so that x_{j-1} is final for the next step.  One launch per block row.
+// (Only used when alpha is wanted without the gradient; the gradient path multiplies with L^-T directly.)
 // ------------------------------------------------------------------------------------------------
-constexpr int VNB = LEAF;
 constexpr int VMAXRHS = 4;
 
-__device__ void trsv_diag_solve_t(const double* L, int64_t ldl, int b0, int k, double* x, int64_t ldx, int nrhs,
-                                  double* xs /*[VMAXRHS][VNB]*/, double* Ls /*[VNB][PLD]*/) {
-  // solve L_bb^T z = x_b in place; the block is staged in shared memory, warp `w` handles rhs w
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  for (int e = tid; e < k * k; e += blockDim.x) {
-    const int r = e / k, c = e % k;
-    if (c <= r) Ls[r * PLD + c] = L[(int64_t)(b0 + r) * ldl + b0 + c];
-  }
-  for (int e = tid; e < nrhs * VNB; e += blockDim.x) {
-    const int rr = e / VNB, i = e % VNB;
-    xs[rr * VNB + i] = (i < k) ? x[(int64_t)rr * ldx + b0 + i] : 0.0;
-  }
-  __syncthreads();
-  if (w < nrhs) {
-    double* z = xs + w * VNB;
-    for (int i = k - 1; i >= 0; i--) {
-      // z_i = (z_i - sum_{r>i} L[r][i] z_r) / L[i][i]
-      double part = 0.0;
-      for (int r = i + 1 + lane; r < k; r += 32) part += Ls[r * PLD + i] * z[r];
-      part = warp_sum(part);
-      if (lane == 0) z[i] = (z[i] - part) / Ls[i * PLD + i];
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  for (int e = tid; e < nrhs * VNB; e += blockDim.x) {
-    const int rr = e / VNB, i = e % VNB;
-    if (i < k) x[(int64_t)rr * ldx + b0 + i] = xs[rr * VNB + i];
-  }
-}
-
-__global__ void __launch_bounds__(256) trsv_lt_step_kernel(const double* L, int64_t ldl, int64_t strideL, double* x,
-                                                            int64_t ldx, int64_t strideX, int N, int nrhs, int j) {
-  extern __shared__ double Ls_dyn[];  // VNB x PLD, used by the CTA that solves a diagonal block
-  __shared__ double xj[VMAXRHS * VNB];
-  __shared__ double xs[VMAXRHS * VNB];
+__global__ void __launch_bounds__(256)
+trsv_lt_step_kernel(const double* __restrict__ L, int64_t ldl, int64_t strideL, const double* __restrict__ Dinv,
+                    int64_t strideD, double* __restrict__ x, int64_t ldx, int64_t strideX, int N, int nrhs, int j) {
+  __shared__ double xj[VMAXRHS * NB];
+  __shared__ double xs[VMAXRHS * NB];
   L += (int64_t)blockIdx.z * strideL;
   x += (int64_t)blockIdx.z * strideX;
-  const int nblk = (N + VNB - 1) / VNB;
+  Dinv += (int64_t)blockIdx.z * strideD;
+  const int nblk = (N + NB - 1) / NB;
   const int tid = threadIdx.x;
   const int c = blockIdx.x;  // column block updated by this CTA
+  const int i = tid & (NB - 1), half = tid >> 7;  // 2 halves split the reduction range
   if (j < nblk) {
-    const int j0 = j * VNB, kj = min(VNB, N - j0), c0 = c * VNB;
-    for (int e = tid; e < nrhs * VNB; e += 256) {
-      const int rr = e / VNB, i = e % VNB;
-      xj[e] = (i < kj) ? x[(int64_t)rr * ldx + j0 + i] : 0.0;
+    const int j0 = j * NB, kj = min(NB, N - j0), c0 = c * NB;
+    for (int e = tid; e < nrhs * NB; e += 256) {
+      const int rr = e / NB, ii = e % NB;
+      xj[e] = (ii < kj) ? x[(int64_t)rr * ldx + j0 + ii] : 0.0;
     }
     __syncthreads();
     // x_c[i] -= sum_r L[j0+r][c0+i] * x_j[r]   (c0 block is always full: c < j)
-    const int i = tid & (VNB - 1), half = tid >> 7;  // 2 halves split the r range
     double acc[VMAXRHS] = {0, 0, 0, 0};
     for (int r = half; r < kj; r += 2) {
       const double l = L[(int64_t)(j0 + r) * ldl + c0 + i];
 #pragma unroll
       for (int rr = 0; rr < VMAXRHS; rr++)
-        if (rr < nrhs) acc[rr] += l * xj[rr * VNB + r];
+        if (rr < nrhs) acc[rr] += l * xj[rr * NB + r];
     }
     __syncthreads();
     if (half == 1)
-      for (int rr = 0; rr < nrhs; rr++) xs[rr * VNB + i] = acc[rr];
+#pragma unroll
+      for (int rr = 0; rr < VMAXRHS; rr++)
+        if (rr < nrhs) xs[rr * NB + i] = acc[rr];
     __syncthreads();
     if (half == 0)
-      for (int rr = 0; rr < nrhs; rr++) x[(int64_t)rr * ldx + c0 + i] -= acc[rr] + xs[rr * VNB + i];
-    __threadfence_block();
+#pragma unroll
+      for (int rr = 0; rr < VMAXRHS; rr++)
+        if (rr < nrhs) x[(int64_t)rr * ldx + c0 + i] -= acc[rr] + xs[rr * NB + i];
     __syncthreads();
   }
   if (c == j - 1) {
-    const int b0 = c * VNB;
-    trsv_diag_solve_t(L, ldl, b0, min(VNB, N - b0), x, ldx, nrhs, xs, Ls_dyn);
+    // x_c <- U_cc x_c ,  U_cc[i][r] (r >= i) at Dinv[c][i*NB + r]
+    const int b0 = c * NB, k = min(NB, N - b0);
+    const double* D = Dinv + (int64_t)c * NB * NB;
+    for (int e = tid; e < nrhs * NB; e += 256) {
+      const int rr = e / NB, ii = e % NB;
+      xj[e] = (ii < k) ? x[(int64_t)rr * ldx + b0 + ii] : 0.0;
+    }
+    __syncthreads();
+    double acc[VMAXRHS] = {0, 0, 0, 0};
+    // thread (i, half) sums r = i + half, i + half + 2, ... ; rows of D are read with stride NB (L2-resident, tiny)
+    for (int r = i + half; r < k; r += 2) {
+      const double u = D[i * NB + r];
+#pragma unroll
+      for (int rr = 0; rr < VMAXRHS; rr++)
+        if (rr < nrhs) acc[rr] += u * xj[rr * NB + r];
+    }
+    if (half == 1)
+#pragma unroll
+      for (int rr = 0; rr < VMAXRHS; rr++)
+        if (rr < nrhs) xs[rr * NB + i] = acc[rr];
+    __syncthreads();
+    if (half == 0 && i < k)
+#pragma unroll
+      for (int rr = 0; rr < VMAXRHS; rr++)
+        if (rr < nrhs) x[(int64_t)rr * ldx + b0 + i] = acc[rr] + xs[rr * NB + i];
   }
 }
 
-int trsv_lower_trans(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* x, int64_t ldx,
-                     int64_t strideX, int N, int nrhs) {
+int trsv_lower_trans(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv, int64_t strideD,
+                     double* x, int64_t ldx, int64_t strideX, int N, int nrhs) {
   if (N <= 0 || nrhs <= 0) return 0;
   if (nrhs > VMAXRHS) return -903;
-  const int nblk = (N + VNB - 1) / VNB;
-  static bool attr = false;
-  const int smem = VNB * PLD * (int)sizeof(double);
-  if (!attr) { GEGP_SET_SMEM(trsv_lt_step_kernel, smem); attr = true; }
-  // step j = nblk: only the diagonal solve of the last block; then j = nblk-1 .. 1
+  const int nblk = (N + NB - 1) / NB;
+  // step j = nblk: only the diagonal multiply of the last block; then j = nblk-1 .. 1
   for (int j = nblk; j >= 1; j--) {
-    trsv_lt_step_kernel<<<dim3(j, 1, ctx.batch), 256, smem, ctx.stream>>>(L, ldl, strideL, x, ldx, strideX, N, nrhs, j);
+    trsv_lt_step_kernel<<<dim3(j, 1, ctx.batch), 256, 0, ctx.stream>>>(L, ldl, strideL, Dinv, strideD, x, ldx, strideX,
+                                                                      N, nrhs, j);
     GEGP_CHECK_LAUNCH();
   }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// y = U x for the upper-triangular U = L^-T (N x N, row-major): one warp per row, x staged through L2.
+// Gives alpha = L^-T (L^-1 r) on the gradient path without any substitution.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+trmv_upper_kernel(const double* __restrict__ U, int64_t ldu, int64_t strideU, const double* __restrict__ x,
+                  int64_t strideX, double* __restrict__ y, int64_t strideY, int N) {
+  U += (int64_t)blockIdx.z * strideU;
+  x += (int64_t)blockIdx.z * strideX;
+  y += (int64_t)blockIdx.z * strideY;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const double* u = U + (int64_t)row * ldu;
+  double a0 = 0.0, a1 = 0.0;
+  int j = (row & ~1) + 2 * lane;  // even start: 16-byte aligned pairs
+  for (; j + 1 < N; j += 64) {
+    const double2 uv = *reinterpret_cast<const double2*>(u + j);
+    const double2 xv = *reinterpret_cast<const double2*>(x + j);
+    if (j >= row) a0 += uv.x * xv.x;
+    a1 += uv.y * xv.y;
+  }
+  if (j < N && j >= row) a0 += u[j] * x[j];
+  const double t = warp_sum(a0 + a1);
+  if (lane == 0) y[row] = t;
+}
+
+int trmv_upper(const Ctx& ctx, const double* U, int64_t ldu, int64_t strideU, const double* x, int64_t strideX,
+               double* y, int64_t strideY, int N) {
+  if (N <= 0) return 0;
+  trmv_upper_kernel<<<dim3((N + 7) / 8, 1, ctx.batch), 256, 0, ctx.stream>>>(U, ldu, strideU, x, strideX, y, strideY, N);
+  GEGP_CHECK_LAUNCH();
   return 0;
 }
 

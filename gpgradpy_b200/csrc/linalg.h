@@ -23,6 +23,7 @@ struct GemmArgs {
   int inner;
   int64_t sAo, sBo, sCo, sAi, sBi, sCi;
   int outer;
+  bool row_owner;  // C aliases A (in-place right multiply): every CTA must own complete rows (one column tile)
 };
 
 GemmArgs gemm_args(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
@@ -32,29 +33,40 @@ GemmArgs gemm_args(const double* A, int64_t lda, const double* B, int64_t ldb, d
 int gemm_f64(const Ctx& ctx, GemmArgs g);
 
 // --- leaves (<= LEAF wide) ---
-// In-place Cholesky of the k x k lower block at A (k <= LEAF); first non-positive pivot is recorded in
-// info[z] (1-based global index row0+i+1) if info[z] was 0.
-int leaf_potf2(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int k, int row0, int* info);
-// B (r x k) <- B * L^-T with L the k x k lower block (substitution, no explicit inverse).
-int leaf_trsm_right(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* B, int64_t ldb,
-                    int64_t strideB, int r, int k);
-// U_blk = (L_blk^-1)^T for every LEAF diagonal block of the N x N lower factor L, written into the
-// (pre-zeroed) N x N buffer U.
-int leaf_trtri_t(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* U, int64_t ldu,
-                 int64_t strideU, int N);
+// Every factor carries the inverse-transposed diagonal blocks Dinv: block b (rows/cols [b*LEAF, (b+1)*LEAF)) is
+// the LEAF x LEAF row-major (ld LEAF) upper-triangular matrix L_bb^-T at Dinv + b*LEAF*LEAF.
+inline int64_t dinv_doubles(int N) { return (int64_t)((N + LEAF - 1) / LEAF) * LEAF * LEAF; }
+
+// In-place Cholesky of the k x k lower block at A (k <= LEAF) and Dinv <- L^-T; the first non-positive pivot is
+// recorded in info[z] (1-based global index row0+i+1) if info[z] was 0.
+int leaf_potf2_inv(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int k, int row0, int* info, double* Dinv,
+                   int64_t strideD);
+// B (r x k) <- B * L^-T for one factored leaf block (k <= LEAF): fused block substitution on the tensor cores with
+// the 32 x 32 diagonal inverses taken from Dinv and one refinement step each (as accurate as a substitution).
+int leaf_trsm(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv, int64_t strideD,
+              double* B, int64_t ldb, int64_t strideB, int r, int k);
+// Diagonal blocks of the N x N buffer U <- Dinv blocks (the rest of U is left untouched).
+int leaf_scatter_dinv(const Ctx& ctx, const double* Dinv, int64_t strideD, double* U, int64_t ldu, int64_t strideU,
+                      int N);
 
 // --- blocked algorithms ---
 // Trapezoid Cholesky: A is m x k (m >= k), lower. Factors the leading k x k block in place (L) and
 // overwrites rows k..m-1 with A21 * L^-T (so appended right-hand-side rows come out forward-solved).
-int chol_trap(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, int k, int row0, int* info);
-// B (r x k) <- B * L^-T for an already factored k x k lower L.
-int trsm_right_rec(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* B, int64_t ldb,
-                   int64_t strideB, int r, int k);
-// Kinv (full symmetric N x N) = L^-T L^-1. U (N x N) is scratch holding L^-T; Kinv doubles as scratch.
-int chol_inverse(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* U, int64_t ldu,
-                 int64_t strideU, double* Kinv, int64_t ldk, int64_t strideK, int N);
-// x <- L^-T x (back substitution), nrhs vectors x[r*ldx + i], blocked by LEAF.
-int trsv_lower_trans(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* x, int64_t ldx,
-                     int64_t strideX, int N, int nrhs);
+// row0 (multiple of LEAF) is the global index of the first row/column; Dinv is indexed by global block.
+int chol_trap(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, int k, int row0, int* info, double* Dinv,
+              int64_t strideD);
+// B (r x k) <- B * L^-T for an already factored k x k lower L (col0: global index of L's first column).
+int trsm_right_rec(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv, int64_t strideD,
+                   int col0, double* B, int64_t ldb, int64_t strideB, int r, int k);
+// Kinv (full symmetric N x N) = L^-T L^-1. U (N x N) receives L^-T (upper triangle; its strictly lower part
+// outside the diagonal blocks is never written nor read); Kinv doubles as scratch.
+int chol_inverse(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv, int64_t strideD,
+                 double* U, int64_t ldu, int64_t strideU, double* Kinv, int64_t ldk, int64_t strideK, int N);
+// x <- L^-T x (blocked back substitution with the Dinv blocks), nrhs vectors x[r*ldx + i].
+int trsv_lower_trans(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv, int64_t strideD,
+                     double* x, int64_t ldx, int64_t strideX, int N, int nrhs);
+// y = U x with U upper triangular (N x N, row-major).
+int trmv_upper(const Ctx& ctx, const double* U, int64_t ldu, int64_t strideU, const double* x, int64_t strideX,
+               double* y, int64_t strideY, int N);
 
 }  // namespace gegp

@@ -20,29 +20,33 @@ static GemmArgs batched(const Ctx& ctx, GemmArgs g, int64_t sA, int64_t sB, int6
   return g;
 }
 
-int trsm_right_rec(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* B, int64_t ldb,
-                   int64_t strideB, int r, int k) {
+static const double* dinv_block(const double* Dinv, int col0) { return Dinv + (int64_t)(col0 / LEAF) * LEAF * LEAF; }
+
+int trsm_right_rec(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv, int64_t strideD,
+                   int col0, double* B, int64_t ldb, int64_t strideB, int r, int k) {
   if (r <= 0 || k <= 0) return 0;
-  if (k <= 64) return leaf_trsm_right(ctx, L, ldl, strideL, B, ldb, strideB, r, k);
+  if (k <= LEAF) return leaf_trsm(ctx, L, ldl, strideL, dinv_block(Dinv, col0), strideD, B, ldb, strideB, r, k);
   // X = [X1 X2], L = [[L11 0],[L21 L22]]:  X1 = B1 L11^-T ; B2 -= X1 L21^T ; X2 = B2 L22^-T
-  int k1 = (k <= LEAF) ? 64 : split_point(k);
-  int rc = trsm_right_rec(ctx, L, ldl, strideL, B, ldb, strideB, r, k1);
+  const int k1 = split_point(k);
+  int rc = trsm_right_rec(ctx, L, ldl, strideL, Dinv, strideD, col0, B, ldb, strideB, r, k1);
   if (rc) return rc;
   GemmArgs g = gemm_args(B, ldb, L + (int64_t)k1 * ldl, ldl, B + k1, ldb, r, k - k1, k1, -1.0, 1.0, true);
   rc = gemm_f64(ctx, batched(ctx, g, strideB, strideL, strideB));
   if (rc) return rc;
-  return trsm_right_rec(ctx, L + (int64_t)k1 * ldl + k1, ldl, strideL, B + k1, ldb, strideB, r, k - k1);
+  return trsm_right_rec(ctx, L + (int64_t)k1 * ldl + k1, ldl, strideL, Dinv, strideD, col0 + k1, B + k1, ldb, strideB, r,
+                        k - k1);
 }
 
-int chol_trap(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, int k, int row0, int* info) {
+int chol_trap(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, int k, int row0, int* info, double* Dinv,
+              int64_t strideD) {
   if (k <= 0) return 0;
   if (k <= LEAF) {
-    int rc = leaf_potf2(ctx, A, lda, strideA, k, row0, info);
+    int rc = leaf_potf2_inv(ctx, A, lda, strideA, k, row0, info, Dinv + (int64_t)(row0 / LEAF) * LEAF * LEAF, strideD);
     if (rc) return rc;
-    return trsm_right_rec(ctx, A, lda, strideA, A + (int64_t)k * lda, lda, strideA, m - k, k);
+    return trsm_right_rec(ctx, A, lda, strideA, Dinv, strideD, row0, A + (int64_t)k * lda, lda, strideA, m - k, k);
   }
   const int k1 = split_point(k);
-  int rc = chol_trap(ctx, A, lda, strideA, m, k1, row0, info);
+  int rc = chol_trap(ctx, A, lda, strideA, m, k1, row0, info, Dinv, strideD);
   if (rc) return rc;
   // trailing update: C = A[k1:, k1:k] -= A[k1:, :k1] * A[k1:k, :k1]^T  (lower part of the square region)
   double* C = A + (int64_t)k1 * lda + k1;
@@ -51,15 +55,16 @@ int chol_trap(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, in
   g.cmode = C_LOWER;
   rc = gemm_f64(ctx, batched(ctx, g, strideA, strideA, strideA));
   if (rc) return rc;
-  return chol_trap(ctx, C, lda, strideA, m - k1, k - k1, row0 + k1, info);
+  return chol_trap(ctx, C, lda, strideA, m - k1, k - k1, row0 + k1, info, Dinv, strideD);
 }
 
 // U = L^-T (upper triangular) by levels: diagonal LEAF blocks first, then for block size bs = LEAF,
 // 2*LEAF, ... every pair (a = [s, s+bs), b = [s+bs, s+2bs)):  U_ab = -(U_aa * L_ba^T) * U_bb.
 // The product in parentheses is staged in T (the Kinv buffer, same coordinates).
-static int inverse_transposed(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* U, int64_t ldu,
-                              int64_t strideU, double* T, int64_t ldt, int64_t strideT, int N) {
-  int rc = leaf_trtri_t(ctx, L, ldl, strideL, U, ldu, strideU, N);
+static int inverse_transposed(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv,
+                              int64_t strideD, double* U, int64_t ldu, int64_t strideU, double* T, int64_t ldt,
+                              int64_t strideT, int N) {
+  int rc = leaf_scatter_dinv(ctx, Dinv, strideD, U, ldu, strideU, N);
   if (rc) return rc;
   for (int bs = LEAF; bs < N; bs *= 2) {
     const int npairs_full = N / (2 * bs);  // pairs whose b block is full
@@ -97,16 +102,12 @@ static int inverse_transposed(const Ctx& ctx, const double* L, int64_t ldl, int6
   return 0;
 }
 
-int chol_inverse(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* U, int64_t ldu,
-                 int64_t strideU, double* Kinv, int64_t ldk, int64_t strideK, int N) {
+int chol_inverse(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv, int64_t strideD,
+                 double* U, int64_t ldu, int64_t strideU, double* Kinv, int64_t ldk, int64_t strideK, int N) {
   if (N <= 0) return 0;
-  // U must start as zero: its strictly lower triangle is read by the GEMMs as part of full tiles.
-  for (int b = 0; b < ctx.batch; b++) {
-    cudaError_t e = cudaMemset2DAsync(U + (int64_t)b * strideU, ldu * sizeof(double), 0, (size_t)N * sizeof(double), N,
-                                      ctx.stream);
-    if (e != cudaSuccess) return -1000 - (int)e;
-  }
-  int rc = inverse_transposed(ctx, L, ldl, strideL, U, ldu, strideU, Kinv, ldk, strideK, N);
+  // Only the upper triangle of U (plus the zero lower parts of its diagonal blocks, which come with Dinv) is
+  // ever read: every GEMM below clips its k range at tile granularity and tiles nest inside the LEAF blocks.
+  int rc = inverse_transposed(ctx, L, ldl, strideL, Dinv, strideD, U, ldu, strideU, Kinv, ldk, strideK, N);
   if (rc) return rc;
   // Kinv = U * U^T, U upper: sum over k >= max(i, j); lower tiles computed, mirrored to the upper half.
   GemmArgs g = gemm_args(U, ldu, U, ldu, Kinv, ldk, N, N, N, 1.0, 0.0, true);

@@ -459,7 +459,7 @@ class GaussianProcess:
             ld = bk.ld_of(N)
             A = torch.empty((N, ld), dtype=fac_src.dtype, device=fac_src.device)
             A[:, :N] = fac_src
-            info = bk.potrf(A, N, 0)
+            info, _dinv = bk.potrf(A, N, 0)
             if int(info.item()) == 0:
                 Lt = torch.tril(A[:, :N])
                 if precon:

@@ -8,6 +8,9 @@
  *                          KernelSqExpGradMod.sq_exp_calc_KernGrad  kernel/KernelSqExp.py:322-410
  *                          CommonFun.calc_Rtensor       base/CommonFun.py:58-84
  *   gegp_potrf          <- scipy cho_factor call sites  kernel/Kernel.py:251,291
+ *   gegp_trsm_rows      <- scipy cho_solve (forward half) eval/GpEvalModel.py:154, eval/GpMeanFun.py:102
+ *   gegp_potri          <- cho_solve(chofac, eye(N))    optz/CalcLkd.py:174,234
+ *   gegp_dgemm          <- the BLAS dgemm behind `@`     kernel/Kernel.py:227,237,252
  *   gegp_lml_eval       <- CalcLkd.calc_lkd_all         optz/CalcLkd.py:270-346  (noise-free :30-95,149-181;
  *                          noisy :185-251), GpHparaGrad.calc_KernGrad_hp / calc_Kcov_grad_hp
  *                          optz/GpHparaGrad.py:13-155, GpMeanFunPoly.calc_model_max_lkd_poly
@@ -37,7 +40,7 @@
 extern "C" {
 #endif
 
-#define GEGP_ABI_VERSION 1
+#define GEGP_ABI_VERSION 2
 
 /* covariance assembly modes (kernel/Kernel.py:220-237 vs :268-277) */
 #define GEGP_MODE_BASE 0       /* varK * (K + diag(noise) + eta*I)                                  */
@@ -83,11 +86,28 @@ int gegp_cross_cov(int n, int n_g, int d, const double* X, const int32_t* grad_s
 
 /* K2: blocked Cholesky on the fp64 tensor cores.  A is (N + n_extra) x lda, lower triangle of the leading
  * N x N block holds the SPD matrix; on exit it holds L (lower) and the n_extra appended rows R are
- * overwritten with R * L^-T (forward-solved right-hand sides).  info_dev: device int, must be 0 on entry. */
-int gegp_potrf(int N, int n_extra, double* A, int64_t lda, int* info_dev, void* stream);
+ * overwritten with R * L^-T (forward-solved right-hand sides).  info_dev: device int, must be 0 on entry.
+ * dinv[gegp_dinv_doubles(N)] receives the inverse-transposed 128 x 128 diagonal blocks of L (block b, row-major
+ * with ld 128, at dinv + b*128*128).  They are part of the factor: later solves against L multiply with their
+ * 32 x 32 diagonal sub-blocks on the tensor cores (each product followed by one refinement step, so the result is
+ * as accurate as a substitution) and the explicit inverse starts from them (scipy cho_factor returns
+ * (c, lower); here the factor is (A, dinv)). */
+int64_t gegp_dinv_doubles(int N);
+int gegp_potrf(int N, int n_extra, double* A, int64_t lda, double* dinv, int* info_dev, void* stream);
 
-/* B (r x ldb, r rows of length N) <- B * L^-T against an existing factor. */
-int gegp_trsm_rows(int N, const double* L, int64_t ldl, double* B, int64_t ldb, int r, void* stream);
+/* B (r x ldb, r rows of length N) <- B * L^-T against an existing factor (L, dinv). */
+int gegp_trsm_rows(int N, const double* L, int64_t ldl, const double* dinv, double* B, int64_t ldb, int r,
+                   void* stream);
+
+/* Explicit inverse from the factor (scipy cho_solve(chofac, eye(N)), optz/CalcLkd.py:174):
+ * U (N x ldu) receives L^-T in its upper triangle, Kinv (N x ldk) the full symmetric (L L^T)^-1. */
+int gegp_potri(int N, const double* L, int64_t ldl, const double* dinv, double* U, int64_t ldu, double* Kinv,
+               int64_t ldk, void* stream);
+
+/* The DMMA GEMM engine every O(N^3) step runs on: C = alpha * A * op(B) + beta * C, row-major;
+ * transb = 0: B is K x N; transb = 1: B is N x K (C = A B^T).  lda, ldb even, A and B 16-byte aligned. */
+int gegp_dgemm(int transb, int M, int N, int K, double alpha, const double* A, int64_t lda, const double* B,
+               int64_t ldb, double beta, double* C, int64_t ldc, void* stream);
 
 /* K3/K5: LML (+ hyper-parameter gradient) for B candidate theta rows, fused build -> factor -> reduce.
  * theta_batch[B, d]; y[N] data vector (values then Fortran-flattened gradients); noise[N] or NULL
@@ -102,17 +122,17 @@ int gegp_lml_eval(int B, const double* theta_batch, const double* varK_batch, in
                   void* work, size_t work_bytes, void* stream);
 
 /* K4 setup: build (varK := 1, kernel/Kernel.py:196-197) + factor + forward-solve of P^-1 (y - H beta).
- * A is (N + 1) x lda; p_out[2N]; on exit row N of A holds w = L^-1 P^-1 (y - H beta).
- * alpha_out[N] (optional) receives K^-1 (y - H beta) (eval/GpEvalModel.py:57). */
+ * A is (N + 1) x lda; dinv[gegp_dinv_doubles(N)]; p_out[2N]; on exit row N of A holds
+ * w = L^-1 P^-1 (y - H beta).  alpha_out[N] (optional) receives K^-1 (y - H beta) (eval/GpEvalModel.py:57). */
 int gegp_predict_setup(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
                        const double* noise, int mode, double eta, const double* y, double beta, double* A,
-                       int64_t lda, double* p_out, double* alpha_out, int* info_dev, void* stream);
+                       int64_t lda, double* dinv, double* p_out, double* alpha_out, int* info_dev, void* stream);
 
 /* K4: posterior mean and standard deviation at nx test points (eval/GpEvalModel.py:154-168):
  * mu = beta + k*^T K^-1 (y - H beta), sig = sqrt(varK) sqrt(max(0, 1 - k*^T K^-1 k*)); sig2_out (optional)
  * receives the unclipped 1 - k*^T K^-1 k*, n_negative_dev counts entries < 0 (the reference asserts on them). */
 int gegp_predict(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
-                 const double* A, int64_t lda, const double* p, int mode, double beta, double varK,
+                 const double* A, int64_t lda, const double* dinv, const double* p, int mode, double beta, double varK,
                  const double* Xs, int nx, double* mu, double* sig, double* sig2_out, int* n_negative_dev,
                  void* work, size_t work_bytes, void* stream);
 

@@ -49,10 +49,13 @@ def test_argument_checks_return_negative_codes_without_touching_the_gpu():
     lib = _lib.load()
     assert lib.gegp_build_cov(0, 0, 3, 0, 0, 0, 0, 0, 0.0, 1.0, 0, 0, 0, 0, 0) == -1      # n <= 0
     assert lib.gegp_build_cov(4, 4, 3, 0, 0, 0, 0, 0, 0.0, 1.0, 0, 0, 0, 0, 0) == -4      # X is NULL
-    assert lib.gegp_potrf(0, 0, 0, 0, 0, 0) == -1
-    assert lib.gegp_potrf(8, 0, 0, 8, 0, 0) == -3
+    assert lib.gegp_potrf(0, 0, 0, 0, 0, 0, 0) == -1
+    assert lib.gegp_potrf(8, 0, 0, 8, 0, 0, 0) == -3
     assert lib.gegp_lml_eval(0, 0, 0, 4, 4, 3, 0, 0, 0, 0, 1, 0.0, 0, 0.0, 0, 0, 0, 0, 0, 0) == -1
-    assert lib.gegp_trsm_rows(8, 0, 8, 0, 8, 1, 0) == -2
+    assert lib.gegp_trsm_rows(8, 0, 8, 0, 0, 8, 1, 0) == -2
+    assert lib.gegp_potri(8, 0, 8, 0, 0, 8, 0, 8, 0) == -2
+    assert lib.gegp_dgemm(0, 4, 4, 4, 1.0, 0, 4, 0, 4, 0.0, 0, 4, 0) == -6
+    assert lib.gegp_dinv_doubles(129) == 2 * 128 * 128
 
 
 def test_no_cpu_fallback_when_library_is_missing(monkeypatch):

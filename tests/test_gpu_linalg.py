@@ -27,7 +27,7 @@ def test_potrf_trapezoid(N, extra):
     A[:N, :N] = torch.as_tensor(np.tril(K)).cuda() + torch.triu(torch.full((N, N), float("nan"), dtype=torch.float64, device="cuda"), 1)
     if extra:
         A[N:, :N] = torch.as_tensor(R).cuda()
-    info = bk.potrf(A, N, extra)
+    info, dinv = bk.potrf(A, N, extra)
     torch.cuda.synchronize()
     assert int(info.item()) == 0
     Lg = np.tril(A[:N, :N].cpu().numpy())
@@ -53,8 +53,21 @@ def test_potrf_not_pd_reports_info():
     ld = bk.ld_of(N)
     A = torch.zeros((N, ld), dtype=torch.float64, device="cuda")
     A[:, :N] = torch.as_tensor(np.tril(K)).cuda()
-    info = bk.potrf(A, N, 0)
+    info, _ = bk.potrf(A, N, 0)
     assert int(info.item()) == 151
+
+
+def _factor_on_gpu(K, extra_rows=0):
+    import torch
+    from gpgradpy_b200 import backend as bk
+    N = K.shape[0]
+    ld = bk.ld_of(N)
+    A = torch.full((N + extra_rows, ld), float("nan"), dtype=torch.float64, device="cuda")
+    A[:N, :N] = torch.as_tensor(np.tril(K)).cuda() + torch.triu(
+        torch.full((N, N), float("nan"), dtype=torch.float64, device="cuda"), 1)
+    info, dinv = bk.potrf(A, N, 0)
+    assert int(info.item()) == 0
+    return A, dinv
 
 
 @pytest.mark.parametrize("N,r", [(50, 3), (128, 200), (333, 17), (1100, 260)])
@@ -63,15 +76,72 @@ def test_trsm_rows(N, r):
     from gpgradpy_b200 import backend as bk
     K = _spd(N, 10 + N)
     Lr = np.linalg.cholesky(K)
+    Lt, dinv = _factor_on_gpu(K)
     ld = bk.ld_of(N)
-    Lt = torch.full((N, ld), float("nan"), dtype=torch.float64, device="cuda")
-    Lt[:, :N] = torch.as_tensor(np.tril(Lr)).cuda() + torch.triu(torch.full((N, N), float("nan"), dtype=torch.float64, device="cuda"), 1)
     rng = np.random.default_rng(5)
     Bm = rng.standard_normal((r, N))
     Bt = torch.zeros((r, ld), dtype=torch.float64, device="cuda")
     Bt[:, :N] = torch.as_tensor(Bm).cuda()
-    bk.trsm_rows(Lt, N, Bt)
+    bk.trsm_rows(Lt, dinv, N, Bt)
     Zr = sla.solve_triangular(Lr, Bm.T, lower=True).T
     e = np.abs(Bt[:, :N].cpu().numpy() - Zr).max() / np.abs(Zr).max()
     print(f"N={N} r={r} err {e:.2e}")
     assert e < 1e-10
+
+
+@pytest.mark.parametrize("N", [5, 31, 32, 33, 64, 65, 96, 97, 127, 128])
+def test_leaf_factor_and_inverse_blocks(N):
+    """One-CTA leaf: L and the stored inverse-transposed block U = L^-T for every 32-block count and ragged size."""
+    K = _spd(N, 77 + N)
+    A, dinv = _factor_on_gpu(K)
+    Lr = np.linalg.cholesky(K)
+    Lg = np.tril(A[:N, :N].cpu().numpy())
+    assert np.abs(Lg - Lr).max() / np.abs(Lr).max() < 1e-12
+    U = dinv.cpu().numpy().reshape(128, 128)
+    Ur = np.linalg.inv(Lr).T
+    assert np.abs(U[:N, :N] - Ur).max() / np.abs(Ur).max() < 1e-11
+    assert np.all(np.tril(U, -1) == 0.0)
+
+
+@pytest.mark.parametrize("N", [60, 128, 200, 385, 1000, 2177])
+def test_potri_explicit_inverse(N):
+    import torch
+    from gpgradpy_b200 import backend as bk
+    K = _spd(N, 31 + N)
+    A, dinv = _factor_on_gpu(K)
+    ld = bk.ld_of(N)
+    # poison the outputs: nothing outside what potri writes may be read
+    U = torch.full((N, ld), float("nan"), dtype=torch.float64, device="cuda")
+    Kinv = torch.full((N, ld), float("nan"), dtype=torch.float64, device="cuda")
+    bk.potri(A, dinv, N, U, Kinv)
+    Kr = np.linalg.inv(K)
+    Kg = Kinv[:, :N].cpu().numpy()
+    e = np.abs(Kg - Kr).max() / np.abs(Kr).max()
+    Ug = np.triu(U[:, :N].cpu().numpy())
+    Ur = np.linalg.inv(np.linalg.cholesky(K)).T
+    eu = np.abs(Ug - Ur).max() / np.abs(Ur).max()
+    print(f"N={N} Kinv err {e:.2e} U err {eu:.2e}")
+    assert e < 1e-10 and eu < 1e-10
+    assert np.array_equal(Kg, Kg.T)
+
+
+@pytest.mark.parametrize("M,N,K,transb", [(1, 1, 1, True), (7, 5, 3, False), (130, 70, 33, True), (128, 128, 128, False),
+                                          (300, 257, 129, True), (1000, 900, 515, False), (2048, 2048, 512, True)])
+def test_dgemm(M, N, K, transb):
+    import torch
+    from gpgradpy_b200 import backend as bk
+    rng = np.random.default_rng(M + N + K)
+    pad = lambda c: (c + 1) // 2 * 2  # even leading dimensions  # noqa: E731
+    A = torch.zeros((M, pad(K)), dtype=torch.float64, device="cuda")
+    A[:, :K] = torch.as_tensor(rng.standard_normal((M, K))).cuda()
+    bs = (N, K) if transb else (K, N)
+    B = torch.zeros((bs[0], pad(bs[1])), dtype=torch.float64, device="cuda")
+    B[:, :bs[1]] = torch.as_tensor(rng.standard_normal(bs)).cuda()
+    C0 = rng.standard_normal((M, N))
+    C = torch.zeros((M, pad(N)), dtype=torch.float64, device="cuda")
+    C[:, :N] = torch.as_tensor(C0).cuda()
+    bk.dgemm(A[:, :K], B[:, :bs[1]], C[:, :N], transb=transb, alpha=-1.5, beta=0.5)
+    Bn = B[:, :bs[1]].cpu().numpy()
+    ref = -1.5 * A[:, :K].cpu().numpy() @ (Bn.T if transb else Bn) + 0.5 * C0
+    e = np.abs(C[:, :N].cpu().numpy() - ref).max() / np.abs(ref).max()
+    assert e < 1e-13
