@@ -6,6 +6,7 @@
 // strides (20 / BN+4 doubles) make every DMMA fragment load bank-conflict free, warp tile WM x WN built
 // from m8n8k4 fp64 MMAs.  Triangular operands are exploited by clipping the k range per output tile.
 #include "linalg.h"
+#include <cstdlib>
 
 namespace gegp {
 
@@ -53,36 +54,74 @@ gemm_f64_kernel(const GemmArgs g) {
   const int wm0 = (warp / Cfg::WARPS_N) * WM, wn0 = (warp % Cfg::WARPS_N) * WN;
   const int lr = lane >> 2, lk = lane & 3;
 
+  // Per-thread copy state, computed once: every thread owns the same 16-byte column chunk `ck` of NA rows of
+  // the A tile and NB rows of the B tile (K-contiguous B), or NB (k-row, column-chunk) slots (row-major B), so
+  // that issuing one k-tile costs a handful of instructions per cp.async and no index arithmetic.
+  constexpr int CPR = BK / 2;                  // 16-byte chunks per K-contiguous tile row
+  constexpr int NA = BM * CPR / T;
+  constexpr int RSTEP = T / CPR;               // tile rows between two chunks of one thread
+  static_assert(BM * CPR % T == 0 && T % CPR == 0, "tile/thread mismatch");
+  const int ck = tid % CPR, r0 = tid / CPR;
+  const double* a_src[NA];
+  bool a_ok[NA];
+#pragma unroll
+  for (int i = 0; i < NA; i++) {
+    const int gr = m0 + r0 + i * RSTEP;
+    a_ok[i] = gr < g.M;
+    a_src[i] = A + (int64_t)(a_ok[i] ? gr : 0) * g.lda + kb + 2 * ck;
+  }
+  const int a_dst = r0 * KPAD + 2 * ck;
+  constexpr int NBK = B_KCONT ? BN * CPR / T : BK * (BN / 2) / T;
+  const double* b_src[NBK];
+  bool b_ok[NBK];
+  int b_dst, b_bytes = 16, b_row0 = 0;
+  if (B_KCONT) {
+#pragma unroll
+    for (int i = 0; i < NBK; i++) {
+      const int gr = n0 + r0 + i * RSTEP;
+      b_ok[i] = gr < g.N;
+      b_src[i] = B + (int64_t)(b_ok[i] ? gr : 0) * g.ldb + kb + 2 * ck;
+    }
+    b_dst = r0 * KPAD + 2 * ck;
+  } else {
+    constexpr int CPRB = BN / 2;               // chunks per k-row of the row-major B tile
+    constexpr int KSTEP = T / CPRB;
+    static_assert(T % CPRB == 0, "tile/thread mismatch");
+    const int cn = tid % CPRB;
+    b_row0 = tid / CPRB;
+    const int gn = n0 + 2 * cn;
+    b_bytes = min(16, max(0, (g.N - gn) * 8));
+#pragma unroll
+    for (int i = 0; i < NBK; i++) {
+      b_ok[i] = true;
+      b_src[i] = B + (int64_t)(kb + b_row0 + i * KSTEP) * g.ldb + (b_bytes ? gn : 0);
+    }
+    b_dst = b_row0 * (BN + 4) + 2 * cn;
+  }
+
   auto load_tile = [&](int stage, int kt) {
     const int k0 = kb + kt * BK;
-    double* a_s = sA + stage * Cfg::A_STAGE;
-    double* b_s = sB + stage * Cfg::B_STAGE;
-    // A: BM rows x 8 chunks of 16 bytes
+    double* a_s = sA + stage * Cfg::A_STAGE + a_dst;
+    double* b_s = sB + stage * Cfg::B_STAGE + b_dst;
+    const int kbytes = min(16, max(0, (ke - k0 - 2 * ck) * 8));   // 16 except in a ragged last k-tile
 #pragma unroll
-    for (int c = tid; c < BM * (BK / 2); c += T) {
-      const int r = c / (BK / 2), ck = c % (BK / 2);
-      const int gr = m0 + r, gk = k0 + 2 * ck;
-      int bytes = (gr < g.M) ? min(16, max(0, (ke - gk) * 8)) : 0;
-      const double* src = bytes ? (A + (int64_t)gr * g.lda + gk) : A;
-      cp_async16(a_s + r * KPAD + 2 * ck, src, bytes);
+    for (int i = 0; i < NA; i++) {
+      cp_async16(a_s + i * RSTEP * KPAD, a_src[i], a_ok[i] ? kbytes : 0);
+      a_src[i] += BK;
     }
     if (B_KCONT) {
 #pragma unroll
-      for (int c = tid; c < BN * (BK / 2); c += T) {
-        const int r = c / (BK / 2), ck = c % (BK / 2);
-        const int gr = n0 + r, gk = k0 + 2 * ck;
-        int bytes = (gr < g.N) ? min(16, max(0, (ke - gk) * 8)) : 0;
-        const double* src = bytes ? (B + (int64_t)gr * g.ldb + gk) : B;
-        cp_async16(b_s + r * KPAD + 2 * ck, src, bytes);
+      for (int i = 0; i < NBK; i++) {
+        cp_async16(b_s + i * RSTEP * KPAD, b_src[i], b_ok[i] ? kbytes : 0);
+        b_src[i] += BK;
       }
     } else {
+      constexpr int KSTEP = T / (BN / 2);
 #pragma unroll
-      for (int c = tid; c < BK * (BN / 2); c += T) {
-        const int kk = c / (BN / 2), cn = c % (BN / 2);
-        const int gk = k0 + kk, gn = n0 + 2 * cn;
-        int bytes = (gk < ke) ? min(16, max(0, (g.N - gn) * 8)) : 0;
-        const double* src = bytes ? (B + (int64_t)gk * g.ldb + gn) : B;
-        cp_async16(b_s + kk * (BN + 4) + 2 * cn, src, bytes);
+      for (int i = 0; i < NBK; i++) {
+        const bool kok = k0 + b_row0 + i * KSTEP < ke;
+        cp_async16(b_s + i * KSTEP * (BN + 4), kok ? b_src[i] : B, kok ? b_bytes : 0);
+        b_src[i] += (int64_t)BK * g.ldb;
       }
     }
   };
@@ -160,6 +199,15 @@ gemm_f64_kernel(const GemmArgs g) {
   }
 }
 
+// useful flops: triangular output halves the tile count, triangular operands halve the k range
+double gemm_useful_flops(const GemmArgs& g) {
+  double f = 2.0 * g.M * (double)g.N * g.K * g.outer * g.inner;
+  if (g.cmode != C_FULL) f *= 0.5 * (g.M >= g.N ? (2.0 - (double)g.N / g.M) : 1.0);
+  if (g.klo_mode == KLO_MAXMN) f *= 1.0 / 3.0;  // sum_{i>=j} (N - i) / (N^2/2 * N)
+  else if (g.klo_mode != KLO_ZERO || g.khi_mode != KHI_K) f *= 0.5;
+  return f;
+}
+
 template <int BM, int BN, int WM, int WN, int STAGES, bool B_KCONT>
 static int launch_cfg(const Ctx& ctx, const GemmArgs& g) {
   using Cfg = GemmCfg<BM, BN, WM, WN, STAGES, B_KCONT>;
@@ -172,14 +220,7 @@ static int launch_cfg(const Ctx& ctx, const GemmArgs& g) {
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.outer * g.inner);
   prof_gemm_begin(ctx.stream);
   kern<<<grid, Cfg::THREADS, Cfg::SMEM, ctx.stream>>>(g);
-  if (prof().on) {
-    // useful flops: triangular output halves the tile count, triangular operands halve the k range
-    double f = 2.0 * g.M * (double)g.N * g.K * g.outer * g.inner;
-    if (g.cmode != C_FULL) f *= 0.5 * (g.M >= g.N ? (2.0 - (double)g.N / g.M) : 1.0);
-    if (g.klo_mode == KLO_MAXMN) f *= 1.0 / 3.0;  // sum_{i>=j} (N - i) / (N^2/2 * N)
-    else if (g.klo_mode != KLO_ZERO || g.khi_mode != KHI_K) f *= 0.5;
-    prof_gemm_end(ctx.stream, f);
-  }
+  if (prof().on) prof_gemm_end(ctx.stream, gemm_useful_flops(g));
   GEGP_CHECK_LAUNCH();
   return 0;
 }
@@ -192,6 +233,7 @@ GemmArgs gemm_args(const double* A, int64_t lda, const double* B, int64_t ldb, d
   g.klo_mode = KLO_ZERO; g.khi_mode = KHI_K; g.cmode = C_FULL;
   g.inner = 1; g.outer = 1;
   g.row_owner = false;
+  g.inner_steps = false; g.iAr = g.iAc = g.iBr = g.iBc = 0;
   g.sAo = g.sBo = g.sCo = g.sAi = g.sBi = g.sCi = 0;
   return g;
 }
@@ -211,6 +253,14 @@ int gemm_f64(const Ctx& ctx, GemmArgs g) {
     if (g.N > 128 || g.A != g.C || g.b_kcont) return -904;
     return launch_cfg<128, 128, 64, 32, 4, false>(ctx, g);
   }
+  static const int exp_cfg = getenv("GEGP_GEMM_CFG") ? atoi(getenv("GEGP_GEMM_CFG")) : 0;  // tuning experiments
+  if (g.b_kcont && big && exp_cfg != 9) {
+    const int rc = gemm_tma_nt(ctx, g);
+    if (rc <= 0) return rc;
+  }
+  if (g.b_kcont && big && exp_cfg == 1) return launch_cfg<128, 128, 32, 32, 4, true>(ctx, g);
+  if (g.b_kcont && big && exp_cfg == 2) return launch_cfg<128, 128, 32, 64, 4, true>(ctx, g);
+  if (g.b_kcont && big && exp_cfg == 5) return launch_cfg<128, 128, 64, 32, 3, true>(ctx, g);
   if (g.b_kcont) {
     if (big) return launch_cfg<128, 128, 64, 32, 4, true>(ctx, g);
     return launch_cfg<64, 64, 32, 32, 4, true>(ctx, g);

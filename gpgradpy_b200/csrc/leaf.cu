@@ -1,12 +1,12 @@
 // Latency-bound leaves of the blocked factorisation.
 //
-// potf2_inv_kernel factors one LEAF x LEAF (128) diagonal block AND inverts the factor inside one CTA:
-// the block lives in shared memory, 32 x 32 diagonal sub-blocks are factored/inverted in the registers of
-// one warp (row per lane, warp shuffles), everything else (panel solves, trailing updates, assembly of the
-// 128 x 128 inverse from the 32 x 32 ones) runs on the fp64 tensor cores (DMMA.8x8x4) straight from
-// shared memory.  The inverse-transposed block U_bb = L_bb^-T is what the blocked algorithms multiply
-// with (panel solves become DMMA GEMMs; the explicit inverse K^-1 starts from these blocks), so there is
-// no substitution kernel on the O(N^3) path.
+// potf2_inv_kernel factors one LEAF x LEAF (128) diagonal block AND inverts the factor inside one CTA.
+// The block lives in shared memory.  Each 32-column panel is factored with one thread per row (the row sits in
+// registers, the pivot column is broadcast through shared memory: one barrier per column), the trailing update
+// and the assembly of the 128 x 128 inverse from the 32 x 32 diagonal inverses run on the fp64 tensor cores
+// (DMMA.8x8x4) straight from shared memory.  The inverse-transposed block U_bb = L_bb^-T is what the blocked
+// algorithms multiply with: leaf solves use its 32 x 32 diagonal blocks (with a refinement step), the explicit
+// inverse K^-1 starts from the whole block.  There is no serial substitution kernel on the O(N^3) path.
 #include "linalg.h"
 
 namespace gegp {
@@ -22,132 +22,71 @@ constexpr unsigned FULL = 0xffffffffu;
 // Shared-memory tile T[NB][PLD]:  L(r,c) = T[r][c] (c <= r) ;  U(i,j) = L^-T (i <= j) = T[i][j+1].
 // The one-column shift keeps both diagonals (L_ii and 1/L_ii).
 
-// Factor + invert the 32 x 32 diagonal sub-block at j0 with one warp: lane r owns row r of L and of M = L^-1.
-__device__ __forceinline__ int warp_potf2_inv32(double* __restrict__ s, int j0, int lane) {
-  double a[32], m[32];
-  const double* row = s + (j0 + lane) * PLD + j0;
+constexpr int SLD = 36;  // == 4 (mod 16): stride of the per-warp 8-row scratch strips
+
+// Factor the 32-column panel at j0 (rows j0 .. kk-1): thread t owns row t in registers (all threads of
+// the CTA run the column loop so that its barrier is a plain __syncthreads).  Per column j the
+// rows of the diagonal block publish their (still unscaled) entry of column j; after ONE barrier every row reads
+// the pivot, forms 1/sqrt(pivot) itself and applies the rank-1 update to its own row.  `col` is a double buffer of
+// 2 x 32 doubles, `rsd[j0 + j]` receives 1 / L_jj.  Returns the first bad pivot (1-based inside the panel) or 0.
+// (No __restrict__ on `col`: other threads rewrite it between barriers and the loads must not be reused.)
+__device__ __forceinline__ int panel_factor32(double* s, double* col, double* rsd, int j0, int kk, int tid) {
+  const int r = tid;
+  const bool active = (r >= j0) && (r < kk);
+  const bool diag = active && (r < j0 + 32);
+  double a[32];
+  const double* row = s + r * PLD + j0;
 #pragma unroll
-  for (int c = 0; c < 32; c++) a[c] = (c <= lane) ? row[c] : 0.0;
-#pragma unroll
-  for (int c = 0; c < 32; c++) m[c] = (c == lane) ? 1.0 : 0.0;
+  for (int c = 0; c < 32; c++) a[c] = (active && j0 + c <= r) ? row[c] : 0.0;
   int bad = 0;
 #pragma unroll
   for (int j = 0; j < 32; j++) {
-    const double piv = __shfl_sync(FULL, a[j], j);
-    if (!(piv > 0.0) && bad == 0) bad = j + 1;  // also catches NaN; uniform over the warp
-    const double dj = sqrt(piv);
-    const double inv = 1.0 / dj;
-    a[j] = (lane == j) ? dj : a[j] * inv;       // column j of L (zero above the diagonal stays zero)
-    if (lane == j) {
+    double* cb = col + (j & 1) * 32;
+    if (diag) cb[r - j0] = a[j];
+    __syncthreads();
+    const double piv = cb[j];
+    if (!(piv > 0.0) && bad == 0) bad = j + 1;   // also catches NaN; the same in every thread
+    const double rs = rsqrt(piv);
+    const double lrj = a[j] * rs;                // rows above the pivot hold 0 here
+    a[j] = lrj;
+    if (r == j0 + j) rsd[r] = rs;
 #pragma unroll
-      for (int c = 0; c <= j; c++) m[c] *= inv;  // row j of M is final
-    }
-    const double lrj = (lane > j) ? a[j] : 0.0;
-#pragma unroll
-    for (int c = j + 1; c < 32; c++) {
-      const double lcj = __shfl_sync(FULL, a[j], c);
-      a[c] -= lrj * lcj;                         // right-looking update of the rows below
-    }
-#pragma unroll
-    for (int c = 0; c <= j; c++) {
-      const double mjc = __shfl_sync(FULL, m[c], j);
-      m[c] -= lrj * mjc;                         // M[r][:] -= L[r][j] * M[j][:]
-    }
+    for (int c = j + 1; c < 32; c++) a[c] -= lrj * (cb[c] * rs);
   }
-  double* wrow = s + (j0 + lane) * PLD + j0;
+  if (active) {
+    double* wrow = s + r * PLD + j0;
 #pragma unroll
-  for (int c = 0; c < 32; c++)
-    if (c <= lane) wrow[c] = a[c];
-#pragma unroll
-  for (int i = 0; i < 32; i++)
-    if (i <= lane) s[(j0 + i) * PLD + j0 + lane + 1] = m[i];  // U(i, lane) = M[lane][i]
+    for (int c = 0; c < 32; c++)
+      if (j0 + c <= r) wrow[c] = a[c];
+  }
   return bad;
 }
 
-// Rows [r_beg, kk) of the 32 columns at j0:  X = B * L_jj^-T, in place, strips of 8 rows per warp.
-// Computed with the inverse U_jj = L_jj^-T plus one refinement step, which makes it as accurate as a
-// substitution:  X1 = B U ;  R = B - X1 L_jj^T ;  X = X1 + R U.   `scr` is this warp's 8 x SLD scratch strip
-// (accumulator layout -> A-fragment layout goes through shared memory).
-constexpr int SLD = 36;  // == 4 (mod 16)
-
-__device__ __forceinline__ void panel_solve32(double* __restrict__ s, double* __restrict__ scr, int j0, int r_beg,
-                                              int kk, int warp, int lane) {
-  const int lr = lane >> 2, lk = lane & 3;
-  const int nstrips = (kk - r_beg) >> 3;
-  for (int st = warp; st < nstrips; st += NW) {
-    const int r0 = r_beg + st * 8;
-    double* brow = s + (r0 + lr) * PLD + j0;
-    double af[8];
-    double acc[4][2];
-    // X1 = B U
+// Inverse of the 32 x 32 diagonal block at j0 by one warp: lane c solves L x = e_c by forward substitution with
+// x in registers and L broadcast from shared memory; U(c, r) = x[r] = (L^-1)[r][c] goes to the shifted upper part.
+__device__ __forceinline__ void diag_inverse32(double* s, const double* rsd, int j0,
+                                               int lane) {
+  double x[32];
 #pragma unroll
-    for (int kq = 0; kq < 8; kq++) af[kq] = brow[4 * kq + lk];
+  for (int r = 0; r < 32; r++) {
+    const double* lrow = s + (j0 + r) * PLD + j0;
+    double acc0 = (r == lane) ? 1.0 : 0.0, acc1 = 0.0;
 #pragma unroll
-    for (int ct = 0; ct < 4; ct++) {
-      acc[ct][0] = acc[ct][1] = 0.0;
-      const int c = ct * 8 + lr;
-#pragma unroll
-      for (int kq = 0; kq <= 2 * ct + 1; kq++) {
-        const int k = 4 * kq + lk;
-        const double b = (k <= c) ? s[(j0 + k) * PLD + j0 + c + 1] : 0.0;
-        dmma884(acc[ct][0], acc[ct][1], af[kq], b);
-      }
+    for (int k = 0; k + 1 < r; k += 2) {
+      acc0 -= lrow[k] * x[k];
+      acc1 -= lrow[k + 1] * x[k + 1];
     }
-#pragma unroll
-    for (int ct = 0; ct < 4; ct++) {
-      scr[lr * SLD + ct * 8 + 2 * lk] = acc[ct][0];
-      scr[lr * SLD + ct * 8 + 2 * lk + 1] = acc[ct][1];
-    }
-    __syncwarp();
-#pragma unroll
-    for (int kq = 0; kq < 8; kq++) af[kq] = -scr[lr * SLD + 4 * kq + lk];   // -X1 as the A operand
-    __syncwarp();
-    // R = B - X1 L_jj^T   (b[k][n] = L_jj(n, k), zero for k > n)
-    double rr[4][2];
-#pragma unroll
-    for (int ct = 0; ct < 4; ct++) {
-      rr[ct][0] = brow[ct * 8 + 2 * lk];
-      rr[ct][1] = brow[ct * 8 + 2 * lk + 1];
-      const int nn = ct * 8 + lr;
-#pragma unroll
-      for (int kq = 0; kq <= 2 * ct + 1; kq++) {
-        const int k = 4 * kq + lk;
-        const double b = (k <= nn) ? s[(j0 + nn) * PLD + j0 + k] : 0.0;
-        dmma884(rr[ct][0], rr[ct][1], af[kq], b);
-      }
-    }
-#pragma unroll
-    for (int ct = 0; ct < 4; ct++) {
-      scr[lr * SLD + ct * 8 + 2 * lk] = rr[ct][0];
-      scr[lr * SLD + ct * 8 + 2 * lk + 1] = rr[ct][1];
-    }
-    __syncwarp();
-#pragma unroll
-    for (int kq = 0; kq < 8; kq++) af[kq] = scr[lr * SLD + 4 * kq + lk];    // R as the A operand
-    __syncwarp();
-    // X = X1 + R U
-#pragma unroll
-    for (int ct = 0; ct < 4; ct++) {
-      const int c = ct * 8 + lr;
-#pragma unroll
-      for (int kq = 0; kq <= 2 * ct + 1; kq++) {
-        const int k = 4 * kq + lk;
-        const double b = (k <= c) ? s[(j0 + k) * PLD + j0 + c + 1] : 0.0;
-        dmma884(acc[ct][0], acc[ct][1], af[kq], b);
-      }
-    }
-#pragma unroll
-    for (int ct = 0; ct < 4; ct++) {
-      brow[ct * 8 + 2 * lk] = acc[ct][0];
-      brow[ct * 8 + 2 * lk + 1] = acc[ct][1];
-    }
-    __syncwarp();
+    if (r & 1) acc0 -= lrow[r - 1] * x[r - 1];
+    x[r] = (r >= lane) ? (acc0 + acc1) * rsd[j0 + r] : 0.0;
   }
+#pragma unroll
+  for (int r = 0; r < 32; r++)
+    if (r >= lane) s[(j0 + lane) * PLD + j0 + r + 1] = x[r];
 }
 
 // Trailing update of the lower triangle of rows/cols [base, kk) with the 32-wide panel at j0:
 // C -= X X^T, 8 x 8 tiles, K = 32.
-__device__ __forceinline__ void trailing_update32(double* __restrict__ s, int j0, int base, int kk, int warp, int lane) {
+__device__ __forceinline__ void trailing_update32(double* s, int j0, int base, int kk, int warp, int lane) {
   const int lr = lane >> 2, lk = lane & 3;
   const int nt = (kk - base) >> 3;
   const int ntiles = nt * (nt + 1) / 2;
@@ -174,7 +113,7 @@ __device__ __forceinline__ void trailing_update32(double* __restrict__ s, int j0
 // Inverse assembly for the block pair a = [a0, a0+sza), b = [b0, b0+szb), a before b:
 //   U_ab = -U_aa * L_ba^T * U_bb
 // phase 1:  P = U_aa * L_ba^T  -> stored where U_ab will live ;  phase 2:  U_ab = -P * U_bb (in place).
-__device__ __forceinline__ void pair_phase1(double* __restrict__ s, int a0, int sza, int b0, int szb, int w, int nw,
+__device__ __forceinline__ void pair_phase1(double* s, int a0, int sza, int b0, int szb, int w, int nw,
                                             int lane) {
   const int lr = lane >> 2, lk = lane & 3;
   const int nit = sza >> 3, njt = szb >> 3;
@@ -195,7 +134,7 @@ __device__ __forceinline__ void pair_phase1(double* __restrict__ s, int a0, int 
 }
 
 template <int MAXKQ>
-__device__ __forceinline__ void pair_phase2(double* __restrict__ s, int a0, int sza, int b0, int szb, int w, int nw,
+__device__ __forceinline__ void pair_phase2(double* s, int a0, int sza, int b0, int szb, int w, int nw,
                                             int lane) {
   const int lr = lane >> 2, lk = lane & 3;
   const int nst = sza >> 3, njt = szb >> 3, nkq = szb >> 2;
@@ -232,48 +171,73 @@ __device__ __forceinline__ void pair_phase2(double* __restrict__ s, int a0, int 
 
 }  // namespace
 
+#ifdef GEGP_LEAF_CLOCKS
+__device__ long long g_leaf_clk[16];
+#define LEAF_CLK(i) do { if (threadIdx.x == 0) g_leaf_clk[i] = clock64(); } while (0)
+#else
+#define LEAF_CLK(i) do { } while (0)
+#endif
+
 // One CTA per problem: A (k x k lower, k <= 128) -> L in place; Dinv (128 x 128, ld 128) <- L^-T (upper
 // triangular, explicit zeros elsewhere).  The first non-positive pivot is recorded in info[z]
 // (1-based global index row0 + i + 1) if info[z] was 0.
 __global__ void __launch_bounds__(LT, 1)
 potf2_inv_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int k, int row0, int* __restrict__ info,
                  double* __restrict__ Dinv, int64_t strideD) {
-  extern __shared__ __align__(16) double s[];  // NB x PLD tile, then NW x 8 x SLD scratch strips
+  extern __shared__ __align__(16) double s[];  // NB x PLD tile
+  __shared__ double col[2 * 32];
+  __shared__ double rsd[NB];
   __shared__ int bad_sh;
   A += (int64_t)blockIdx.z * strideA;
   Dinv += (int64_t)blockIdx.z * strideD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int kk = (k + 31) & ~31;  // padded with an identity block up to a multiple of 32
   if (tid == 0) bad_sh = 0;
-  for (int e = tid; e < kk * NB; e += LT) {
-    const int r = e >> 7, c = e & (NB - 1);
-    if (c >= kk) continue;
-    double v = (r == c) ? 1.0 : 0.0;
-    if (r < k && c <= r) v = A[(int64_t)r * lda + c];
-    if (c <= r) s[r * PLD + c] = v;
+  LEAF_CLK(0);
+  // lower triangle, two columns per thread (A is 16-byte aligned, lda even)
+#pragma unroll 4
+  for (int e = tid; e < kk * (NB / 2); e += LT) {
+    const int r = e >> 6, c = (e & 63) * 2;
+    if (c > r) continue;
+    double2 v = make_double2((r == c) ? 1.0 : 0.0, (r == c + 1) ? 1.0 : 0.0);
+    if (r < k) {
+      if (c + 1 < k) v = *reinterpret_cast<const double2*>(A + (int64_t)r * lda + c);
+      else v.x = A[(int64_t)r * lda + c];
+    }
+    s[r * PLD + c] = v.x;
+    if (c + 1 <= r) s[r * PLD + c + 1] = v.y;
   }
   __syncthreads();
+  LEAF_CLK(1);
 
   for (int j0 = 0; j0 < kk; j0 += 32) {
-    if (warp == 0) {
-      const int bad = warp_potf2_inv32(s, j0, lane);
-      if (lane == 0 && bad && bad_sh == 0 && j0 + bad <= k) bad_sh = j0 + bad;
+    {
+      const int bad = panel_factor32(s, col, rsd, j0, kk, tid);
+      if (tid == 0 && bad && bad_sh == 0 && j0 + bad <= k) bad_sh = j0 + bad;
     }
     __syncthreads();
+    LEAF_CLK(2 + (j0 >> 5) * 2);
     if (j0 + 32 < kk) {
-      panel_solve32(s, s + NB * PLD + warp * 8 * SLD, j0, j0 + 32, kk, warp, lane);
-      __syncthreads();
       trailing_update32(s, j0, j0 + 32, kk, warp, lane);
       __syncthreads();
     }
+    LEAF_CLK(3 + (j0 >> 5) * 2);
   }
   // L is final: write it out while the inverse is assembled
-  for (int e = tid; e < k * NB; e += LT) {
-    const int r = e >> 7, c = e & (NB - 1);
-    if (c <= r) A[(int64_t)r * lda + c] = s[r * PLD + c];
+#pragma unroll 4
+  for (int e = tid; e < k * (NB / 2); e += LT) {
+    const int r = e >> 6, c = (e & 63) * 2;
+    if (c > r) continue;
+    if (c + 1 <= r) *reinterpret_cast<double2*>(A + (int64_t)r * lda + c) = make_double2(s[r * PLD + c], s[r * PLD + c + 1]);
+    else A[(int64_t)r * lda + c] = s[r * PLD + c];
   }
   if (tid == 0 && bad_sh) atomicCAS(info + blockIdx.z, 0, row0 + bad_sh);
 
+  // 32 x 32 diagonal inverses: one warp per block
+  LEAF_CLK(10);
+  if (warp * 32 < kk) diag_inverse32(s, rsd, warp * 32, lane);
+  __syncthreads();
+  LEAF_CLK(11);
   // level 1: pairs of 32-blocks -> 64-blocks
   if (kk >= 64) {
     const int npairs = (kk >= 128) ? 2 : 1;
@@ -283,6 +247,7 @@ potf2_inv_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int k, in
     pair_phase2<8>(s, pr * 64, 32, pr * 64 + 32, 32, w, nw, lane);
     __syncthreads();
   }
+  LEAF_CLK(12);
   // level 2: [0,64) with [64,kk)
   if (kk > 64) {
     pair_phase1(s, 0, 64, 64, kk - 64, warp, NW, lane);
@@ -290,18 +255,32 @@ potf2_inv_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int k, in
     pair_phase2<16>(s, 0, 64, 64, kk - 64, warp, NW, lane);
     __syncthreads();
   }
-  for (int e = tid; e < NB * NB; e += LT) {
-    const int i = e >> 7, j = e & (NB - 1);
-    Dinv[e] = (i < kk && j < kk && j >= i) ? s[i * PLD + j + 1] : 0.0;
+  LEAF_CLK(13);
+#pragma unroll 4
+  for (int e = tid; e < NB * (NB / 2); e += LT) {
+    const int i = e >> 6, j = (e & 63) * 2;
+    double2 v = make_double2(0.0, 0.0);
+    if (i < kk && j < kk) {
+      if (j >= i) v.x = s[i * PLD + j + 1];
+      if (j + 1 >= i) v.y = s[i * PLD + j + 2];
+    }
+    *reinterpret_cast<double2*>(Dinv + i * NB + j) = v;
   }
+  LEAF_CLK(14);
 }
+
+#ifdef GEGP_LEAF_CLOCKS
+extern "C" int gegp_debug_leaf_clocks(long long* out16) {
+  return (int)cudaMemcpyFromSymbol(out16, g_leaf_clk, sizeof(long long) * 16);
+}
+#endif
 
 int leaf_potf2_inv(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int k, int row0, int* info, double* Dinv,
                    int64_t strideD) {
   if (k <= 0) return 0;
   if (k > NB) return -901;
   static bool attr = false;
-  const int smem = (NB * PLD + NW * 8 * SLD) * (int)sizeof(double);
+  const int smem = NB * PLD * (int)sizeof(double);
   if (!attr) { GEGP_SET_SMEM(potf2_inv_kernel, smem); attr = true; }
   potf2_inv_kernel<<<dim3(1, 1, ctx.batch), LT, smem, ctx.stream>>>(A, lda, strideA, k, row0, info, Dinv, strideD);
   GEGP_CHECK_LAUNCH();
@@ -320,7 +299,7 @@ int leaf_potf2_inv(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int 
 // ------------------------------------------------------------------------------------------------
 constexpr int TW = 16;  // warps per CTA of the leaf solve
 
-__device__ __forceinline__ void frag_c_to_a(double* __restrict__ scr, const double (&c)[4][2], double (&a)[8], int lr,
+__device__ __forceinline__ void frag_c_to_a(double* scr, const double (&c)[4][2], double (&a)[8], int lr,
                                             int lk, double sign) {
   __syncwarp();
 #pragma unroll

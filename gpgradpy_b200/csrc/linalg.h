@@ -23,6 +23,8 @@ struct GemmArgs {
   int inner;
   int64_t sAo, sBo, sCo, sAi, sBi, sCi;
   int outer;
+  bool inner_steps;        // iAr..iBc below are valid (needed by the TMA kernel when inner > 1)
+  int iAr, iAc, iBr, iBc;  // inner-batch steps of A and B as (rows, columns): sAi == iAr*lda + iAc, sBi likewise
   bool row_owner;  // C aliases A (in-place right multiply): every CTA must own complete rows (one column tile)
 };
 
@@ -31,6 +33,10 @@ GemmArgs gemm_args(const double* A, int64_t lda, const double* B, int64_t ldb, d
 
 // C = alpha*A*op(B) + beta*C on fp64 tensor cores (DMMA). Returns 0 or a negative launch error.
 int gemm_f64(const Ctx& ctx, GemmArgs g);
+// TMA + mbarrier warp-specialised kernel for the K-contiguous (A * B^T) case and large tiles.
+// 0: launched; 1: not covered (use the cp.async engine); < 0: launch error.
+int gemm_tma_nt(const Ctx& ctx, const GemmArgs& g);
+double gemm_useful_flops(const GemmArgs& g);
 
 // --- leaves (<= LEAF wide) ---
 // Every factor carries the inverse-transposed diagonal blocks Dinv: block b (rows/cols [b*LEAF, (b+1)*LEAF)) is

@@ -86,6 +86,7 @@ static int inverse_transposed(const Ctx& ctx, const double* L, int64_t ldl, int6
       g1.klo_mode = KLO_M0;
       g1.outer = ctx.batch; g1.inner = inner;
       g1.sAo = strideU; g1.sBo = strideL; g1.sCo = strideT; g1.sAi = pstepU; g1.sBi = pstepL; g1.sCi = pstepT;
+      g1.inner_steps = true; g1.iAr = g1.iAc = g1.iBr = g1.iBc = 2 * bs;
       rc = gemm_f64(ctx, g1);
       if (rc) return rc;
       // U_ab = -T_ab (bs x bsz) * U_bb (bsz x bsz upper, element (k,j) nonzero for k <= j) -> NN, k < n0+BN
