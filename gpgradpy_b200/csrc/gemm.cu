@@ -245,8 +245,10 @@ int gemm_f64(const Ctx& ctx, GemmArgs g) {
   if ((g.lda & 1) || (g.ldb & 1) || (reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15) ||
       (g.sAo & 1) || (g.sAi & 1) || (g.sBo & 1) || (g.sBi & 1))
     return -900;
-  // Large tile when it still fills the machine, small tile otherwise (batched small problems).
-  const long tiles_big = (long)((g.M + 127) / 128) * ((g.N + 127) / 128) * g.outer * g.inner;
+  // Large tile when one problem still fills the machine with it, small tile otherwise.  The choice depends on the
+  // shape of ONE problem only, never on the batch count: a candidate evaluated alone, in a batch, or on another rank
+  // of a sharded batch goes through the same kernels and gives bit-identical results.
+  const long tiles_big = (long)((g.M + 127) / 128) * ((g.N + 127) / 128) * g.inner;
   const bool big = (g.cmode == C_FULL ? tiles_big : tiles_big / 2) >= 120 && g.M >= 128 && g.N >= 128;
   if (g.row_owner) {
     // in-place right multiply: one column tile must cover all of N so that a CTA only overwrites rows it alone reads
