@@ -83,6 +83,7 @@ def workspace(nbytes: int) -> torch.Tensor:
 
 
 def free_workspace():
+    _graph_cache.clear()
     _ws_cache.clear()
 
 
@@ -169,8 +170,22 @@ def dgemm(A: torch.Tensor, B: torch.Tensor, C: torch.Tensor, *, transb: bool, al
     return C
 
 
+def _lml_workspace(lib, op, n, n_g, d, B, max_ws_bytes):
+    """Workspace for B candidates (or the largest chunk of them that fits); cudaMemGetInfo only when it must grow."""
+    need_all = int(lib.gegp_workspace_bytes(op, n, n_g, d, B)) + 4 * B + 256
+    cached = _ws_cache.get(torch.cuda.current_device())
+    if cached is not None and cached.numel() >= need_all and (max_ws_bytes is None or need_all <= max_ws_bytes):
+        return cached
+    per1 = int(lib.gegp_workspace_bytes(op, n, n_g, d, 1))
+    if max_ws_bytes is None:
+        free, _total = torch.cuda.mem_get_info()
+        max_ws_bytes = int(0.6 * (free + (cached.numel() if cached is not None else 0)))
+    chunk = max(1, min(B, (max_ws_bytes - 4096 - 4 * B) // per1))
+    return workspace(int(lib.gegp_workspace_bytes(op, n, n_g, d, chunk)) + 4 * B + 256)
+
+
 def lml_eval(X, y, theta_batch, *, n_g=None, slot=None, mode=L.MODE_PRECON, eta=0.0, noise=None, varK_batch=None,
-             pnlt_grad=0.0, want_grad=True, want_alpha=False, max_ws_bytes=None):
+             pnlt_grad=0.0, want_grad=True, want_alpha=False, max_ws_bytes=None, out=None):
     """gegp_lml_eval for B candidate rows -> (out [B, 9+d] device tensor, alpha [B, N] or None)."""
     lib = L.load()
     X, y = to_dev(X), to_dev(y)
@@ -184,22 +199,89 @@ def lml_eval(X, y, theta_batch, *, n_g=None, slot=None, mode=L.MODE_PRECON, eta=
     vk = to_dev(varK_batch).reshape(-1) if noisy else None
     if noisy:
         assert vk.numel() == B
-    out = torch.empty((B, L.out_len(d)), dtype=F64, device=device())
+    if out is None:
+        out = torch.empty((B, L.out_len(d)), dtype=F64, device=device())
     alpha = torch.empty((B, N), dtype=F64, device=device()) if want_alpha else None
     op = L.OP_LML_GRAD if want_grad else L.OP_LML
-    per1 = int(lib.gegp_workspace_bytes(op, n, n_g, d, 1))
-    if max_ws_bytes is None:
-        free, _total = torch.cuda.mem_get_info()
-        cached = _ws_cache.get(torch.cuda.current_device())
-        max_ws_bytes = int(0.6 * (free + (cached.numel() if cached is not None else 0)))
-    chunk = max(1, min(B, (max_ws_bytes - 4096 - 4 * B) // per1))
-    nbytes = int(lib.gegp_workspace_bytes(op, n, n_g, d, chunk)) + 4 * B + 256
-    ws = workspace(nbytes)
+    ws = _lml_workspace(lib, op, n, n_g, d, B, max_ws_bytes)
     rc = lib.gegp_lml_eval(B, _p(th), _p(vk), n, n_g, d, _p(X), _p(slot), _p(y), _p(noise), int(mode), float(eta),
                            int(noisy), float(pnlt_grad), int(bool(want_grad)), _p(out), _p(alpha), _p(ws), ws.numel(),
                            _stream())
     _check(rc, "gegp_lml_eval")
     return out, alpha
+
+
+class LmlGraph:
+    """One captured CUDA graph of gegp_lml_eval for a fixed problem (data, shapes, mode, flags).
+
+    The ~300 kernel launches of one evaluation are recorded once and replayed with new hyper-parameters, which
+    are written into static device buffers before the replay.  Used for the optimiser's inner loop, where the
+    same-shaped evaluation is repeated hundreds of times (optz/OptzLkd.py:249-270).
+    """
+
+    def __init__(self, X, y, B, *, n_g, slot, mode, eta, noise, noisy, pnlt_grad, want_grad):
+        n, d = X.shape
+        self.key_tensors = (X, y, slot, noise)          # keep the captured buffers alive
+        self.theta = torch.empty((B, d), dtype=F64, device=device())
+        self.varK = torch.ones(B, dtype=F64, device=device()) if noisy else None
+        self.out = torch.empty((B, L.out_len(d)), dtype=F64, device=device())
+        kw = dict(n_g=n_g, slot=slot, mode=mode, eta=eta, noise=noise if noisy else None, varK_batch=self.varK,
+                  pnlt_grad=pnlt_grad, want_grad=want_grad, out=self.out)
+        self.theta.fill_(1.0)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                   # warm-up: function attributes, tensor maps, workspace growth
+            lml_eval(X, y, self.theta, **kw)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        L.profile_begin(False)
+        with torch.cuda.graph(self.graph):
+            lml_eval(X, y, self.theta, **kw)
+        self.n_launches = L.profile_end()["launches"]          # kernels recorded in the graph
+        self.ws = _ws_cache.get(torch.cuda.current_device())   # the captured workspace must stay allocated
+
+    def __call__(self, theta_rows, varK_rows=None):
+        src = theta_rows if isinstance(theta_rows, torch.Tensor) else torch.as_tensor(
+            np.ascontiguousarray(theta_rows, dtype=np.float64))
+        self.theta.copy_(src.reshape(self.theta.shape), non_blocking=True)
+        if self.varK is not None:
+            self.varK.copy_(torch.as_tensor(np.ascontiguousarray(varK_rows, dtype=np.float64)).reshape(-1))
+        self.graph.replay()
+        replay_stats["replays"] += 1
+        replay_stats["kernel_launches"] += self.n_launches
+        return self.out
+
+
+_graph_cache: dict = {}
+replay_stats = {"replays": 0, "kernel_launches": 0}   # kernels launched through graph replays (bench.py reports them)
+
+
+def lml_eval_graphed(X, y, theta_batch, *, n_g=None, slot=None, mode=L.MODE_PRECON, eta=0.0, noise=None,
+                     varK_batch=None, pnlt_grad=0.0, want_grad=True):
+    """Same result as lml_eval(...)[0], through a cached CUDA graph.  X, y, slot, noise must be device tensors that
+    stay alive and unchanged in place between calls (the graph holds their addresses)."""
+    n, d = X.shape
+    n_g = n if n_g is None else n_g
+    B = int(np.prod(theta_batch.shape)) // d
+    noisy = noise is not None
+    key = (torch.cuda.current_device(), X.data_ptr(), y.data_ptr(), _p(slot), _p(noise), n, n_g, d, B, int(mode),
+           float(eta), float(pnlt_grad), bool(want_grad), noisy)
+    g = _graph_cache.get(key)
+    ws_now = _ws_cache.get(torch.cuda.current_device())
+    if g is not None and g.ws is not ws_now:   # the workspace was re-allocated since the capture
+        g = None
+    if g is None:
+        if len(_graph_cache) >= 8:
+            _graph_cache.clear()
+        g = LmlGraph(X, y, B, n_g=n_g, slot=slot, mode=mode, eta=eta, noise=noise, noisy=noisy, pnlt_grad=pnlt_grad,
+                     want_grad=want_grad)
+        _graph_cache[key] = g
+    return g(theta_batch, varK_batch)
+
+
+def free_graphs():
+    _graph_cache.clear()
 
 
 class PredictState:

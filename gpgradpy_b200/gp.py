@@ -61,6 +61,8 @@ class DeviceMatrix:
 
 
 class GaussianProcess:
+    use_cuda_graphs = True      # replay a captured CUDA graph for repeated noise-free evaluations (not in the reference)
+
     # ---- options (names and defaults of gpgradpy/src/GaussianProcess.py:27-113) ----
     print_txt_data = False
     save_data_npz = False
@@ -357,8 +359,14 @@ class GaussianProcess:
         # host -> device through pinned staging buffers (kept, so a refresh re-uses them)
         self._x_pin = bk.pinned_like(getattr(self, "_x_pin", None), x_scl)
         self._y_pin = bk.pinned_like(getattr(self, "_y_pin", None), self._y_host)
-        self._X_dev = self._x_pin.to(bk.device(), non_blocking=True)
-        self._y_dev = self._y_pin.to(bk.device(), non_blocking=True)
+        # device buffers are kept while the shapes stay the same, so captured CUDA graphs remain valid after a refresh
+        if getattr(self, "_X_dev", None) is not None and tuple(self._X_dev.shape) == tuple(self._x_pin.shape) \
+                and tuple(self._y_dev.shape) == tuple(self._y_pin.shape):
+            self._X_dev.copy_(self._x_pin, non_blocking=True)
+            self._y_dev.copy_(self._y_pin, non_blocking=True)
+        else:
+            self._X_dev = self._x_pin.to(bk.device(), non_blocking=True)
+            self._y_dev = self._y_pin.to(bk.device(), non_blocking=True)
         self._dev_ready = True
 
     # ---- scaled / unscaled accessors (GaussianProcess.py:399-457)
@@ -479,11 +487,18 @@ class GaussianProcess:
         return self.lkd_varK_pnlt_c1 * var_fval * mx ** 2, 2 * self.lkd_varK_pnlt_c1 * var_fval * mx
 
     def _eval_rows(self, theta_rows, *, want_grad, varK_rows=None, noise_vec=None, pnlt_grad=0.0):
-        """Device evaluation of B candidate rows -> torch [B, 9+d] (see GEGP_OUT_* in include/gegp.h)."""
+        """Device evaluation of B candidate rows -> torch [B, 9+d] (see GEGP_OUT_* in include/gegp.h).
+
+        Noise-free evaluations of a fixed data set replay a captured CUDA graph (the optimiser repeats the same-shaped
+        evaluation hundreds of times); everything else goes through the plain stream path."""
         self._ensure_device()
-        out, _ = bk.lml_eval(self._X_dev, self._y_dev, theta_rows, n_g=self.n_grad, slot=self._slot_dev,
-                             mode=self._mode, eta=self._etaK, noise=noise_vec, varK_batch=varK_rows,
-                             pnlt_grad=pnlt_grad, want_grad=want_grad)
+        kw = dict(n_g=self.n_grad, slot=self._slot_dev, mode=self._mode, eta=self._etaK, pnlt_grad=pnlt_grad,
+                  want_grad=want_grad)
+        single = int(np.prod(tuple(theta_rows.shape))) == self.dim   # one candidate: the optimiser's inner loop
+        if self.use_cuda_graphs and single and noise_vec is None and pnlt_grad == 0.0:
+            th = theta_rows if hasattr(theta_rows, "is_cuda") else np.asarray(theta_rows, dtype=float)
+            return bk.lml_eval_graphed(self._X_dev, self._y_dev, th, **kw)
+        out, _ = bk.lml_eval(self._X_dev, self._y_dev, theta_rows, noise=noise_vec, varK_batch=varK_rows, **kw)
         return out
 
     def calc_lkd_all(self, hp_vals, calc_lkd=True, calc_cond=False, calc_grad=False, lkd_use_adj_mtd=None):
