@@ -156,7 +156,9 @@ int gegp_potrf(int N, int n_extra, double* A, int64_t lda, double* dinv, int* in
   if (!dinv || (reinterpret_cast<uintptr_t>(dinv) & 15)) return -5;
   if (!info_dev) return -6;
   Ctx ctx{(cudaStream_t)stream, 1};
-  return chol_trap(ctx, A, lda, 0, N + n_extra, N, 0, info_dev, dinv, 0);
+  const int rc = chol_trap(ctx, A, lda, 0, N + n_extra, N, 0, info_dev, dinv, 0);
+  if (rc) return rc;
+  return leaf_dinv_assemble(ctx, A, lda, 0, dinv, 0, N);   // hand out a complete factor (A, dinv)
 }
 
 int gegp_trsm_rows(int N, const double* L, int64_t ldl, const double* dinv, double* B, int64_t ldb, int r,
@@ -256,6 +258,8 @@ int gegp_lml_eval(int B, const double* theta_batch, const double* varK_batch, in
     if (want_grad) {
       double* U = wk + L.U;
       double* Kinv = wk + L.Kinv;
+      rc = leaf_dinv_assemble(ctx, A, L.ld, sC, D, sC, N);
+      if (rc) return rc;
       rc = chol_inverse(ctx, A, L.ld, sC, D, sC, U, L.ld, sC, Kinv, L.ld, sC, N);
       if (rc) return rc;
       alpha_t = W + L.ld;
@@ -265,6 +269,8 @@ int gegp_lml_eval(int B, const double* theta_batch, const double* varK_batch, in
                            wk + L.Part, sC, outb, outlen);
       if (rc) return rc;
     } else if (alpha_out) {
+      rc = leaf_dinv_assemble(ctx, A, L.ld, sC, D, sC, N);
+      if (rc) return rc;
       rc = trsv_lower_trans(ctx, A, L.ld, sC, D, sC, W, L.ld, sC, N, 1);
       if (rc) return rc;
     }
@@ -303,6 +309,8 @@ int gegp_predict_setup(int n, int n_g, int d, const double* X, const int32_t* gr
   rc = launch_append_res(ctx, N, n, y, beta, pinv, row);
   if (rc) return rc;
   rc = chol_trap(ctx, A, lda, 0, N + 1, N, 0, info_dev, dinv, 0);
+  if (rc) return rc;
+  rc = leaf_dinv_assemble(ctx, A, lda, 0, dinv, 0, N);
   if (rc) return rc;
   if (alpha_out) {
     cudaError_t e = cudaMemcpyAsync(alpha_out, row, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream);

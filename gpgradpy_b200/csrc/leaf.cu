@@ -24,89 +24,191 @@ constexpr unsigned FULL = 0xffffffffu;
 
 constexpr int SLD = 36;  // == 4 (mod 16): stride of the per-warp 8-row scratch strips
 
-// Factor the 32-column panel at j0 (rows j0 .. kk-1): thread t owns row t in registers (all threads of
-// the CTA run the column loop so that its barrier is a plain __syncthreads).  Per column j the
-// rows of the diagonal block publish their (still unscaled) entry of column j; after ONE barrier every row reads
-// the pivot, forms 1/sqrt(pivot) itself and applies the rank-1 update to its own row.  `col` is a double buffer of
-// 2 x 32 doubles, `rsd[j0 + j]` receives 1 / L_jj.  Returns the first bad pivot (1-based inside the panel) or 0.
-// (No __restrict__ on `col`: other threads rewrite it between barriers and the loads must not be reused.)
-__device__ __forceinline__ int panel_factor32(double* s, double* col, double* rsd, int j0, int kk, int tid) {
-  const int r = tid;
-  const bool active = (r >= j0) && (r < kk);
-  const bool diag = active && (r < j0 + 32);
-  double a[32];
-  const double* row = s + r * PLD + j0;
+// Factor the 32-column panel at j0 (rows j0 .. kk-1): thread t owns row t in registers (all threads of the CTA
+// run the loop so that its barriers are plain __syncthreads).  The panel is processed in micro-blocks of MB columns
+// with two barriers each instead of one barrier per column:
+//   1. the rows of the diagonal block publish their MB entries of the micro-block columns;
+//   2. every thread factors the MB x MB diagonal micro-block itself (registers; the rsqrt chain is the only serial
+//      part), solves its own row against it, and the diagonal-block rows publish their solved entries;
+//   3. every thread applies the rank-MB update to the remaining columns of its row.
+// `cb` is 32 x MB doubles, `xb` 32 x MB doubles, `rsd[j0 + j]` receives 1 / L_jj, `bad` (shared, initialised to
+// INT_MAX) the first non-positive pivot (1-based, leaf-local).
+constexpr int MB = 8;
+constexpr int UBLD = 34;  // row stride of the 32 x 32 U_jj staging block (even: double2 rows)
+
+template <int m0>
+__device__ __forceinline__ void panel_micro_block(double (&a)[32], double* cb, double* xb, double* rsd, int* bad,
+                                                  int j0, int r, bool diag, bool warp_active) {
+  if (diag) {
 #pragma unroll
-  for (int c = 0; c < 32; c++) a[c] = (active && j0 + c <= r) ? row[c] : 0.0;
-  int bad = 0;
-#pragma unroll
-  for (int j = 0; j < 32; j++) {
-    double* cb = col + (j & 1) * 32;
-    if (diag) cb[r - j0] = a[j];
-    __syncthreads();
-    const double piv = cb[j];
-    if (!(piv > 0.0) && bad == 0) bad = j + 1;   // also catches NaN; the same in every thread
-    const double rs = rsqrt(piv);
-    const double lrj = a[j] * rs;                // rows above the pivot hold 0 here
-    a[j] = lrj;
-    if (r == j0 + j) rsd[r] = rs;
-#pragma unroll
-    for (int c = j + 1; c < 32; c++) a[c] -= lrj * (cb[c] * rs);
+    for (int i = 0; i < MB; i += 2)
+      *reinterpret_cast<double2*>(cb + (r - j0) * MB + i) = make_double2(a[m0 + i], a[m0 + i + 1]);
   }
-  if (active) {
+  __syncthreads();
+  double x[MB];
+#pragma unroll
+  for (int i = 0; i < MB; i++) x[i] = 0.0;
+  if (warp_active) {
+    // factor the micro-block (rows m0 .. m0+MB-1 of cb): lm[i][k] (k < i) and rinv[i]
+    double lm[MB][MB], rinv[MB];
+#pragma unroll
+    for (int i = 0; i < MB; i++)
+#pragma unroll
+      for (int k = 0; k <= i; k++) lm[i][k] = cb[(m0 + i) * MB + k];
+#pragma unroll
+    for (int j = 0; j < MB; j++) {
+      const double piv = lm[j][j];
+      if (!(piv > 0.0) && r == j0 + m0 + j) atomicMin(bad, j0 + m0 + j + 1);   // also catches NaN
+      const double rs = rsqrt(piv);
+      rinv[j] = rs;
+      if (r == j0 + m0 + j) rsd[r] = rs;
+#pragma unroll
+      for (int i = j + 1; i < MB; i++) lm[i][j] *= rs;
+#pragma unroll
+      for (int i = j + 1; i < MB; i++)
+#pragma unroll
+        for (int k = j + 1; k <= i; k++) lm[i][k] -= lm[i][j] * lm[k][j];
+    }
+    // own row against the micro-block
+#pragma unroll
+    for (int i = 0; i < MB; i++) {
+      double v = a[m0 + i];
+#pragma unroll
+      for (int k = 0; k < i; k++) v -= x[k] * lm[i][k];
+      x[i] = v * rinv[i];
+      a[m0 + i] = x[i];
+    }
+    if (diag && m0 + MB < 32) {
+#pragma unroll
+      for (int i = 0; i < MB; i += 2)
+        *reinterpret_cast<double2*>(xb + (r - j0) * MB + i) = make_double2(x[i], x[i + 1]);
+    }
+  }
+  if (m0 + MB < 32) {
+    __syncthreads();
+    if (warp_active) {
+#pragma unroll
+      for (int c = m0 + MB; c < 32; c++) {
+        const double2* xc = reinterpret_cast<const double2*>(xb + c * MB);
+        double v0 = a[c], v1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < MB; i += 4) {
+          const double2 p = xc[i / 2], q = xc[i / 2 + 1];
+          v0 -= x[i] * p.x;
+          v1 -= x[i + 1] * p.y;
+          v0 -= x[i + 2] * q.x;
+          v1 -= x[i + 3] * q.y;
+        }
+        a[c] = v0 + v1;
+      }
+    }
+  }
+}
+
+// Rows: thread t < 128 owns row t of the leaf.  Threads 128..159 own 32 VIRTUAL rows e_i^T (identity): the panel
+// solve turns them into e_i^T L_jj^-T, i.e. row i of U_jj = L_jj^-T, so the 32 x 32 diagonal inverse the leaf solves
+// need comes out of the same substitution at no extra cost on the critical path.  Finished columns go straight
+// from registers to global memory (L into A, U_jj into the diagonal 32-blocks of Dinv).
+__device__ __forceinline__ void panel_factor32(double* s, double* cb, double* xb, double* rsd, int* bad, int j0, int kk,
+                                               int tid, double* ub) {
+  const int r = tid;
+  const bool virt = (tid >= NB) && (tid < NB + 32);
+  const int vi = tid - NB;                                   // virtual row index
+  const bool active = ((r >= j0) && (r < kk)) || virt;
+  const bool diag = (r >= j0) && (r < j0 + 32) && (r < kk);
+  const bool warp_active = virt || (((tid | 31) >= j0) && ((tid & ~31) < kk));   // some row of this warp takes part
+  double a[32];
+  const double* row = s + (virt ? 0 : r) * PLD + j0;
+#pragma unroll
+  for (int c = 0; c < 32; c++) {
+    double v = 0.0;
+    if (virt) v = (c == vi) ? 1.0 : 0.0;
+    else if (active && j0 + c <= r) v = row[c];
+    a[c] = v;
+  }
+  panel_micro_block<0>(a, cb, xb, rsd, bad, j0, r, diag, warp_active);
+  panel_micro_block<8>(a, cb, xb, rsd, bad, j0, r, diag, warp_active);
+  panel_micro_block<16>(a, cb, xb, rsd, bad, j0, r, diag, warp_active);
+  panel_micro_block<24>(a, cb, xb, rsd, bad, j0, r, diag, warp_active);
+  static_assert(MB == 8, "four micro-blocks per 32-column panel");
+  if (virt) {
+    double* urow = ub + vi * UBLD;                           // U_jj(vi, c), c >= vi (zero below)
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) *reinterpret_cast<double2*>(urow + c) = make_double2(a[c], a[c + 1]);
+  } else if (active) {
     double* wrow = s + r * PLD + j0;
 #pragma unroll
     for (int c = 0; c < 32; c++)
       if (j0 + c <= r) wrow[c] = a[c];
   }
-  return bad;
 }
 
-// Inverse of the 32 x 32 diagonal block at j0 by one warp: lane c solves L x = e_c by forward substitution with
-// x in registers and L broadcast from shared memory; U(c, r) = x[r] = (L^-1)[r][c] goes to the shifted upper part.
-__device__ __forceinline__ void diag_inverse32(double* s, const double* rsd, int j0,
-                                               int lane) {
-  double x[32];
-#pragma unroll
-  for (int r = 0; r < 32; r++) {
-    const double* lrow = s + (j0 + r) * PLD + j0;
-    double acc0 = (r == lane) ? 1.0 : 0.0, acc1 = 0.0;
-#pragma unroll
-    for (int k = 0; k + 1 < r; k += 2) {
-      acc0 -= lrow[k] * x[k];
-      acc1 -= lrow[k + 1] * x[k + 1];
-    }
-    if (r & 1) acc0 -= lrow[r - 1] * x[r - 1];
-    x[r] = (r >= lane) ? (acc0 + acc1) * rsd[j0 + r] : 0.0;
+// Coalesced write-out of a finished panel (after the barrier that follows panel_factor32): the 32 columns of L at
+// j0 for rows j0..k-1 go to A, the 32 x 32 block U_jj goes to the diagonal 32-block of Dinv.  Fire and forget: the
+// stores drain while the trailing update runs.
+__device__ __forceinline__ void store_panel(const double* s, const double* ub, double* __restrict__ A, int64_t lda,
+                                            double* __restrict__ Dinv, int j0, int k, int tid) {
+  const int cpair = (tid & 15) * 2;                           // column pair inside the panel
+  for (int r = j0 + (tid >> 4); r < k; r += LT / 16) {
+    const int c = j0 + cpair;
+    const double* sp = s + r * PLD + c;
+    double* gp = A + (int64_t)r * lda + c;
+    if (c + 1 <= r) *reinterpret_cast<double2*>(gp) = *reinterpret_cast<const double2*>(sp);
+    else if (c <= r) gp[0] = sp[0];
   }
-#pragma unroll
-  for (int r = 0; r < 32; r++)
-    if (r >= lane) s[(j0 + lane) * PLD + j0 + r + 1] = x[r];
+  for (int e = tid; e < 32 * 16; e += LT) {
+    const int i = e >> 4, c = (e & 15) * 2;
+    const double2 v = *reinterpret_cast<const double2*>(ub + i * UBLD + c);
+    double* gp = Dinv + (j0 + i) * NB + j0 + c;
+    if (c >= i) *reinterpret_cast<double2*>(gp) = v;
+    else if (c + 1 >= i) gp[1] = v.y;
+  }
 }
 
-// Trailing update of the lower triangle of rows/cols [base, kk) with the 32-wide panel at j0:
-// C -= X X^T, 8 x 8 tiles, K = 32.
+// Trailing update of the lower triangle of rows/cols [base, kk) with the 32-wide panel at j0:  C -= X X^T.
+// Work unit: one row of 8 x 8 tiles times a group of up to four column tiles (shared A fragments, four independent
+// accumulator chains); units are dealt round-robin to the warps.
 __device__ __forceinline__ void trailing_update32(double* s, int j0, int base, int kk, int warp, int lane) {
   const int lr = lane >> 2, lk = lane & 3;
   const int nt = (kk - base) >> 3;
-  const int ntiles = nt * (nt + 1) / 2;
-  for (int t = warp; t < ntiles; t += NW) {
-    int rt = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
-    while ((rt + 1) * (rt + 2) / 2 <= t) rt++;
-    while (rt * (rt + 1) / 2 > t) rt--;
-    const int ct = t - rt * (rt + 1) / 2;
-    const int r0 = base + rt * 8, c0 = base + ct * 8;
-    double* cp = s + (r0 + lr) * PLD + c0 + 2 * lk;
-    double acc0 = cp[0], acc1 = cp[1];
+  int g = warp;                                   // index of this warp's next unit
+  int first = 0;                                  // index of the first unit of row tile rt
+  for (int rt = 0; rt < nt; rt++) {
+    const int ng = (rt >> 2) + 1;                 // column groups of row tile rt: tiles 0..rt
+    for (; g < first + ng; g += NW) {
+      const int cg = g - first;
+      const int r0 = base + rt * 8;
+      double af[8];
 #pragma unroll
-    for (int kq = 0; kq < 8; kq++) {
-      const double a = -s[(r0 + lr) * PLD + j0 + 4 * kq + lk];
-      const double b = s[(c0 + lr) * PLD + j0 + 4 * kq + lk];
-      dmma884(acc0, acc1, a, b);
+      for (int kq = 0; kq < 8; kq++) af[kq] = -s[(r0 + lr) * PLD + j0 + 4 * kq + lk];
+      double acc[4][2];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int ct = min(cg * 4 + u, rt);
+        const double* cp = s + (r0 + lr) * PLD + base + ct * 8 + 2 * lk;
+        acc[u][0] = cp[0];
+        acc[u][1] = cp[1];
+      }
+#pragma unroll
+      for (int kq = 0; kq < 8; kq++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int ct = min(cg * 4 + u, rt);
+          const double b = s[(base + ct * 8 + lr) * PLD + j0 + 4 * kq + lk];
+          dmma884(acc[u][0], acc[u][1], af[kq], b);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int ct = cg * 4 + u;
+        if (ct > rt) continue;
+        double* cp = s + (r0 + lr) * PLD + base + ct * 8 + 2 * lk;
+        const int r = r0 + lr, c = base + ct * 8 + 2 * lk;
+        if (c <= r) cp[0] = acc[u][0];        // entries right of the diagonal are not part of L: never touched
+        if (c + 1 <= r) cp[1] = acc[u][1];
+      }
     }
-    const int r = r0 + lr, c = c0 + 2 * lk;
-    if (c <= r) cp[0] = acc0;        // entries right of the diagonal belong to U: never touched
-    if (c + 1 <= r) cp[1] = acc1;
+    first += ng;
   }
 }
 
@@ -116,20 +218,28 @@ __device__ __forceinline__ void trailing_update32(double* s, int j0, int base, i
 __device__ __forceinline__ void pair_phase1(double* s, int a0, int sza, int b0, int szb, int w, int nw,
                                             int lane) {
   const int lr = lane >> 2, lk = lane & 3;
-  const int nit = sza >> 3, njt = szb >> 3;
-  for (int t = w; t < nit * njt; t += nw) {
-    const int it = t / njt, jt = t - it * njt;
+  const int nit = sza >> 3, njg = szb >> 5;   // row tiles of 8, column groups of 4 tiles (szb is a multiple of 32)
+  for (int t = w; t < nit * njg; t += nw) {
+    const int it = t / njg, jg = t - it * njg;
     const int i = it * 8 + lr;
-    double acc0 = 0.0, acc1 = 0.0;
+    double acc[4][2];
+#pragma unroll
+    for (int u = 0; u < 4; u++) acc[u][0] = acc[u][1] = 0.0;
     for (int kq = 2 * it; kq < (sza >> 2); kq++) {
       const int k = 4 * kq + lk;
       const double a = (k >= i) ? s[(a0 + i) * PLD + a0 + k + 1] : 0.0;       // U_aa(i,k)
-      const double b = s[(b0 + jt * 8 + lr) * PLD + a0 + k];                  // L(b0+j, a0+k)
-      dmma884(acc0, acc1, a, b);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const double b = s[(b0 + (jg * 4 + u) * 8 + lr) * PLD + a0 + k];      // L(b0+j, a0+k)
+        dmma884(acc[u][0], acc[u][1], a, b);
+      }
     }
-    double* o = s + (a0 + i) * PLD + b0 + jt * 8 + 2 * lk + 1;
-    o[0] = acc0;
-    o[1] = acc1;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      double* o = s + (a0 + i) * PLD + b0 + (jg * 4 + u) * 8 + 2 * lk + 1;
+      o[0] = acc[u][0];
+      o[1] = acc[u][1];
+    }
   }
 }
 
@@ -145,15 +255,19 @@ __device__ __forceinline__ void pair_phase2(double* s, int a0, int sza, int b0, 
     for (int kq = 0; kq < MAXKQ; kq++) af[kq] = (kq < nkq) ? s[i * PLD + b0 + 4 * kq + lk + 1] : 0.0;
     double acc[MAXKQ / 2][2];
 #pragma unroll
-    for (int jt = 0; jt < MAXKQ / 2; jt++) {
-      acc[jt][0] = acc[jt][1] = 0.0;
-      if (jt < njt) {
-        const int j = jt * 8 + lr;
+    for (int jt = 0; jt < MAXKQ / 2; jt++) acc[jt][0] = acc[jt][1] = 0.0;
+    // k outer, column tiles inner: consecutive DMMAs hit independent accumulators
 #pragma unroll
-        for (int kq = 0; kq <= 2 * jt + 1; kq++) {
-          const int k = 4 * kq + lk;
-          const double b = (k <= j) ? s[(b0 + k) * PLD + b0 + j + 1] : 0.0;   // U_bb(k,j)
-          dmma884(acc[jt][0], acc[jt][1], af[kq], b);
+    for (int kq = 0; kq < MAXKQ; kq++) {
+      if (kq < nkq) {
+        const int k = 4 * kq + lk;
+#pragma unroll
+        for (int jt = kq / 2; jt < MAXKQ / 2; jt++) {
+          if (jt < njt) {
+            const int j = jt * 8 + lr;
+            const double b = (k <= j) ? s[(b0 + k) * PLD + b0 + j + 1] : 0.0;   // U_bb(k,j)
+            dmma884(acc[jt][0], acc[jt][1], af[kq], b);
+          }
         }
       }
     }
@@ -181,65 +295,82 @@ __device__ long long g_leaf_clk[16];
 // One CTA per problem: A (k x k lower, k <= 128) -> L in place; Dinv (128 x 128, ld 128) <- L^-T (upper
 // triangular, explicit zeros elsewhere).  The first non-positive pivot is recorded in info[z]
 // (1-based global index row0 + i + 1) if info[z] was 0.
+// Stage the lower triangle of a leaf block (k x k, identity padded to kk) into the shared tile with cp.async.
+__device__ __forceinline__ void stage_lower(double* s, const double* __restrict__ A, int64_t lda, int k, int kk, int tid,
+                                            int nthreads) {
+  // 16-byte chunks, all in flight at once (A is 16-byte aligned, lda even).  A chunk that crosses the diagonal
+  // also drops one element into the shifted upper part, which is (re)written later.
+  for (int e = tid; e < kk * (NB / 2); e += nthreads) {
+    const int r = e >> 6, c = (e & 63) * 2;
+    if (c > r) continue;
+    if (r < k) {
+      cp_async16(s + r * PLD + c, A + (int64_t)r * lda + c, (c + 1 < k) ? 16 : 8);
+    } else {   // identity padding
+      s[r * PLD + c] = (r == c) ? 1.0 : 0.0;
+      if (c + 1 <= r) s[r * PLD + c + 1] = (r == c + 1) ? 1.0 : 0.0;
+    }
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+}
+
 __global__ void __launch_bounds__(LT, 1)
 potf2_inv_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int k, int row0, int* __restrict__ info,
                  double* __restrict__ Dinv, int64_t strideD) {
   extern __shared__ __align__(16) double s[];  // NB x PLD tile
-  __shared__ double col[2 * 32];
+  __shared__ __align__(16) double cb[32 * MB];
+  __shared__ __align__(16) double xb[32 * MB];
+  __shared__ __align__(16) double ub[32 * UBLD];
   __shared__ double rsd[NB];
   __shared__ int bad_sh;
   A += (int64_t)blockIdx.z * strideA;
   Dinv += (int64_t)blockIdx.z * strideD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int kk = (k + 31) & ~31;  // padded with an identity block up to a multiple of 32
-  if (tid == 0) bad_sh = 0;
+  if (tid == 0) bad_sh = 0x7fffffff;
   LEAF_CLK(0);
-  // lower triangle, two columns per thread (A is 16-byte aligned, lda even)
-#pragma unroll 4
-  for (int e = tid; e < kk * (NB / 2); e += LT) {
-    const int r = e >> 6, c = (e & 63) * 2;
-    if (c > r) continue;
-    double2 v = make_double2((r == c) ? 1.0 : 0.0, (r == c + 1) ? 1.0 : 0.0);
-    if (r < k) {
-      if (c + 1 < k) v = *reinterpret_cast<const double2*>(A + (int64_t)r * lda + c);
-      else v.x = A[(int64_t)r * lda + c];
-    }
-    s[r * PLD + c] = v.x;
-    if (c + 1 <= r) s[r * PLD + c + 1] = v.y;
-  }
+  stage_lower(s, A, lda, k, kk, tid, LT);
   __syncthreads();
   LEAF_CLK(1);
-
   for (int j0 = 0; j0 < kk; j0 += 32) {
-    {
-      const int bad = panel_factor32(s, col, rsd, j0, kk, tid);
-      if (tid == 0 && bad && bad_sh == 0 && j0 + bad <= k) bad_sh = j0 + bad;
-    }
+    panel_factor32(s, cb, xb, rsd, &bad_sh, j0, kk, tid, ub);
     __syncthreads();
     LEAF_CLK(2 + (j0 >> 5) * 2);
+    store_panel(s, ub, A, lda, Dinv, j0, k, tid);
     if (j0 + 32 < kk) {
       trailing_update32(s, j0, j0 + 32, kk, warp, lane);
       __syncthreads();
     }
     LEAF_CLK(3 + (j0 >> 5) * 2);
   }
-  // L is final: write it out while the inverse is assembled
-#pragma unroll 4
-  for (int e = tid; e < k * (NB / 2); e += LT) {
-    const int r = e >> 6, c = (e & 63) * 2;
-    if (c > r) continue;
-    if (c + 1 <= r) *reinterpret_cast<double2*>(A + (int64_t)r * lda + c) = make_double2(s[r * PLD + c], s[r * PLD + c + 1]);
-    else A[(int64_t)r * lda + c] = s[r * PLD + c];
-  }
-  if (tid == 0 && bad_sh) atomicCAS(info + blockIdx.z, 0, row0 + bad_sh);
-
-  // 32 x 32 diagonal inverses: one warp per block
+  if (tid == 0 && bad_sh <= k) atomicCAS(info + blockIdx.z, 0, row0 + bad_sh);
   LEAF_CLK(10);
-  if (warp * 32 < kk) diag_inverse32(s, rsd, warp * 32, lane);
+}
+
+// Complete the Dinv blocks of a factor: the leaf kernel leaves only the 32 x 32 diagonal inverses there; this
+// kernel (one CTA per 128-block, all blocks in parallel, off the factorisation's critical path) assembles the full
+// 128 x 128 inverse-transposed block U_bb = L_bb^-T by block doubling on the tensor cores and writes it back with
+// explicit zeros below the diagonal.
+__global__ void __launch_bounds__(LT, 1)
+dinv_assemble_kernel(const double* __restrict__ L, int64_t ldl, int64_t strideL, double* __restrict__ Dinv,
+                     int64_t strideD, int N) {
+  extern __shared__ __align__(16) double s[];  // NB x PLD tile
+  const int b0 = blockIdx.x * NB;
+  const int k = min(NB, N - b0);
+  const int kk = (k + 31) & ~31;
+  L += (int64_t)blockIdx.z * strideL + (int64_t)b0 * ldl + b0;
+  Dinv += (int64_t)blockIdx.z * strideD + (int64_t)blockIdx.x * NB * NB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  stage_lower(s, L, ldl, k, kk, tid, LT);
   __syncthreads();
-  LEAF_CLK(11);
-  // level 1: pairs of 32-blocks -> 64-blocks
-  if (kk >= 64) {
+  for (int e = tid; e < kk * 32; e += LT) {      // diagonal 32-blocks of U, shifted one column right
+    const int i = e >> 5, c = (i & ~31) + (e & 31);
+    if (c >= i) cp_async8(s + i * PLD + c + 1, Dinv + i * NB + c);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  if (kk >= 64) {   // level 1: pairs of 32-blocks -> 64-blocks
     const int npairs = (kk >= 128) ? 2 : 1;
     const int nw = NW / npairs, pr = warp / nw, w = warp - pr * nw;
     pair_phase1(s, pr * 64, 32, pr * 64 + 32, 32, w, nw, lane);
@@ -247,26 +378,36 @@ potf2_inv_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int k, in
     pair_phase2<8>(s, pr * 64, 32, pr * 64 + 32, 32, w, nw, lane);
     __syncthreads();
   }
-  LEAF_CLK(12);
-  // level 2: [0,64) with [64,kk)
-  if (kk > 64) {
+  if (kk > 64) {    // level 2: [0,64) with [64,kk)
     pair_phase1(s, 0, 64, 64, kk - 64, warp, NW, lane);
     __syncthreads();
     pair_phase2<16>(s, 0, 64, 64, kk - 64, warp, NW, lane);
     __syncthreads();
   }
-  LEAF_CLK(13);
-#pragma unroll 4
-  for (int e = tid; e < NB * (NB / 2); e += LT) {
-    const int i = e >> 6, j = (e & 63) * 2;
-    double2 v = make_double2(0.0, 0.0);
-    if (i < kk && j < kk) {
-      if (j >= i) v.x = s[i * PLD + j + 1];
-      if (j + 1 >= i) v.y = s[i * PLD + j + 2];
+  for (int i = warp; i < NB; i += NW) {
+    const double* srow = s + i * PLD + 1;
+    double* grow = Dinv + i * NB;
+#pragma unroll
+    for (int j = 2 * lane; j < NB; j += 64) {
+      double2 v = make_double2(0.0, 0.0);
+      if (i < kk && j < kk) {
+        if (j >= i) v.x = srow[j];
+        if (j + 1 >= i) v.y = srow[j + 1];
+      }
+      *reinterpret_cast<double2*>(grow + j) = v;
     }
-    *reinterpret_cast<double2*>(Dinv + i * NB + j) = v;
   }
-  LEAF_CLK(14);
+}
+
+int leaf_dinv_assemble(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* Dinv, int64_t strideD,
+                       int N) {
+  if (N <= 0) return 0;
+  static bool attr = false;
+  const int smem = NB * PLD * (int)sizeof(double);
+  if (!attr) { GEGP_SET_SMEM(dinv_assemble_kernel, smem); attr = true; }
+  dinv_assemble_kernel<<<dim3((N + NB - 1) / NB, 1, ctx.batch), LT, smem, ctx.stream>>>(L, ldl, strideL, Dinv, strideD, N);
+  GEGP_CHECK_LAUNCH();
+  return 0;
 }
 
 #ifdef GEGP_LEAF_CLOCKS
@@ -322,19 +463,15 @@ leaf_trsm_kernel(const double* __restrict__ L, int64_t ldl, int64_t strideL, con
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lk = lane & 3;
   const int kk = (k + 31) & ~31;
-  // stage L (lower, identity padded) and the 32 x 32 diagonal blocks of U (shifted one column right)
-  for (int e = tid; e < kk * NB; e += TW * 32) {
-    const int i = e >> 7, c = e & (NB - 1);
-    if (c >= kk) continue;
-    if (c <= i) {
-      double v = (i == c) ? 1.0 : 0.0;
-      if (i < k) v = L[(int64_t)i * ldl + c];
-      s[i * PLD + c] = v;
-    } else if ((c >> 5) == (i >> 5)) {
-      s[i * PLD + c + 1] = Dinv[i * NB + c];
-    }
-    if (c == i) s[i * PLD + c + 1] = Dinv[i * NB + c];
+  stage_lower(s, L, ldl, k, kk, tid, TW * 32);
+  __syncthreads();
+  // ... then the 32 x 32 diagonal blocks of U = L^-T, shifted one column right (8-byte copies: odd offsets)
+  for (int e = tid; e < kk * 32; e += TW * 32) {
+    const int i = e >> 5, c = (i & ~31) + (e & 31);
+    if (c >= i) cp_async8(s + i * PLD + c + 1, Dinv + i * NB + c);
   }
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
   double* scr = s + NB * PLD + warp * 8 * SLD;
   const int nb32 = kk >> 5;

@@ -47,6 +47,10 @@ inline int64_t dinv_doubles(int N) { return (int64_t)((N + LEAF - 1) / LEAF) * L
 // recorded in info[z] (1-based global index row0+i+1) if info[z] was 0.
 int leaf_potf2_inv(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int k, int row0, int* info, double* Dinv,
                    int64_t strideD);
+// After leaf_potf2_inv only the 32 x 32 diagonal inverses of each Dinv block are valid (enough for leaf_trsm);
+// this completes every block to the full 128 x 128 L_bb^-T (needed by chol_inverse and trsv_lower_trans).
+int leaf_dinv_assemble(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* Dinv, int64_t strideD,
+                       int N);
 // B (r x k) <- B * L^-T for one factored leaf block (k <= LEAF): fused block substitution on the tensor cores with
 // the 32 x 32 diagonal inverses taken from Dinv and one refinement step each (as accurate as a substitution).
 int leaf_trsm(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv, int64_t strideD,

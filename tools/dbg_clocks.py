@@ -21,8 +21,8 @@ for it in range(3):
     out = (ctypes.c_longlong * 16)()
     lib.gegp_debug_leaf_clocks(out)
     c = list(out)
-    names = ["load", "panel0", "upd0", "panel1", "upd1", "panel2", "upd2", "panel3", "upd3(none)", "Lstore", "diaginv", "pair L1", "pair L2", "dinv store"]
-    idx = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14]
-    print("iter", it, "total cycles", c[14] - c[0])
+    names = ["load", "panel0", "upd0", "panel1", "upd1", "panel2", "upd2", "panel3", "upd3(none)", "tail"]
+    idx = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10]
+    print("iter", it, "total cycles", c[10] - c[0])
     for i, nm in enumerate(names):
         print(f"   {nm:12s} {c[idx[i + 1]] - c[idx[i]]:8d}")
