@@ -248,8 +248,17 @@ int gemm_f64(const Ctx& ctx, GemmArgs g) {
   // Large tile when one problem still fills the machine with it, small tile otherwise.  The choice depends on the
   // shape of ONE problem only, never on the batch count: a candidate evaluated alone, in a batch, or on another rank
   // of a sharded batch goes through the same kernels and gives bit-identical results.
-  const long tiles_big = (long)((g.M + 127) / 128) * ((g.N + 127) / 128) * g.inner;
-  const bool big = (g.cmode == C_FULL ? tiles_big : tiles_big / 2) >= 120 && g.M >= 128 && g.N >= 128;
+  const long rt = (g.M + 127) / 128, ct = (g.N + 127) / 128;
+  long tiles_big = rt * ct;
+  if (g.cmode != C_FULL) {   // tiles strictly above the diagonal are skipped
+    const long sq = rt < ct ? rt : ct;
+    tiles_big -= sq * (sq - 1) / 2 + (ct > rt ? (ct - rt) * rt : 0);
+  }
+  tiles_big *= g.inner;
+  // Measured on B200 (d=10, n=500 and d=20, n=1000 evaluations): below ~1000 tiles of 128 x 128 the one-CTA-per-SM
+  // TMA kernel loses more to wave quantisation (148 tiles per wave) than it gains over the 64 x 64 kernel.
+  static const int big_min = getenv("GEGP_BIG_TILES") ? atoi(getenv("GEGP_BIG_TILES")) : 1000;
+  const bool big = tiles_big >= big_min && g.M >= 128 && g.N >= 128;
   if (g.row_owner) {
     // in-place right multiply: one column tile must cover all of N so that a CTA only overwrites rows it alone reads
     if (g.N > 128 || g.A != g.C || g.b_kcont) return -904;
