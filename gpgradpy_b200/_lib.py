@@ -16,9 +16,10 @@ ABI_VERSION = 2
 MODE_BASE, MODE_PRECON, MODE_PRECON_COV = 0, 1, 2
 OUT_LML, OUT_SIGMA2, OUT_BETA, OUT_LOGDET, OUT_INFO, OUT_QUAD, OUT_DVARK, OUT_DVARF, OUT_DVARG, OUT_GRAD = range(10)
 OP_LML, OP_LML_GRAD, OP_PREDICT = 0, 1, 2
+OPT_TMA_MIN_TILES = 1
 
 EXPORTS = (
-    "gegp_abi_version", "gegp_workspace_bytes", "gegp_ld", "gegp_build_cov", "gegp_cross_cov", "gegp_potrf",
+    "gegp_abi_version", "gegp_set_option", "gegp_workspace_bytes", "gegp_ld", "gegp_build_cov", "gegp_cross_cov", "gegp_potrf",
     "gegp_trsm_rows", "gegp_dinv_doubles", "gegp_potri", "gegp_dgemm", "gegp_lml_eval", "gegp_predict_setup", "gegp_predict", "gegp_profile_begin", "gegp_profile_end",
 )
 
@@ -44,6 +45,8 @@ def load():
     i, i64, dbl, sz = C.c_int, C.c_int64, C.c_double, C.c_size_t
     lib.gegp_abi_version.restype = i
     lib.gegp_abi_version.argtypes = []
+    lib.gegp_set_option.restype = i
+    lib.gegp_set_option.argtypes = [i, i]
     lib.gegp_workspace_bytes.restype = sz
     lib.gegp_workspace_bytes.argtypes = [i, i, i, i, i]
     lib.gegp_ld.restype = i64

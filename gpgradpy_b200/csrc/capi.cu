@@ -96,6 +96,16 @@ int gegp_profile_end(long* launches, long* gemm_launches, double* gemm_ms, doubl
 
 int64_t gegp_ld(int N) { return round_up(N, 16); }
 
+int gegp_set_option(int key, int value) {
+  if (key == GEGP_OPT_TMA_MIN_TILES) {
+    if (value < 1) return -2;
+    const int old = tma_min_tiles();
+    tma_min_tiles() = value;
+    return old;
+  }
+  return -1;
+}
+
 size_t gegp_workspace_bytes(int op, int n, int n_g, int d, int arg) {
   if (bad_geom(n, n_g, d) || arg <= 0) return 0;
   const int N = n + n_g * d;
@@ -252,7 +262,7 @@ int gegp_lml_eval(int B, const double* theta_batch, const double* varK_batch, in
     double* D = wk + L.D;
     rc = chol_trap(ctx, A, L.ld, sC, N + 2, N, 0, info, D, sC);
     if (rc) return rc;
-    rc = launch_lml_finalize(ctx, N, A, L.ld, sC, pinv, sC, noisy, varK, W, sC, outb, outlen, info);
+    rc = launch_lml_finalize(ctx, N, A, L.ld, sC, pinv, sC, noisy, varK, W, sC, outb, outlen, info, want_grad ? 0 : d);
     if (rc) return rc;
     double* alpha_t = W;  // preconditioned alpha = L^-T w
     if (want_grad) {

@@ -225,6 +225,12 @@ static int launch_cfg(const Ctx& ctx, const GemmArgs& g) {
   return 0;
 }
 
+static int g_tma_min_tiles = -1;
+int& tma_min_tiles() {
+  if (g_tma_min_tiles < 0) g_tma_min_tiles = getenv("GEGP_BIG_TILES") ? atoi(getenv("GEGP_BIG_TILES")) : 1000;
+  return g_tma_min_tiles;
+}
+
 GemmArgs gemm_args(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
                    int M, int N, int K, double alpha, double beta, bool b_kcont) {
   GemmArgs g{};
@@ -257,8 +263,7 @@ int gemm_f64(const Ctx& ctx, GemmArgs g) {
   tiles_big *= g.inner;
   // Measured on B200 (d=10, n=500 and d=20, n=1000 evaluations): below ~1000 tiles of 128 x 128 the one-CTA-per-SM
   // TMA kernel loses more to wave quantisation (148 tiles per wave) than it gains over the 64 x 64 kernel.
-  static const int big_min = getenv("GEGP_BIG_TILES") ? atoi(getenv("GEGP_BIG_TILES")) : 1000;
-  const bool big = tiles_big >= big_min && g.M >= 128 && g.N >= 128;
+  const bool big = tiles_big >= tma_min_tiles() && g.M >= 128 && g.N >= 128;
   if (g.row_owner) {
     // in-place right multiply: one column tile must cover all of N so that a CTA only overwrites rows it alone reads
     if (g.N > 128 || g.A != g.C || g.b_kcont) return -904;

@@ -38,7 +38,7 @@ int launch_append_rhs(const Ctx& ctx, int N, int n, const double* y, const doubl
 // out layout per problem (GEGP_OUT_* in gegp.h)
 int launch_lml_finalize(const Ctx& ctx, int N, const double* A, int64_t lda, int64_t strideA, const double* pinv,
                         int64_t strideP, int noisy, const double* varK, double* w, int64_t strideW, double* out,
-                        int64_t strideOut, const int* info);
+                        int64_t strideOut, const int* info, int zero_grad_d);
 int launch_lml_grad(const Ctx& ctx, const Geom& gm, const double* theta, int64_t strideTheta, const double* Kinv,
                     int64_t ldk, int64_t strideK, const double* alpha_t, int64_t strideAlpha, const double* pinv,
                     int64_t strideP, int mode, double eta, int noisy, const double* varK, double pnlt_grad, double* partial,

@@ -37,6 +37,8 @@ int gemm_f64(const Ctx& ctx, GemmArgs g);
 // 0: launched; 1: not covered (use the cp.async engine); < 0: launch error.
 int gemm_tma_nt(const Ctx& ctx, const GemmArgs& g);
 double gemm_useful_flops(const GemmArgs& g);
+// smallest number of 128 x 128 output tiles (of one problem) for which the TMA kernel is chosen (tuning knob)
+int& tma_min_tiles();
 
 // --- leaves (<= LEAF wide) ---
 // Every factor carries the inverse-transposed diagonal blocks Dinv: block b (rows/cols [b*LEAF, (b+1)*LEAF)) is

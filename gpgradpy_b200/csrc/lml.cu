@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(1024)
 lml_finalize_kernel(int N, const double* __restrict__ A_all, int64_t lda, int64_t strideA,
                     const double* __restrict__ pinv_all, int64_t strideP, int noisy, const double* __restrict__ varK,
                     double* __restrict__ w_all, int64_t strideW, double* __restrict__ out_all, int64_t strideOut,
-                    const int* __restrict__ info) {
+                    const int* __restrict__ info, int zero_grad_d) {
   __shared__ double sh[32];
   const int z = blockIdx.x;
   const double* A = A_all + z * strideA;
@@ -66,14 +66,15 @@ lml_finalize_kernel(int N, const double* __restrict__ A_all, int64_t lda, int64_
     out[GEGP_OUT_DVARK] = 0.0;
     out[GEGP_OUT_DVARF] = 0.0;
     out[GEGP_OUT_DVARG] = 0.0;
+    for (int m = 0; m < zero_grad_d; m++) out[GEGP_OUT_GRAD + m] = 0.0;   // gradient not requested: defined zeros
   }
 }
 
 int launch_lml_finalize(const Ctx& ctx, int N, const double* A, int64_t lda, int64_t strideA, const double* pinv,
                         int64_t strideP, int noisy, const double* varK, double* w, int64_t strideW, double* out,
-                        int64_t strideOut, const int* info) {
+                        int64_t strideOut, const int* info, int zero_grad_d) {
   lml_finalize_kernel<<<ctx.batch, 1024, 0, ctx.stream>>>(N, A, lda, strideA, pinv, strideP, noisy, varK, w, strideW, out,
-                                                          strideOut, info);
+                                                          strideOut, info, zero_grad_d);
   GEGP_CHECK_LAUNCH();
   return 0;
 }

@@ -56,6 +56,7 @@ def test_argument_checks_return_negative_codes_without_touching_the_gpu():
     assert lib.gegp_potri(8, 0, 8, 0, 0, 8, 0, 8, 0) == -2
     assert lib.gegp_dgemm(0, 4, 4, 4, 1.0, 0, 4, 0, 4, 0.0, 0, 4, 0) == -6
     assert lib.gegp_dinv_doubles(129) == 2 * 128 * 128
+    assert lib.gegp_set_option(99, 1) == -1 and lib.gegp_set_option(_lib.OPT_TMA_MIN_TILES, 0) == -2
 
 
 def test_no_cpu_fallback_when_library_is_missing(monkeypatch):

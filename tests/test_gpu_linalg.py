@@ -145,3 +145,49 @@ def test_dgemm(M, N, K, transb):
     ref = -1.5 * A[:, :K].cpu().numpy() @ (Bn.T if transb else Bn) + 0.5 * C0
     e = np.abs(C[:, :N].cpu().numpy() - ref).max() / np.abs(ref).max()
     assert e < 1e-13
+
+
+@pytest.fixture
+def force_tma():
+    """Route every GEMM with M, N >= 128 through the TMA kernel (normally only >= 1000 tiles)."""
+    from gpgradpy_b200 import _lib
+    lib = _lib.load()
+    old = lib.gegp_set_option(_lib.OPT_TMA_MIN_TILES, 1)
+    assert old >= 1
+    yield
+    lib.gegp_set_option(_lib.OPT_TMA_MIN_TILES, old)
+
+
+@pytest.mark.parametrize("M,N,K,transb", [(128, 128, 16, True), (130, 257, 33, True), (300, 257, 129, True),
+                                          (1000, 900, 515, True), (4096, 4096, 256, True)])
+def test_dgemm_tma_kernel(force_tma, M, N, K, transb):
+    test_dgemm(M, N, K, transb)
+
+
+@pytest.mark.parametrize("N,extra", [(300, 0), (640, 5), (1000, 2), (2500, 130)])
+def test_potrf_trapezoid_tma(force_tma, N, extra):
+    test_potrf_trapezoid(N, extra)
+
+
+@pytest.mark.parametrize("N", [385, 1000, 2177])
+def test_potri_tma(force_tma, N):
+    test_potri_explicit_inverse(N)
+
+
+def test_tma_and_cpasync_kernels_agree():
+    """Same product on both engines (different k order inside a k-tile): equal to rounding."""
+    import torch
+    from gpgradpy_b200 import backend as bk, _lib
+    lib = _lib.load()
+    A = torch.randn((700, 520), dtype=torch.float64, device="cuda")
+    B = torch.randn((400, 520), dtype=torch.float64, device="cuda")
+    C1 = torch.zeros((700, 400), dtype=torch.float64, device="cuda")
+    C2 = torch.zeros((700, 400), dtype=torch.float64, device="cuda")
+    bk.dgemm(A, B, C1, transb=True)
+    old = lib.gegp_set_option(_lib.OPT_TMA_MIN_TILES, 1)
+    try:
+        bk.dgemm(A, B, C2, transb=True)
+    finally:
+        lib.gegp_set_option(_lib.OPT_TMA_MIN_TILES, old)
+    ref = A @ B.T
+    assert (C1 - ref).abs().max().item() < 1e-12 and (C2 - ref).abs().max().item() < 1e-12
