@@ -274,9 +274,6 @@ int gemm_f64(const Ctx& ctx, GemmArgs g) {
     const int rc = gemm_tma_nt(ctx, g);
     if (rc <= 0) return rc;
   }
-  if (g.b_kcont && big && exp_cfg == 1) return launch_cfg<128, 128, 32, 32, 4, true>(ctx, g);
-  if (g.b_kcont && big && exp_cfg == 2) return launch_cfg<128, 128, 32, 64, 4, true>(ctx, g);
-  if (g.b_kcont && big && exp_cfg == 5) return launch_cfg<128, 128, 64, 32, 3, true>(ctx, g);
   if (g.b_kcont) {
     if (big) return launch_cfg<128, 128, 64, 32, 4, true>(ctx, g);
     return launch_cfg<64, 64, 32, 32, 4, true>(ctx, g);

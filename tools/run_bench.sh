@@ -1,8 +1,12 @@
-set -x
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_b200.json 2> gpurun_out/bench_b200.err
-cat gpurun_out/bench_ref.json gpurun_out/bench_b200.json
 tail -3 gpurun_out/bench_b200.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_v2_c2.csv python bench.py --steps 2 --warmup 3 --no-phases > gpurun_out/ncu_launch.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:gemm_tma_nt -s 5 -c 1 -o gpurun_out/gemm_tma_c2 -f python tools/one_eval.py 500 10 1 1 > gpurun_out/ncu_tma.log 2>&1
-tail -2 gpurun_out/ncu_tma.log
+ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_v2_c2.csv python bench.py --steps 2 --warmup 3 --no-phases > gpurun_out/ncu_launch.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_v2_c3.csv python tools/one_eval.py 1000 20 1 2 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gemm_f64_kernel -s 60 -c 1 -o gpurun_out/gemm64_c2 -f python tools/one_eval.py 500 10 1 1 > gpurun_out/ncu_g64.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gemm_tma_nt -s 8 -c 1 -o gpurun_out/gemm_tma_c3 -f python tools/one_eval.py 1000 20 1 1 > gpurun_out/ncu_tma3.log 2>&1
+python tools/c35_probe.py c3 > gpurun_out/c3_predict.log 2>&1
+python tools/c4_scan.py 1024 1 > gpurun_out/c4_scan.log 2>&1
+python tools/c4_scan.py 1024 0 >> gpurun_out/c4_scan.log 2>&1
+cat gpurun_out/c3_predict.log gpurun_out/c4_scan.log
