@@ -284,17 +284,19 @@ def run_b200(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic = None
     try:   # dram bytes of the dominant launch from the committed ncu --set full capture (per launch)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01", "gemm_tma_ncu.json"))).get("dram_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01", "dominant_kernel_ncu.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"kernel": "gemm_tma_nt_kernel (TMA + mbarrier ring, fp64 DMMA.8x8x4) + gemm_f64_kernel (cp.async) for "
-                          "the row-major-B product and small tiles: all O(N^3) work of one evaluation",
+    roofline = {"kernel": "fp64 DMMA.8x8x4 GEMM engine = all O(N^3) work of one evaluation: gemm_f64_kernel<64,64,32,32,4> "
+                          "(cp.async ring) carries this workload's products (< 1000 tiles of 128x128 each); "
+                          "gemm_tma_nt_kernel<128,64,4,2> (TMA + mbarrier ring) takes over above that (the c3 numbers)",
                 "bound": "tensor", "achieved": N ** 3 / ph["gemm_ms_per_eval"] * 1e-9, "peak": FP64_DMMA_PEAK_TFLOPS,
                 "unit": "TFLOP/s", "frac": N ** 3 / ph["gemm_ms_per_eval"] * 1e-9 / FP64_DMMA_PEAK_TFLOPS,
                 "traffic": traffic,
                 "algorithmic_flops_per_eval": float(N) ** 3,
                 "note": "achieved = N^3 (SURVEY 8d: N^3/3 factor + 2N^3/3 inverse) / summed CUDA-event duration of all "
-                        "GEMM launches of one evaluation; peak = measured fp64 DMMA issue peak of this pool's B200 "
+                        "GEMM launches of one evaluation; traffic = dram bytes of ONE captured launch of the dominant kernel "
+                        "(profiles/r01/ncu_full_summary_v2.txt); peak = measured fp64 DMMA issue peak of this pool's B200 "
                         "(profiles/r01/dmma_peak.log; cuBLAS DGEMM reaches %.2f); MEASURED_PEAKS.json has no fp64 entry"
                         % FP64_DGEMM_TFLOPS,
                 "hbm_build": {"bound": "hbm", "achieved": ph["build_full_gbs"], "peak": hbm_peak, "unit": "GB/s",
