@@ -157,6 +157,153 @@ build_cov_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideTh
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast builder for the common case (every point carries a gradient, n even).  Same contract as
+// build_cov_kernel, restructured so that the inner loop costs ~5 instructions per stored element instead of
+// ~55 and every store is a 16-byte st.global.v2.f64 (each thread owns two neighbouring b points; a warp writes
+// one contiguous 512-byte row segment per instruction):
+//   * exp(-sum theta r^2) once per pair, folded with varK;
+//   * every gradient-gradient entry is a product  c_i(a,b) * w_j(a,b)  of a row factor c_i = -4 w_i k and a
+//     column factor w_j = theta_j s_j r_j, so the (i, j) loop is: 3 LDS, 2 DADD, 4 DMUL, 1 STG.128 per two entries;
+//   * the diagonal corrections (2 theta_i s_i^2 k on block (i,i); noise and nugget on the matrix diagonal) are
+//     applied by separate fix-up stores of the owning thread after the bulk stores.
+// PVEC: per-row scales P^-1 (preconditioned matrix with observation noise) instead of one scale per dimension.
+// ------------------------------------------------------------------------------------------------
+constexpr int FTA = 8;    // a-points per CTA (8 thread rows x 1): many small CTAs balance the triangular work (32: -20 %)
+constexpr int FTB = 64;   // b-points per CTA (32 threads x 2); 128 measured slightly slower
+
+template <bool PVEC>
+__global__ void __launch_bounds__(BUILD_THREADS)
+build_cov_fast_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideTheta, NoiseSpec ns,
+                      const double* __restrict__ pinv_all, int64_t strideP, int mode, double eta,
+                      double* __restrict__ out_all, int64_t ld, int64_t strideOut, int lower_only) {
+  extern __shared__ __align__(16) double sm[];
+  const int d = gm.d, n = gm.n;
+  double* xa = sm;                 // [FTA][d]
+  double* xb = xa + FTA * d;       // [d][FTB]  (transposed: a thread reads its two b's with one LDS.128)
+  double* th = xb + d * FTB;       // [d] theta
+  double* ts = th + d;             // [d] theta_i * s_i  (s_i: gradient scale 1/sqrt(2 theta_i) for precon without noise)
+  double* dg = ts + d;             // [d] 2 theta_i s_i^2
+
+  const int tid = threadIdx.x;
+  const int a0 = blockIdx.y * FTA, b0 = blockIdx.x * FTB;
+  const int z = blockIdx.z;
+  const double* theta = theta_all + z * strideTheta;
+  const double* pinv = pinv_all ? pinv_all + z * strideP : nullptr;
+  double* out = out_all + z * strideOut;
+  const bool noise = (ns.noise != nullptr);
+  const double varK = ns.varK_all ? ns.varK_all[z] : ns.varK;
+  const bool precon = (mode == GEGP_MODE_PRECON);
+
+  for (int e = tid; e < FTA * d; e += BUILD_THREADS) {
+    const int a = e / d, i = e - a * d;
+    xa[e] = (a0 + a < n) ? gm.X[(int64_t)(a0 + a) * d + i] : 0.0;
+  }
+  for (int e = tid; e < FTB * d; e += BUILD_THREADS) {
+    const int b = e / d, i = e - b * d;
+    xb[i * FTB + b] = (b0 + b < n) ? gm.X[(int64_t)(b0 + b) * d + i] : 0.0;
+  }
+  for (int e = tid; e < d; e += BUILD_THREADS) {
+    const double t = theta[e];
+    const double sgi = (precon && !PVEC) ? 1.0 / sqrt(2.0 * t) : 1.0;
+    th[e] = t;
+    ts[e] = t * sgi;
+    dg[e] = 2.0 * t * sgi * sgi;
+  }
+  __syncthreads();
+
+  constexpr int TXN = FTB / 2, TYN = BUILD_THREADS / TXN;
+  const int tx = tid % TXN, ty = tid / TXN;
+  const int b = b0 + 2 * tx;
+  if (b >= n) return;                      // n is even: b + 1 < n as well
+  const double2* xbp = reinterpret_cast<const double2*>(xb + 2 * tx);   // xbp[i * FTB / 2] = (x_b,i , x_{b+1},i)
+  const int64_t nn = n;
+
+#pragma unroll 1
+  for (int q = 0; q < FTA / TYN; q++) {
+    const int al = ty + TYN * q, a = a0 + al;
+    if (a >= n) continue;
+    const double* xav = xa + al * d;
+    double e0 = 0.0, e1 = 0.0;
+    for (int i = 0; i < d; i++) {
+      const double2 xbv = xbp[i * (FTB / 2)];
+      const double r0 = xav[i] - xbv.x, r1 = xav[i] - xbv.y;
+      e0 -= th[i] * (r0 * r0);
+      e1 -= th[i] * (r1 * r1);
+    }
+    const double k0 = varK * exp(e0), k1 = varK * exp(e1);
+    const bool lo0 = !lower_only || a >= b, lo1 = !lower_only || a >= b + 1;   // lower-triangle membership of the pair
+    // ---- value row a
+    {
+      double* orow = out + (int64_t)a * ld;
+      double sra = 1.0, sc0 = 1.0, sc1 = 1.0;
+      if (PVEC) { sra = pinv[a]; sc0 = pinv[b]; sc1 = pinv[b + 1]; }
+      const double v0 = (k0 * sra) * sc0, v1 = (k1 * sra) * sc1;
+      if (lo0 && lo1) *reinterpret_cast<double2*>(orow + b) = make_double2(v0, v1);
+      else if (lo0) orow[b] = v0;
+      if (!lower_only) {                       // value row, gradient columns: +2 theta_j r_j k
+        double* op = orow + nn + b;
+        for (int j = 0; j < d; j++, op += nn) {
+          const double2 xbv = xbp[j * (FTB / 2)];
+          double w0 = ts[j] * (xav[j] - xbv.x), w1 = ts[j] * (xav[j] - xbv.y);
+          if (PVEC) { const double2 sc = *reinterpret_cast<const double2*>(pinv + nn + j * nn + b); w0 *= sc.x; w1 *= sc.y; }
+          *reinterpret_cast<double2*>(op) = make_double2((2.0 * w0) * (k0 * sra), (2.0 * w1) * (k1 * sra));
+        }
+      }
+    }
+    // ---- gradient rows (i, a)
+    for (int i = 0; i < d; i++) {
+      const double2 xbi = xbp[i * (FTB / 2)];
+      double wi0 = ts[i] * (xav[i] - xbi.x), wi1 = ts[i] * (xav[i] - xbi.y);   // row-scaled u_i
+      double wc0 = wi0, wc1 = wi1;                                               // column-scaled u_i (block (i,i))
+      double sc0 = 1.0, sc1 = 1.0, dgi0 = dg[i], dgi1 = dg[i];
+      const int64_t row = nn + (int64_t)i * nn + a;
+      if (PVEC) {
+        const double sr = pinv[row];
+        const double2 scd = *reinterpret_cast<const double2*>(pinv + nn + i * nn + b);
+        sc0 = pinv[b]; sc1 = pinv[b + 1];
+        wc0 = wi0 * scd.x; wc1 = wi1 * scd.y;
+        wi0 *= sr; wi1 *= sr;
+        dgi0 = dg[i] * sr * scd.x; dgi1 = dg[i] * sr * scd.y;
+      }
+      double* orow = out + row * ld;
+      // gradient-value: -2 theta_i r_i k   (always in the lower triangle)
+      *reinterpret_cast<double2*>(orow + b) = make_double2((-2.0 * wi0) * (k0 * sc0), (-2.0 * wi1) * (k1 * sc1));
+      const double c0 = -4.0 * wi0 * k0, c1 = -4.0 * wi1 * k1;
+      const int jend = lower_only ? i : d;
+      double* op = orow + nn + b;
+      for (int j = 0; j < jend; j++, op += nn) {
+        if (j == i) continue;                   // only reachable when !lower_only
+        const double2 xbv = xbp[j * (FTB / 2)];
+        double w0 = ts[j] * (xav[j] - xbv.x), w1 = ts[j] * (xav[j] - xbv.y);
+        if (PVEC) { const double2 sc = *reinterpret_cast<const double2*>(pinv + nn + j * nn + b); w0 *= sc.x; w1 *= sc.y; }
+        *reinterpret_cast<double2*>(op) = make_double2(c0 * w0, c1 * w1);
+      }
+      // block (i, i): (2 theta_i - 4 theta_i^2 r_i^2) k, scaled
+      {
+        double* od = orow + nn + (int64_t)i * nn + b;
+        const double v0 = dgi0 * k0 + c0 * wc0, v1 = dgi1 * k1 + c1 * wc1;
+        if (lo0 && lo1) *reinterpret_cast<double2*>(od) = make_double2(v0, v1);
+        else if (lo0) od[0] = v0;
+      }
+    }
+    // ---- same point: noise and nugget on the matrix diagonal (after the bulk stores of this thread)
+    if (a == b || a == b + 1) {
+      const double sr = PVEC ? pinv[a] : 1.0;
+      double vv = 1.0;
+      if (noise) vv += noise_at(ns, z, a);
+      out[(int64_t)a * ld + a] = varK * ((vv * sr) * sr + ((mode == GEGP_MODE_PRECON_COV) ? eta * vv : eta));
+      for (int i = 0; i < d; i++) {
+        const int64_t row = nn + (int64_t)i * nn + a;
+        const double sg2 = PVEC ? pinv[row] * pinv[row] : dg[i] / (2.0 * th[i]);   // s_i^2
+        double v = 2.0 * th[i];
+        if (noise) v += noise_at(ns, z, (int)row);
+        out[row * ld + row] = varK * (v * sg2 + ((mode == GEGP_MODE_PRECON_COV) ? eta * v : eta));
+      }
+    }
+  }
+}
+
 // Cross covariance rows for prediction: Kx[x][col] = K(x*_x ; training datum col) * pinv[col]
 // value columns: k ; gradient column (j, slot): -2 th_j r_j k with r = x_train - x_test
 // (eval/GpEvalModel.py:133-139 builds K(X, X*) and keeps its value columns; this is its transpose).
@@ -236,6 +383,28 @@ int launch_prep_p(const Ctx& ctx, const Geom& gm, const double* theta, int64_t s
 int launch_build_cov(const Ctx& ctx, const Geom& gm, const double* theta, int64_t strideTheta, NoiseSpec ns,
                      const double* pinv, int64_t strideP, int mode, double eta, double* out, int64_t ld,
                      int64_t strideOut, int lower_only) {
+  // fast path: all points carry gradients, even n (16-byte aligned column blocks), aligned even-stride output
+  const size_t fsmem = (size_t)(FTA * gm.d + gm.d * FTB + 3 * gm.d) * sizeof(double);
+  const bool use_pvec = (mode == GEGP_MODE_PRECON) && ns.noise != nullptr;
+  if (gm.slot == nullptr && gm.ng == gm.n && (gm.n & 1) == 0 && (ld & 1) == 0 && (strideOut & 1) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0 && fsmem <= 200 * 1024 &&
+      (!use_pvec || ((strideP & 1) == 0 && (reinterpret_cast<uintptr_t>(pinv) & 15) == 0))) {
+    static size_t fsmem_set[2] = {0, 0};
+    if (fsmem > 48 * 1024 && fsmem > fsmem_set[use_pvec]) {
+      if (use_pvec) GEGP_SET_SMEM(build_cov_fast_kernel<true>, fsmem);
+      else GEGP_SET_SMEM(build_cov_fast_kernel<false>, fsmem);
+      fsmem_set[use_pvec] = fsmem;
+    }
+    dim3 grid((gm.n + FTB - 1) / FTB, (gm.n + FTA - 1) / FTA, ctx.batch);
+    if (use_pvec)
+      build_cov_fast_kernel<true><<<grid, BUILD_THREADS, fsmem, ctx.stream>>>(gm, theta, strideTheta, ns, pinv, strideP, mode,
+                                                                            eta, out, ld, strideOut, lower_only);
+    else
+      build_cov_fast_kernel<false><<<grid, BUILD_THREADS, fsmem, ctx.stream>>>(gm, theta, strideTheta, ns, pinv, strideP, mode,
+                                                                             eta, out, ld, strideOut, lower_only);
+    GEGP_CHECK_LAUNCH();
+    return 0;
+  }
   const size_t smem = (size_t)(TA * gm.d + gm.d * TB + 2 * gm.d) * sizeof(double) + (TA + TB) * sizeof(int);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
