@@ -40,6 +40,7 @@ gemm_f64_kernel(const GemmArgs g) {
   const double* __restrict__ A = g.A + zo * g.sAo + zi * g.sAi;
   const double* __restrict__ B = g.B + zo * g.sBo + zi * g.sBi;
   double* __restrict__ C = g.C + zo * g.sCo + zi * g.sCi;
+  double* __restrict__ Ct = g.Ct ? g.Ct + zo * g.sCto + zi * g.sCti : nullptr;
 
   int kb = 0, ke = g.K;
   if (g.klo_mode == KLO_M0) kb = m0;
@@ -195,6 +196,10 @@ gemm_f64_kernel(const GemmArgs g) {
         if (st0 && col < row) C[(int64_t)col * g.ldc + row] = v0;
         if (st1 && col + 1 < row) C[(int64_t)(col + 1) * g.ldc + row] = v1;
       }
+      if (Ct) {
+        if (st0) Ct[(int64_t)col * g.ldct + row] = v0;
+        if (st1) Ct[(int64_t)(col + 1) * g.ldct + row] = v1;
+      }
     }
   }
 }
@@ -240,6 +245,7 @@ GemmArgs gemm_args(const double* A, int64_t lda, const double* B, int64_t ldb, d
   g.inner = 1; g.outer = 1;
   g.row_owner = false;
   g.inner_steps = false; g.iAr = g.iAc = g.iBr = g.iBc = 0;
+  g.Ct = nullptr; g.ldct = 0; g.sCto = g.sCti = 0;
   g.sAo = g.sBo = g.sCo = g.sAi = g.sBi = g.sCi = 0;
   return g;
 }

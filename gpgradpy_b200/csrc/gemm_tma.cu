@@ -83,6 +83,8 @@ struct TmaGemmArgs {
   int klo_mode, khi_mode, cmode;
   int inner;
   int iAr, iAc, iBr, iBc;  // inner-batch row / column steps of the operands (tensor-map coordinates)
+  double* Ct;              // optional transposed second destination
+  int64_t ldct, sCto, sCti;
 };
 
 template <class Cfg>
@@ -179,6 +181,7 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   // ===== epilogue =====
   double* __restrict__ C = g.C + zo * g.sCo + zi * g.sCi;
+  double* __restrict__ Ct = g.Ct ? g.Ct + zo * g.sCto + zi * g.sCti : nullptr;
   const bool vec_ok = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll
   for (int i = 0; i < TMI; i++) {
@@ -206,6 +209,10 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (g.cmode == C_LOWER_MIRROR) {
         if (st0 && col < row) C[(int64_t)col * g.ldc + row] = v0;
         if (st1 && col + 1 < row) C[(int64_t)(col + 1) * g.ldc + row] = v1;
+      }
+      if (Ct) {
+        if (st0) Ct[(int64_t)col * g.ldct + row] = v0;
+        if (st1) Ct[(int64_t)(col + 1) * g.ldct + row] = v1;
       }
     }
   }
@@ -281,6 +288,7 @@ static int launch_tma(const Ctx& ctx, const GemmArgs& g, uint64_t a_d0, uint64_t
   t.M = g.M; t.N = g.N; t.K = g.K; t.alpha = g.alpha; t.beta = g.beta;
   t.klo_mode = g.klo_mode; t.khi_mode = g.khi_mode; t.cmode = g.cmode;
   t.inner = g.inner; t.iAr = g.iAr; t.iAc = g.iAc; t.iBr = g.iBr; t.iBc = g.iBc;
+  t.Ct = g.Ct; t.ldct = g.ldct; t.sCto = g.sCto; t.sCti = g.sCti;
   static bool attr_set = false;
   if (!attr_set) {
     GEGP_SET_SMEM(gemm_tma_nt_kernel<Cfg>, Cfg::SMEM);

@@ -587,25 +587,31 @@ int leaf_trsm(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, con
 }
 
 // ------------------------------------------------------------------------------------------------
-// U diagonal blocks <- Dinv blocks (start of the explicit inverse; the rest of U is produced by GEMMs).
+// U diagonal blocks <- Dinv blocks and their transposes (start of the explicit inverse; the rest of U is produced
+// by GEMMs).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 scatter_dinv_kernel(const double* __restrict__ Dinv, int64_t strideD, double* __restrict__ U, int64_t ldu,
-                    int64_t strideU, int N) {
+                    int64_t strideU, double* __restrict__ W, int64_t ldw, int64_t strideW, int N) {
   Dinv += (int64_t)blockIdx.z * strideD + (int64_t)blockIdx.x * NB * NB;
   U += (int64_t)blockIdx.z * strideU;
+  W += (int64_t)blockIdx.z * strideW;
   const int b0 = blockIdx.x * NB;
   const int k = min(NB, N - b0);
   for (int e = threadIdx.x; e < NB * NB; e += 256) {
     const int i = e >> 7, j = e & (NB - 1);
-    if (i < k && j < k) U[(int64_t)(b0 + i) * ldu + b0 + j] = Dinv[e];
+    if (i < k && j < k) {
+      U[(int64_t)(b0 + i) * ldu + b0 + j] = Dinv[e];             // L_bb^-T: upper triangular, zeros below
+      W[(int64_t)(b0 + i) * ldw + b0 + j] = Dinv[j * NB + i];    // L_bb^-1: lower triangular, zeros above
+    }
   }
 }
 
 int leaf_scatter_dinv(const Ctx& ctx, const double* Dinv, int64_t strideD, double* U, int64_t ldu, int64_t strideU,
-                      int N) {
+                      double* W, int64_t ldw, int64_t strideW, int N) {
   if (N <= 0) return 0;
-  scatter_dinv_kernel<<<dim3((N + NB - 1) / NB, 1, ctx.batch), 256, 0, ctx.stream>>>(Dinv, strideD, U, ldu, strideU, N);
+  scatter_dinv_kernel<<<dim3((N + NB - 1) / NB, 1, ctx.batch), 256, 0, ctx.stream>>>(Dinv, strideD, U, ldu, strideU, W, ldw,
+                                                                                  strideW, N);
   GEGP_CHECK_LAUNCH();
   return 0;
 }

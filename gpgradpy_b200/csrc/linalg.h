@@ -25,6 +25,9 @@ struct GemmArgs {
   int outer;
   bool inner_steps;        // iAr..iBc below are valid (needed by the TMA kernel when inner > 1)
   int iAr, iAc, iBr, iBc;  // inner-batch steps of A and B as (rows, columns): sAi == iAr*lda + iAc, sBi likewise
+  // optional second, transposed destination: Ct[col * ldct + row] = value for every stored C(row, col)
+  double* Ct;
+  int64_t ldct, sCto, sCti;
   bool row_owner;  // C aliases A (in-place right multiply): every CTA must own complete rows (one column tile)
 };
 
@@ -57,9 +60,10 @@ int leaf_dinv_assemble(const Ctx& ctx, const double* L, int64_t ldl, int64_t str
 // the 32 x 32 diagonal inverses taken from Dinv and one refinement step each (as accurate as a substitution).
 int leaf_trsm(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv, int64_t strideD,
               double* B, int64_t ldb, int64_t strideB, int r, int k);
-// Diagonal blocks of the N x N buffer U <- Dinv blocks (the rest of U is left untouched).
+// Diagonal blocks of the N x N buffer U <- Dinv blocks (upper triangular), diagonal blocks of W <- their transposes
+// (lower triangular); the rest of both buffers is left untouched.
 int leaf_scatter_dinv(const Ctx& ctx, const double* Dinv, int64_t strideD, double* U, int64_t ldu, int64_t strideU,
-                      int N);
+                      double* W, int64_t ldw, int64_t strideW, int N);
 
 // --- blocked algorithms ---
 // Trapezoid Cholesky: A is m x k (m >= k), lower. Factors the leading k x k block in place (L) and
@@ -70,8 +74,9 @@ int chol_trap(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, in
 // B (r x k) <- B * L^-T for an already factored k x k lower L (col0: global index of L's first column).
 int trsm_right_rec(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv, int64_t strideD,
                    int col0, double* B, int64_t ldb, int64_t strideB, int r, int k);
-// Kinv (full symmetric N x N) = L^-T L^-1. U (N x N) receives L^-T (upper triangle; its strictly lower part
-// outside the diagonal blocks is never written nor read); Kinv doubles as scratch.
+// Kinv (full symmetric N x N) = L^-T L^-1. U (N x N) receives L^-T in its upper triangle (its strictly lower part
+// outside the diagonal blocks is never written nor read).  Kinv doubles as scratch: while U is built its lower triangle
+// holds the transpose L^-1, so that every product of the inverse is an A * B^T with K-contiguous operands (TMA kernel).
 int chol_inverse(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv, int64_t strideD,
                  double* U, int64_t ldu, int64_t strideU, double* Kinv, int64_t ldk, int64_t strideK, int N);
 // x <- L^-T x (blocked back substitution with the Dinv blocks), nrhs vectors x[r*ldx + i].

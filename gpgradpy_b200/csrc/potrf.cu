@@ -58,13 +58,15 @@ int chol_trap(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, in
   return chol_trap(ctx, C, lda, strideA, m - k1, k - k1, row0 + k1, info, Dinv, strideD);
 }
 
-// U = L^-T (upper triangular) by levels: diagonal LEAF blocks first, then for block size bs = LEAF,
-// 2*LEAF, ... every pair (a = [s, s+bs), b = [s+bs, s+2bs)):  U_ab = -(U_aa * L_ba^T) * U_bb.
-// The product in parentheses is staged in T (the Kinv buffer, same coordinates).
+// U = L^-T by levels: diagonal LEAF blocks first, then for block size bs = LEAF, 2*LEAF, ... every pair
+// (a = [s, s+bs), b = [s+bs, s+2bs)):  U_ab = -(U_aa * L_ba^T) * U_bb.  The product in parentheses is staged in the
+// upper triangle of T (the Kinv buffer, same coordinates as U_ab).  The LOWER triangle of T meanwhile collects
+// W = U^T = L^-1, so the second product is written  -(T_ab) * (W_bb)^T  with the K-contiguous lower-triangular W_bb:
+// both products are A * B^T and run on the TMA kernel; each U_ab is stored a second time, transposed, as W_ba.
 static int inverse_transposed(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv,
                               int64_t strideD, double* U, int64_t ldu, int64_t strideU, double* T, int64_t ldt,
                               int64_t strideT, int N) {
-  int rc = leaf_scatter_dinv(ctx, Dinv, strideD, U, ldu, strideU, N);
+  int rc = leaf_scatter_dinv(ctx, Dinv, strideD, U, ldu, strideU, T, ldt, strideT, N);
   if (rc) return rc;
   for (int bs = LEAF; bs < N; bs *= 2) {
     const int npairs_full = N / (2 * bs);  // pairs whose b block is full
@@ -81,7 +83,7 @@ static int inverse_transposed(const Ctx& ctx, const double* L, int64_t ldl, int6
       const double* Uaa = U + (int64_t)s * ldu + s;
       const double* Lba = L + (int64_t)(s + bs) * ldl + s;
       double* Tab = T + (int64_t)s * ldt + s + bs;
-      // T_ab (bs x bsz) = U_aa (bs x bs, upper: k >= i) * L_ba^T  -> NT, k clipped below by m0
+      // T_ab (bs x bsz) = U_aa (bs x bs, upper: k >= i) * L_ba^T  -> k clipped below by m0
       GemmArgs g1 = gemm_args(Uaa, ldu, Lba, ldl, Tab, ldt, bs, bsz, bs, 1.0, 0.0, true);
       g1.klo_mode = KLO_M0;
       g1.outer = ctx.batch; g1.inner = inner;
@@ -89,13 +91,17 @@ static int inverse_transposed(const Ctx& ctx, const double* L, int64_t ldl, int6
       g1.inner_steps = true; g1.iAr = g1.iAc = g1.iBr = g1.iBc = 2 * bs;
       rc = gemm_f64(ctx, g1);
       if (rc) return rc;
-      // U_ab = -T_ab (bs x bsz) * U_bb (bsz x bsz upper, element (k,j) nonzero for k <= j) -> NN, k < n0+BN
-      const double* Ubb = U + (int64_t)(s + bs) * ldu + s + bs;
+      // U_ab = -T_ab (bs x bsz) * W_bb^T,  W_bb = L_bb^-1 (bsz x bsz lower: element (j, k) nonzero for k <= j, read
+      // from the lower triangle of T; k clipped above by n0 + BN); the transposed copy W_ba = U_ab^T goes there too.
+      const double* Wbb = T + (int64_t)(s + bs) * ldt + s + bs;
       double* Uab = U + (int64_t)s * ldu + s + bs;
-      GemmArgs g2 = gemm_args(Tab, ldt, Ubb, ldu, Uab, ldu, bs, bsz, bsz, -1.0, 0.0, false);
+      double* Wba = T + (int64_t)(s + bs) * ldt + s;
+      GemmArgs g2 = gemm_args(Tab, ldt, Wbb, ldt, Uab, ldu, bs, bsz, bsz, -1.0, 0.0, true);
       g2.khi_mode = KHI_N0;
+      g2.Ct = Wba; g2.ldct = ldt; g2.sCto = strideT; g2.sCti = pstepT;
       g2.outer = ctx.batch; g2.inner = inner;
-      g2.sAo = strideT; g2.sBo = strideU; g2.sCo = strideU; g2.sAi = pstepT; g2.sBi = pstepU; g2.sCi = pstepU;
+      g2.sAo = strideT; g2.sBo = strideT; g2.sCo = strideU; g2.sAi = pstepT; g2.sBi = pstepT; g2.sCi = pstepU;
+      g2.inner_steps = true; g2.iAr = g2.iAc = g2.iBr = g2.iBc = 2 * bs;
       rc = gemm_f64(ctx, g2);
       if (rc) return rc;
     }
@@ -106,8 +112,9 @@ static int inverse_transposed(const Ctx& ctx, const double* L, int64_t ldl, int6
 int chol_inverse(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv, int64_t strideD,
                  double* U, int64_t ldu, int64_t strideU, double* Kinv, int64_t ldk, int64_t strideK, int N) {
   if (N <= 0) return 0;
-  // Only the upper triangle of U (plus the zero lower parts of its diagonal blocks, which come with Dinv) is
-  // ever read: every GEMM below clips its k range at tile granularity and tiles nest inside the LEAF blocks.
+  // Only the upper triangle of U (plus the zero lower parts of its diagonal blocks, which come with Dinv) is ever
+  // read, and only the lower triangle of W = L^-1 inside Kinv (plus the zero upper parts of its diagonal blocks):
+  // every GEMM below clips its k range at tile granularity and tiles nest inside the LEAF blocks.
   int rc = inverse_transposed(ctx, L, ldl, strideL, Dinv, strideD, U, ldu, strideU, Kinv, ldk, strideK, N);
   if (rc) return rc;
   // Kinv = U * U^T, U upper: sum over k >= max(i, j); lower tiles computed, mirrored to the upper half.
