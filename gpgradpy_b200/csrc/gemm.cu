@@ -232,7 +232,7 @@ static int launch_cfg(const Ctx& ctx, const GemmArgs& g) {
 
 static int g_tma_min_tiles = -1;
 int& tma_min_tiles() {
-  if (g_tma_min_tiles < 0) g_tma_min_tiles = getenv("GEGP_BIG_TILES") ? atoi(getenv("GEGP_BIG_TILES")) : 1000;
+  if (g_tma_min_tiles < 0) g_tma_min_tiles = getenv("GEGP_BIG_TILES") ? atoi(getenv("GEGP_BIG_TILES")) : 400;
   return g_tma_min_tiles;
 }
 
@@ -267,8 +267,9 @@ int gemm_f64(const Ctx& ctx, GemmArgs g) {
     tiles_big -= sq * (sq - 1) / 2 + (ct > rt ? (ct - rt) * rt : 0);
   }
   tiles_big *= g.inner;
-  // Measured on B200 (d=10, n=500 and d=20, n=1000 evaluations): below ~1000 tiles of 128 x 128 the one-CTA-per-SM
-  // TMA kernel loses more to wave quantisation (148 tiles per wave) than it gains over the 64 x 64 kernel.
+  // Measured on B200 (d=10, n=500 and d=20, n=1000 evaluations): with fewer than ~400 tiles of 128 x 128 per problem
+  // the TMA kernel (128 x 64 tiles, 296 resident CTAs) loses more to wave quantisation than it gains over the
+  // 64 x 64 cp.async kernel; between 400 and 1000 the two are equal, above the TMA kernel wins.
   const bool big = tiles_big >= tma_min_tiles() && g.M >= 128 && g.N >= 128;
   if (g.row_owner) {
     // in-place right multiply: one column tile must cover all of N so that a CTA only overwrites rows it alone reads

@@ -69,7 +69,7 @@ int gegp_abi_version(void);
 
 /* Tuning knobs (process-wide).  Returns the previous value (>= 0) or a negative argument error.
  * GEGP_OPT_TMA_MIN_TILES: the 128 x 128-tile TMA GEMM kernel is used for products with at least this many output
- * tiles per problem (default 1000, measured); smaller products run on the 64 x 64-tile cp.async kernel.  The
+ * tiles per problem (default 400, measured); smaller products run on the 64 x 64-tile cp.async kernel.  The
  * choice depends on the shape of one problem only, never on the batch count (bit-identical results across
  * batch sizes and ranks). */
 #define GEGP_OPT_TMA_MIN_TILES 1
