@@ -438,7 +438,8 @@ int leaf_potf2_inv(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int 
 // running entirely on the fp64 tensor cores.  A warp owns an 8-row strip; a CTA of 16 warps owns 128 rows and
 // stages the L block and the U_jj blocks in the same shifted shared-memory tile the factor kernel uses.
 // ------------------------------------------------------------------------------------------------
-constexpr int TW = 16;  // warps per CTA of the leaf solve
+// TW: warps per CTA of the leaf solve (each warp owns an 8-row strip): 16 for tall panels, 8 when that still gives
+// every CTA an SM of its own (half the tensor-pipe time per CTA on the latency-critical mid-size problems).
 
 __device__ __forceinline__ void frag_c_to_a(double* scr, const double (&c)[4][2], double (&a)[8], int lr,
                                             int lk, double sign) {
@@ -453,6 +454,7 @@ __device__ __forceinline__ void frag_c_to_a(double* scr, const double (&c)[4][2]
   for (int kq = 0; kq < 8; kq++) a[kq] = sign * scr[lr * SLD + 4 * kq + lk];
 }
 
+template <int TW>
 __global__ void __launch_bounds__(TW * 32, 1)
 leaf_trsm_kernel(const double* __restrict__ L, int64_t ldl, int64_t strideL, const double* __restrict__ Dinv,
                  int64_t strideD, double* __restrict__ B, int64_t ldb, int64_t strideB, int r, int k) {
@@ -572,18 +574,26 @@ leaf_trsm_kernel(const double* __restrict__ L, int64_t ldl, int64_t strideL, con
   }
 }
 
+template <int TW>
+static int launch_leaf_trsm(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv,
+                            int64_t strideD, double* B, int64_t ldb, int64_t strideB, int r, int k) {
+  static bool attr = false;
+  const int smem = (NB * PLD + TW * 8 * SLD) * (int)sizeof(double);
+  if (!attr) { GEGP_SET_SMEM(leaf_trsm_kernel<TW>, smem); attr = true; }
+  const int nctas = (r + TW * 8 - 1) / (TW * 8);
+  leaf_trsm_kernel<TW><<<dim3(nctas, 1, ctx.batch), TW * 32, smem, ctx.stream>>>(L, ldl, strideL, Dinv, strideD, B, ldb,
+                                                                                strideB, r, k);
+  GEGP_CHECK_LAUNCH();
+  return 0;
+}
+
 int leaf_trsm(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv, int64_t strideD,
               double* B, int64_t ldb, int64_t strideB, int r, int k) {
   if (r <= 0 || k <= 0) return 0;
   if (k > NB) return -902;
-  static bool attr = false;
-  const int smem = (NB * PLD + TW * 8 * SLD) * (int)sizeof(double);
-  if (!attr) { GEGP_SET_SMEM(leaf_trsm_kernel, smem); attr = true; }
-  const int nctas = (r + TW * 8 - 1) / (TW * 8);
-  leaf_trsm_kernel<<<dim3(nctas, 1, ctx.batch), TW * 32, smem, ctx.stream>>>(L, ldl, strideL, Dinv, strideD, B, ldb,
-                                                                            strideB, r, k);
-  GEGP_CHECK_LAUNCH();
-  return 0;
+  // (both variants do the same arithmetic per 8-row strip: results are bit-identical whichever is chosen)
+  if (ctx.batch == 1 && r <= 148 * 64) return launch_leaf_trsm<8>(ctx, L, ldl, strideL, Dinv, strideD, B, ldb, strideB, r, k);
+  return launch_leaf_trsm<16>(ctx, L, ldl, strideL, Dinv, strideD, B, ldb, strideB, r, k);
 }
 
 // ------------------------------------------------------------------------------------------------
