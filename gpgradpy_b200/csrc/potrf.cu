@@ -3,6 +3,7 @@
 // of the LML gradient (reference: scipy cho_factor / cho_solve at kernel/Kernel.py:251,
 // optz/CalcLkd.py:154,174).
 #include "linalg.h"
+#include <cstdlib>
 
 namespace gegp {
 
@@ -37,25 +38,98 @@ int trsm_right_rec(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL
                         k - k1);
 }
 
-int chol_trap(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, int k, int row0, int* info, double* Dinv,
-              int64_t strideD) {
+// ------------------------------------------------------------------------------------------------
+// Look-ahead.  The trailing update of a recursion node,  C -= P P^T,  is split into the block column the NEXT leaf
+// needs (its first LEAF columns, on the caller's stream) and the rest (on a low-priority side stream).  The next
+// leaf's factor + solve (one SM, then a few SMs: latency bound) then runs concurrently with the bulk of the update;
+// the caller's stream re-joins the side stream right after that leaf, before anything touches the rest of C.
+// Every output element is still produced by exactly one GEMM with the same k order, so results do not change.
+// One side stream and one event pair per recursion depth and device; fork/join is capturable in a CUDA graph.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct LookAhead {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork[40], join[40];
+  int pending = -1;   // depth whose join event the caller's stream still has to wait for
+  bool ok = false;
+};
+
+LookAhead* look_ahead() {
+  static LookAhead per_dev[16];
+  static bool init[16] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  LookAhead& la = per_dev[dev];
+  if (!init[dev]) {
+    init[dev] = true;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo: numerically largest = lowest priority
+    la.ok = cudaStreamCreateWithPriority(&la.side, cudaStreamNonBlocking, lo) == cudaSuccess;
+    for (int i = 0; i < 40 && la.ok; i++)
+      la.ok = cudaEventCreateWithFlags(&la.fork[i], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&la.join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (getenv("GEGP_NO_LOOKAHEAD")) la.ok = false;
+  }
+  return la.ok ? &la : nullptr;
+}
+
+int chol_node(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t lda, int64_t strideA, int m, int k, int row0,
+              int* info, double* Dinv, int64_t strideD) {
   if (k <= 0) return 0;
   if (k <= LEAF) {
     int rc = leaf_potf2_inv(ctx, A, lda, strideA, k, row0, info, Dinv + (int64_t)(row0 / LEAF) * LEAF * LEAF, strideD);
     if (rc) return rc;
-    return trsm_right_rec(ctx, A, lda, strideA, Dinv, strideD, row0, A + (int64_t)k * lda, lda, strideA, m - k, k);
+    rc = trsm_right_rec(ctx, A, lda, strideA, Dinv, strideD, row0, A + (int64_t)k * lda, lda, strideA, m - k, k);
+    if (rc) return rc;
+    if (la && la->pending >= 0) {   // re-join the bulk update that ran beside this leaf
+      if (cudaStreamWaitEvent(ctx.stream, la->join[la->pending], 0) != cudaSuccess) return -1100;
+      la->pending = -1;
+    }
+    return 0;
   }
   const int k1 = split_point(k);
-  int rc = chol_trap(ctx, A, lda, strideA, m, k1, row0, info, Dinv, strideD);
+  int rc = chol_node(ctx, la, depth + 1, A, lda, strideA, m, k1, row0, info, Dinv, strideD);
   if (rc) return rc;
   // trailing update: C = A[k1:, k1:k] -= A[k1:, :k1] * A[k1:k, :k1]^T  (lower part of the square region)
   double* C = A + (int64_t)k1 * lda + k1;
   const double* P = A + (int64_t)k1 * lda;
-  GemmArgs g = gemm_args(P, lda, P, lda, C, lda, m - k1, k - k1, k1, -1.0, 1.0, true);
-  g.cmode = C_LOWER;
-  rc = gemm_f64(ctx, batched(ctx, g, strideA, strideA, strideA));
-  if (rc) return rc;
-  return chol_trap(ctx, C, lda, strideA, m - k1, k - k1, row0 + k1, info, Dinv, strideD);
+  const int mc = m - k1, kc = k - k1;
+  const int w = kc < LEAF ? kc : LEAF;
+  if (la && depth < 40 && kc > w) {
+    if (cudaEventRecord(la->fork[depth], ctx.stream) != cudaSuccess) return -1101;
+    if (cudaStreamWaitEvent(la->side, la->fork[depth], 0) != cudaSuccess) return -1102;
+    GemmArgs g1 = gemm_args(P, lda, P, lda, C, lda, mc, w, k1, -1.0, 1.0, true);   // the next leaf's block column
+    g1.cmode = C_LOWER;
+    rc = gemm_f64(ctx, batched(ctx, g1, strideA, strideA, strideA));
+    if (rc) return rc;
+    const double* P2 = P + (int64_t)w * lda;
+    GemmArgs g2 = gemm_args(P2, lda, P2, lda, C + (int64_t)w * lda + w, lda, mc - w, kc - w, k1, -1.0, 1.0, true);
+    g2.cmode = C_LOWER;
+    Ctx side{la->side, ctx.batch};
+    rc = gemm_f64(side, batched(side, g2, strideA, strideA, strideA));
+    if (rc) return rc;
+    if (cudaEventRecord(la->join[depth], la->side) != cudaSuccess) return -1103;
+    la->pending = depth;
+  } else {
+    GemmArgs g = gemm_args(P, lda, P, lda, C, lda, mc, kc, k1, -1.0, 1.0, true);
+    g.cmode = C_LOWER;
+    rc = gemm_f64(ctx, batched(ctx, g, strideA, strideA, strideA));
+    if (rc) return rc;
+  }
+  return chol_node(ctx, la, depth + 1, C, lda, strideA, mc, kc, row0 + k1, info, Dinv, strideD);
+}
+}  // namespace
+
+int chol_trap(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, int k, int row0, int* info, double* Dinv,
+              int64_t strideD) {
+  LookAhead* la = look_ahead();
+  if (la) la->pending = -1;
+  const int rc = chol_node(ctx, la, 0, A, lda, strideA, m, k, row0, info, Dinv, strideD);
+  if (la && la->pending >= 0) {   // cannot happen (every fork is followed by a leaf), kept as a safety net
+    cudaStreamWaitEvent(ctx.stream, la->join[la->pending], 0);
+    la->pending = -1;
+  }
+  return rc;
 }
 
 // U = L^-T by levels: diagonal LEAF blocks first, then for block size bs = LEAF, 2*LEAF, ... every pair
