@@ -108,12 +108,25 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
+def _use_all_host_threads():
+    """Give the host BLAS every core (returns the thread count actually in effect)."""
+    want = os.cpu_count() or 1
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=want)
+        got = [p.get("num_threads", 1) for p in threadpoolctl.threadpool_info() if p.get("user_api") == "blas"]
+        return int(max(got)) if got else want
+    except Exception:
+        return int(os.environ.get("OMP_NUM_THREADS", want))
+
+
 def run_reference(args):
     """The reference's algorithm on the host cores (oracle port of calc_lkd_all, noise-free precon)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import gegp_oracle as O     # the one place bench.py executes oracle/ as the thing measured
+    cores = _use_all_host_threads()          # torchrun exports OMP_NUM_THREADS=1: undo that for the CPU arm
     n, d = WORKLOADS[args.workload]
     x, f, g, theta = make_problem(n, d)
     eta = O.nugget(n, d, "precon")[1]
@@ -126,7 +139,6 @@ def run_reference(args):
         O.lkd_wo_noise(x, f, g, step_theta(theta, s, 0), "precon", eta, calc_grad=True)
     dt = time.perf_counter() - t0
     val = steps / dt
-    cores = os.cpu_count()
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": 1, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -314,11 +326,12 @@ def run_b200(args):
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import gegp_oracle as O   # checker / baseline only
+        cores = _use_all_host_threads()
         t0 = time.perf_counter()
         ref = O.lkd_wo_noise(x, f, g, step_theta(theta, W + K - 1, 0), "precon", eta, calc_grad=True)
         dt = time.perf_counter() - t0
         got = last.cpu().numpy()[0]
-        cpu_baseline = {"value": 1.0 / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+        cpu_baseline = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "1 full LML+gradient evaluation of the same workload (NumPy/SciPy port of the "
                                   "reference algorithm, all host BLAS threads)",
                         "parity_vs_gpu_last_step": {

@@ -39,9 +39,12 @@ else:
     buf = torch.empty((N, ld), dtype=torch.float64, device="cuda")
     dinv = bk.dinv_buffer(N)
     for mode_name in ("base", "rescale_origin", "precon"):
-        if mode_name == "rescale_origin":
-            xr, fr, gr, c = O.rescale_origin(x, f, g, O.vreq_rescale_origin(n, d))[:4] if False else (x, f, g, 1.0)
-        eta = O.nugget(n, d, mode_name if mode_name != "rescale_origin" else "base")[1]
+        if mode_name == "rescale_origin":   # same GP in rescaled coordinates: x_s = (x - x_last) c, theta_s = theta / c^2
+            xr, _, _, c = O.rescale_origin(x, f, g, O.vreq_rescale_origin(n, d))[:4]
+            X = bk.to_dev(xr); TH = bk.to_dev(th / c ** 2)
+        else:
+            X = bk.to_dev(x); TH = bk.to_dev(th)
+        eta = O.nugget(n, d, mode_name)[1]
         mode = L.MODE_PRECON if mode_name == "precon" else L.MODE_BASE
         ms_b = ev(lambda: bk.build_cov(X, TH, mode=mode, eta=eta, out=buf, uplo=0), reps=2)
         ms_l = ev(lambda: bk.build_cov(X, TH, mode=mode, eta=eta, out=buf, uplo=1), reps=2)

@@ -1,4 +1,5 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python tools/perf_probe.py 2>&1 | tee gpurun_out/perf_s4.log
 python tools/one_eval.py 500 10 1 4 | tail -2
 GEGP_NO_LOOKAHEAD=1 python tools/one_eval.py 500 10 1 4 | tail -1
 python tools/one_eval.py 1000 20 1 3 | tail -1
