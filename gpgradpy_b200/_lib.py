@@ -12,15 +12,17 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgegp.so")
 
 # mirrors of the #defines in include/gegp.h
-ABI_VERSION = 2
+ABI_VERSION = 3
 MODE_BASE, MODE_PRECON, MODE_PRECON_COV = 0, 1, 2
 OUT_LML, OUT_SIGMA2, OUT_BETA, OUT_LOGDET, OUT_INFO, OUT_QUAD, OUT_DVARK, OUT_DVARF, OUT_DVARG, OUT_GRAD = range(10)
 OP_LML, OP_LML_GRAD, OP_PREDICT = 0, 1, 2
 OPT_TMA_MIN_TILES = 1
+OPT_LOOKAHEAD = 2
 
 EXPORTS = (
     "gegp_abi_version", "gegp_set_option", "gegp_workspace_bytes", "gegp_ld", "gegp_build_cov", "gegp_cross_cov", "gegp_potrf",
     "gegp_trsm_rows", "gegp_dinv_doubles", "gegp_potri", "gegp_dgemm", "gegp_lml_eval", "gegp_predict_setup", "gegp_predict", "gegp_profile_begin", "gegp_profile_end",
+    "gegp_lml_layout", "gegp_symv", "gegp_lanczos_step", "gegp_lincomb", "gegp_quad_grad_work_bytes", "gegp_quad_grad",
 )
 
 
@@ -71,6 +73,18 @@ def load():
     lib.gegp_predict_setup.argtypes = [i, i, i, dp, ip, dp, dp, i, dbl, dp, dbl, dp, i64, dp, dp, dp, ip, vp]
     lib.gegp_predict.restype = i
     lib.gegp_predict.argtypes = [i, i, i, dp, ip, dp, dp, i64, dp, dp, i, dbl, dbl, dp, i, dp, dp, dp, ip, vp, sz, vp]
+    lib.gegp_lml_layout.restype = i
+    lib.gegp_lml_layout.argtypes = [i, i, i, i, i, C.POINTER(i64)]
+    lib.gegp_symv.restype = i
+    lib.gegp_symv.argtypes = [i, dp, i64, dp, dp, vp]
+    lib.gegp_lanczos_step.restype = i
+    lib.gegp_lanczos_step.argtypes = [i, i, dp, i64, dp, dp, dp, vp]
+    lib.gegp_lincomb.restype = i
+    lib.gegp_lincomb.argtypes = [i, i, dp, i64, dp, dp, vp]
+    lib.gegp_quad_grad_work_bytes.restype = sz
+    lib.gegp_quad_grad_work_bytes.argtypes = [i, i, i]
+    lib.gegp_quad_grad.restype = i
+    lib.gegp_quad_grad.argtypes = [i, i, i, dp, ip, dp, dp, i, dbl, i, dp, dp, vp, sz, vp]
     lib.gegp_profile_begin.restype = None
     lib.gegp_profile_begin.argtypes = [i]
     lib.gegp_profile_end.restype = i

@@ -5,6 +5,8 @@ Python/PyTorch, and there is no CPU fallback (a missing CUDA device or library r
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -329,3 +331,130 @@ def predict(st: PredictState, Xs, varK: float, *, chunk_bytes: int = 1 << 30):
                           cx * row_bytes, _stream())
     _check(rc, "gegp_predict")
     return mu, sig, sig2, nneg
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# 2-norm condition number and its hyper-parameter gradient (kernel/Kernel.py:240,280; optz/GpHparaCon.py:161-235)
+# ----------------------------------------------------------------------------------------------------------------
+def symv(M: torch.Tensor, x: torch.Tensor, y: torch.Tensor, N: int):
+    """y[:N] = M[:N, :N] @ x[:N] (gegp_symv; M is an [N, ld] row-major device buffer)."""
+    rc = L.load().gegp_symv(N, _p(M), M.stride(0), _p(x), _p(y), _stream())
+    _check(rc, "gegp_symv")
+    return y
+
+
+def extreme_eig(M: torch.Tensor, N: int, *, k: int = 40, tol: float = 1e-12, max_cycles: int = 12, v0=None):
+    """Largest eigenpair of the symmetric device matrix M[:N, :N]: restarted Lanczos with full re-orthogonalisation.
+
+    The matrix-vector products and the orthogonalisation run on the device (gegp_symv, gegp_lanczos_step,
+    gegp_lincomb); the k x k tridiagonal eigenproblem of each cycle is host work.  Returns (lambda, v [N] device
+    tensor with |v| = 1, relative residual estimate, cycles)."""
+    from scipy.linalg import eigh_tridiagonal
+    lib = L.load()
+    k = int(max(2, min(k, N, 200)))
+    ld = ld_of(N)
+    dev = device()
+    V = torch.zeros((k + 1, ld), dtype=F64, device=dev)
+    w = torch.zeros(ld, dtype=F64, device=dev)
+    r = torch.zeros(ld, dtype=F64, device=dev)
+    ab = torch.zeros((2, k), dtype=F64, device=dev)
+    coef = torch.zeros(k, dtype=F64, device=dev)
+    one = torch.ones(1, dtype=F64, device=dev)
+    if v0 is None:   # fixed start vector (deterministic results): not orthogonal to any smooth or oscillating mode
+        v0 = to_dev(np.random.default_rng(12345).standard_normal(N))
+    V[0, :N] = v0[:N]
+    rc = lib.gegp_lincomb(N, 1, _p(V), ld, _p(one), _p(r), _stream())      # normalise
+    _check(rc, "gegp_lincomb")
+    V[0].copy_(r)
+    lam, resid, cycles = float("nan"), float("inf"), 0
+    for cycles in range(1, max_cycles + 1):
+        for j in range(k):
+            rc = lib.gegp_symv(N, _p(M), M.stride(0), _p(V[j]), _p(w), _stream())
+            _check(rc, "gegp_symv")
+            rc = lib.gegp_lanczos_step(N, j, _p(V), ld, _p(w), _p(ab[0]), _p(ab[1]), _stream())
+            _check(rc, "gegp_lanczos_step")
+        h = ab.cpu().numpy()
+        a, b = h[0], h[1]
+        scale = max(float(np.max(np.abs(a))), 1e-300)
+        m = k
+        for j in range(k):            # breakdown: an invariant subspace was found after j + 1 steps
+            if not (b[j] > 1e-14 * scale):
+                m = j + 1
+                break
+        evals, evecs = eigh_tridiagonal(a[:m], b[:m - 1]) if m > 1 else (a[:1], np.ones((1, 1)))
+        lam, s = float(evals[-1]), evecs[:, -1]
+        resid = abs(float(b[m - 1]) * float(s[-1])) / max(abs(lam), 1e-300)
+        coef[:m] = to_dev(np.ascontiguousarray(s))
+        rc = lib.gegp_lincomb(N, m, _p(V), ld, _p(coef), _p(r), _stream())
+        _check(rc, "gegp_lincomb")
+        V[0].copy_(r)
+        if resid <= tol or m < k:
+            break
+    return lam, r[:N].clone(), resid, cycles
+
+
+def cond2(Kfull: torch.Tensor, Kinv: torch.Tensor, N: int, *, tol: float = 1e-12):
+    """kappa_2 = lambda_max(K) * lambda_max(K^-1) with both extreme eigenvectors.
+    -> dict(cond, lam_max, lam_min, v_max, v_min, resid_max, resid_min)."""
+    lmax, vmax, r1, _ = extreme_eig(Kfull, N, tol=tol)
+    imax, vmin, r2, _ = extreme_eig(Kinv, N, tol=tol)
+    lmin = 1.0 / imax
+    return dict(cond=lmax * imax, lam_max=lmax, lam_min=lmin, v_max=vmax, v_min=vmin, resid_max=r1, resid_min=r2)
+
+
+def quad_grad(X, theta, v, *, n_g=None, slot=None, eta=0.0, noisy=False, varK=1.0):
+    """gegp_quad_grad: v^T (dKcov/dhp) v for every hyper-parameter (base mode) -> device row laid out as GEGP_OUT_*."""
+    lib = L.load()
+    X, theta, v = to_dev(X), to_dev(theta), to_dev(v)
+    n, d = X.shape
+    n_g = n if n_g is None else n_g
+    out = torch.zeros(L.out_len(d), dtype=F64, device=device())
+    vk = to_dev(np.array([float(varK)]))
+    nbytes = int(lib.gegp_quad_grad_work_bytes(n, n_g, d))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=device())
+    rc = lib.gegp_quad_grad(n, n_g, d, _p(X), _p(slot), _p(theta), _p(v), L.MODE_BASE, float(eta), int(bool(noisy)),
+                            _p(vk), _p(out), _p(ws), nbytes, _stream())
+    _check(rc, "gegp_quad_grad")
+    return out
+
+
+def lml_views(n: int, n_g: int, d: int):
+    """Views of candidate 0's arrays inside the shared workspace, valid right after a B = 1 lml_eval(want_grad=True)
+    (eager or graph replay) on this device: dict(A [N+2, ld] factor, U [N, ld], Kinv [N, ld], ld)."""
+    lib = L.load()
+    o = (C.c_int64 * 8)()
+    rc = lib.gegp_lml_layout(n, n_g, d, 1, 1, o)
+    _check(rc, "gegp_lml_layout")
+    header, ld, per, offA, offP, _offD, offU, offK = (int(x) for x in o)
+    ws = _ws_cache.get(torch.cuda.current_device())
+    assert ws is not None and ws.numel() >= header + 8 * per, "no likelihood evaluation has run on this device yet"
+    dbl = ws[header:header + 8 * per].view(F64)
+    N = n + n_g * d
+    return dict(A=dbl[offA:offA + (N + 2) * ld].view(N + 2, ld), U=dbl[offU:offU + N * ld].view(N, ld),
+                Kinv=dbl[offK:offK + N * ld].view(N, ld), p=dbl[offP:offP + N], pinv=dbl[offP + ld:offP + ld + N], ld=ld)
+
+
+def cond2_of_matrix(K: torch.Tensor, N: int, *, tol: float = 1e-12):
+    """Condition number of an explicit symmetric positive-definite device matrix K[:N, :N] ([N, ld] buffer):
+    factor a copy, explicit inverse, then cond2().  A failed factorisation is retried once on K + delta I and the
+    shift is taken out of lambda_min again (K is then numerically singular: kappa ~ 1 / eps)."""
+    ld = ld_of(N)
+    shift = 0.0
+    for attempt in range(2):
+        A = torch.empty((N, ld), dtype=F64, device=K.device)
+        A[:, :N] = K[:, :N]
+        if shift:
+            A[:, :N].diagonal().add_(shift)
+        info, dinv = potrf(A, N, 0)
+        if int(info.item()) == 0:
+            break
+        if attempt == 1:   # still not positive definite: report "numerically singular"
+            return dict(cond=1e18, lam_max=float("nan"), lam_min=0.0, v_max=None, v_min=None, shift=shift)
+        shift = 1e-13 * float(torch.sum(torch.abs(K[:, :N]), dim=1).max().item())
+    U, Kinv = potri(A, dinv, N)
+    res = cond2(K if K.stride(0) % 2 == 0 and K.data_ptr() % 16 == 0 else K.contiguous(), Kinv, N, tol=tol)
+    if shift:
+        lmin = max(res["lam_min"] - shift, 2.3e-16 * res["lam_max"])
+        res["lam_min"], res["cond"] = lmin, res["lam_max"] / lmin
+    res["shift"] = shift
+    return res

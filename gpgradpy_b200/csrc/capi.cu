@@ -2,6 +2,8 @@
 #include "kernels.h"
 #include "linalg.h"
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include <vector>
 
@@ -28,6 +30,49 @@ void prof_gemm_end(cudaStream_t s, double flops) {
   cudaEventRecord(next_event(), s);
   g_prof.gemm_flops += flops;
   g_prof.gemm_launches++;
+}
+
+struct TlMark { cudaEvent_t b, e; cudaStream_t s; char label[48]; };
+static std::vector<TlMark> g_tl;
+static int g_tl_state = -1;   // -1 unknown, 0 off, 1 on
+bool timeline_on() {
+  if (g_tl_state < 0) g_tl_state = getenv("GEGP_TIMELINE") ? 1 : 0;
+  return g_tl_state == 1;
+}
+void timeline_begin(cudaStream_t s, const char* label, int a, int b, int c) {
+  if (!timeline_on()) return;
+  TlMark m{};
+  cudaEventCreate(&m.b);
+  cudaEventCreate(&m.e);
+  m.s = s;
+  snprintf(m.label, sizeof(m.label), "%s:%d:%d:%d", label, a, b, c);
+  cudaEventRecord(m.b, s);
+  g_tl.push_back(m);
+}
+void timeline_end(cudaStream_t s) {
+  if (!timeline_on() || g_tl.empty()) return;
+  cudaEventRecord(g_tl.back().e, s);
+}
+static void timeline_dump() {
+  if (!timeline_on() || g_tl.empty()) return;
+  cudaDeviceSynchronize();
+  FILE* f = fopen(getenv("GEGP_TIMELINE"), "w");
+  if (f) {
+    for (const TlMark& m : g_tl) {
+      float t0 = 0.f, t1 = 0.f;
+      cudaEventElapsedTime(&t0, g_tl[0].b, m.b);
+      cudaEventElapsedTime(&t1, g_tl[0].b, m.e);
+      fprintf(f, "%s %p %.1f %.1f\n", m.label, (void*)m.s, t0 * 1e3, t1 * 1e3);
+    }
+    fclose(f);
+  }
+  for (TlMark& m : g_tl) { cudaEventDestroy(m.b); cudaEventDestroy(m.e); }
+  g_tl.clear();
+}
+static int g_lookahead = -1;
+int& lookahead_enabled() {
+  if (g_lookahead < 0) g_lookahead = getenv("GEGP_NO_LOOKAHEAD") ? 0 : 1;
+  return g_lookahead;
 }
 }  // namespace gegp
 
@@ -91,6 +136,7 @@ int gegp_profile_end(long* launches, long* gemm_launches, double* gemm_ms, doubl
   if (gemm_flops) *gemm_flops = g_prof.gemm_flops;
   g_prof.on = false;
   g_ev_used = 0;
+  timeline_dump();
   return 0;
 }
 
@@ -101,6 +147,11 @@ int gegp_set_option(int key, int value) {
     if (value < 1) return -2;
     const int old = tma_min_tiles();
     tma_min_tiles() = value;
+    return old;
+  }
+  if (key == GEGP_OPT_LOOKAHEAD) {
+    const int old = lookahead_enabled();
+    lookahead_enabled() = value ? 1 : 0;
     return old;
   }
   return -1;
@@ -290,6 +341,87 @@ int gegp_lml_eval(int B, const double* theta_batch, const double* varK_batch, in
     }
   }
   return 0;
+}
+
+int gegp_lml_layout(int n, int n_g, int d, int want_grad, int B, int64_t* out8) {
+  if (bad_geom(n, n_g, d)) return -1;
+  if (B <= 0) return -5;
+  if (!out8) return -6;
+  const int N = n + n_g * d;
+  const LmlLayout L = lml_layout(n, d, N, want_grad != 0);
+  out8[0] = (int64_t)info_header_bytes(B);
+  out8[1] = L.ld;
+  out8[2] = (int64_t)L.per_cand_doubles;
+  out8[3] = (int64_t)L.A;
+  out8[4] = (int64_t)L.P;
+  out8[5] = (int64_t)L.D;
+  out8[6] = want_grad ? (int64_t)L.U : -1;
+  out8[7] = want_grad ? (int64_t)L.Kinv : -1;
+  return 0;
+}
+
+int gegp_symv(int N, const double* M, int64_t ld, const double* x, double* y, void* stream) {
+  if (N <= 0) return -1;
+  if (!M || (reinterpret_cast<uintptr_t>(M) & 15)) return -2;
+  if (ld < N || (ld & 1)) return -3;
+  if (!x || (reinterpret_cast<uintptr_t>(x) & 15)) return -4;
+  if (!y) return -5;
+  Ctx ctx{(cudaStream_t)stream, 1};
+  return symv_full(ctx, N, M, ld, x, y);
+}
+
+int gegp_lanczos_step(int N, int j, double* V, int64_t ldv, double* w, double* alpha, double* beta, void* stream) {
+  if (N <= 0) return -1;
+  if (j < 0 || j >= 255) return -2;
+  if (!V) return -3;
+  if (ldv < N) return -4;
+  if (!w) return -5;
+  if (!alpha) return -6;
+  if (!beta) return -7;
+  Ctx ctx{(cudaStream_t)stream, 1};
+  return lanczos_step(ctx, N, j, V, ldv, w, alpha, beta);
+}
+
+int gegp_lincomb(int N, int k, const double* V, int64_t ldv, const double* coef, double* out, void* stream) {
+  if (N <= 0) return -1;
+  if (k < 1 || k > 256) return -2;
+  if (!V) return -3;
+  if (ldv < N) return -4;
+  if (!coef) return -5;
+  if (!out) return -6;
+  Ctx ctx{(cudaStream_t)stream, 1};
+  return lincomb_rows(ctx, N, k, V, ldv, coef, out);
+}
+
+size_t gegp_quad_grad_work_bytes(int n, int n_g, int d) {
+  if (bad_geom(n, n_g, d)) return 0;
+  const int N = n + n_g * d;
+  return ((size_t)round_up(N, 2) + (size_t)round_up((int64_t)lml_grad_partial_doubles(n, d), 2)) * sizeof(double);
+}
+
+int gegp_quad_grad(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+                   const double* v, int mode, double eta, int noisy, const double* varK_dev, double* out, void* work,
+                   size_t work_bytes, void* stream) {
+  if (bad_geom(n, n_g, d)) return -1;
+  if (!X) return -4;
+  if (n_g != n && !grad_slot) return -5;
+  if (!theta) return -6;
+  if (!v) return -7;
+  if (mode != GEGP_MODE_BASE) return -8;
+  if (noisy && !varK_dev) return -11;
+  if (!out) return -12;
+  if (!work || (reinterpret_cast<uintptr_t>(work) & 15)) return -13;
+  if (work_bytes < gegp_quad_grad_work_bytes(n, n_g, d)) return -14;
+  const int N = n + n_g * d;
+  Ctx ctx{(cudaStream_t)stream, 1};
+  Geom gm{n, n_g, d, N, X, (n_g == n) ? nullptr : grad_slot};
+  double* ones = reinterpret_cast<double*>(work);           // p^-1 = 1 in base mode
+  double* partial = ones + round_up(N, 2);
+  NoiseSpec ns{nullptr, 0, nullptr, 1.0, 0};
+  int rc = launch_prep_p(ctx, gm, theta, 0, ns, GEGP_MODE_BASE, nullptr, ones, 0);
+  if (rc) return rc;
+  return launch_lml_grad(ctx, gm, theta, 0, nullptr, 0, 0, v, 0, ones, 0, mode, eta, noisy, varK_dev, 0.0, partial, 0, out,
+                         0, 1);
 }
 
 int gegp_predict_setup(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,

@@ -224,7 +224,9 @@ static int launch_cfg(const Ctx& ctx, const GemmArgs& g) {
   }
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.outer * g.inner);
   prof_gemm_begin(ctx.stream);
+  timeline_begin(ctx.stream, "gemm", g.M, g.N, g.K);
   kern<<<grid, Cfg::THREADS, Cfg::SMEM, ctx.stream>>>(g);
+  timeline_end(ctx.stream);
   if (prof().on) prof_gemm_end(ctx.stream, gemm_useful_flops(g));
   GEGP_CHECK_LAUNCH();
   return 0;

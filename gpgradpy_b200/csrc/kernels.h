@@ -42,7 +42,7 @@ int launch_lml_finalize(const Ctx& ctx, int N, const double* A, int64_t lda, int
 int launch_lml_grad(const Ctx& ctx, const Geom& gm, const double* theta, int64_t strideTheta, const double* Kinv,
                     int64_t ldk, int64_t strideK, const double* alpha_t, int64_t strideAlpha, const double* pinv,
                     int64_t strideP, int mode, double eta, int noisy, const double* varK, double pnlt_grad, double* partial,
-                    int64_t stridePartial, double* out, int64_t strideOut);
+                    int64_t stridePartial, double* out, int64_t strideOut, int quad = 0);
 int launch_predict_rows(const Ctx& ctx, int N, const double* Z, int64_t ldz, int nx, const double* w, double beta,
                         double varK, double* mu, double* sig, double* sig2, int* n_negative);
 

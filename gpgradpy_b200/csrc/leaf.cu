@@ -423,7 +423,9 @@ int leaf_potf2_inv(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int 
   static bool attr = false;
   const int smem = NB * PLD * (int)sizeof(double);
   if (!attr) { GEGP_SET_SMEM(potf2_inv_kernel, smem); attr = true; }
+  timeline_begin(ctx.stream, "potf2", row0, k);
   potf2_inv_kernel<<<dim3(1, 1, ctx.batch), LT, smem, ctx.stream>>>(A, lda, strideA, k, row0, info, Dinv, strideD);
+  timeline_end(ctx.stream);
   GEGP_CHECK_LAUNCH();
   return 0;
 }
@@ -581,8 +583,10 @@ static int launch_leaf_trsm(const Ctx& ctx, const double* L, int64_t ldl, int64_
   const int smem = (NB * PLD + TW * 8 * SLD) * (int)sizeof(double);
   if (!attr) { GEGP_SET_SMEM(leaf_trsm_kernel<TW>, smem); attr = true; }
   const int nctas = (r + TW * 8 - 1) / (TW * 8);
+  timeline_begin(ctx.stream, "ltrsm", r, k);
   leaf_trsm_kernel<TW><<<dim3(nctas, 1, ctx.batch), TW * 32, smem, ctx.stream>>>(L, ldl, strideL, Dinv, strideD, B, ldb,
                                                                                 strideB, r, k);
+  timeline_end(ctx.stream);
   GEGP_CHECK_LAUNCH();
   return 0;
 }

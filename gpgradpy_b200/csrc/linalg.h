@@ -86,4 +86,14 @@ int trsv_lower_trans(const Ctx& ctx, const double* L, int64_t ldl, int64_t strid
 int trmv_upper(const Ctx& ctx, const double* U, int64_t ldu, int64_t strideU, const double* x, int64_t strideX,
                double* y, int64_t strideY, int N);
 
+
+// --- extreme eigenpairs (Lanczos building blocks, csrc/eig.cu) ---
+// y = M x for a dense row-major N x ld matrix.
+int symv_full(const Ctx& ctx, int N, const double* M, int64_t ld, const double* x, double* y);
+// One Lanczos step with full re-orthogonalisation: V rows 0..j orthonormal, w = M v_j on entry; writes alpha[j],
+// beta[j] (device) and V row j+1 (j < 255).
+int lanczos_step(const Ctx& ctx, int N, int j, double* V, int64_t ldv, double* w, double* alpha, double* beta);
+// out = normalised sum_i coef[i] V_i (k <= 256, coef on the device).
+int lincomb_rows(const Ctx& ctx, int N, int k, const double* V, int64_t ldv, const double* coef, double* out);
+
 }  // namespace gegp

@@ -111,7 +111,7 @@ lml_grad_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideThe
                 int64_t ldk, int64_t strideK, const double* __restrict__ alpha_all, int64_t strideAlpha,
                 const double* __restrict__ pinv_all, int64_t strideP, const double* __restrict__ out_all,
                 int64_t strideOut, int noisy, double pnlt_grad, double* __restrict__ partial_all,
-                int64_t stridePartial) {
+                int64_t stridePartial, int quad) {
   extern __shared__ double sm[];
   const int d = gm.d, n = gm.n, ng = gm.ng, N = gm.N;
   double* vs = sm;              // [d][GB]  v_j = pinv[col_j] * u_j
@@ -132,8 +132,9 @@ lml_grad_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideThe
   for (int e = tid; e < d; e += GB) { xa[e] = gm.X[(int64_t)a * d + e]; th[e] = theta[e]; }
   __syncthreads();
 
-  const double c1 = noisy ? 0.5 : (pnlt_grad / N + 1.0 / (2.0 * outz[GEGP_OUT_SIGMA2]));
-  const double c2 = 0.5;
+  // quad: W = alpha alpha^T only (quadratic forms v^T dK/dhp v for the condition-number gradient); Kinv is not read
+  const double c1 = quad ? 1.0 : (noisy ? 0.5 : (pnlt_grad / N + 1.0 / (2.0 * outz[GEGP_OUT_SIGMA2])));
+  const double c2 = quad ? 0.0 : 0.5;
   const int sa = gm.slot ? gm.slot[a] : a;
   const bool valid = (b < n);
   const int sb = valid ? (gm.slot ? gm.slot[b] : b) : -1;
@@ -157,7 +158,7 @@ lml_grad_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideThe
     }
     kk = exp(e);
     const double pa0 = pinv[a], pb0 = pinv[b];
-    const double W00 = pa0 * pb0 * (c1 * alpha[a] * alpha[b] - c2 * Kinv[(int64_t)a * ldk + b]);
+    const double W00 = pa0 * pb0 * (c1 * alpha[a] * alpha[b] - (quad ? 0.0 : c2 * Kinv[(int64_t)a * ldk + b]));
     S = W00;
     if (same) dv = W00;
   } else {
@@ -177,14 +178,16 @@ lml_grad_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideThe
       const double* krow = Kinv + (int64_t)row * ldk;
       const double rb = gm.X[(int64_t)b * d + i];
       const double ri = xa[i] - rb, ui = th[i] * ri;
-      const double Wi0 = pr * pinv[b] * (c1 * ar * alpha[b] - c2 * krow[b]);
+      const double Wi0 = pr * pinv[b] * (c1 * ar * alpha[b] - (quad ? 0.0 : c2 * krow[b]));
       double rowdot = 0.0, Wii = 0.0;
       if (sb >= 0) {
         double dot = 0.0, kii = 0.0;
-        for (int j = 0; j < d; j++) {
-          const double kv = krow[n + j * ng + sb];
-          dot += vs[j * GB + tid] * kv;
-          if (j == i) kii = kv;
+        if (!quad) {
+          for (int j = 0; j < d; j++) {
+            const double kv = krow[n + j * ng + sb];
+            dot += vs[j * GB + tid] * kv;
+            if (j == i) kii = kv;
+          }
         }
         rowdot = pr * (c1 * ar * Ab - c2 * dot);
         const int coli = n + i * ng + sb;
@@ -269,7 +272,7 @@ size_t lml_grad_partial_doubles(int n, int d) {
 int launch_lml_grad(const Ctx& ctx, const Geom& gm, const double* theta, int64_t strideTheta, const double* Kinv,
                     int64_t ldk, int64_t strideK, const double* alpha_t, int64_t strideAlpha, const double* pinv,
                     int64_t strideP, int mode, double eta, int noisy, const double* varK, double pnlt_grad,
-                    double* partial, int64_t stridePartial, double* out, int64_t strideOut) {
+                    double* partial, int64_t stridePartial, double* out, int64_t strideOut, int quad) {
   const int d = gm.d;
   const size_t smem = (size_t)(d * GB + (d + 1) * GB + 2 * d) * sizeof(double);
   static size_t smem_set = 0;
@@ -279,7 +282,8 @@ int launch_lml_grad(const Ctx& ctx, const Geom& gm, const double* theta, int64_t
   }
   dim3 grid((gm.n + GB - 1) / GB, gm.n, ctx.batch);
   lml_grad_kernel<<<grid, GB, smem, ctx.stream>>>(gm, theta, strideTheta, Kinv, ldk, strideK, alpha_t, strideAlpha, pinv,
-                                                  strideP, out, strideOut, noisy, pnlt_grad, partial, stridePartial);
+                                                  strideP, out, strideOut, noisy, pnlt_grad, partial, stridePartial,
+                                                  quad);
   GEGP_CHECK_LAUNCH();
   const int64_t nparts = (int64_t)grid.x * grid.y;
   lml_grad_finalize_kernel<<<ctx.batch, 256, (2 * d + 2) * sizeof(double), ctx.stream>>>(

@@ -39,18 +39,24 @@ int trsm_right_rec(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL
 }
 
 // ------------------------------------------------------------------------------------------------
-// Look-ahead.  The trailing update of a recursion node,  C -= P P^T,  is split into the block column the NEXT leaf
-// needs (its first LEAF columns, on the caller's stream) and the rest (on a low-priority side stream).  The next
-// leaf's factor + solve (one SM, then a few SMs: latency bound) then runs concurrently with the bulk of the update;
-// the caller's stream re-joins the side stream right after that leaf, before anything touches the rest of C.
+// Look-ahead.  The factorisation's critical path is the chain  leaf factor -> leaf solve -> update of the next
+// leaf's diagonal block -> next leaf factor  (one CTA, then a few: latency bound).  It runs on its own
+// HIGHEST-priority stream (`hi`, forked from and re-joined to the caller's stream), so that its CTAs take the next
+// free SM ahead of queued GEMM tiles.  The trailing update of a recursion node,  C -= P P^T,  is split three ways:
+//   * the next leaf's diagonal block (LEAF x LEAF)                      -> on the chain (`hi`);
+//   * the rest of the next leaf's block column ((mc - LEAF) x LEAF)     -> stream `col` (high priority): only the
+//     leaf SOLVE needs it, so it runs beside the leaf factor;
+//   * everything right of that block column                            -> stream `bulk` (lowest priority): re-joined
+//     right after the next leaf, before anything touches the rest of C.
 // Every output element is still produced by exactly one GEMM with the same k order, so results do not change.
-// One side stream and one event pair per recursion depth and device; fork/join is capturable in a CUDA graph.
+// One event pair per recursion depth and device; fork/join is capturable in a CUDA graph.
 // ------------------------------------------------------------------------------------------------
 namespace {
 struct LookAhead {
-  cudaStream_t side = nullptr;
-  cudaEvent_t fork[40], join[40];
-  int pending = -1;   // depth whose join event the caller's stream still has to wait for
+  cudaStream_t hi = nullptr, col = nullptr, bulk = nullptr;
+  cudaEvent_t fork[40], join[40], col_done, begin, end;
+  int pending = -1;        // depth whose bulk join event the chain still has to wait for
+  bool col_pending = false;
   bool ok = false;
 };
 
@@ -63,14 +69,16 @@ LookAhead* look_ahead() {
   if (!init[dev]) {
     init[dev] = true;
     int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo: numerically largest = lowest priority
-    la.ok = cudaStreamCreateWithPriority(&la.side, cudaStreamNonBlocking, lo) == cudaSuccess;
-    for (int i = 0; i < 40 && la.ok; i++)
-      la.ok = cudaEventCreateWithFlags(&la.fork[i], cudaEventDisableTiming) == cudaSuccess &&
-              cudaEventCreateWithFlags(&la.join[i], cudaEventDisableTiming) == cudaSuccess;
-    if (getenv("GEGP_NO_LOOKAHEAD")) la.ok = false;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo: numerically largest = lowest priority; hi: greatest
+    const int mid = hi < lo ? hi + 1 : hi;
+    la.ok = cudaStreamCreateWithPriority(&la.hi, cudaStreamNonBlocking, hi) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&la.col, cudaStreamNonBlocking, mid) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&la.bulk, cudaStreamNonBlocking, lo) == cudaSuccess;
+    auto mk = [&](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
+    for (int i = 0; i < 40 && la.ok; i++) la.ok = mk(&la.fork[i]) && mk(&la.join[i]);
+    la.ok = la.ok && mk(&la.col_done) && mk(&la.begin) && mk(&la.end);
   }
-  return la.ok ? &la : nullptr;
+  return (la.ok && lookahead_enabled()) ? &la : nullptr;
 }
 
 int chol_node(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t lda, int64_t strideA, int m, int k, int row0,
@@ -79,6 +87,10 @@ int chol_node(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t lda, 
   if (k <= LEAF) {
     int rc = leaf_potf2_inv(ctx, A, lda, strideA, k, row0, info, Dinv + (int64_t)(row0 / LEAF) * LEAF * LEAF, strideD);
     if (rc) return rc;
+    if (la && la->col_pending) {   // the rows below the diagonal block were updated beside the leaf factor
+      if (cudaStreamWaitEvent(ctx.stream, la->col_done, 0) != cudaSuccess) return -1104;
+      la->col_pending = false;
+    }
     rc = trsm_right_rec(ctx, A, lda, strideA, Dinv, strideD, row0, A + (int64_t)k * lda, lda, strideA, m - k, k);
     if (rc) return rc;
     if (la && la->pending >= 0) {   // re-join the bulk update that ran beside this leaf
@@ -95,21 +107,36 @@ int chol_node(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t lda, 
   const double* P = A + (int64_t)k1 * lda;
   const int mc = m - k1, kc = k - k1;
   const int w = kc < LEAF ? kc : LEAF;
-  if (la && depth < 40 && kc > w) {
+  if (la && depth < 40 && mc > w) {
     if (cudaEventRecord(la->fork[depth], ctx.stream) != cudaSuccess) return -1101;
-    if (cudaStreamWaitEvent(la->side, la->fork[depth], 0) != cudaSuccess) return -1102;
-    GemmArgs g1 = gemm_args(P, lda, P, lda, C, lda, mc, w, k1, -1.0, 1.0, true);   // the next leaf's block column
-    g1.cmode = C_LOWER;
-    rc = gemm_f64(ctx, batched(ctx, g1, strideA, strideA, strideA));
+    // (a) the next leaf's diagonal block, on the chain
+    GemmArgs g0 = gemm_args(P, lda, P, lda, C, lda, w, w, k1, -1.0, 1.0, true);
+    g0.cmode = C_LOWER;
+    rc = gemm_f64(ctx, batched(ctx, g0, strideA, strideA, strideA));
     if (rc) return rc;
-    const double* P2 = P + (int64_t)w * lda;
-    GemmArgs g2 = gemm_args(P2, lda, P2, lda, C + (int64_t)w * lda + w, lda, mc - w, kc - w, k1, -1.0, 1.0, true);
-    g2.cmode = C_LOWER;
-    Ctx side{la->side, ctx.batch};
-    rc = gemm_f64(side, batched(side, g2, strideA, strideA, strideA));
-    if (rc) return rc;
-    if (cudaEventRecord(la->join[depth], la->side) != cudaSuccess) return -1103;
-    la->pending = depth;
+    // (b) the rest of its block column, beside the leaf factor
+    {
+      if (cudaStreamWaitEvent(la->col, la->fork[depth], 0) != cudaSuccess) return -1105;
+      const double* P1 = P + (int64_t)w * lda;
+      GemmArgs g1 = gemm_args(P1, lda, P, lda, C + (int64_t)w * lda, lda, mc - w, w, k1, -1.0, 1.0, true);
+      Ctx cc{la->col, ctx.batch};
+      rc = gemm_f64(cc, batched(cc, g1, strideA, strideA, strideA));
+      if (rc) return rc;
+      if (cudaEventRecord(la->col_done, la->col) != cudaSuccess) return -1106;
+      la->col_pending = true;
+    }
+    // (c) everything right of that block column, lowest priority
+    if (kc > w) {
+      if (cudaStreamWaitEvent(la->bulk, la->fork[depth], 0) != cudaSuccess) return -1102;
+      const double* P2 = P + (int64_t)w * lda;
+      GemmArgs g2 = gemm_args(P2, lda, P2, lda, C + (int64_t)w * lda + w, lda, mc - w, kc - w, k1, -1.0, 1.0, true);
+      g2.cmode = C_LOWER;
+      Ctx bc{la->bulk, ctx.batch};
+      rc = gemm_f64(bc, batched(bc, g2, strideA, strideA, strideA));
+      if (rc) return rc;
+      if (cudaEventRecord(la->join[depth], la->bulk) != cudaSuccess) return -1103;
+      la->pending = depth;
+    }
   } else {
     GemmArgs g = gemm_args(P, lda, P, lda, C, lda, mc, kc, k1, -1.0, 1.0, true);
     g.cmode = C_LOWER;
@@ -122,13 +149,22 @@ int chol_node(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t lda, 
 
 int chol_trap(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, int k, int row0, int* info, double* Dinv,
               int64_t strideD) {
-  LookAhead* la = look_ahead();
-  if (la) la->pending = -1;
-  const int rc = chol_node(ctx, la, 0, A, lda, strideA, m, k, row0, info, Dinv, strideD);
-  if (la && la->pending >= 0) {   // cannot happen (every fork is followed by a leaf), kept as a safety net
-    cudaStreamWaitEvent(ctx.stream, la->join[la->pending], 0);
-    la->pending = -1;
-  }
+  LookAhead* la = (k > LEAF) ? look_ahead() : nullptr;
+  if (!la) return chol_node(ctx, nullptr, 0, A, lda, strideA, m, k, row0, info, Dinv, strideD);
+  la->pending = -1;
+  la->col_pending = false;
+  if (cudaEventRecord(la->begin, ctx.stream) != cudaSuccess) return -1107;
+  if (cudaStreamWaitEvent(la->hi, la->begin, 0) != cudaSuccess) return -1108;
+  const Ctx chain{la->hi, ctx.batch};
+  const int rc = chol_node(chain, la, 0, A, lda, strideA, m, k, row0, info, Dinv, strideD);
+  // every fork is followed by a leaf, which re-joins `col` and `bulk`; the waits below are a safety net that also
+  // keeps a failed run (rc != 0) from leaving work un-joined inside a stream capture
+  if (la->col_pending) cudaStreamWaitEvent(la->hi, la->col_done, 0);
+  if (la->pending >= 0) cudaStreamWaitEvent(la->hi, la->join[la->pending], 0);
+  la->col_pending = false;
+  la->pending = -1;
+  if (cudaEventRecord(la->end, la->hi) != cudaSuccess) return -1109;
+  if (cudaStreamWaitEvent(ctx.stream, la->end, 0) != cudaSuccess) return -1110;
   return rc;
 }
 

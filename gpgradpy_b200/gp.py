@@ -457,8 +457,10 @@ class GaussianProcess:
             Kc, _ = bk.build_cov(X, theta, noise=noise, mode=L.MODE_BASE, eta=etaK, varK=varK, **kw)
             Kcor, Kcov, fac_src, pvec = None, DeviceMatrix(Kc), Kc, None
         condK = None
-        if calc_cond:   # host NumPy, exactly like the reference (np.linalg.cond); not part of the CUDA hot path
-            condK = float(np.linalg.cond(fac_src.cpu().numpy(), p=self.cond_norm))
+        if calc_cond:   # kappa_2 of the matrix that is factored (kernel/Kernel.py:240,280), device Lanczos
+            assert self.cond_norm == 2, "the CUDA path implements the recommended 2-norm condition number"
+            self._last_cond = bk.cond2_of_matrix(fac_src, N)
+            condK = float(self._last_cond["cond"])
             if (not precon) and condK > self.cond_max_abs:
                 calc_chofac = False
         Kcov_chofac = None
@@ -502,24 +504,26 @@ class GaussianProcess:
         return out
 
     def calc_lkd_all(self, hp_vals, calc_lkd=True, calc_cond=False, calc_grad=False, lkd_use_adj_mtd=None):
-        """(LkdInfo, b_chofac_good) -- optz/CalcLkd.py:270-346, adjoint form only (the reference default)."""
+        """(LkdInfo, b_chofac_good) -- optz/CalcLkd.py:270-346, adjoint form only (the reference default).
+
+        With calc_cond the 2-norm condition number of the factored matrix (and, outside precon mode, its
+        hyper-parameter gradient, optz/GpHparaCon.py:161-235) is computed on the device from the factor and the
+        explicit inverse this very evaluation leaves in the workspace."""
         assert self.cond_eta_is_const, "variable-nugget LML is not on the CUDA path yet (SURVEY 8f item 3)"
         theta = np.asarray(hp_vals.theta, dtype=float)
         d = self.dim
-        cond = None
-        if calc_cond:
-            cond = self.calc_all_K_w_chofac(None, hp_vals, calc_chofac=False, calc_cond=True,
-                                            varK=None if self.b_has_noisy_data else 1)[4]
+        need_inv = calc_grad or calc_cond      # the condition number iterates with the explicit inverse
+        hi = self.hp_info_optz_lkd
         if self.b_has_noisy_data:
             noise = self.calc_noise_vec(hp_vals)
-            o = self._eval_rows(theta[None, :], want_grad=calc_grad, varK_rows=np.array([hp_vals.varK]),
+            o = self._eval_rows(theta[None, :], want_grad=need_inv, varK_rows=np.array([hp_vals.varK]),
                                 noise_vec=noise).cpu().numpy()[0]
             if o[L.OUT_INFO] != 0:
-                return LkdInfo(cond=self._cond_on_failure(hp_vals)), False
+                cond, cond_grad = self._cond_on_failure(hp_vals, calc_grad)
+                return LkdInfo(cond=cond, cond_grad=cond_grad), False
             info = LkdInfo(hp_beta=np.array([o[L.OUT_BETA]]), ln_det_Kmat=o[L.OUT_LOGDET], ln_lkd=o[L.OUT_LML],
-                           data_vec=self._y_host, cond=cond)
+                           data_vec=self._y_host)
             if calc_grad:
-                hi = self.hp_info_optz_lkd
                 g = np.zeros(hi.n_hp)
                 g[hi.idx_theta] = o[L.OUT_GRAD:L.OUT_GRAD + d]
                 if hi.has_varK:
@@ -529,29 +533,93 @@ class GaussianProcess:
                 if hi.has_var_fgrad:
                     g[hi.idx_var_fgrad] = o[L.OUT_DVARG]
                 info.ln_lkd_grad = g
+            if calc_cond:
+                info.cond, info.cond_grad = self._cond_from_workspace(hp_vals, calc_grad)
             return info, True
         pn_val = pn_grad = 0.0
         if self.lkd_varK_pnlt_use:   # the penalty slope depends on sigma^2: one value-only pass first
             o0 = self._eval_rows(theta[None, :], want_grad=False).cpu().numpy()[0]
             pn_val, pn_grad = self.calc_lkd_varK_pnlt(o0[L.OUT_SIGMA2], self.get_scl_eval_data()[0])
-        o = self._eval_rows(theta[None, :], want_grad=calc_grad, pnlt_grad=pn_grad).cpu().numpy()[0]
+        o = self._eval_rows(theta[None, :], want_grad=need_inv, pnlt_grad=pn_grad).cpu().numpy()[0]
         if o[L.OUT_INFO] != 0:
-            return LkdInfo(cond=self._cond_on_failure(hp_vals)), False
-        info = LkdInfo(hp_beta=np.array([o[L.OUT_BETA]]), hp_varK=o[L.OUT_SIGMA2], ln_det_Kmat=o[L.OUT_LOGDET],
-                       cond=cond)
+            cond, cond_grad = self._cond_on_failure(hp_vals, calc_grad)
+            return LkdInfo(cond=cond, cond_grad=cond_grad), False
+        info = LkdInfo(hp_beta=np.array([o[L.OUT_BETA]]), hp_varK=o[L.OUT_SIGMA2], ln_det_Kmat=o[L.OUT_LOGDET])
         if calc_lkd:
             info.ln_lkd = o[L.OUT_LML] - pn_val
             if calc_grad:
                 info.ln_lkd_grad = o[L.OUT_GRAD:L.OUT_GRAD + d].copy()
+        if calc_cond:
+            info.cond, info.cond_grad = self._cond_from_workspace(hp_vals, calc_grad)
         return info, True
 
-    def _cond_on_failure(self, hp_vals):
-        """Failed Cholesky: the reference substitutes -cond for the objective (optz/OptzLkd.py:75-77)."""
+    # ------------------------------------------------------------------ condition number (optz/GpHparaCon.py:139-235)
+    def _cond_matrix_args(self, hp_vals):
+        """(theta, noise / varK or None, varK) of the matrix the likelihood factors (kernel/Kernel.py:128-138,213-237)."""
+        theta = np.asarray(hp_vals.theta, dtype=float)
+        if self.b_has_noisy_data:
+            varK = float(hp_vals.varK)
+            nv = self.calc_noise_vec(hp_vals)
+            return theta, (bk.to_dev(nv / varK) if np.any(nv) else None), varK
+        return theta, None, 1.0
+
+    def _cond_grad_from_vectors(self, hp_vals, res, varK):
+        """dkappa/dhp = (v_max^T dKcov v_max - kappa v_min^T dKcov v_min) / max(lambda_min, 1e-16)
+        (optz/GpHparaCon.py:178-193), the quadratic forms evaluated with dKcov/dhp generated on the fly."""
+        if self.wellcond_mtd == "precon":
+            return None          # the reference has no condition-number gradient in precon mode (:171-173)
+        if res.get("v_max") is None:
+            return np.zeros(self.hp_info_optz_lkd.n_hp)
+        hi, d = self.hp_info_optz_lkd, self.dim
+        theta = np.asarray(hp_vals.theta, dtype=float)
+        noisy = self.b_has_noisy_data
+        kw = dict(n_g=self.n_grad, slot=self._slot_dev, eta=self._etaK, noisy=noisy, varK=varK)
+        qa = bk.quad_grad(self._X_dev, theta, res["v_max"], **kw).cpu().numpy()
+        qi = bk.quad_grad(self._X_dev, theta, res["v_min"], **kw).cpu().numpy()
+        q = (qa - res["cond"] * qi) / max(res["lam_min"], 1e-16)     # lam_min of Kcov (varK included)
+        g = np.zeros(hi.n_hp)
+        if hi.has_theta:
+            g[hi.idx_theta] = q[L.OUT_GRAD:L.OUT_GRAD + d]
+        if noisy:
+            if hi.has_varK:
+                g[hi.idx_varK] = q[L.OUT_DVARK]
+            if hi.has_var_fval:
+                g[hi.idx_var_fval] = q[L.OUT_DVARF]
+            if hi.has_var_fgrad:
+                g[hi.idx_var_fgrad] = q[L.OUT_DVARG]
+        return g
+
+    def _cond_from_workspace(self, hp_vals, calc_grad):
+        """Condition number (+ gradient) of the matrix whose factor L, L^-T and explicit inverse the likelihood
+        evaluation that has just run left in the workspace: the matrix itself is rebuilt into the (no longer needed)
+        L^-T buffer for the lambda_max products, lambda_min comes from products with the inverse."""
+        assert self.cond_norm == 2, "the CUDA path implements the recommended 2-norm condition number"
+        theta, noise, varK = self._cond_matrix_args(hp_vals)
+        v = bk.lml_views(self.n_eval, self.n_grad, self.dim)
+        mode, N = self._mode, self.n_data
+        if self.wellcond_mtd == "precon" and calc_grad:
+            # reference quirk (optz/CalcLkd.py:341-343): with calc_grad the number returned in precon mode is kappa of
+            # the UN-preconditioned Kcov = P Kt P, whose inverse is P^-1 Kt^-1 P^-1
+            mode = L.MODE_PRECON_COV
+            v["Kinv"][:, :N].mul_(v["pinv"][:, None]).mul_(v["pinv"][None, :])
+        bk.build_cov(self._X_dev, theta, n_g=self.n_grad, slot=self._slot_dev, noise=noise, mode=mode,
+                     eta=self._etaK, varK=varK, out=v["U"])
+        res = bk.cond2(v["U"], v["Kinv"], N)
+        self._last_cond = res
+        return float(res["cond"]), (self._cond_grad_from_vectors(hp_vals, res, varK) if calc_grad else None)
+
+    def _cond_on_failure(self, hp_vals, calc_grad=False):
+        """Failed Cholesky: the reference substitutes -cond (and -cond_grad) for the objective (optz/OptzLkd.py:75-77).
+        The matrix is numerically singular; it is factored once more with a tiny diagonal shift (backend.cond2_of_matrix)."""
         try:
-            return self.calc_all_K_w_chofac(None, hp_vals, calc_chofac=False, calc_cond=True,
-                                            varK=None if self.b_has_noisy_data else 1)[4]
+            theta, noise, varK = self._cond_matrix_args(hp_vals)
+            K = bk.build_cov(self._X_dev, theta, n_g=self.n_grad, slot=self._slot_dev, noise=noise, mode=self._mode,
+                             eta=self._etaK, varK=varK)[0]
+            res = bk.cond2_of_matrix(K, self.n_data)
+            self._last_cond = res
+            return float(res["cond"]), (self._cond_grad_from_vectors(hp_vals, res, varK) if calc_grad else None)
         except Exception:
-            return np.inf
+            return np.inf, (np.zeros(self.hp_info_optz_lkd.n_hp) if calc_grad else None)
 
     def calc_lkd_batch(self, hp_vec_rows, calc_grad=False):
         """LML (and d/dtheta) of many noise-free candidate rows at once, sharded over the process group.
@@ -586,8 +654,12 @@ class GaussianProcess:
                     b = self.hp_info_optz_lkd.bvec_log_optz
                     grad = grad.copy()
                     grad[b] *= 10 ** hp_vec[b] * np.log(10)
-            else:
-                val, grad = -cond_val, np.zeros(hp_vec.size)
+                    if self.b_use_cond_cstr and cond_grad is not None:
+                        cond_grad = cond_grad.copy()
+                        cond_grad[b] *= 10 ** hp_vec[b] * np.log(10)
+            else:   # failed Cholesky: the condition number becomes the objective (optz/OptzLkd.py:75-77)
+                val = -cond_val
+                grad = -cond_grad if cond_grad is not None else np.zeros(hp_vec.size)
             self._lkd_val, self._lkd_grad, self._cond_val, self._cond_grad = val, grad, cond_val, cond_grad
             if calc_grad:
                 self._last_hp_vec = hp_vec.copy()
@@ -603,8 +675,7 @@ class GaussianProcess:
         return self.calc_store_likelihood(hp_vec)[2]
 
     def return_cond_grad(self, hp_vec):
-        raise NotImplementedError("condition-number gradient (optz/GpHparaCon.py:161-235) is outside the CUDA hot path; "
-                                  "use wellcond_mtd='precon' for fits")
+        return self.calc_store_likelihood(hp_vec)[3]
 
     # ------------------------------------------------------------------ start points (optz/GpHparaX0.py)
     def get_hp_x0_lhs_median(self, i_optz, hp_optz_info, n_x0):
@@ -699,38 +770,117 @@ class GaussianProcess:
         return hp_vals
 
     def optz_hp_max_lkd(self, hp_x0_all, optz_bound):
+        """optz/OptzLkd.py:185-333: SLSQP from every start row, with the condition-number constraint
+        kappa_2 <= cond_max outside precon mode; the best feasible solution wins."""
         assert self.optz_mtd == "SLSQP", "the reference recommends SLSQP; trust-constr is not wired here"
         opt = {"ftol": self.optz_tol_obj, "eps": self.optz_tol_x, "maxiter": self.optz_iter_max, "disp": False}
         if hp_x0_all.ndim == 1:
             hp_x0_all = hp_x0_all[None, :]
         n_optz = hp_x0_all.shape[0]
         ok = np.zeros(n_optz, bool)
+        con_good = np.zeros(n_optz, bool)
         nit = np.full(n_optz, np.nan)
         obj = np.full(n_optz, np.nan)
+        cond_all = np.full(n_optz, np.nan)
         sol = np.full((n_optz, self.hp_info_optz_lkd.n_hp), np.nan)
-        if self.b_use_cond_cstr:
-            raise NotImplementedError("fits with the condition-number constraint (base / rescale modes) are the next "
-                                      "row of SURVEY 8f; the CUDA fit path is wellcond_mtd='precon'")
+        n_cho_fail = n_cond2big = 0
+        max_init_cond = np.nan
+        nlc = self.condnum_nlc if self.b_use_cond_cstr else []
         for i in range(n_optz):
+            x0 = hp_x0_all[i, :]
             self._last_hp_vec = None
-            res = minimize(self.return_optz_val, hp_x0_all[i, :], method="SLSQP", jac=self.return_optz_grad,
-                           bounds=optz_bound, options=opt)
+            if self.b_use_cond_cstr:
+                lkd_val, _, cond_val = self.calc_store_likelihood(x0)[:3]
+                max_init_cond = np.nanmax((max_init_cond, cond_val))
+                if np.isnan(lkd_val):
+                    n_cho_fail += 1
+                if cond_val > self.cond_max:
+                    n_cond2big += 1
+            self._last_hp_vec = None
+            res = minimize(self.return_optz_val, x0, method="SLSQP", jac=self.return_optz_grad, bounds=optz_bound,
+                           constraints=nlc, options=opt)
             sol[i, :], obj[i], ok[i], nit[i] = res.x, res.fun, res.success, res.nit
-        best = sol[np.nanargmin(obj), :]
+            if self.b_use_cond_cstr:
+                cond_all[i] = self.return_cond_val(res.x)
+                con_good[i] = cond_all[i] < 1.01 * self.cond_max
+            else:
+                con_good[i] = True
+        if np.any(con_good):
+            obj_ok, sol_ok = obj[con_good], sol[con_good, :]
+        else:
+            print("*** No solutions satisfy the constraints for the GP hyperparameter optimization ***")
+            obj_ok, sol_ok = obj, sol
+        best = sol_ok[np.nanargmin(obj_ok), :]
         info = {"hp_optz_success": float(np.mean(ok)), "hp_optz_iter_mean": float(np.mean(nit)),
-                "hp_optz_iter_max": float(np.max(nit)), "hp_optz_con_good": 1.0, "optz_n_cho_fail": 0,
-                "optz_n_cond2big": 0, "optz_max_init_cond": np.nan}
-        return best, np.nan, info
+                "hp_optz_iter_max": float(np.max(nit)), "hp_optz_con_good": float(np.mean(con_good)),
+                "optz_n_cho_fail": n_cho_fail, "optz_n_cond2big": n_cond2big, "optz_max_init_cond": max_init_cond}
+        cond_val = np.nan
+        if self.b_use_cond_cstr:   # final condition number of the chosen solution (:323-331)
+            best_vals = self.hp_vec2dataclass(self.hp_info_optz_lkd, best)
+            cond_val = self.calc_all_K_w_chofac(None, best_vals, calc_chofac=False, calc_cond=True,
+                                                varK=None if self.b_has_noisy_data else 1)[4]
+        return best, cond_val, info
+
+    def rescaling_data_w_theta_sol(self, X_scl_v1, xvec_scale_v1, hp_theta, tol_min_dist_x=1e-15):
+        """base/GpWellCond.py:42-76: anisotropic re-scaling of x by sqrt(theta / geometric-mean theta), corrected so
+        that the minimum pairwise distance is v_req again; returns the isotropic theta estimate in the new coordinates."""
+        from scipy.spatial.distance import pdist
+        assert X_scl_v1.shape[0] > 1, "This method should only be called if n_eval > 1"
+        if self.optz_log_hp_theta:
+            theta_sol, log_theta = 10 ** hp_theta, hp_theta
+        else:
+            theta_sol, log_theta = hp_theta, np.log10(hp_theta)
+        vreq = self.calc_mtd_rescale_origin_vreq(X_scl_v1.shape[0], self.dim)
+        theta_star = 10 ** np.mean(log_theta)
+        scale_v2 = np.sqrt(theta_sol / theta_star)
+        min_dist = max(float(np.min(pdist(X_scl_v1 * scale_v2[None, :]))), tol_min_dist_x)
+        corr = vreq / min_dist
+        dist2 = np.dot(log_theta, log_theta) - np.dot(log_theta, np.ones(self.dim)) ** 2 / self.dim
+        est = np.ones(self.dim) * theta_star / corr ** 2
+        return (np.log10(est) if self.optz_log_hp_theta else est), dist2, xvec_scale_v1 * scale_v2 * corr
+
+    def optz_hp_max_lkd_mtd_rescale(self, i_optz, hp_x0, optz_bound):
+        """optz/OptzLkd.py:116-183: optimise, re-scale x with the solution's theta, optimise again from the isotropic
+        estimate -- up to cond_vreq_max_iter times or until theta is isotropic within cond_vreq_iter_tol."""
+        assert "rescale" in self.wellcond_mtd
+        best_hp, cond_val, info = self.optz_hp_max_lkd(hp_x0, optz_bound)
+        if self.n_eval <= 1:
+            return best_hp, cond_val, info
+        max_iter, idx = self.cond_vreq_max_iter, self.hp_info_optz_lkd.idx_theta
+        theta_all = np.full((max_iter, self.dim), np.nan)
+        dist_all = np.full(max_iter, np.nan)
+        scale_all = np.full((max_iter, self.dim), np.nan)
+        theta_new = best_hp[idx]
+        for cnt in range(max_iter):
+            theta_new, dist, scale_new = self.rescaling_data_w_theta_sol(self.DataScl.x_scl, self.DataScl.xvec_scale,
+                                                                         theta_new)
+            theta_all[cnt, :], dist_all[cnt], scale_all[cnt, :] = theta_new, dist, scale_new
+            if cnt == max_iter - 1 or dist < self.cond_vreq_iter_tol:
+                break
+            x0 = best_hp.copy()
+            x0[idx] = theta_new
+            best_hp, cond_val = self.optz_hp_max_lkd(x0, optz_bound)[:2]
+        k = int(np.nanargmin(dist_all))
+        self.DataScl.set_xscale_data(xvec_scale_in=scale_all[k, :])
+        self._dev_ready = False          # the scaled training data changed: refresh the device copy
+        self._last_hp_vec = None
+        best_final = best_hp.copy()
+        best_final[idx] = theta_all[k, :]
+        return best_final, cond_val, info
 
     def optz_hp(self, i_optz):
         if self.n_eval <= self.hp_const_n_eval:
-            hp_vals, info, cond_val = self.get_init_hp_vals(), None, np.nan
+            hp_vals, info = self.get_init_hp_vals(), None
+            cond_val = self.calc_all_K_w_chofac(None, hp_vals, calc_chofac=False, calc_cond=True)[4]
             t_optz = t_cho = t_x0 = 0
         else:
             self._time_chofac = 0
             hp_x0, bound, t_x0 = self.select_hp_optz_x0(i_optz, self.hp_info_optz_lkd)
             t0 = time.time()
-            hp_optz, cond_val, info = self.optz_hp_max_lkd(hp_x0, bound)
+            if "rescale" in self.wellcond_mtd and self.cond_vreq_max_iter > 1:
+                hp_optz, cond_val, info = self.optz_hp_max_lkd_mtd_rescale(i_optz, hp_x0, bound)
+            else:
+                hp_optz, cond_val, info = self.optz_hp_max_lkd(hp_x0, bound)
             t_optz, t_cho = time.time() - t0, self._time_chofac
             hp_vals = self.optz_closed_form_hp(self.hp_vec2dataclass(self.hp_info_optz_lkd, hp_optz))
         self.store_new_para_surr(i_optz, hp_vals, info, cond_val, t_optz, t_cho, t_x0)

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define GEGP_ABI_VERSION 2
+#define GEGP_ABI_VERSION 3
 
 /* covariance assembly modes (kernel/Kernel.py:220-237 vs :268-277) */
 #define GEGP_MODE_BASE 0       /* varK * (K + diag(noise) + eta*I)                                  */
@@ -73,6 +73,7 @@ int gegp_abi_version(void);
  * choice depends on the shape of one problem only, never on the batch count (bit-identical results across
  * batch sizes and ranks). */
 #define GEGP_OPT_TMA_MIN_TILES 1
+#define GEGP_OPT_LOOKAHEAD 2
 int gegp_set_option(int key, int value);
 
 size_t gegp_workspace_bytes(int op, int n, int n_g, int d, int arg);
@@ -143,6 +144,35 @@ int gegp_predict(int n, int n_g, int d, const double* X, const int32_t* grad_slo
                  const double* A, int64_t lda, const double* dinv, const double* p, int mode, double beta, double varK,
                  const double* Xs, int nx, double* mu, double* sig, double* sig2_out, int* n_negative_dev,
                  void* work, size_t work_bytes, void* stream);
+
+/* Where gegp_lml_eval keeps its per-candidate arrays inside `work` (candidate 0; candidate c adds
+ * c * per_candidate_doubles), so that a caller can go on working with the factor and the explicit inverse of the
+ * evaluation it has just run (condition number, below).  out[8] = { header_bytes, ld, per_candidate_doubles,
+ * offset of A (factor L, lower), of p (p then p^-1, ld apart), of dinv, of U (= L^-T, upper), of Kinv (full inverse) },
+ * offsets in doubles after the header; U and Kinv are -1 unless want_grad. */
+int gegp_lml_layout(int n, int n_g, int d, int want_grad, int B, int64_t* out8);
+
+/* Condition number kappa_2 of the regularised matrix and its hyper-parameter gradient (kernel/Kernel.py:240,280:
+ * np.linalg.cond(., 2); optz/GpHparaCon.py:161-235: full np.linalg.eig, then
+ * dkappa/dhp = (v_max^T dK v_max - kappa v_min^T dK v_min) / lambda_min).  Here the two extreme eigenpairs come from
+ * a Lanczos iteration with full re-orthogonalisation whose kernels are below (the k x k tridiagonal eigenproblem
+ * and the restart loop are host logic): lambda_max from products with K (gegp_symv on the matrix gegp_build_cov
+ * wrote), lambda_min from products with the explicit inverse gegp_lml_eval / gegp_potri left on the device.
+ *   gegp_symv:         y = M x, M row-major N x ld (ld even, M 16-byte aligned).
+ *   gegp_lanczos_step: V[(k+1), ldv] rows 0..j orthonormal, w = M v_j on entry; on exit alpha[j] = v_j.w,
+ *                      beta[j] = |w_orth| (device scalars) and V row j+1 = w_orth / beta[j].   j < 255.
+ *   gegp_lincomb:      out = normalised sum_i coef[i] V_i (Ritz vector), coef[k] on the device, k <= 256.
+ *   gegp_quad_grad:    q_hp = v^T (dKcov/dhp) v for hp = theta_1..theta_d (out[GEGP_OUT_GRAD + m]) and, when
+ *                      noisy, varK / var_fval / var_fgrad (GEGP_OUT_DVARK/DVARF/DVARG), dKcov/dtheta generated on
+ *                      the fly (optz/GpHparaGrad.py:13-56, :58-98).  GEGP_MODE_BASE only (the reference has no
+ *                      condition-number gradient in precon mode).  work >= gegp_quad_grad_work_bytes(n, d). */
+int gegp_symv(int N, const double* M, int64_t ld, const double* x, double* y, void* stream);
+int gegp_lanczos_step(int N, int j, double* V, int64_t ldv, double* w, double* alpha, double* beta, void* stream);
+int gegp_lincomb(int N, int k, const double* V, int64_t ldv, const double* coef, double* out, void* stream);
+size_t gegp_quad_grad_work_bytes(int n, int n_g, int d);
+int gegp_quad_grad(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+                   const double* v, int mode, double eta, int noisy, const double* varK_dev, double* out,
+                   void* work, size_t work_bytes, void* stream);
 
 /* Instrumentation for bench.py (not on the product path): count kernel launches, and (time_gemm != 0)
  * bracket every DMMA GEMM launch with CUDA events on its stream.  gegp_profile_end synchronises the device. */

@@ -457,6 +457,47 @@ def lkd_w_noise(X, fval, grad, theta, varK, noise_vec, mode="precon", eta=None, 
 
 
 # ----------------------------------------------------------------------------------------------
+# condition number and its gradient  (optz/GpHparaCon.py:161-235; kernel/Kernel.py:240,280)
+# ----------------------------------------------------------------------------------------------
+
+def cond_l2_w_grad(Kmat, Kgrad_hp=None):
+    """kappa_2 = np.linalg.cond(K, 2); d kappa/d hp = sum((v_max v_max^T - kappa v_min v_min^T) * dK/dhp)
+    / max(lambda_min, 1e-16) from a full eigen-decomposition (optz/GpHparaCon.py:161-193).  The reference calls the
+    general np.linalg.eig on the symmetric matrix; eigh gives the same extreme pairs with orthonormal vectors."""
+    cond = float(np.linalg.cond(Kmat, p=2))
+    if Kgrad_hp is None:
+        return cond, None
+    w, V = np.linalg.eigh(Kmat)
+    vmax, vmin = V[:, -1], V[:, 0]
+    emin = max(float(w[0]), 1e-16)
+    diff = np.outer(vmax, vmax) - cond * np.outer(vmin, vmin)
+    return cond, np.array([np.sum(diff * Kgrad_hp[i]) / emin for i in range(Kgrad_hp.shape[0])])
+
+
+def cond_wo_noise(X, theta, mode, eta, mask=None, calc_grad=True):
+    """Condition number of the matrix calc_lkd_all factors for noise-free data (K + eta-term, varK := 1) and its
+    theta-gradient (optz/CalcLkd.py:322-343).  The reference has no gradient in precon mode (:171-173)."""
+    ka = all_K_w_chofac(X, theta, mode, eta, None, 1.0, mask, calc_chofac=False)
+    if mode == "precon":
+        # reference quirk: without calc_grad the number is kappa(Kcor + eta I) (kernel/Kernel.py:240); with calc_grad
+        # calc_lkd_all overwrites it with kappa of the UN-preconditioned Kcov = P (Kcor + eta I) P (optz/CalcLkd.py:341)
+        N = ka.Kern.shape[0]
+        return cond_l2_w_grad(ka.Kcov if calc_grad else ka.Kcor + eta * np.eye(N))[0], None
+    return cond_l2_w_grad(ka.Kcov, kerngrad_hp(X, theta, mode, eta, mask) if calc_grad else None)
+
+
+def cond_w_noise(X, theta, varK, noise_vec, mode, eta, has_var_fval=False, has_var_fgrad=False, mask=None,
+                 calc_grad=True):
+    """Noisy-data counterpart: kappa_2(Kcov) and d/d[theta.., varK, var_fval?, var_fgrad?] (optz/CalcLkd.py:299-320)."""
+    ka = all_K_w_chofac(X, theta, mode, eta, noise_vec, varK, mask, calc_chofac=False)
+    if mode == "precon":   # same quirk as cond_wo_noise
+        N = ka.Kern.shape[0]
+        return cond_l2_w_grad(ka.Kcov if calc_grad else varK * (ka.Kcor + eta * np.eye(N)))[0], None
+    D = kcov_grad_hp_noisy(X, theta, ka.Kern, mode, eta, varK, has_var_fval, has_var_fgrad, mask)
+    return cond_l2_w_grad(ka.Kcov, D)
+
+
+# ----------------------------------------------------------------------------------------------
 # posterior  (eval/GpEvalModel.py:17-57, 59-198)
 # ----------------------------------------------------------------------------------------------
 

@@ -1,0 +1,84 @@
+"""Generate tests/golden/cond_*.npz by running the REFERENCE: 2-norm condition number of the factored matrix and its
+hyper-parameter gradient (optz/GpHparaCon.py:161-235 through calc_lkd_all(calc_cond=True, calc_grad=True)), and
+one hyper-parameter fit per conditioning mode with the condition-number constraint (optz/OptzLkd.py:185-333).
+
+TEST INFRASTRUCTURE ONLY; runs in the build container (needs /root/reference).
+
+    python oracle/make_golden_cond.py
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(HERE, "ref_shim"))
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+from gpgradpy.src.GaussianProcess import GaussianProcess  # noqa: E402  (the reference)
+from oracle import gegp_oracle as O  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b)) / max(1e-300, float(np.max(np.abs(b)))))
+
+
+def case_cond(name, n, d, mode, theta, seed=0, lo=-2.0, hi=2.0, std_f=0.0, std_g=0.0, varK=None):
+    x, f, g = O.synthetic_problem(n, d, seed, lo, hi)
+    GP = GaussianProcess(d, True, "SqExp", mode)
+    GP.set_data(x, f, std_f * np.ones(n), g, std_g * np.ones(g.shape))
+    th = np.asarray(theta, float)
+    hp = GP.make_hp_class(theta=th, varK=varK)
+    info, ok = GP.calc_lkd_all(hp, calc_cond=True, calc_grad=True)
+    cond_nograd = GP.calc_lkd_all(hp, calc_cond=True, calc_grad=False)[0].cond
+    xs = GP.get_scl_x_w_dist()[0]
+    fs, _, gs, _ = GP.get_scl_eval_data()
+    out = dict(x=x, fval=f, grad=g, theta=th, mode=mode, eta=GP._etaK, ok=ok, cond=info.cond, cond_nograd=cond_nograd, x_scl=xs, fval_scl=fs,
+               grad_scl=gs, std_f=std_f, std_g=std_g, varK=np.nan if varK is None else varK,
+               ln_lkd=info.ln_lkd, ln_lkd_grad=info.ln_lkd_grad)
+    if info.cond_grad is not None:
+        out["cond_grad"] = info.cond_grad
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    if varK is None:
+        c, cg = O.cond_wo_noise(xs, th, mode, GP._etaK)
+    else:
+        c, cg = O.cond_w_noise(xs, th, varK, GP.calc_noise_vec(hp), mode, GP._etaK)
+    c0 = (O.cond_wo_noise(xs, th, mode, GP._etaK, calc_grad=False)[0] if varK is None else
+          O.cond_w_noise(xs, th, varK, GP.calc_noise_vec(hp), mode, GP._etaK, calc_grad=False)[0])
+    print(name, f"cond {info.cond:.6e} oracle rel {rel(c, info.cond):.2e} nograd {cond_nograd:.6e} rel {rel(c0, cond_nograd):.2e}",
+          "" if info.cond_grad is None else f"grad rel {rel(cg, info.cond_grad):.2e}", flush=True)
+
+
+def case_fit(name, n, d, mode, seed=1):
+    """set_hpara('optz') with the history protocol of SURVEY appendix B.12; stores the start point the reference's
+    40-candidate scan picked, so that both implementations can be started from the same x0."""
+    x, f, g = O.synthetic_problem(n, d, seed)
+    GP = GaussianProcess(d, True, "SqExp", mode)
+    GP.init_optz_surr(3)
+    GP.set_data(x[:1], f[:1], np.zeros(1), g[:1], np.zeros((1, d)))
+    GP.set_hpara("optz", 0)
+    GP.set_data(x, f, np.zeros(n), g, np.zeros((n, d)))
+    hp_x0, bound, _ = GP.select_hp_optz_x0(1, GP.hp_info_optz_lkd)
+    GP.set_hpara("optz", 1)
+    hp = GP.hp_vals
+    info, ok = GP.calc_lkd_all(hp, calc_cond=True, calc_grad=False)
+    out = dict(x=x, fval=f, grad=g, mode=mode, hp_x0=hp_x0, lb=bound.lb, ub=bound.ub, theta=hp.theta, varK=hp.varK,
+               beta=hp.beta, ln_lkd=info.ln_lkd, cond=info.cond, eta=GP._etaK,
+               xvec_scale=GP.DataScl.xvec_scale if GP.b_use_data_scl else np.ones(d))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "theta", hp.theta, "lml", info.ln_lkd, "cond", f"{info.cond:.3e}", flush=True)
+
+
+if __name__ == "__main__":
+    case_cond("cond_d2_n12_base", 12, 2, "base", [0.6, 1.4])
+    case_cond("cond_d3_n20_base", 20, 3, "base", [0.9, 0.5, 1.6], seed=1)
+    case_cond("cond_d2_n16_rescale_origin", 16, 2, "rescale_origin", [0.5, 0.9], seed=2)
+    case_cond("cond_d3_n14_precon", 14, 3, "precon", [0.3, 0.2, 0.5], seed=3)
+    case_cond("cond_d2_n14_noisy_base", 14, 2, "base", [0.7, 1.1], seed=4, std_f=1e-2, std_g=5e-2, varK=40.0)
+    case_cond("cond_d4_n40_base_illcond", 40, 4, "base", [0.02, 0.03, 0.05, 0.04], seed=5)
+    case_fit("fit_d2_n20_base", 20, 2, "base")
+    case_fit("fit_d2_n20_rescale_origin", 20, 2, "rescale_origin")

@@ -121,3 +121,29 @@ def test_nugget_formulas(golden_dir):
         g = _load(golden_dir, name)
         n, d = g["x"].shape
         assert _rel(O.nugget(n, d, mode)[1], g["eta"]) < 1e-15
+
+
+COND = [("cond_d2_n12_base", 1e-9), ("cond_d3_n20_base", 1e-10), ("cond_d2_n16_rescale_origin", 1e-10),
+        ("cond_d3_n14_precon", 1e-8), ("cond_d2_n14_noisy_base", 1e-8), ("cond_d4_n40_base_illcond", 1e-5)]
+
+
+@pytest.mark.parametrize("name,tol", COND)
+def test_condition_number_and_gradient(golden_dir, name, tol):
+    """kappa_2 and d kappa / d hp (optz/GpHparaCon.py:161-235) as calc_lkd_all(calc_cond=True) returns them; the
+    tolerance follows eps * kappa (lambda_min is only known to an absolute eps * lambda_max)."""
+    g = _load(golden_dir, name)
+    mode, eta = str(g["mode"]), float(g["eta"])
+    if np.isnan(g["varK"]):
+        c, cg = O.cond_wo_noise(g["x_scl"], g["theta"], mode, eta)
+        c0 = O.cond_wo_noise(g["x_scl"], g["theta"], mode, eta, calc_grad=False)[0]
+    else:
+        n, d = g["x"].shape
+        noise = np.hstack((np.full(n, float(g["std_f"]) ** 2), np.full(n * d, float(g["std_g"]) ** 2)))
+        c, cg = O.cond_w_noise(g["x_scl"], g["theta"], float(g["varK"]), noise, mode, eta)
+        c0 = O.cond_w_noise(g["x_scl"], g["theta"], float(g["varK"]), noise, mode, eta, calc_grad=False)[0]
+    assert abs(c - g["cond"]) < tol * g["cond"]
+    assert abs(c0 - g["cond_nograd"]) < tol * g["cond_nograd"]
+    if "cond_grad" in g:
+        assert np.max(np.abs(cg - g["cond_grad"])) < 10 * tol * np.max(np.abs(g["cond_grad"]))
+    else:
+        assert cg is None and mode == "precon"
