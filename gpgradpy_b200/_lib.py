@@ -22,7 +22,7 @@ OPT_LOOKAHEAD = 2
 EXPORTS = (
     "gegp_abi_version", "gegp_set_option", "gegp_workspace_bytes", "gegp_ld", "gegp_build_cov", "gegp_cross_cov", "gegp_potrf",
     "gegp_trsm_rows", "gegp_dinv_doubles", "gegp_potri", "gegp_dgemm", "gegp_lml_eval", "gegp_predict_setup", "gegp_predict", "gegp_profile_begin", "gegp_profile_end",
-    "gegp_lml_layout", "gegp_symv", "gegp_lanczos_step", "gegp_lincomb", "gegp_quad_grad_work_bytes", "gegp_quad_grad",
+    "gegp_lml_layout", "gegp_symv", "gegp_row_abs_sum", "gegp_lanczos_step", "gegp_lincomb", "gegp_quad_grad_work_bytes", "gegp_quad_grad",
 )
 
 
@@ -77,6 +77,8 @@ def load():
     lib.gegp_lml_layout.argtypes = [i, i, i, i, i, C.POINTER(i64)]
     lib.gegp_symv.restype = i
     lib.gegp_symv.argtypes = [i, dp, i64, dp, dp, vp]
+    lib.gegp_row_abs_sum.restype = i
+    lib.gegp_row_abs_sum.argtypes = [i, dp, i64, dp, vp]
     lib.gegp_lanczos_step.restype = i
     lib.gegp_lanczos_step.argtypes = [i, i, dp, i64, dp, dp, dp, vp]
     lib.gegp_lincomb.restype = i

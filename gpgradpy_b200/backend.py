@@ -343,6 +343,14 @@ def symv(M: torch.Tensor, x: torch.Tensor, y: torch.Tensor, N: int):
     return y
 
 
+def row_abs_sum(M: torch.Tensor, N: int) -> torch.Tensor:
+    """Gershgorin row sums sum_c |M[r, c]| of an [N, ld] device buffer (gegp_row_abs_sum)."""
+    out = torch.empty(N, dtype=F64, device=M.device)
+    rc = L.load().gegp_row_abs_sum(N, _p(M), M.stride(0), _p(out), _stream())
+    _check(rc, "gegp_row_abs_sum")
+    return out
+
+
 def extreme_eig(M: torch.Tensor, N: int, *, k: int = 40, tol: float = 1e-12, max_cycles: int = 12, v0=None):
     """Largest eigenpair of the symmetric device matrix M[:N, :N]: restarted Lanczos with full re-orthogonalisation.
 

@@ -370,6 +370,15 @@ int gegp_symv(int N, const double* M, int64_t ld, const double* x, double* y, vo
   return symv_full(ctx, N, M, ld, x, y);
 }
 
+int gegp_row_abs_sum(int N, const double* M, int64_t ld, double* out, void* stream) {
+  if (N <= 0) return -1;
+  if (!M || (reinterpret_cast<uintptr_t>(M) & 15)) return -2;
+  if (ld < N || (ld & 1)) return -3;
+  if (!out) return -4;
+  Ctx ctx{(cudaStream_t)stream, 1};
+  return row_abs_sum(ctx, N, M, ld, out);
+}
+
 int gegp_lanczos_step(int N, int j, double* V, int64_t ldv, double* w, double* alpha, double* beta, void* stream) {
   if (N <= 0) return -1;
   if (j < 0 || j >= 255) return -2;

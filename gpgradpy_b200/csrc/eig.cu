@@ -32,6 +32,26 @@ symv_kernel(int N, const double* __restrict__ M, int64_t ld, const double* __res
   if (lane == 0) y[row] = s;
 }
 
+// out[row] = sum_c |M[row, c]| : the Gershgorin row sums behind the variable nugget
+// eta = max_row sum|K| / (cond_max_target - 1)  (kernel/Kernel.py:229-234, 269-274).
+__global__ void __launch_bounds__(SYMV_ROWS * 32)
+row_abs_sum_kernel(int N, const double* __restrict__ M, int64_t ld, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int row = blockIdx.x * SYMV_ROWS + w;
+  if (row >= N) return;
+  const double* mr = M + (int64_t)row * ld;
+  double s0 = 0.0, s1 = 0.0;
+  const int N2 = N & ~1;
+  for (int c = 2 * lane; c < N2; c += 64) {
+    const double2 m = *reinterpret_cast<const double2*>(mr + c);
+    s0 += fabs(m.x);
+    s1 += fabs(m.y);
+  }
+  if ((N & 1) && lane == 0) s0 += fabs(mr[N - 1]);
+  const double s = warp_sum(s0 + s1);
+  if (lane == 0) out[row] = s;
+}
+
 // One Lanczos step in ONE CTA (fixed reduction order: deterministic).  On entry V rows 0..j hold the orthonormal
 // basis and w = M v_j.  alpha_j = v_j . w ;  w -= alpha_j v_j + beta_{j-1} v_{j-1} ;  two classical Gram-Schmidt
 // sweeps against v_0..v_j ;  beta_j = |w| ;  v_{j+1} = w / beta_j.
@@ -106,6 +126,13 @@ lincomb_kernel(int N, int k, const double* __restrict__ V, int64_t ldv, const do
 int symv_full(const Ctx& ctx, int N, const double* M, int64_t ld, const double* x, double* y) {
   if (N <= 0) return 0;
   symv_kernel<<<(N + SYMV_ROWS - 1) / SYMV_ROWS, SYMV_ROWS * 32, 0, ctx.stream>>>(N, M, ld, x, y);
+  GEGP_CHECK_LAUNCH();
+  return 0;
+}
+
+int row_abs_sum(const Ctx& ctx, int N, const double* M, int64_t ld, double* out) {
+  if (N <= 0) return 0;
+  row_abs_sum_kernel<<<(N + SYMV_ROWS - 1) / SYMV_ROWS, SYMV_ROWS * 32, 0, ctx.stream>>>(N, M, ld, out);
   GEGP_CHECK_LAUNCH();
   return 0;
 }

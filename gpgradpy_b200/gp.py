@@ -443,11 +443,8 @@ class GaussianProcess:
             assert self.use_grad is True, "self.wellcond_mtd should be base if use_grad is False"
         if self.cond_eta_is_const:
             etaK = self._etaK
-        else:  # variable nugget from Gershgorin row sums (kernel/Kernel.py:229-234, 269-274)
-            M = bk.build_cov(X, theta, noise=noise, mode=L.MODE_PRECON, eta=0.0, **kw)[0] if precon else Kern
-            rs = torch.sum(torch.abs(M), dim=1)
-            idx_etaK_argmax = int(torch.argmax(rs).item())
-            etaK = float(rs[idx_etaK_argmax].item()) / (self.cond_max_target - 1)
+        else:
+            etaK, idx_etaK_argmax = self._variable_eta(theta, noise, Kern)
         if precon:
             Kt, p = bk.build_cov(X, theta, noise=noise, mode=L.MODE_PRECON, eta=etaK, varK=varK, **kw)
             Kcor = DeviceMatrix(Kt / varK - etaK * torch.eye(N, dtype=Kt.dtype, device=Kt.device))
@@ -479,6 +476,26 @@ class GaussianProcess:
         self._time_chofac += time.time() - t0
         return DeviceMatrix(Kern), Kcor, Kcov, Kcov_chofac, condK, etaK, idx_etaK_argmax
 
+    def _variable_eta(self, theta, noise_div, Kern=None):
+        """Variable nugget from the Gershgorin row sums of Kcor (precon) or of the noise-free Kern (otherwise):
+        eta = max_row sum|.| / (cond_max_target - 1)  (kernel/Kernel.py:229-234, 269-274) -> (eta, argmax row)."""
+        self._ensure_device()
+        kw = dict(n_g=self.n_grad, slot=self._slot_dev)
+        if self.wellcond_mtd == "precon":
+            M = bk.build_cov(self._X_dev, theta, noise=noise_div, mode=L.MODE_PRECON, eta=0.0, **kw)[0]
+        else:
+            M = Kern if Kern is not None else bk.build_cov(self._X_dev, theta, mode=L.MODE_BASE, eta=0.0, **kw)[0]
+        rs = bk.row_abs_sum(M, self.n_data).cpu().numpy()
+        idx = int(np.argmax(rs))
+        return float(rs[idx]) / (self.cond_max_target - 1), idx
+
+    def _eta_for(self, hp_vals):
+        """The nugget the likelihood uses at these hyper-parameters (constant, or Gershgorin-based)."""
+        if self.cond_eta_is_const:
+            return self._etaK
+        theta, noise_div, _ = self._cond_matrix_args(hp_vals)
+        return self._variable_eta(theta, noise_div)[0]
+
     # ------------------------------------------------------------------ likelihood
     def calc_lkd_varK_pnlt(self, varK, fval_vec):
         """optz/CalcLkd.py:118-133."""
@@ -488,16 +505,16 @@ class GaussianProcess:
         mx = max(varK - self.lkd_varK_pnlt_c2 * var_fval, 0)
         return self.lkd_varK_pnlt_c1 * var_fval * mx ** 2, 2 * self.lkd_varK_pnlt_c1 * var_fval * mx
 
-    def _eval_rows(self, theta_rows, *, want_grad, varK_rows=None, noise_vec=None, pnlt_grad=0.0):
+    def _eval_rows(self, theta_rows, *, want_grad, varK_rows=None, noise_vec=None, pnlt_grad=0.0, eta=None):
         """Device evaluation of B candidate rows -> torch [B, 9+d] (see GEGP_OUT_* in include/gegp.h).
 
         Noise-free evaluations of a fixed data set replay a captured CUDA graph (the optimiser repeats the same-shaped
         evaluation hundreds of times); everything else goes through the plain stream path."""
         self._ensure_device()
-        kw = dict(n_g=self.n_grad, slot=self._slot_dev, mode=self._mode, eta=self._etaK, pnlt_grad=pnlt_grad,
-                  want_grad=want_grad)
+        kw = dict(n_g=self.n_grad, slot=self._slot_dev, mode=self._mode, eta=self._etaK if eta is None else eta,
+                  pnlt_grad=pnlt_grad, want_grad=want_grad)
         single = int(np.prod(tuple(theta_rows.shape))) == self.dim   # one candidate: the optimiser's inner loop
-        if self.use_cuda_graphs and single and noise_vec is None and pnlt_grad == 0.0:
+        if self.use_cuda_graphs and single and noise_vec is None and pnlt_grad == 0.0 and eta is None:
             th = theta_rows if hasattr(theta_rows, "is_cuda") else np.asarray(theta_rows, dtype=float)
             return bk.lml_eval_graphed(self._X_dev, self._y_dev, th, **kw)
         out, _ = bk.lml_eval(self._X_dev, self._y_dev, theta_rows, noise=noise_vec, varK_batch=varK_rows, **kw)
@@ -509,15 +526,18 @@ class GaussianProcess:
         With calc_cond the 2-norm condition number of the factored matrix (and, outside precon mode, its
         hyper-parameter gradient, optz/GpHparaCon.py:161-235) is computed on the device from the factor and the
         explicit inverse this very evaluation leaves in the workspace."""
-        assert self.cond_eta_is_const, "variable-nugget LML is not on the CUDA path yet (SURVEY 8f item 3)"
         theta = np.asarray(hp_vals.theta, dtype=float)
         d = self.dim
         need_inv = calc_grad or calc_cond      # the condition number iterates with the explicit inverse
+        # variable nugget (rescale_eta_vary): eta follows the matrix; like the reference, its theta-dependence is not
+        # differentiated (optz/GpHparaGrad.py:40-50 uses the constant _etaK, and only in precon mode)
+        eta = None if self.cond_eta_is_const else self._eta_for(hp_vals)
+        self._eta_used = self._etaK if eta is None else eta
         hi = self.hp_info_optz_lkd
         if self.b_has_noisy_data:
             noise = self.calc_noise_vec(hp_vals)
             o = self._eval_rows(theta[None, :], want_grad=need_inv, varK_rows=np.array([hp_vals.varK]),
-                                noise_vec=noise).cpu().numpy()[0]
+                                noise_vec=noise, eta=eta).cpu().numpy()[0]
             if o[L.OUT_INFO] != 0:
                 cond, cond_grad = self._cond_on_failure(hp_vals, calc_grad)
                 return LkdInfo(cond=cond, cond_grad=cond_grad), False
@@ -538,9 +558,9 @@ class GaussianProcess:
             return info, True
         pn_val = pn_grad = 0.0
         if self.lkd_varK_pnlt_use:   # the penalty slope depends on sigma^2: one value-only pass first
-            o0 = self._eval_rows(theta[None, :], want_grad=False).cpu().numpy()[0]
+            o0 = self._eval_rows(theta[None, :], want_grad=False, eta=eta).cpu().numpy()[0]
             pn_val, pn_grad = self.calc_lkd_varK_pnlt(o0[L.OUT_SIGMA2], self.get_scl_eval_data()[0])
-        o = self._eval_rows(theta[None, :], want_grad=need_inv, pnlt_grad=pn_grad).cpu().numpy()[0]
+        o = self._eval_rows(theta[None, :], want_grad=need_inv, pnlt_grad=pn_grad, eta=eta).cpu().numpy()[0]
         if o[L.OUT_INFO] != 0:
             cond, cond_grad = self._cond_on_failure(hp_vals, calc_grad)
             return LkdInfo(cond=cond, cond_grad=cond_grad), False
@@ -573,7 +593,7 @@ class GaussianProcess:
         hi, d = self.hp_info_optz_lkd, self.dim
         theta = np.asarray(hp_vals.theta, dtype=float)
         noisy = self.b_has_noisy_data
-        kw = dict(n_g=self.n_grad, slot=self._slot_dev, eta=self._etaK, noisy=noisy, varK=varK)
+        kw = dict(n_g=self.n_grad, slot=self._slot_dev, eta=getattr(self, "_eta_used", self._etaK), noisy=noisy, varK=varK)
         qa = bk.quad_grad(self._X_dev, theta, res["v_max"], **kw).cpu().numpy()
         qi = bk.quad_grad(self._X_dev, theta, res["v_min"], **kw).cpu().numpy()
         q = (qa - res["cond"] * qi) / max(res["lam_min"], 1e-16)     # lam_min of Kcov (varK included)
@@ -603,7 +623,7 @@ class GaussianProcess:
             mode = L.MODE_PRECON_COV
             v["Kinv"][:, :N].mul_(v["pinv"][:, None]).mul_(v["pinv"][None, :])
         bk.build_cov(self._X_dev, theta, n_g=self.n_grad, slot=self._slot_dev, noise=noise, mode=mode,
-                     eta=self._etaK, varK=varK, out=v["U"])
+                     eta=getattr(self, "_eta_used", self._etaK), varK=varK, out=v["U"])
         res = bk.cond2(v["U"], v["Kinv"], N)
         self._last_cond = res
         return float(res["cond"]), (self._cond_grad_from_vectors(hp_vals, res, varK) if calc_grad else None)
@@ -614,7 +634,7 @@ class GaussianProcess:
         try:
             theta, noise, varK = self._cond_matrix_args(hp_vals)
             K = bk.build_cov(self._X_dev, theta, n_g=self.n_grad, slot=self._slot_dev, noise=noise, mode=self._mode,
-                             eta=self._etaK, varK=varK)[0]
+                             eta=getattr(self, "_eta_used", self._etaK), varK=varK)[0]
             res = bk.cond2_of_matrix(K, self.n_data)
             self._last_cond = res
             return float(res["cond"]), (self._cond_grad_from_vectors(hp_vals, res, varK) if calc_grad else None)
@@ -954,11 +974,14 @@ class GaussianProcess:
         noise = self.calc_noise_vec(hp)   # NOT divided by varK: the reference sets varK = 1 first (kernel/Kernel.py:196-197,218)
         noise = None if not np.any(noise) else noise
         beta = float(np.atleast_1d(hp.beta)[0])
+        eta = self._etaK
+        if not self.cond_eta_is_const:   # variable nugget: Gershgorin row sums with varK := 1 (kernel/Kernel.py:196-197)
+            eta = self._variable_eta(np.asarray(hp.theta, dtype=float), None if noise is None else bk.to_dev(noise))[0]
         self._pred = bk.predict_setup(self._X_dev, self._y_dev, np.asarray(hp.theta, dtype=float), beta,
                                       n_g=self.n_grad, slot=self._slot_dev, noise=noise, mode=self._mode,
-                                      eta=self._etaK)
+                                      eta=eta)
         self.data_vec = self._y_host
-        self.etaK_eval = self._etaK
+        self.etaK_eval = eta
         self.condK = None
         if calc_cond:
             self.condK = self.calc_all_K_w_chofac(None, hp, b_normlz_w_varK=True, calc_chofac=False, calc_cond=True)[4]

@@ -167,6 +167,9 @@ int gegp_lml_layout(int n, int n_g, int d, int want_grad, int B, int64_t* out8);
  *                      the fly (optz/GpHparaGrad.py:13-56, :58-98).  GEGP_MODE_BASE only (the reference has no
  *                      condition-number gradient in precon mode).  work >= gegp_quad_grad_work_bytes(n, d). */
 int gegp_symv(int N, const double* M, int64_t ld, const double* x, double* y, void* stream);
+/* out[row] = sum_c |M[row, c]|: Gershgorin row sums of the built matrix for the variable nugget
+ * eta = max_row / (cond_max_target - 1) of wellcond_mtd = 'rescale_eta_vary' (kernel/Kernel.py:229-234, 269-274). */
+int gegp_row_abs_sum(int N, const double* M, int64_t ld, double* out, void* stream);
 int gegp_lanczos_step(int N, int j, double* V, int64_t ldv, double* w, double* alpha, double* beta, void* stream);
 int gegp_lincomb(int N, int k, const double* V, int64_t ldv, const double* coef, double* out, void* stream);
 size_t gegp_quad_grad_work_bytes(int n, int n_g, int d);

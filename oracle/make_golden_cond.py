@@ -53,6 +53,26 @@ def case_cond(name, n, d, mode, theta, seed=0, lo=-2.0, hi=2.0, std_f=0.0, std_g
           "" if info.cond_grad is None else f"grad rel {rel(cg, info.cond_grad):.2e}", flush=True)
 
 
+def case_eta_vary(name, n, d, theta, seed=0):
+    """wellcond_mtd='rescale_eta_vary': nugget from the Gershgorin row sums (kernel/Kernel.py:269-274), v_min = 1 data."""
+    x, f, g = O.synthetic_problem(n, d, seed)
+    GP = GaussianProcess(d, True, "SqExp", "rescale_eta_vary")
+    GP.set_data(x, f, np.zeros(n), g, np.zeros((n, d)))
+    th = np.asarray(theta, float)
+    hp = GP.make_hp_class(theta=th)
+    info, ok = GP.calc_lkd_all(hp, calc_cond=True, calc_grad=True)
+    xs, Rt = GP.get_scl_x_w_dist()
+    eta, idx = GP.calc_all_K_w_chofac(Rt, hp, varK=1)[5:7]
+    rng = np.random.default_rng(11)
+    xt = rng.uniform(-2, 2, (12, d))
+    GP.set_hpara("set", 1, GP.make_hp_class(theta=th, varK=info.hp_varK, beta=info.hp_beta))
+    mu, sig = GP.eval_model(xt)[:2]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), x=x, fval=f, grad=g, theta=th, eta=eta, idx=idx, ok=ok,
+                        ln_lkd=info.ln_lkd, ln_lkd_grad=info.ln_lkd_grad, hp_varK=info.hp_varK, hp_beta=info.hp_beta,
+                        cond=info.cond, cond_grad=info.cond_grad, x_test=xt, mu=mu, sig=sig, x_scl=xs)
+    print(name, "eta", eta, "idx", idx, "lml", info.ln_lkd, "cond", info.cond, flush=True)
+
+
 def case_fit(name, n, d, mode, seed=1):
     """set_hpara('optz') with the history protocol of SURVEY appendix B.12; stores the start point the reference's
     40-candidate scan picked, so that both implementations can be started from the same x0."""
@@ -80,5 +100,8 @@ if __name__ == "__main__":
     case_cond("cond_d3_n14_precon", 14, 3, "precon", [0.3, 0.2, 0.5], seed=3)
     case_cond("cond_d2_n14_noisy_base", 14, 2, "base", [0.7, 1.1], seed=4, std_f=1e-2, std_g=5e-2, varK=40.0)
     case_cond("cond_d4_n40_base_illcond", 40, 4, "base", [0.02, 0.03, 0.05, 0.04], seed=5)
+    case_eta_vary("etavary_d3_n18", 18, 3, [0.4, 0.7, 0.3], seed=6)
+    if "--no-fit" in sys.argv:
+        sys.exit(0)
     case_fit("fit_d2_n20_base", 20, 2, "base")
     case_fit("fit_d2_n20_rescale_origin", 20, 2, "rescale_origin")

@@ -170,3 +170,25 @@ def test_constrained_fit_vs_reference(golden_dir, name):
     # the whole public path as well
     GP.set_hpara("optz", 1)
     assert GP.hp_vals.varK > 0 and np.isfinite(GP.Kcov_cond_all[1])
+
+
+def test_variable_nugget_mode(golden_dir):
+    """wellcond_mtd='rescale_eta_vary': Gershgorin nugget from the device row sums (gegp_row_abs_sum), then LML,
+    gradient, condition number and posterior against the reference."""
+    from gpgradpy_b200.gp import GaussianProcess
+    g = _load(golden_dir, "etavary_d3_n18")
+    n, d = g["x"].shape
+    GP = GaussianProcess(d, True, "SqExp", "rescale_eta_vary")
+    GP.set_data(g["x"], g["fval"], np.zeros(n), g["grad"], np.zeros((n, d)))
+    hp = GP.make_hp_class(theta=g["theta"])
+    tup = GP.calc_all_K_w_chofac(None, hp, varK=1)
+    assert abs(tup[5] - g["eta"]) < 1e-12 * g["eta"] and tup[6] == int(g["idx"])
+    info, ok = GP.calc_lkd_all(hp, calc_cond=True, calc_grad=True)
+    assert ok and abs(info.ln_lkd - g["ln_lkd"]) < 1e-8 * abs(g["ln_lkd"])
+    assert np.max(np.abs(info.ln_lkd_grad - g["ln_lkd_grad"])) < 1e-8 * np.max(np.abs(g["ln_lkd_grad"]))
+    assert abs(info.cond - g["cond"]) < 1e-8 * g["cond"]
+    assert np.max(np.abs(info.cond_grad - g["cond_grad"])) < 1e-7 * np.max(np.abs(g["cond_grad"]))
+    GP.set_hpara("set", 1, GP.make_hp_class(theta=g["theta"], varK=float(g["hp_varK"]), beta=g["hp_beta"]))
+    mu, sig = GP.eval_model(g["x_test"])[:2]
+    assert np.max(np.abs(mu - g["mu"])) < 1e-8 * np.max(np.abs(g["mu"]))
+    assert np.max(np.abs(sig - g["sig"])) < 1e-6 * np.max(np.abs(g["sig"]))

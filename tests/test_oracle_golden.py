@@ -147,3 +147,16 @@ def test_condition_number_and_gradient(golden_dir, name, tol):
         assert np.max(np.abs(cg - g["cond_grad"])) < 10 * tol * np.max(np.abs(g["cond_grad"]))
     else:
         assert cg is None and mode == "precon"
+
+
+def test_variable_nugget(golden_dir):
+    """rescale_eta_vary: data rescaled to v_min = 1 (GaussianProcess.py:348-350), eta = max Gershgorin row sum /
+    (cond_max_target - 1) (kernel/Kernel.py:269-274); LML and gradient with that nugget."""
+    g = _load(golden_dir, "etavary_d3_n18")
+    xs, fs, gs = O.rescale_origin(g["x"], g["fval"], g["grad"], 1.0)[:3]
+    assert np.max(np.abs(xs - g["x_scl"])) < 1e-13 * np.max(np.abs(g["x_scl"]))
+    ka = O.all_K_w_chofac(xs, g["theta"], "rescale_eta_vary", None, eta_is_const=False)
+    assert abs(ka.eta - g["eta"]) < 1e-12 * g["eta"] and ka.idx_eta_argmax == int(g["idx"])
+    o = O.lkd_wo_noise(xs, fs, gs, g["theta"], "base", ka.eta)
+    assert abs(o.ln_lkd - g["ln_lkd"]) < 1e-9 * abs(g["ln_lkd"])
+    assert np.max(np.abs(o.ln_lkd_grad - g["ln_lkd_grad"])) < 1e-8 * np.max(np.abs(g["ln_lkd_grad"]))
