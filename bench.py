@@ -255,10 +255,17 @@ def run_b200(args):
         run = lambda grad: bk.lml_eval(Xd, yd, thd, mode=L.MODE_PRECON, eta=eta_, want_grad=grad)  # noqa: E731
         run(True)
         ms_grad, ms_val = ev_ms(lambda: run(True), reps), ev_ms(lambda: run(False), reps)
-        L.profile_begin(True)
-        for _ in range(reps):
+        # per-launch GEMM timing: with the look-ahead on, GEMMs of different streams overlap and their event-bracketed
+        # durations would count the same wall time more than once, so this pass runs the single-stream schedule
+        old_la = L.load().gegp_set_option(L.OPT_LOOKAHEAD, 0)
+        try:
             run(True)
-        pr = L.profile_end()
+            L.profile_begin(True)
+            for _ in range(reps):
+                run(True)
+            pr = L.profile_end()
+        finally:
+            L.load().gegp_set_option(L.OPT_LOOKAHEAD, old_la)
         gemm_ms = pr["gemm_ms"] / reps
         ld = bk.ld_of(N_)
         buf = torch.empty((N_ + 2, ld), dtype=torch.float64, device="cuda")
@@ -307,7 +314,8 @@ def run_b200(args):
                 "traffic": traffic,
                 "algorithmic_flops_per_eval": float(N) ** 3,
                 "note": "achieved = N^3 (SURVEY 8d: N^3/3 factor + 2N^3/3 inverse) / summed CUDA-event duration of all "
-                        "GEMM launches of one evaluation; traffic = dram bytes of ONE captured launch of the dominant kernel "
+                        "GEMM launches of one evaluation (timed on the single-stream schedule: with the look-ahead on, "
+                        "launches of different streams overlap); traffic = dram bytes of ONE captured launch of the dominant kernel "
                         "(profiles/r01/ncu_full_summary_v2.txt); peak = measured fp64 DMMA issue peak of this pool's B200 "
                         "(profiles/r01/dmma_peak.log; cuBLAS DGEMM reaches %.2f); MEASURED_PEAKS.json has no fp64 entry"
                         % FP64_DGEMM_TFLOPS,

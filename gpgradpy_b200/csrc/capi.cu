@@ -149,6 +149,12 @@ int gegp_set_option(int key, int value) {
     tma_min_tiles() = value;
     return old;
   }
+  if (key == GEGP_OPT_SMALL_TILE_MAX) {
+    if (value < 0) return -2;
+    const int old = small_tile_max();
+    small_tile_max() = value;
+    return old;
+  }
   if (key == GEGP_OPT_LOOKAHEAD) {
     const int old = lookahead_enabled();
     lookahead_enabled() = value ? 1 : 0;

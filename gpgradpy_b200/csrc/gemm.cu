@@ -238,6 +238,12 @@ int& tma_min_tiles() {
   return g_tma_min_tiles;
 }
 
+static int g_small_tile_max = -1;
+int& small_tile_max() {
+  if (g_small_tile_max < 0) g_small_tile_max = getenv("GEGP_SMALL_TILES") ? atoi(getenv("GEGP_SMALL_TILES")) : 36;
+  return g_small_tile_max;
+}
+
 GemmArgs gemm_args(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
                    int M, int N, int K, double alpha, double beta, bool b_kcont) {
   GemmArgs g{};
@@ -285,6 +291,16 @@ int gemm_f64(const Ctx& ctx, GemmArgs g) {
   }
   if (g.b_kcont) {
     if (big) return launch_cfg<128, 128, 64, 32, 4, true>(ctx, g);
+    // A product with only a handful of 64 x 64 tiles (the diagonal-block updates on the factorisation's critical
+    // path: 128 x 128 x K, lower) is bound by the latency of ONE CTA walking K; 32 x 32 tiles put it on 4x as many
+    // SMs.  Same k order per output element, so the result does not depend on the tile size (tested bit for bit),
+    // which is why this choice -- unlike the TMA one -- may look at the batch count.
+    long t64 = ((g.M + 63) / 64) * (long)((g.N + 63) / 64);
+    if (g.cmode != C_FULL) {
+      const long r64 = (g.M + 63) / 64, c64 = (g.N + 63) / 64, sq = r64 < c64 ? r64 : c64;
+      t64 -= sq * (sq - 1) / 2 + (c64 > r64 ? (c64 - r64) * r64 : 0);
+    }
+    if (t64 * g.inner * g.outer <= small_tile_max()) return launch_cfg<32, 32, 16, 16, 4, true>(ctx, g);
     return launch_cfg<64, 64, 32, 32, 4, true>(ctx, g);
   } else {
     if (big) return launch_cfg<128, 128, 64, 32, 4, false>(ctx, g);

@@ -42,6 +42,8 @@ int gemm_tma_nt(const Ctx& ctx, const GemmArgs& g);
 double gemm_useful_flops(const GemmArgs& g);
 // smallest number of 128 x 128 output tiles (of one problem) for which the TMA kernel is chosen (tuning knob)
 int& tma_min_tiles();
+// largest number of 64 x 64 output tiles (of one problem) for which the 32 x 32-tile kernel is chosen (tuning knob)
+int& small_tile_max();
 
 // --- leaves (<= LEAF wide) ---
 // Every factor carries the inverse-transposed diagonal blocks Dinv: block b (rows/cols [b*LEAF, (b+1)*LEAF)) is

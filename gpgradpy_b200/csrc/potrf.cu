@@ -52,12 +52,35 @@ int trsm_right_rec(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL
 // One event pair per recursion depth and device; fork/join is capturable in a CUDA graph.
 // ------------------------------------------------------------------------------------------------
 namespace {
+// a trailing update with fewer 128 x 128 tiles than this is cut into just-in-time pieces (env GEGP_SPLIT_TILES)
+int split_max_tiles() {
+  static const int v = getenv("GEGP_SPLIT_TILES") ? atoi(getenv("GEGP_SPLIT_TILES")) : 1000;
+  return v;
+}
+constexpr int MAX_PIECES = 256;
+struct Piece { int c0, c1; cudaEvent_t done; bool live; };   // global column range a queued bulk GEMM writes
 struct LookAhead {
-  cudaStream_t hi = nullptr, col = nullptr, bulk = nullptr;
-  cudaEvent_t fork[40], join[40], col_done, begin, end;
-  int pending = -1;        // depth whose bulk join event the chain still has to wait for
+  static constexpr int NBULK = 16;
+  cudaStream_t hi = nullptr, col = nullptr, bulk[NBULK] = {};   // one bulk stream per recursion depth (FIFO each)
+  cudaEvent_t fork[40], col_done, begin, end;
+  Piece piece[MAX_PIECES];
   bool col_pending = false;
   bool ok = false;
+  // the chain must not touch columns [c0, c1) before every queued bulk piece that writes them has finished
+  int join_columns(cudaStream_t chain, int c0, int c1) {
+    for (int i = 0; i < MAX_PIECES; i++) {
+      Piece& p = piece[i];
+      if (!p.live || p.c1 <= c0 || p.c0 >= c1) continue;
+      if (cudaStreamWaitEvent(chain, p.done, 0) != cudaSuccess) return -1100;
+      p.live = false;
+    }
+    return 0;
+  }
+  Piece* free_piece() {
+    for (int i = 0; i < MAX_PIECES; i++)
+      if (!piece[i].live) return &piece[i];
+    return nullptr;
+  }
 };
 
 LookAhead* look_ahead() {
@@ -73,9 +96,12 @@ LookAhead* look_ahead() {
     const int mid = hi < lo ? hi + 1 : hi;
     la.ok = cudaStreamCreateWithPriority(&la.hi, cudaStreamNonBlocking, hi) == cudaSuccess &&
             cudaStreamCreateWithPriority(&la.col, cudaStreamNonBlocking, mid) == cudaSuccess &&
-            cudaStreamCreateWithPriority(&la.bulk, cudaStreamNonBlocking, lo) == cudaSuccess;
+            true;
+    for (int i = 0; i < LookAhead::NBULK && la.ok; i++)
+      la.ok = cudaStreamCreateWithPriority(&la.bulk[i], cudaStreamNonBlocking, lo) == cudaSuccess;
     auto mk = [&](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
-    for (int i = 0; i < 40 && la.ok; i++) la.ok = mk(&la.fork[i]) && mk(&la.join[i]);
+    for (int i = 0; i < 40 && la.ok; i++) la.ok = mk(&la.fork[i]);
+    for (int i = 0; i < MAX_PIECES && la.ok; i++) { la.ok = mk(&la.piece[i].done); la.piece[i].live = false; }
     la.ok = la.ok && mk(&la.col_done) && mk(&la.begin) && mk(&la.end);
   }
   return (la.ok && lookahead_enabled()) ? &la : nullptr;
@@ -85,19 +111,15 @@ int chol_node(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t lda, 
               int* info, double* Dinv, int64_t strideD) {
   if (k <= 0) return 0;
   if (k <= LEAF) {
-    int rc = leaf_potf2_inv(ctx, A, lda, strideA, k, row0, info, Dinv + (int64_t)(row0 / LEAF) * LEAF * LEAF, strideD);
+    int rc = 0;
+    if (la && (rc = la->join_columns(ctx.stream, row0, row0 + k))) return rc;   // (never pending in practice)
+    rc = leaf_potf2_inv(ctx, A, lda, strideA, k, row0, info, Dinv + (int64_t)(row0 / LEAF) * LEAF * LEAF, strideD);
     if (rc) return rc;
     if (la && la->col_pending) {   // the rows below the diagonal block were updated beside the leaf factor
       if (cudaStreamWaitEvent(ctx.stream, la->col_done, 0) != cudaSuccess) return -1104;
       la->col_pending = false;
     }
-    rc = trsm_right_rec(ctx, A, lda, strideA, Dinv, strideD, row0, A + (int64_t)k * lda, lda, strideA, m - k, k);
-    if (rc) return rc;
-    if (la && la->pending >= 0) {   // re-join the bulk update that ran beside this leaf
-      if (cudaStreamWaitEvent(ctx.stream, la->join[la->pending], 0) != cudaSuccess) return -1100;
-      la->pending = -1;
-    }
-    return 0;
+    return trsm_right_rec(ctx, A, lda, strideA, Dinv, strideD, row0, A + (int64_t)k * lda, lda, strideA, m - k, k);
   }
   const int k1 = split_point(k);
   int rc = chol_node(ctx, la, depth + 1, A, lda, strideA, m, k1, row0, info, Dinv, strideD);
@@ -108,6 +130,8 @@ int chol_node(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t lda, 
   const int mc = m - k1, kc = k - k1;
   const int w = kc < LEAF ? kc : LEAF;
   if (la && depth < 40 && mc > w) {
+    // every queued bulk piece that writes the columns this update touches must have finished
+    if ((rc = la->join_columns(ctx.stream, row0 + k1, row0 + k))) return rc;
     if (cudaEventRecord(la->fork[depth], ctx.stream) != cudaSuccess) return -1101;
     // (a) the next leaf's diagonal block, on the chain
     GemmArgs g0 = gemm_args(P, lda, P, lda, C, lda, w, w, k1, -1.0, 1.0, true);
@@ -125,17 +149,37 @@ int chol_node(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t lda, 
       if (cudaEventRecord(la->col_done, la->col) != cudaSuccess) return -1106;
       la->col_pending = true;
     }
-    // (c) everything right of that block column, lowest priority
+    // (c) everything right of that block column, lowest priority.  A bulk that is itself latency-bound (too small
+    // for the TMA kernel) is cut along the left spine of the right child -- the sibling of the first leaf, then the
+    // sibling of that pair, ... -- and queued smallest first: each piece is joined only when the recursion reaches
+    // the columns it writes, so the chain keeps running beside the large pieces.
     if (kc > w) {
-      if (cudaStreamWaitEvent(la->bulk, la->fork[depth], 0) != cudaSuccess) return -1102;
-      const double* P2 = P + (int64_t)w * lda;
-      GemmArgs g2 = gemm_args(P2, lda, P2, lda, C + (int64_t)w * lda + w, lda, mc - w, kc - w, k1, -1.0, 1.0, true);
-      g2.cmode = C_LOWER;
-      Ctx bc{la->bulk, ctx.batch};
-      rc = gemm_f64(bc, batched(bc, g2, strideA, strideA, strideA));
-      if (rc) return rc;
-      if (cudaEventRecord(la->join[depth], la->bulk) != cudaSuccess) return -1103;
-      la->pending = depth;
+      cudaStream_t bs = la->bulk[depth < LookAhead::NBULK ? depth : LookAhead::NBULK - 1];
+      if (cudaStreamWaitEvent(bs, la->fork[depth], 0) != cudaSuccess) return -1102;
+      int cut[40];
+      int ncut = 0;
+      cut[ncut++] = kc;
+      const long big_tiles = ((long)(mc - w + 127) / 128) * ((kc - w + 127) / 128);
+      if (big_tiles < split_max_tiles()) {
+        int sz = kc;
+        while (sz > LEAF && ncut < 39) { sz = split_point(sz); cut[ncut++] = sz; }   // sizes along the left spine
+      } else {
+        cut[ncut++] = w;
+      }
+      // cut[] is decreasing: kc = cut[0] > cut[1] > ... > cut[ncut-1] = w; pieces [cut[i+1], cut[i]) , smallest first
+      Ctx bc{bs, ctx.batch};
+      for (int i = ncut - 2; i >= 0; i--) {
+        const int a = cut[i + 1], b = cut[i];
+        const double* Pa = P + (int64_t)a * lda;
+        GemmArgs g2 = gemm_args(Pa, lda, Pa, lda, C + (int64_t)a * lda + a, lda, mc - a, b - a, k1, -1.0, 1.0, true);
+        g2.cmode = C_LOWER;
+        rc = gemm_f64(bc, batched(bc, g2, strideA, strideA, strideA));
+        if (rc) return rc;
+        Piece* pc = la->free_piece();
+        if (!pc) return -1111;
+        if (cudaEventRecord(pc->done, bs) != cudaSuccess) return -1103;
+        pc->c0 = row0 + k1 + a; pc->c1 = row0 + k1 + b; pc->live = true;
+      }
     }
   } else {
     GemmArgs g = gemm_args(P, lda, P, lda, C, lda, mc, kc, k1, -1.0, 1.0, true);
@@ -151,7 +195,7 @@ int chol_trap(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, in
               int64_t strideD) {
   LookAhead* la = (k > LEAF) ? look_ahead() : nullptr;
   if (!la) return chol_node(ctx, nullptr, 0, A, lda, strideA, m, k, row0, info, Dinv, strideD);
-  la->pending = -1;
+  for (int i = 0; i < MAX_PIECES; i++) la->piece[i].live = false;
   la->col_pending = false;
   if (cudaEventRecord(la->begin, ctx.stream) != cudaSuccess) return -1107;
   if (cudaStreamWaitEvent(la->hi, la->begin, 0) != cudaSuccess) return -1108;
@@ -160,9 +204,8 @@ int chol_trap(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, in
   // every fork is followed by a leaf, which re-joins `col` and `bulk`; the waits below are a safety net that also
   // keeps a failed run (rc != 0) from leaving work un-joined inside a stream capture
   if (la->col_pending) cudaStreamWaitEvent(la->hi, la->col_done, 0);
-  if (la->pending >= 0) cudaStreamWaitEvent(la->hi, la->join[la->pending], 0);
+  la->join_columns(la->hi, 0, 1 << 30);
   la->col_pending = false;
-  la->pending = -1;
   if (cudaEventRecord(la->end, la->hi) != cudaSuccess) return -1109;
   if (cudaStreamWaitEvent(ctx.stream, la->end, 0) != cudaSuccess) return -1110;
   return rc;

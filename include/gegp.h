@@ -73,7 +73,8 @@ int gegp_abi_version(void);
  * choice depends on the shape of one problem only, never on the batch count (bit-identical results across
  * batch sizes and ranks). */
 #define GEGP_OPT_TMA_MIN_TILES 1
-#define GEGP_OPT_LOOKAHEAD 2
+#define GEGP_OPT_LOOKAHEAD 2       /* 0: single-stream factorisation; 1 (default): look-ahead on priority streams */
+#define GEGP_OPT_SMALL_TILE_MAX 3  /* products with at most this many 64 x 64 tiles in total use 32 x 32 tiles (36) */
 int gegp_set_option(int key, int value);
 
 size_t gegp_workspace_bytes(int op, int n, int n_g, int d, int arg);

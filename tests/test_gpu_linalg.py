@@ -191,3 +191,25 @@ def test_tma_and_cpasync_kernels_agree():
         lib.gegp_set_option(_lib.OPT_TMA_MIN_TILES, old)
     ref = A @ B.T
     assert (C1 - ref).abs().max().item() < 1e-12 and (C2 - ref).abs().max().item() < 1e-12
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 1408), (100, 130, 78), (300, 128, 128)])
+def test_small_and_regular_tiles_agree_bit_for_bit(M, N, K):
+    """32 x 32-tile and 64 x 64-tile cp.async kernels accumulate every output element in the same k order:
+    identical results (which is what allows the tile choice to depend on how much work is in flight)."""
+    import torch
+    from gpgradpy_b200 import backend as bk, _lib
+    lib = _lib.load()
+    A = torch.randn((M, K), dtype=torch.float64, device="cuda")
+    B = torch.randn((N, K), dtype=torch.float64, device="cuda")
+    C0 = torch.randn((M, N), dtype=torch.float64, device="cuda")
+    C1, C2 = C0.clone(), C0.clone()
+    old = lib.gegp_set_option(_lib.OPT_SMALL_TILE_MAX, 1000)
+    try:
+        bk.dgemm(A, B, C1, transb=True, alpha=-1.0, beta=1.0)
+        lib.gegp_set_option(_lib.OPT_SMALL_TILE_MAX, 0)
+        bk.dgemm(A, B, C2, transb=True, alpha=-1.0, beta=1.0)
+    finally:
+        lib.gegp_set_option(_lib.OPT_SMALL_TILE_MAX, old)
+    assert torch.equal(C1, C2)
+    assert (C1 - (C0 - A @ B.T)).abs().max().item() < 1e-11
