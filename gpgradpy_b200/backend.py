@@ -333,6 +333,25 @@ def predict(st: PredictState, Xs, varK: float, *, chunk_bytes: int = 1 << 30):
     return mu, sig, sig2, nneg
 
 
+def predict_grad(st: PredictState, Xs, varK: float, *, chunk_bytes: int = 1 << 30):
+    """gegp_predict_grad -> (mu, sig, sig2, dmudx [nx, d], dsigdx [nx, d], n_negative) device tensors."""
+    lib = L.load()
+    Xs = to_dev(Xs)
+    nx, d = Xs.shape[0], st.d
+    dev = device()
+    mu, sig, sig2 = (torch.empty(nx, dtype=F64, device=dev) for _ in range(3))
+    dmu, dsg = (torch.empty((nx, d), dtype=F64, device=dev) for _ in range(2))
+    nneg = torch.zeros(1, dtype=torch.int32, device=dev)
+    per_x = (d + 1) * ld_of(st.N) * 8
+    cx = max(1, min(nx, chunk_bytes // per_x))
+    ws = workspace(cx * per_x)
+    rc = lib.gegp_predict_grad(st.n, st.n_g, st.d, _p(st.X), _p(st.slot), _p(st.theta), _p(st.A), st.A.stride(0),
+                               _p(st.dinv), _p(st.p), int(st.mode), st.beta, float(varK), _p(Xs), nx, _p(mu), _p(sig),
+                               _p(sig2), _p(dmu), _p(dsg), _p(nneg), _p(ws), cx * per_x, _stream())
+    _check(rc, "gegp_predict_grad")
+    return mu, sig, sig2, dmu, dsg, nneg
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # 2-norm condition number and its hyper-parameter gradient (kernel/Kernel.py:240,280; optz/GpHparaCon.py:161-235)
 # ----------------------------------------------------------------------------------------------------------------

@@ -347,6 +347,55 @@ cross_cov_kernel(Geom gm, const double* __restrict__ theta, const double* __rest
   }
 }
 
+// Cross covariance WITH its derivatives with respect to the test point (eval/GpEvalModel.py:133-139 keeps the
+// test-gradient columns of K(X, X*) for calc_grad; kernel/KernelSqExp.py:392-408 gives the blocks).  Per test point
+// x the output holds d + 1 consecutive rows: row 0 = k*(x) as cross_cov_kernel writes it, row 1 + j = d k*(x) / d x*_j:
+//   value entry a      :  +2 th_j r_j k                         (r = x_train - x_test)
+//   gradient entry (i,a): (2 th_i delta_ij - 4 th_i th_j r_i r_j) k
+// every entry scaled by pinv of its training row.
+__global__ void __launch_bounds__(256)
+cross_cov_dx_kernel(Geom gm, const double* __restrict__ theta, const double* __restrict__ pinv,
+                    const double* __restrict__ Xs, int nx, double* __restrict__ out, int64_t ld) {
+  extern __shared__ double sm[];
+  const int d = gm.d, n = gm.n, ng = gm.ng;
+  double* xv = sm;          // [d] the test point of this CTA row
+  double* th = xv + d;      // [d]
+  const int tid = threadIdx.x, x = blockIdx.y;
+  for (int e = tid; e < d; e += 256) { xv[e] = Xs[(int64_t)x * d + e]; th[e] = theta[e]; }
+  __syncthreads();
+  const int b = blockIdx.x * 256 + tid;  // training point
+  if (b >= n) return;
+  const int sb = gm.slot ? gm.slot[b] : b;
+  const double* xb = gm.X + (int64_t)b * d;
+  double e = 0.0;
+  for (int i = 0; i < d; i++) {
+    const double r = xb[i] - xv[i];
+    e -= th[i] * (r * r);
+  }
+  const double k = exp(e);
+  double* base = out + (int64_t)x * (d + 1) * ld;
+  const double pb = pinv ? pinv[b] : 1.0;
+  base[b] = k * pb;
+  for (int j = 0; j < d; j++) {
+    const double rj = xb[j] - xv[j];
+    base[(int64_t)(1 + j) * ld + b] = (2.0 * th[j] * rj * k) * pb;
+  }
+  if (sb >= 0) {
+    for (int i = 0; i < d; i++) {
+      const int col = n + i * ng + sb;
+      const double pc = pinv ? pinv[col] : 1.0;
+      const double ri = xb[i] - xv[i];
+      const double ui = th[i] * ri;
+      base[col] = (-2.0 * ui * k) * pc;
+      for (int j = 0; j < d; j++) {
+        const double rj = xb[j] - xv[j];
+        const double v = ((i == j) ? 2.0 * th[i] : 0.0) - 4.0 * ui * th[j] * rj;
+        base[(int64_t)(1 + j) * ld + col] = (v * k) * pc;
+      }
+    }
+  }
+}
+
 // rows[0] = pinv .* y ; rows[1] = pinv .* H  (H = [1_n ; 0], eval/GpMeanFun.py:172-191)
 __global__ void append_rhs_kernel(int N, int n, const double* __restrict__ y, const double* __restrict__ pinv,
                                   int64_t strideP, double* __restrict__ rows, int64_t ld, int64_t strideRows) {
@@ -423,6 +472,16 @@ int launch_cross_cov(const Ctx& ctx, const Geom& gm, const double* theta, const 
   const size_t smem = (size_t)(8 * gm.d + gm.d) * sizeof(double);
   dim3 grid((gm.n + 255) / 256, (nx + 7) / 8, 1);
   cross_cov_kernel<<<grid, 256, smem, ctx.stream>>>(gm, theta, pinv, Xs, nx, out, ld);
+  GEGP_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_cross_cov_dx(const Ctx& ctx, const Geom& gm, const double* theta, const double* pinv, const double* Xs, int nx,
+                        double* out, int64_t ld) {
+  if (nx <= 0) return 0;
+  const size_t smem = (size_t)(2 * gm.d) * sizeof(double);
+  dim3 grid((gm.n + 255) / 256, nx, 1);
+  cross_cov_dx_kernel<<<grid, 256, smem, ctx.stream>>>(gm, theta, pinv, Xs, nx, out, ld);
   GEGP_CHECK_LAUNCH();
   return 0;
 }

@@ -519,4 +519,47 @@ int gegp_predict(int n, int n_g, int d, const double* X, const int32_t* grad_slo
   return 0;
 }
 
+int gegp_predict_grad(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+                      const double* A, int64_t lda, const double* dinv, const double* p, int mode, double beta,
+                      double varK, const double* Xs, int nx, double* mu, double* sig, double* sig2_out, double* dmudx,
+                      double* dsigdx, int* n_negative_dev, void* work, size_t work_bytes, void* stream) {
+  if (bad_geom(n, n_g, d)) return -1;
+  if (!X) return -4;
+  if (n_g != n && !grad_slot) return -5;
+  if (!theta) return -6;
+  if (!A) return -7;
+  const int N = n + n_g * d;
+  if (lda < N || (lda & 1)) return -8;
+  if (!dinv) return -9;
+  if (!p) return -10;
+  if (!Xs || nx < 0) return -14;
+  if (!mu) return -16;
+  if (!sig) return -17;
+  if (!dmudx) return -19;
+  if (!dsigdx) return -20;
+  if (!work || (reinterpret_cast<uintptr_t>(work) & 15)) return -22;
+  (void)mode;
+  const int64_t ldz = gegp_ld(N);
+  const size_t per_x = (size_t)(d + 1) * ldz * sizeof(double);
+  const int chunk = (int)std::min<size_t>((size_t)nx, work_bytes / per_x);
+  if (nx > 0 && chunk < 1) return -23;
+  Ctx ctx{(cudaStream_t)stream, 1};
+  Geom gm{n, n_g, d, N, X, (n_g == n) ? nullptr : grad_slot};
+  const double* pinv = p + N;
+  const double* w = A + (int64_t)N * lda;
+  double* Z = reinterpret_cast<double*>(work);
+  for (int x0 = 0; x0 < nx; x0 += chunk) {
+    const int cx = std::min(chunk, nx - x0);
+    int rc = launch_cross_cov_dx(ctx, gm, theta, pinv, Xs + (int64_t)x0 * d, cx, Z, ldz);
+    if (rc) return rc;
+    rc = trsm_right_rec(ctx, A, lda, 0, dinv, 0, 0, Z, ldz, 0, cx * (d + 1), N);
+    if (rc) return rc;
+    rc = launch_predict_grad_rows(ctx, N, d, Z, ldz, cx, w, beta, varK, mu + x0, sig + x0,
+                                  sig2_out ? sig2_out + x0 : nullptr, dmudx + (int64_t)x0 * d, dsigdx + (int64_t)x0 * d,
+                                  n_negative_dev);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 }  // extern "C"

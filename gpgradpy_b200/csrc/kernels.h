@@ -32,6 +32,11 @@ int launch_scale_vec(const Ctx& ctx, int N, const double* a, int64_t strideA, co
                      double* out, int64_t strideOut);
 int launch_cross_cov(const Ctx& ctx, const Geom& gm, const double* theta, const double* pinv, const double* Xs, int nx,
                      double* out, int64_t ld);
+int launch_cross_cov_dx(const Ctx& ctx, const Geom& gm, const double* theta, const double* pinv, const double* Xs, int nx,
+                        double* out, int64_t ld);
+int launch_predict_grad_rows(const Ctx& ctx, int N, int d, const double* Z, int64_t ldz, int nx, const double* w,
+                             double beta, double varK, double* mu, double* sig, double* sig2, double* dmu, double* dsig,
+                             int* n_negative);
 int launch_append_rhs(const Ctx& ctx, int N, int n, const double* y, const double* pinv, int64_t strideP, double* rows,
                       int64_t ld, int64_t strideRows);
 

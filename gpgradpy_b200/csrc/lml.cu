@@ -319,6 +319,62 @@ predict_rows_kernel(int N, const double* __restrict__ Z, int64_t ldz, int nx, co
   }
 }
 
+// Posterior with x-derivatives: per test point the d + 1 solved rows z0 = L^-1 P^-1 k*, z_j = L^-1 P^-1 dk*/dx_j give
+//   mu = beta + z0.w ; sig2 = 1 - |z0|^2 ; dmu/dx_j = z_j.w ; dsig/dx_j = -varK (z_j.z0) / sig   (0 where sig = 0)
+// (eval/GpEvalModel.py:319-354: calc_dmudx, calc_dsigdx).
+__global__ void __launch_bounds__(256)
+predict_grad_rows_kernel(int N, int d, const double* __restrict__ Z, int64_t ldz, const double* __restrict__ w,
+                         double beta, double varK, double* __restrict__ mu, double* __restrict__ sig,
+                         double* __restrict__ sig2, double* __restrict__ dmu, double* __restrict__ dsig,
+                         int* __restrict__ n_negative) {
+  __shared__ double sh[32];
+  __shared__ double sig_sh;
+  const int x = blockIdx.x;
+  const double* z0 = Z + (int64_t)x * (d + 1) * ldz;
+  double d1 = 0, d2 = 0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double v = z0[i];
+    d1 += v * w[i];
+    d2 += v * v;
+  }
+  d1 = block_sum(d1, sh);
+  d2 = block_sum(d2, sh);
+  if (threadIdx.x == 0) {
+    const double s2 = 1.0 - d2;
+    mu[x] = beta + d1;
+    if (sig2) sig2[x] = s2;
+    if (s2 < 0 && n_negative) atomicAdd(n_negative, 1);
+    sig_sh = sqrt(fmax(s2, 0.0)) * sqrt(varK);
+    sig[x] = sig_sh;
+  }
+  __syncthreads();
+  const double sg = sig_sh;
+  for (int j = 0; j < d; j++) {
+    const double* zj = z0 + (int64_t)(1 + j) * ldz;
+    double a = 0, b = 0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      const double v = zj[i];
+      a += v * w[i];
+      b += v * z0[i];
+    }
+    a = block_sum(a, sh);
+    b = block_sum(b, sh);
+    if (threadIdx.x == 0) {
+      dmu[(int64_t)x * d + j] = a;
+      dsig[(int64_t)x * d + j] = (sg != 0.0) ? -(varK * b) / sg : 0.0;
+    }
+  }
+}
+
+int launch_predict_grad_rows(const Ctx& ctx, int N, int d, const double* Z, int64_t ldz, int nx, const double* w,
+                             double beta, double varK, double* mu, double* sig, double* sig2, double* dmu, double* dsig,
+                             int* n_negative) {
+  if (nx <= 0) return 0;
+  predict_grad_rows_kernel<<<nx, 256, 0, ctx.stream>>>(N, d, Z, ldz, w, beta, varK, mu, sig, sig2, dmu, dsig, n_negative);
+  GEGP_CHECK_LAUNCH();
+  return 0;
+}
+
 int launch_predict_rows(const Ctx& ctx, int N, const double* Z, int64_t ldz, int nx, const double* w, double beta,
                         double varK, double* mu, double* sig, double* sig2, int* n_negative) {
   if (nx <= 0) return 0;

@@ -990,10 +990,11 @@ class GaussianProcess:
         self.invKernEta_fdiff = DeviceMatrix(self._pred.alpha) if good else None
 
     def eval_model(self, x2model_in, calc_grad=False, calc_hess=False, squeeze_nx=False):
-        """(mu, sig, None, None, None, None) -- eval/GpEvalModel.py:59-198 for calc_grad = calc_hess = False."""
+        """(mu, sig, dmudx, dsigdx, None, None) -- eval/GpEvalModel.py:59-198.  calc_grad adds d mu / d x and
+        d sig / d x [nx, dim] (:170-173, 319-354); Hessians (calc_hess) are not on the CUDA path."""
         assert self.KernEta_chofac is not None, "To evaluate the surr the Cholesky decomposition is required"
-        if calc_grad or calc_hess:
-            raise NotImplementedError("surrogate x-derivatives (eval/GpEvalModel.py:170-180) are outside the CUDA hot path")
+        if calc_hess:
+            raise NotImplementedError("surrogate Hessians (eval/GpEvalModel.py:175-180, 356-382) are outside the CUDA hot path")
         x = np.asarray(x2model_in, dtype=float)
         if x.ndim == 1:
             x = x[None, :]
@@ -1005,16 +1006,23 @@ class GaussianProcess:
             raise Exception("Cannot change hp_vals between calling setup_eval_model() and eval_model()")
         if self.b_use_data_scl:
             x = self.DataScl.x_init_2_scl(x)
-        mu, sig, sig2, nneg = bk.predict(self._pred, x, float(self.hp_vals.varK))
+        dmudx = dsigdx = None
+        if calc_grad:
+            mu, sig, sig2, dmudx, dsigdx, nneg = bk.predict_grad(self._pred, x, float(self.hp_vals.varK))
+            dmudx, dsigdx = dmudx.cpu().numpy(), dsigdx.cpu().numpy()
+        else:
+            mu, sig, sig2, nneg = bk.predict(self._pred, x, float(self.hp_vals.varK))
         mu, sig = mu.cpu().numpy(), sig.cpu().numpy()
         n_bad = int(nneg.item())
         assert n_bad == 0, ("The variance of the surr should be non-negative but min(sig2_wo_sigK) = "
                             f"{float(sig2.min().item())}")
         if self.b_use_data_scl:
-            mu, sig = self.data_scl_2_init(mu, sig)[:2]
+            mu, sig, dmudx, dsigdx = self.data_scl_2_init(mu, sig, dmudx, dsigdx)[:4]
         if squeeze_nx:
             mu, sig = mu[0], sig[0]
-        return mu, sig, None, None, None, None
+            if calc_grad:
+                dmudx, dsigdx = dmudx[0, :], dsigdx[0, :]
+        return mu, sig, dmudx, dsigdx, None, None
 
 
 def _pdist(x):

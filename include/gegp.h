@@ -146,6 +146,14 @@ int gegp_predict(int n, int n_g, int d, const double* X, const int32_t* grad_slo
                  const double* Xs, int nx, double* mu, double* sig, double* sig2_out, int* n_negative_dev,
                  void* work, size_t work_bytes, void* stream);
 
+/* K4 with x-derivatives (eval_model(calc_grad=True), eval/GpEvalModel.py:170-173, 319-354): additionally
+ * dmudx[nx, d] = d mu / d x and dsigdx[nx, d] = d sig / d x.  The derivative columns of K(X, X*) are generated on the
+ * fly and forward-solved beside k* (d + 1 rows per test point): work >= (d + 1) * gegp_ld(N) * 8 bytes per point. */
+int gegp_predict_grad(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+                      const double* A, int64_t lda, const double* dinv, const double* p, int mode, double beta,
+                      double varK, const double* Xs, int nx, double* mu, double* sig, double* sig2_out, double* dmudx,
+                      double* dsigdx, int* n_negative_dev, void* work, size_t work_bytes, void* stream);
+
 /* Where gegp_lml_eval keeps its per-candidate arrays inside `work` (candidate 0; candidate c adds
  * c * per_candidate_doubles), so that a caller can go on working with the factor and the explicit inverse of the
  * evaluation it has just run (condition number, below).  out[8] = { header_bytes, ld, per_candidate_doubles,

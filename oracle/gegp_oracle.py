@@ -522,6 +522,31 @@ def eval_model(X, fval, grad, theta, varK, beta, Xs, mode="precon", eta=None, no
     return mu, sig, sig2, n_neg
 
 
+def eval_model_grad(X, fval, grad, theta, varK, beta, Xs, mode="precon", eta=None, noise_vec=None, mask=None):
+    """eval_model(calc_grad=True): additionally d mu / d x and d sig / d x, [nx, d]
+    (eval/GpEvalModel.py:134-139 test-gradient columns of K(X, X*); :319-354 calc_dmudx / calc_dsigdx)."""
+    n, d = X.shape
+    nx = Xs.shape[0]
+    if eta is None:
+        eta = nugget(n, d, mode)[1]
+    ka = all_K_w_chofac(X, theta, mode, eta, noise_vec, 1.0, mask)
+    g = _sel(n, mask).size
+    y = make_data_vec(fval, grad)
+    H = aug_vand(n, g, d)
+    a = linalg.cho_solve(ka.chofac, y - H @ np.atleast_1d(beta))
+    Kg = kern_grad(X, Xs, theta, mask, None)           # [N, nx (1 + d)]
+    Kyx, dKxy = Kg[:, :nx], Kg[:, nx:].T               # dKxy[(j, x), row]
+    KinvK = linalg.cho_solve(ka.chofac, Kyx)           # [N, nx]
+    sig2 = 1.0 - np.einsum("ij,ij->j", Kyx, KinvK)
+    sigK = np.sqrt(varK)
+    sig = np.sqrt(np.maximum(sig2, 0.0)) * sigK
+    mu = float(np.atleast_1d(beta)[0]) + Kyx.T @ a
+    dmudx = (dKxy @ a).reshape((nx, d), order="F")
+    inv_sig = np.divide(1.0, sig, out=np.zeros_like(sig), where=sig != 0)
+    t2 = np.sum(dKxy * np.tile(KinvK.T, (d, 1)), axis=1).reshape((nx, d), order="F") * sigK ** 2
+    return mu, sig, dmudx, -inv_sig[:, None] * t2
+
+
 # ----------------------------------------------------------------------------------------------
 # rescaling (base/Rescaling.py:72-125, 199-214; SURVEY appendix A)
 # ----------------------------------------------------------------------------------------------

@@ -73,6 +73,31 @@ def case_eta_vary(name, n, d, theta, seed=0):
     print(name, "eta", eta, "idx", idx, "lml", info.ln_lkd, "cond", info.cond, flush=True)
 
 
+def case_surr_grad(name, n, d, mode, seed=0, mask=None):
+    """eval_model(calc_grad=True): d mu / d x and d sig / d x (eval/GpEvalModel.py:170-173, 319-354)."""
+    x, f, g = O.synthetic_problem(n, d, seed)
+    g_in = g if mask is None else g[mask]
+    GP = GaussianProcess(d, True, "SqExp", mode)
+    GP.set_data(x, f, np.zeros(n), g_in, np.zeros(g_in.shape), mask)
+    th = O.bench_theta(d)
+    info, ok = GP.calc_lkd_all(GP.make_hp_class(theta=th))
+    rng = np.random.default_rng(200 + seed)
+    xt = rng.uniform(-2, 2, (10, d))
+    xt[:2] = x[:2] + 1e-2
+    GP.set_hpara("set", 1, GP.make_hp_class(theta=th, varK=info.hp_varK, beta=info.hp_beta))
+    mu, sig, dmu, dsig = GP.eval_model(xt, calc_grad=True)[:4]
+    xs = GP.get_scl_x_w_dist()[0]
+    fs, _, gs, _ = GP.get_scl_eval_data()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), x=x, fval=f, grad=g_in, theta=th, mode=mode, eta=GP._etaK,
+                        hp_varK=info.hp_varK, hp_beta=info.hp_beta, x_test=xt, mu=mu, sig=sig, dmudx=dmu, dsigdx=dsig,
+                        mask=np.zeros(0, bool) if mask is None else mask, x_scl=xs, fval_scl=fs, grad_scl=gs)
+    if mask is None and mode == "precon":
+        o = O.eval_model_grad(xs, fs, gs, th, info.hp_varK, info.hp_beta, xt, mode, GP._etaK)
+        print(name, "oracle rel dmu", rel(o[2], dmu), "dsig", rel(o[3], dsig), flush=True)
+    else:
+        print(name, "stored", flush=True)
+
+
 def case_fit(name, n, d, mode, seed=1):
     """set_hpara('optz') with the history protocol of SURVEY appendix B.12; stores the start point the reference's
     40-candidate scan picked, so that both implementations can be started from the same x0."""
@@ -101,6 +126,10 @@ if __name__ == "__main__":
     case_cond("cond_d2_n14_noisy_base", 14, 2, "base", [0.7, 1.1], seed=4, std_f=1e-2, std_g=5e-2, varK=40.0)
     case_cond("cond_d4_n40_base_illcond", 40, 4, "base", [0.02, 0.03, 0.05, 0.04], seed=5)
     case_eta_vary("etavary_d3_n18", 18, 3, [0.4, 0.7, 0.3], seed=6)
+    case_surr_grad("surrgrad_d3_n20_precon", 20, 3, "precon")
+    case_surr_grad("surrgrad_d2_n15_rescale_origin", 15, 2, "rescale_origin", seed=1)
+    m = np.zeros(14, bool); m[:9] = True
+    case_surr_grad("surrgrad_d3_n14_mask", 14, 3, "precon", seed=2, mask=m)
     if "--no-fit" in sys.argv:
         sys.exit(0)
     case_fit("fit_d2_n20_base", 20, 2, "base")

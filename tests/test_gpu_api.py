@@ -138,3 +138,32 @@ def test_gradient_free_gp():
     ref = O.lkd_wo_noise(x, f, np.zeros((0, 3)), th, "base", GP._etaK, mask=mask)
     assert ok and abs(info.ln_lkd - ref.ln_lkd) < 1e-8 * abs(ref.ln_lkd)
     assert np.max(np.abs(info.ln_lkd_grad - ref.ln_lkd_grad)) < 1e-7 * np.max(np.abs(ref.ln_lkd_grad))
+
+
+@pytest.mark.parametrize("name", ["surrgrad_d3_n20_precon", "surrgrad_d2_n15_rescale_origin", "surrgrad_d3_n14_mask"])
+def test_eval_model_x_gradients(golden_dir, name):
+    """eval_model(calc_grad=True) -> (mu, sig, dmudx, dsigdx, None, None) against the reference
+    (eval/GpEvalModel.py:170-173, 319-354), incl. a rescale mode (derivatives mapped back to the initial
+    coordinates) and partial gradients; plus a central finite difference of mu and sig themselves."""
+    g = _load(golden_dir, name)
+    mode = str(g["mode"])
+    mask = g["mask"] if g["mask"].size else None
+    GP = _gp(g, mode, mask)
+    GP.set_hpara("set", 1, GP.make_hp_class(theta=g["theta"], varK=float(g["hp_varK"]), beta=g["hp_beta"]))
+    xt = g["x_test"]
+    mu, sig, dmu, dsig, h1, h2 = GP.eval_model(xt, calc_grad=True)
+    assert h1 is None and h2 is None and dmu.shape == xt.shape and dsig.shape == xt.shape
+    assert np.max(np.abs(mu - g["mu"])) < 1e-8 * np.max(np.abs(g["mu"]))
+    assert np.max(np.abs(sig - g["sig"])) < 1e-6 * np.max(np.abs(g["sig"]))
+    assert np.max(np.abs(dmu - g["dmudx"])) < 1e-8 * np.max(np.abs(g["dmudx"]))
+    assert np.max(np.abs(dsig - g["dsigdx"])) < 1e-6 * np.max(np.abs(g["dsigdx"]))
+    eps = 1e-5
+    for j in range(xt.shape[1]):
+        e = np.zeros(xt.shape[1]); e[j] = eps
+        mp, sp = GP.eval_model(xt + e)[:2]
+        mm, sm = GP.eval_model(xt - e)[:2]
+        assert np.max(np.abs((mp - mm) / (2 * eps) - dmu[:, j])) < 1e-5 * np.max(np.abs(dmu))
+        assert np.max(np.abs((sp - sm) / (2 * eps) - dsig[:, j])) < 1e-4 * np.max(np.abs(dsig))
+    m1, s1, d1, ds1 = GP.eval_model(xt[3], calc_grad=True, squeeze_nx=True)[:4]
+    assert np.isscalar(m1) or m1.shape == ()
+    assert d1.shape == (xt.shape[1],) and np.allclose(d1, dmu[3]) and np.allclose(ds1, dsig[3])

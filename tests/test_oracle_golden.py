@@ -160,3 +160,26 @@ def test_variable_nugget(golden_dir):
     o = O.lkd_wo_noise(xs, fs, gs, g["theta"], "base", ka.eta)
     assert abs(o.ln_lkd - g["ln_lkd"]) < 1e-9 * abs(g["ln_lkd"])
     assert np.max(np.abs(o.ln_lkd_grad - g["ln_lkd_grad"])) < 1e-8 * np.max(np.abs(g["ln_lkd_grad"]))
+
+
+@pytest.mark.parametrize("name", ["surrgrad_d3_n20_precon", "surrgrad_d2_n15_rescale_origin", "surrgrad_d3_n14_mask"])
+def test_surrogate_x_gradients(golden_dir, name):
+    """eval_model(calc_grad=True): d mu / d x, d sig / d x in the scaled coordinates, mapped back like
+    base/Rescaling.py:160-183 (mu = mu_s / s + f_last, d/dx = d/dx_s * c / s)."""
+    g = _load(golden_dir, name)
+    mode = str(g["mode"])
+    mask = g["mask"] if g["mask"].size else None
+    xs, xt = g["x_scl"], g["x_test"]
+    c = s = 1.0
+    f_last = 0.0
+    if mode != "precon":
+        _, _, _, c, s, f_last = O.rescale_origin(g["x"], g["fval"], g["grad"], O.vreq_rescale_origin(*g["x"].shape))
+        xt = (xt - g["x"][-1][None, :]) * c
+    varK = float(g["hp_varK"])
+    mu, sig, dmu, dsig = O.eval_model_grad(xs, g["fval_scl"], g["grad_scl"], g["theta"], varK, g["hp_beta"], xt,
+                                           "precon" if mode == "precon" else "base", float(g["eta"]), mask=mask)
+    mu, sig, dmu, dsig = mu / s + f_last, sig / s, dmu * c / s, dsig * c / s
+    assert np.max(np.abs(mu - g["mu"])) < 1e-8 * np.max(np.abs(g["mu"]))
+    assert np.max(np.abs(sig - g["sig"])) < 1e-6 * np.max(np.abs(g["sig"]))
+    assert np.max(np.abs(dmu - g["dmudx"])) < 1e-8 * np.max(np.abs(g["dmudx"]))
+    assert np.max(np.abs(dsig - g["dsigdx"])) < 1e-6 * np.max(np.abs(g["dsigdx"]))
