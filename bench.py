@@ -270,13 +270,22 @@ def run_b200(args):
         ld = bk.ld_of(N_)
         buf = torch.empty((N_ + 2, ld), dtype=torch.float64, device="cuda")
         dinv_ = bk.dinv_buffer(N_)
-        ms_full = ev_ms(lambda: bk.build_cov(Xd, thd[0], mode=L.MODE_PRECON, eta=eta_, out=buf[:N_]), reps)
-        ms_low = ev_ms(lambda: bk.build_cov(Xd, thd[0], mode=L.MODE_PRECON, eta=eta_, out=buf[:N_], uplo=1), reps)
+        # the builder runs for tens of microseconds at c2: time a back-to-back burst so that the host-side launch
+        # preparation of one call hides behind the previous kernel (every launch rewrites all 8 N^2 bytes; the
+        # matrix is larger than L2)
+        burst = 20 if N_ < 10000 else 4
+
+        def build_burst(uplo):
+            for _ in range(burst):
+                bk.build_cov(Xd, thd[0], mode=L.MODE_PRECON, eta=eta_, out=buf[:N_], uplo=uplo)
+        ms_full = ev_ms(lambda: build_burst(0), reps) / burst
+        ms_low = ev_ms(lambda: build_burst(1), reps) / burst
 
         def fac():
             bk.build_cov(Xd, thd[0], mode=L.MODE_PRECON, eta=eta_, out=buf[:N_], uplo=1)
             bk.potrf(buf, N_, 0, dinv_)
-        ms_chol = ev_ms(fac, reps) - ms_low
+        ms_one_low = ev_ms(lambda: bk.build_cov(Xd, thd[0], mode=L.MODE_PRECON, eta=eta_, out=buf[:N_], uplo=1), reps)
+        ms_chol = ev_ms(fac, reps) - ms_one_low
         del buf
         return {"n": n_, "d": d_, "N": N_, "lml_grad_ms": ms_grad, "lml_only_ms": ms_val,
                 "lml_grad_evals_per_s": 1e3 / ms_grad, "overall_tflops_N3": N_ ** 3 / ms_grad * 1e-9,
