@@ -8,7 +8,7 @@ def ev(fn, reps=5):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
     return best
-for (M, Nn, K, tb) in [(4096, 4096, 4096, True), (8192, 8192, 8192, True), (16384, 16384, 128, True), (16384, 16384, 1024, True)]:
+for (M, Nn, K, tb) in [(2048, 2048, 2048, True), (1536, 1536, 768, True), (2560, 1280, 1408, True), (2048, 2048, 128, True), (1200, 1200, 640, True)]:
     A = torch.randn((M, K), dtype=torch.float64, device="cuda")
     Bm = torch.randn((Nn, K) if tb else (K, Nn), dtype=torch.float64, device="cuda")
     Cm = torch.zeros((M, Nn), dtype=torch.float64, device="cuda")
