@@ -23,7 +23,7 @@ OPT_SMALL_TILE_MAX = 3
 EXPORTS = (
     "gegp_abi_version", "gegp_set_option", "gegp_workspace_bytes", "gegp_ld", "gegp_build_cov", "gegp_cross_cov", "gegp_potrf",
     "gegp_trsm_rows", "gegp_dinv_doubles", "gegp_potri", "gegp_dgemm", "gegp_lml_eval", "gegp_predict_setup", "gegp_predict", "gegp_profile_begin", "gegp_profile_end",
-    "gegp_predict_grad", "gegp_lml_layout", "gegp_symv", "gegp_row_abs_sum", "gegp_lanczos_step", "gegp_lincomb", "gegp_quad_grad_work_bytes", "gegp_quad_grad",
+    "gegp_predict_grad", "gegp_predict_hess", "gegp_lml_layout", "gegp_symv", "gegp_row_abs_sum", "gegp_lanczos_step", "gegp_lincomb", "gegp_quad_grad_work_bytes", "gegp_quad_grad",
 )
 
 
@@ -77,6 +77,9 @@ def load():
     lib.gegp_predict_grad.restype = i
     lib.gegp_predict_grad.argtypes = [i, i, i, dp, ip, dp, dp, i64, dp, dp, i, dbl, dbl, dp, i, dp, dp, dp, dp, dp, ip, vp,
                                       sz, vp]
+    lib.gegp_predict_hess.restype = i
+    lib.gegp_predict_hess.argtypes = [i, i, i, dp, ip, dp, dp, i64, dp, dp, dp, i, dbl, dbl, dp, dp, dp, dp, dp, dp, dp, ip,
+                                      vp, sz, vp]
     lib.gegp_lml_layout.restype = i
     lib.gegp_lml_layout.argtypes = [i, i, i, i, i, C.POINTER(i64)]
     lib.gegp_symv.restype = i

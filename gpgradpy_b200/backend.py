@@ -352,6 +352,26 @@ def predict_grad(st: PredictState, Xs, varK: float, *, chunk_bytes: int = 1 << 3
     return mu, sig, sig2, dmu, dsg, nneg
 
 
+def predict_hess(st: PredictState, xs, varK: float):
+    """gegp_predict_hess at ONE test point -> (mu, sig, sig2, dmudx [d], dsigdx [d], hess3 [3, d, d], n_negative)."""
+    lib = L.load()
+    xs = to_dev(xs).reshape(-1)
+    d = st.d
+    assert xs.numel() == d and st.alpha is not None
+    dev = device()
+    mu, sig, sig2 = (torch.empty(1, dtype=F64, device=dev) for _ in range(3))
+    dmu, dsg = (torch.empty(d, dtype=F64, device=dev) for _ in range(2))
+    h3 = torch.empty((3, d, d), dtype=F64, device=dev)
+    nneg = torch.zeros(1, dtype=torch.int32, device=dev)
+    nbytes = (d + 2) * ld_of(st.N) * 8
+    ws = workspace(nbytes)
+    rc = lib.gegp_predict_hess(st.n, st.n_g, st.d, _p(st.X), _p(st.slot), _p(st.theta), _p(st.A), st.A.stride(0),
+                               _p(st.dinv), _p(st.p), _p(st.alpha), int(st.mode), st.beta, float(varK), _p(xs), _p(mu),
+                               _p(sig), _p(sig2), _p(dmu), _p(dsg), _p(h3), _p(nneg), _p(ws), nbytes, _stream())
+    _check(rc, "gegp_predict_hess")
+    return mu, sig, sig2, dmu, dsg, h3, nneg
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # 2-norm condition number and its hyper-parameter gradient (kernel/Kernel.py:240,280; optz/GpHparaCon.py:161-235)
 # ----------------------------------------------------------------------------------------------------------------

@@ -562,4 +562,50 @@ int gegp_predict_grad(int n, int n_g, int d, const double* X, const int32_t* gra
   return 0;
 }
 
+int gegp_predict_hess(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+                      const double* A, int64_t lda, const double* dinv, const double* p, const double* alpha, int mode,
+                      double beta, double varK, const double* xs, double* mu, double* sig, double* sig2_out,
+                      double* dmudx, double* dsigdx, double* hess3, int* n_negative_dev, void* work, size_t work_bytes,
+                      void* stream) {
+  if (bad_geom(n, n_g, d)) return -1;
+  if (!X) return -4;
+  if (n_g != n && !grad_slot) return -5;
+  if (!theta) return -6;
+  if (!A) return -7;
+  const int N = n + n_g * d;
+  if (lda < N || (lda & 1)) return -8;
+  if (!dinv) return -9;
+  if (!p) return -10;
+  if (!alpha) return -11;
+  if (!xs) return -15;
+  if (!mu) return -16;
+  if (!sig) return -17;
+  if (!dmudx) return -19;
+  if (!dsigdx) return -20;
+  if (!hess3) return -21;
+  if (!work || (reinterpret_cast<uintptr_t>(work) & 15)) return -23;
+  (void)mode;
+  const int64_t ldz = gegp_ld(N);
+  if (work_bytes < (size_t)(d + 2) * ldz * sizeof(double)) return -24;
+  Ctx ctx{(cudaStream_t)stream, 1};
+  Geom gm{n, n_g, d, N, X, (n_g == n) ? nullptr : grad_slot};
+  const double* pinv = p + N;
+  const double* w = A + (int64_t)N * lda;
+  double* Z = reinterpret_cast<double*>(work);
+  double* bvec = Z + (int64_t)(d + 1) * ldz;          // K^-1 k* (un-preconditioned)
+  int rc = launch_cross_cov_dx(ctx, gm, theta, pinv, xs, 1, Z, ldz);
+  if (rc) return rc;
+  rc = trsm_right_rec(ctx, A, lda, 0, dinv, 0, 0, Z, ldz, 0, d + 1, N);
+  if (rc) return rc;
+  rc = launch_predict_grad_rows(ctx, N, d, Z, ldz, 1, w, beta, varK, mu, sig, sig2_out, dmudx, dsigdx, n_negative_dev);
+  if (rc) return rc;
+  cudaError_t e = cudaMemcpyAsync(bvec, Z, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream);
+  if (e != cudaSuccess) return -1000 - (int)e;
+  rc = trsv_lower_trans(ctx, A, lda, 0, dinv, 0, bvec, ldz, 0, N, 1);   // L^-T z0
+  if (rc) return rc;
+  rc = launch_scale_vec(ctx, N, bvec, 0, pinv, 0, bvec, 0);              // P^-1 .
+  if (rc) return rc;
+  return launch_predict_hess(ctx, gm, theta, xs, alpha, bvec, Z, ldz, hess3);
+}
+
 }  // extern "C"

@@ -37,6 +37,8 @@ int launch_cross_cov_dx(const Ctx& ctx, const Geom& gm, const double* theta, con
 int launch_predict_grad_rows(const Ctx& ctx, int N, int d, const double* Z, int64_t ldz, int nx, const double* w,
                              double beta, double varK, double* mu, double* sig, double* sig2, double* dmu, double* dsig,
                              int* n_negative);
+int launch_predict_hess(const Ctx& ctx, const Geom& gm, const double* theta, const double* xs, const double* a,
+                        const double* b, const double* Z, int64_t ldz, double* out);
 int launch_append_rhs(const Ctx& ctx, int N, int n, const double* y, const double* pinv, int64_t strideP, double* rows,
                       int64_t ld, int64_t strideRows);
 

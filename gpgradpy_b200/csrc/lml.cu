@@ -375,6 +375,71 @@ int launch_predict_grad_rows(const Ctx& ctx, int N, int d, const double* Z, int6
   return 0;
 }
 
+// Surrogate Hessian contractions for ONE test point (eval/GpEvalModel.py:175-180, 356-382; the second x-derivatives of
+// the cross covariance are kernel/KernelSqExp.py:66-88 for value entries and :432-468 for gradient entries).
+// CTA (i, k):  out[0][i,k] = sum_col d2k*[i,k,col] a[col]    (a = K^-1 (y - H beta)      -> d2mu/dx2)
+//              out[1][i,k] = sum_col d2k*[i,k,col] b[col]    (b = K^-1 k*                -> term1 of d2sig2/dx2)
+//              out[2][i,k] = z_i . z_k                        (forward-solved derivative rows -> term2)
+// with r = x_train - x*:  value entry a      : (4 th_i th_k r_i r_k - 2 th_i delta_ik) k
+//   gradient entry (j, a): (4 th_i th_j (delta_ik r_j + delta_jk r_i) + 4 delta_ij th_i th_k r_k
+//                           - 8 th_i th_j th_k r_i r_j r_k) k
+__global__ void __launch_bounds__(256)
+predict_hess_kernel(Geom gm, const double* __restrict__ theta, const double* __restrict__ xs,
+                    const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ Z,
+                    int64_t ldz, double* __restrict__ out) {
+  __shared__ double sh[32];
+  const int d = gm.d, n = gm.n, ng = gm.ng, N = gm.N;
+  const int i = blockIdx.y, k = blockIdx.x;
+  const double thi = theta[i], thk = theta[k];
+  double s0 = 0.0, s1 = 0.0;
+  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+    const double* xp = gm.X + (int64_t)p * d;
+    double e = 0.0;
+    for (int q = 0; q < d; q++) {
+      const double r = xp[q] - xs[q];
+      e -= theta[q] * (r * r);
+    }
+    const double kk = exp(e);
+    const double ri = xp[i] - xs[i], rk = xp[k] - xs[k];
+    const double hv = (4.0 * thi * thk * ri * rk - ((i == k) ? 2.0 * thi : 0.0)) * kk;
+    s0 += hv * a[p];
+    s1 += hv * b[p];
+    const int sp = gm.slot ? gm.slot[p] : p;
+    if (sp >= 0) {
+      for (int j = 0; j < d; j++) {
+        const double thj = theta[j], rj = xp[j] - xs[j];
+        double v = -8.0 * thi * thj * thk * ri * rj * rk;
+        if (i == k) v += 4.0 * thi * thj * rj;
+        if (j == k) v += 4.0 * thi * thj * ri;
+        if (i == j) v += 4.0 * thi * thk * rk;
+        v *= kk;
+        const int col = n + j * ng + sp;
+        s0 += v * a[col];
+        s1 += v * b[col];
+      }
+    }
+  }
+  s0 = block_sum(s0, sh);
+  s1 = block_sum(s1, sh);
+  const double* zi = Z + (int64_t)(1 + i) * ldz;
+  const double* zk = Z + (int64_t)(1 + k) * ldz;
+  double s2 = 0.0;
+  for (int c = threadIdx.x; c < N; c += blockDim.x) s2 += zi[c] * zk[c];
+  s2 = block_sum(s2, sh);
+  if (threadIdx.x == 0) {
+    out[i * d + k] = s0;
+    out[d * d + i * d + k] = s1;
+    out[2 * d * d + i * d + k] = s2;
+  }
+}
+
+int launch_predict_hess(const Ctx& ctx, const Geom& gm, const double* theta, const double* xs, const double* a,
+                        const double* b, const double* Z, int64_t ldz, double* out) {
+  predict_hess_kernel<<<dim3(gm.d, gm.d, 1), 256, 0, ctx.stream>>>(gm, theta, xs, a, b, Z, ldz, out);
+  GEGP_CHECK_LAUNCH();
+  return 0;
+}
+
 int launch_predict_rows(const Ctx& ctx, int N, const double* Z, int64_t ldz, int nx, const double* w, double beta,
                         double varK, double* mu, double* sig, double* sig2, int* n_negative) {
   if (nx <= 0) return 0;

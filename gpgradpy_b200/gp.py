@@ -990,11 +990,12 @@ class GaussianProcess:
         self.invKernEta_fdiff = DeviceMatrix(self._pred.alpha) if good else None
 
     def eval_model(self, x2model_in, calc_grad=False, calc_hess=False, squeeze_nx=False):
-        """(mu, sig, dmudx, dsigdx, None, None) -- eval/GpEvalModel.py:59-198.  calc_grad adds d mu / d x and
-        d sig / d x [nx, dim] (:170-173, 319-354); Hessians (calc_hess) are not on the CUDA path."""
+        """(mu, sig, dmudx, dsigdx, d2mudx2, d2sigdx2) -- eval/GpEvalModel.py:59-198.  calc_grad adds d mu / d x and
+        d sig / d x [nx, dim] (:170-173, 319-354); calc_hess adds the Hessians [1, dim, dim] for ONE point per call,
+        like the reference (:175-180, 356-382)."""
         assert self.KernEta_chofac is not None, "To evaluate the surr the Cholesky decomposition is required"
         if calc_hess:
-            raise NotImplementedError("surrogate Hessians (eval/GpEvalModel.py:175-180, 356-382) are outside the CUDA hot path")
+            assert calc_grad, "To return the hessian calc_grad must also be set to True"
         x = np.asarray(x2model_in, dtype=float)
         if x.ndim == 1:
             x = x[None, :]
@@ -1006,8 +1007,18 @@ class GaussianProcess:
             raise Exception("Cannot change hp_vals between calling setup_eval_model() and eval_model()")
         if self.b_use_data_scl:
             x = self.DataScl.x_init_2_scl(x)
-        dmudx = dsigdx = None
-        if calc_grad:
+        dmudx = dsigdx = d2mudx2 = d2sigdx2 = None
+        if calc_hess:
+            assert x.shape[0] == 1, "calc_hess can only be used on one point per call"
+            varK = float(self.hp_vals.varK)
+            mu, sig, sig2, dmudx, dsigdx, h3, nneg = bk.predict_hess(self._pred, x[0], varK)
+            dmudx, dsigdx, h3 = dmudx.cpu().numpy()[None, :], dsigdx.cpu().numpy()[None, :], h3.cpu().numpy()
+            d2mudx2 = h3[0][None, :, :]
+            d2sig2 = -2.0 * varK * (h3[1] + h3[2])                       # eval/GpEvalModel.py:366-371
+            s = float(sig.item())
+            s = np.nan if s == 0 else s                                  # :374-375
+            d2sigdx2 = ((d2sig2 - 2.0 * np.outer(dsigdx[0], dsigdx[0])) / (2.0 * s))[None, :, :]
+        elif calc_grad:
             mu, sig, sig2, dmudx, dsigdx, nneg = bk.predict_grad(self._pred, x, float(self.hp_vals.varK))
             dmudx, dsigdx = dmudx.cpu().numpy(), dsigdx.cpu().numpy()
         else:
@@ -1017,12 +1028,14 @@ class GaussianProcess:
         assert n_bad == 0, ("The variance of the surr should be non-negative but min(sig2_wo_sigK) = "
                             f"{float(sig2.min().item())}")
         if self.b_use_data_scl:
-            mu, sig, dmudx, dsigdx = self.data_scl_2_init(mu, sig, dmudx, dsigdx)[:4]
+            mu, sig, dmudx, dsigdx, d2mudx2, d2sigdx2 = self.data_scl_2_init(mu, sig, dmudx, dsigdx, d2mudx2, d2sigdx2)
         if squeeze_nx:
             mu, sig = mu[0], sig[0]
             if calc_grad:
                 dmudx, dsigdx = dmudx[0, :], dsigdx[0, :]
-        return mu, sig, dmudx, dsigdx, None, None
+            if calc_hess:
+                d2mudx2, d2sigdx2 = d2mudx2[0, :, :], d2sigdx2[0, :, :]
+        return mu, sig, dmudx, dsigdx, d2mudx2, d2sigdx2
 
 
 def _pdist(x):

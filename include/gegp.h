@@ -154,6 +154,19 @@ int gegp_predict_grad(int n, int n_g, int d, const double* X, const int32_t* gra
                       double varK, const double* Xs, int nx, double* mu, double* sig, double* sig2_out, double* dmudx,
                       double* dsigdx, int* n_negative_dev, void* work, size_t work_bytes, void* stream);
 
+/* Surrogate Hessians at ONE test point xs[d] (eval_model(calc_grad=True, calc_hess=True), eval/GpEvalModel.py:175-180,
+ * 356-382; the reference also takes one point per call).  alpha[N] = K^-1 (y - H beta) from gegp_predict_setup.
+ * Besides mu, sig, dmudx[d], dsigdx[d] it returns hess3[3, d, d]:
+ *   hess3[0] = d2mu/dx2,  hess3[1] = (d2 kstar / dx2) . (K^-1 kstar)  (term1),
+ *   hess3[2] = (d kstar / dx) K^-1 (d kstar / dx)^T  (term2), kstar = K(X, xs);
+ * the caller forms d2sig2/dx2 = -2 varK (term1 + term2) and d2sig/dx2 = (d2sig2/dx2 - 2 dsig dsig^T) / (2 sig).
+ * work >= (d + 2) * gegp_ld(N) * 8 bytes. */
+int gegp_predict_hess(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+                      const double* A, int64_t lda, const double* dinv, const double* p, const double* alpha, int mode,
+                      double beta, double varK, const double* xs, double* mu, double* sig, double* sig2_out,
+                      double* dmudx, double* dsigdx, double* hess3, int* n_negative_dev, void* work, size_t work_bytes,
+                      void* stream);
+
 /* Where gegp_lml_eval keeps its per-candidate arrays inside `work` (candidate 0; candidate c adds
  * c * per_candidate_doubles), so that a caller can go on working with the factor and the explicit inverse of the
  * evaluation it has just run (condition number, below).  out[8] = { header_bytes, ld, per_candidate_doubles,

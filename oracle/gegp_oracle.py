@@ -547,6 +547,50 @@ def eval_model_grad(X, fval, grad, theta, varK, beta, Xs, mode="precon", eta=Non
     return mu, sig, dmudx, -inv_sig[:, None] * t2
 
 
+def kern_hess_x(X, xs, theta):
+    """Second derivatives of the cross covariance k*(x) with respect to the test point x, [d, d, N], every training
+    point carrying a gradient (kernel/KernelSqExp.py:66-88 value entries, :432-468 gradient entries; the reference
+    builds them with R = x_test - x_train)."""
+    n, d = X.shape
+    rho = xs[None, :] - X                                # [n, d] = x_test - x_train
+    k = np.exp(-np.sum(theta[None, :] * rho ** 2, axis=1))
+    H = np.zeros((d, d, n * (d + 1)))
+    for kk in range(d):
+        for i in range(d):
+            H[kk, i, :n] = (-2.0 * theta[i] * (i == kk) + 4.0 * theta[i] * theta[kk] * rho[:, i] * rho[:, kk]) * k
+            for j in range(d):
+                H[kk, i, n + j * n: n + (j + 1) * n] = (
+                    -4.0 * theta[i] * theta[j] * ((i == kk) * rho[:, j] + (j == kk) * rho[:, i])
+                    - 4.0 * (i == j) * theta[i] * theta[kk] * rho[:, kk]
+                    + 8.0 * theta[i] * theta[j] * theta[kk] * rho[:, i] * rho[:, j] * rho[:, kk]) * k
+    return H
+
+
+def eval_model_hess(X, fval, grad, theta, varK, beta, xs, mode="precon", eta=None):
+    """eval_model(calc_grad=True, calc_hess=True) at ONE point: (mu, sig, dmudx, dsigdx, d2mudx2, d2sigdx2)
+    (eval/GpEvalModel.py:175-180, 356-382)."""
+    n, d = X.shape
+    if eta is None:
+        eta = nugget(n, d, mode)[1]
+    xs = np.atleast_2d(xs)
+    mu, sig, dmu, dsig = eval_model_grad(X, fval, grad, theta, varK, beta, xs, mode, eta)
+    ka = all_K_w_chofac(X, theta, mode, eta, None, 1.0, None)
+    y = make_data_vec(fval, grad)
+    H = aug_vand(n, n, d)
+    a = linalg.cho_solve(ka.chofac, y - H @ np.atleast_1d(beta))
+    Kg = kern_grad(X, xs, theta, None, None)
+    Kyx, dKxy = Kg[:, :1], Kg[:, 1:].T
+    KinvK = linalg.cho_solve(ka.chofac, Kyx)[:, 0]
+    d2K = kern_hess_x(X, xs[0], theta)
+    d2mu = d2K @ a
+    term1 = d2K @ KinvK
+    term2 = dKxy @ linalg.cho_solve(ka.chofac, dKxy.T)
+    d2sig2 = -2.0 * varK * (term1 + term2)
+    s = sig[0] if sig[0] != 0 else np.nan
+    d2sig = (d2sig2 - 2.0 * np.outer(dsig[0], dsig[0])) / (2.0 * s)
+    return mu, sig, dmu, dsig, d2mu[None], d2sig[None]
+
+
 # ----------------------------------------------------------------------------------------------
 # rescaling (base/Rescaling.py:72-125, 199-214; SURVEY appendix A)
 # ----------------------------------------------------------------------------------------------

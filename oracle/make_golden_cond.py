@@ -98,6 +98,31 @@ def case_surr_grad(name, n, d, mode, seed=0, mask=None):
         print(name, "stored", flush=True)
 
 
+def case_surr_hess(name, n, d, mode, seed=0, npts=4):
+    """eval_model(calc_grad=True, calc_hess=True), one point per call (eval/GpEvalModel.py:175-180, 356-382)."""
+    x, f, g = O.synthetic_problem(n, d, seed)
+    GP = GaussianProcess(d, True, "SqExp", mode)
+    GP.set_data(x, f, np.zeros(n), g, np.zeros(g.shape))
+    th = O.bench_theta(d)
+    info, ok = GP.calc_lkd_all(GP.make_hp_class(theta=th))
+    rng = np.random.default_rng(300 + seed)
+    xt = rng.uniform(-2, 2, (npts, d))
+    GP.set_hpara("set", 1, GP.make_hp_class(theta=th, varK=info.hp_varK, beta=info.hp_beta))
+    res = [GP.eval_model(xt[i], calc_grad=True, calc_hess=True) for i in range(npts)]
+    xs = GP.get_scl_x_w_dist()[0]
+    fs, _, gs, _ = GP.get_scl_eval_data()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), x=x, fval=f, grad=g, theta=th, mode=mode, eta=GP._etaK,
+                        hp_varK=info.hp_varK, hp_beta=info.hp_beta, x_test=xt, x_scl=xs, fval_scl=fs, grad_scl=gs,
+                        mu=np.array([r[0][0] for r in res]), sig=np.array([r[1][0] for r in res]),
+                        dmudx=np.array([r[2][0] for r in res]), dsigdx=np.array([r[3][0] for r in res]),
+                        d2mudx2=np.array([r[4][0] for r in res]), d2sigdx2=np.array([r[5][0] for r in res]))
+    if mode == "precon":
+        o = O.eval_model_hess(xs, fs, gs, th, info.hp_varK, info.hp_beta, xt[0], mode, GP._etaK)
+        print(name, "oracle rel d2mu", rel(o[4][0], res[0][4][0]), "d2sig", rel(o[5][0], res[0][5][0]), flush=True)
+    else:
+        print(name, "stored", flush=True)
+
+
 def case_fit(name, n, d, mode, seed=1):
     """set_hpara('optz') with the history protocol of SURVEY appendix B.12; stores the start point the reference's
     40-candidate scan picked, so that both implementations can be started from the same x0."""
@@ -130,6 +155,8 @@ if __name__ == "__main__":
     case_surr_grad("surrgrad_d2_n15_rescale_origin", 15, 2, "rescale_origin", seed=1)
     m = np.zeros(14, bool); m[:9] = True
     case_surr_grad("surrgrad_d3_n14_mask", 14, 3, "precon", seed=2, mask=m)
+    case_surr_hess("surrhess_d3_n16_precon", 16, 3, "precon")
+    case_surr_hess("surrhess_d2_n12_rescale_origin", 12, 2, "rescale_origin", seed=1)
     if "--no-fit" in sys.argv:
         sys.exit(0)
     case_fit("fit_d2_n20_base", 20, 2, "base")

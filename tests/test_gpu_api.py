@@ -167,3 +167,33 @@ def test_eval_model_x_gradients(golden_dir, name):
     m1, s1, d1, ds1 = GP.eval_model(xt[3], calc_grad=True, squeeze_nx=True)[:4]
     assert np.isscalar(m1) or m1.shape == ()
     assert d1.shape == (xt.shape[1],) and np.allclose(d1, dmu[3]) and np.allclose(ds1, dsig[3])
+
+
+@pytest.mark.parametrize("name", ["surrhess_d3_n16_precon", "surrhess_d2_n12_rescale_origin"])
+def test_eval_model_hessians(golden_dir, name):
+    """eval_model(calc_grad=True, calc_hess=True), one point per call like the reference
+    (eval/GpEvalModel.py:175-180, 356-382): d2mudx2, d2sigdx2 [1, d, d]; plus a finite difference of the gradients."""
+    g = _load(golden_dir, name)
+    mode = str(g["mode"])
+    GP = _gp(g, mode)
+    GP.set_hpara("set", 1, GP.make_hp_class(theta=g["theta"], varK=float(g["hp_varK"]), beta=g["hp_beta"]))
+    d = g["x"].shape[1]
+    for p in range(g["x_test"].shape[0]):
+        xt = g["x_test"][p]
+        mu, sig, dmu, dsig, h_mu, h_sig = GP.eval_model(xt, calc_grad=True, calc_hess=True)
+        assert h_mu.shape == (1, d, d) and h_sig.shape == (1, d, d)
+        assert abs(mu[0] - g["mu"][p]) < 1e-8 * abs(g["mu"][p]) and abs(sig[0] - g["sig"][p]) < 1e-6 * abs(g["sig"][p])
+        assert np.max(np.abs(dmu[0] - g["dmudx"][p])) < 1e-8 * np.max(np.abs(g["dmudx"][p]))
+        assert np.max(np.abs(h_mu[0] - g["d2mudx2"][p])) < 1e-8 * np.max(np.abs(g["d2mudx2"][p]))
+        assert np.max(np.abs(h_sig[0] - g["d2sigdx2"][p])) < 1e-5 * np.max(np.abs(g["d2sigdx2"][p]))
+    xt = g["x_test"][0]
+    _, _, _, _, h_mu, h_sig = GP.eval_model(xt, calc_grad=True, calc_hess=True)
+    eps = 1e-5
+    for j in range(d):
+        e = np.zeros(d); e[j] = eps
+        gp_, sp_ = GP.eval_model(xt + e, calc_grad=True)[2:4]
+        gm_, sm_ = GP.eval_model(xt - e, calc_grad=True)[2:4]
+        assert np.max(np.abs((gp_[0] - gm_[0]) / (2 * eps) - h_mu[0][:, j])) < 1e-5 * np.max(np.abs(h_mu))
+        assert np.max(np.abs((sp_[0] - sm_[0]) / (2 * eps) - h_sig[0][:, j])) < 1e-4 * np.max(np.abs(h_sig))
+    out = GP.eval_model(xt, calc_grad=True, calc_hess=True, squeeze_nx=True)
+    assert out[4].shape == (d, d) and out[5].shape == (d, d)

@@ -183,3 +183,13 @@ def test_surrogate_x_gradients(golden_dir, name):
     assert np.max(np.abs(sig - g["sig"])) < 1e-6 * np.max(np.abs(g["sig"]))
     assert np.max(np.abs(dmu - g["dmudx"])) < 1e-8 * np.max(np.abs(g["dmudx"]))
     assert np.max(np.abs(dsig - g["dsigdx"])) < 1e-6 * np.max(np.abs(g["dsigdx"]))
+
+
+def test_surrogate_hessians(golden_dir):
+    """eval_model(calc_hess=True) at single points: d2 mu / dx2, d2 sig / dx2 (eval/GpEvalModel.py:356-382)."""
+    g = _load(golden_dir, "surrhess_d3_n16_precon")
+    for p in range(g["x_test"].shape[0]):
+        o = O.eval_model_hess(g["x_scl"], g["fval_scl"], g["grad_scl"], g["theta"], float(g["hp_varK"]), g["hp_beta"],
+                              g["x_test"][p], "precon", float(g["eta"]))
+        assert np.max(np.abs(o[4][0] - g["d2mudx2"][p])) < 1e-8 * np.max(np.abs(g["d2mudx2"][p]))
+        assert np.max(np.abs(o[5][0] - g["d2sigdx2"][p])) < 1e-6 * np.max(np.abs(g["d2sigdx2"][p]))
