@@ -1038,6 +1038,40 @@ class GaussianProcess:
         return mu, sig, dmudx, dsigdx, d2mudx2, d2sigdx2
 
 
+    def eval_model_var(self, x2model_in, calc_grad=False, calc_hess=False, squeeze_nx=False):
+        """(sig2, dsig2dx, None) -- eval/GpEvalModel.py:200-317: posterior variance varK (1 - k*^T K^-1 k*) and its
+        x-gradient -2 varK (dk*/dx)^T K^-1 k* = 2 sig dsig/dx.  Like the reference: no rescale modes, no Hessian."""
+        assert self.KernEta_chofac is not None, "To evaluate the surr the Cholesky decomposition is required"
+        if self.b_use_data_scl:
+            raise Exception("The method eval_model_var() is not setup for cases where data must be rescaled")
+        if calc_hess:
+            assert calc_grad, "To return the hessian calc_grad must also be set to True"
+            raise Exception("Must add method to calculate d2sig2dx2")          # the reference's own message (:303)
+        x = np.asarray(x2model_in, dtype=float)
+        if x.ndim == 1:
+            x = x[None, :]
+        elif x.ndim != 2:
+            raise Exception(f"x2model_in should be a 2d array but it has shape {x.shape}")
+        if squeeze_nx:
+            assert x.shape[0] == 1, "If squeeze_nx is True, then x_acq must only have one point"
+        if not (self.hp_vals == self._hp_vals_model_setup):
+            raise Exception("Cannot change hp_vals between calling setup_eval_model() and eval_model()")
+        varK = float(self.hp_vals.varK)
+        dsig2dx = None
+        if calc_grad:
+            _, sig, sig2, _, dsig, nneg = bk.predict_grad(self._pred, x, varK)
+            dsig2dx = (2.0 * sig[:, None] * dsig).cpu().numpy()
+        else:
+            _, sig, sig2, nneg = bk.predict(self._pred, x, varK)
+        sig2 = varK * sig2.cpu().numpy()
+        assert int(nneg.item()) == 0, f"The variance of the surr should be non-negative but min(sig2) = {sig2.min()}"
+        if squeeze_nx:
+            sig2 = sig2[0]
+            if calc_grad:
+                dsig2dx = dsig2dx[0, :]
+        return sig2, dsig2dx, None
+
+
 def _pdist(x):
     from scipy.spatial.distance import pdist
     return pdist(x)

@@ -86,11 +86,15 @@ def case_surr_grad(name, n, d, mode, seed=0, mask=None):
     xt[:2] = x[:2] + 1e-2
     GP.set_hpara("set", 1, GP.make_hp_class(theta=th, varK=info.hp_varK, beta=info.hp_beta))
     mu, sig, dmu, dsig = GP.eval_model(xt, calc_grad=True)[:4]
+    extra = {}
+    if not GP.b_use_data_scl:
+        s2, ds2 = GP.eval_model_var(xt, calc_grad=True)[:2]
+        extra = dict(sig2=s2, dsig2dx=ds2)
     xs = GP.get_scl_x_w_dist()[0]
     fs, _, gs, _ = GP.get_scl_eval_data()
     np.savez_compressed(os.path.join(OUT, name + ".npz"), x=x, fval=f, grad=g_in, theta=th, mode=mode, eta=GP._etaK,
                         hp_varK=info.hp_varK, hp_beta=info.hp_beta, x_test=xt, mu=mu, sig=sig, dmudx=dmu, dsigdx=dsig,
-                        mask=np.zeros(0, bool) if mask is None else mask, x_scl=xs, fval_scl=fs, grad_scl=gs)
+                        mask=np.zeros(0, bool) if mask is None else mask, x_scl=xs, fval_scl=fs, grad_scl=gs, **extra)
     if mask is None and mode == "precon":
         o = O.eval_model_grad(xs, fs, gs, th, info.hp_varK, info.hp_beta, xt, mode, GP._etaK)
         print(name, "oracle rel dmu", rel(o[2], dmu), "dsig", rel(o[3], dsig), flush=True)

@@ -164,6 +164,11 @@ def test_eval_model_x_gradients(golden_dir, name):
         mm, sm = GP.eval_model(xt - e)[:2]
         assert np.max(np.abs((mp - mm) / (2 * eps) - dmu[:, j])) < 1e-5 * np.max(np.abs(dmu))
         assert np.max(np.abs((sp - sm) / (2 * eps) - dsig[:, j])) < 1e-4 * np.max(np.abs(dsig))
+    if "sig2" in g:     # eval_model_var (eval/GpEvalModel.py:200-317): variance and its x-gradient
+        s2, ds2, h = GP.eval_model_var(xt, calc_grad=True)
+        assert h is None
+        assert np.max(np.abs(s2 - g["sig2"])) < 1e-6 * np.max(np.abs(g["sig2"]))
+        assert np.max(np.abs(ds2 - g["dsig2dx"])) < 1e-6 * np.max(np.abs(g["dsig2dx"]))
     m1, s1, d1, ds1 = GP.eval_model(xt[3], calc_grad=True, squeeze_nx=True)[:4]
     assert np.isscalar(m1) or m1.shape == ()
     assert d1.shape == (xt.shape[1],) and np.allclose(d1, dmu[3]) and np.allclose(ds1, dsig[3])

@@ -183,6 +183,9 @@ def test_surrogate_x_gradients(golden_dir, name):
     assert np.max(np.abs(sig - g["sig"])) < 1e-6 * np.max(np.abs(g["sig"]))
     assert np.max(np.abs(dmu - g["dmudx"])) < 1e-8 * np.max(np.abs(g["dmudx"]))
     assert np.max(np.abs(dsig - g["dsigdx"])) < 1e-6 * np.max(np.abs(g["dsigdx"]))
+    if "sig2" in g:     # eval_model_var (eval/GpEvalModel.py:200-317): sig^2 and d sig^2 / dx = 2 sig dsig/dx
+        assert np.max(np.abs(sig ** 2 - g["sig2"])) < 1e-6 * np.max(np.abs(g["sig2"]))
+        assert np.max(np.abs(2 * sig[:, None] * dsig - g["dsig2dx"])) < 1e-6 * np.max(np.abs(g["dsig2dx"]))
 
 
 def test_surrogate_hessians(golden_dir):
