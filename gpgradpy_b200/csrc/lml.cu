@@ -229,44 +229,48 @@ lml_grad_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideThe
 //   noisy     : dLML/dtheta_m = varK (G_m + [precon] 2 eta DG_m)
 //               dLML/dvarK    = SK + eta (DV + sum_m 2 th_m DG_m) [precon]  |  SK + eta (DV + sum DG_m) [base]
 //               dLML/dvar_f   = (1 + eta) DV [precon] | DV [base] ; dLML/dvar_g likewise with sum_m DG_m
+// stage 1: one CTA per (column c of the partial table, problem z): fixed-order sum over the CTAs' partials
 __global__ void __launch_bounds__(256)
+lml_grad_colsum_kernel(int np, int64_t nparts, double* __restrict__ partial_all, int64_t stridePartial) {
+  __shared__ double sh[32];
+  const int c = blockIdx.x, z = blockIdx.y;
+  double* part = partial_all + z * stridePartial;
+  double s = 0.0;
+  for (int64_t p = threadIdx.x; p < nparts; p += blockDim.x) s += part[p * np + c];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) part[nparts * np + c] = s;     // the column sums sit right behind the partial table
+}
+
+// stage 2: assemble the gradient entries of `out` from the 2d+2 column sums
+__global__ void __launch_bounds__(64)
 lml_grad_finalize_kernel(int d, int64_t nparts, const double* __restrict__ partial_all, int64_t stridePartial,
                          const double* __restrict__ theta_all, int64_t strideTheta, int mode, double eta, int noisy,
-                         const double* __restrict__ varK, double* __restrict__ out_all, int64_t strideOut) {
-  __shared__ double sh[32];
-  extern __shared__ double tot[];  // [2d+2]
-  const int z = blockIdx.x, np = 2 * d + 2;
-  const double* part = partial_all + z * stridePartial;
-  for (int c = 0; c < np; c++) {
-    double s = 0.0;
-    for (int64_t p = threadIdx.x; p < nparts; p += blockDim.x) s += part[p * np + c];
-    s = block_sum(s, sh);
-    if (threadIdx.x == 0) tot[c] = s;
+                         const double* __restrict__ varK, double* __restrict__ out_all, int64_t strideOut, int B) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= B) return;
+  const int np = 2 * d + 2;
+  const double* tot = partial_all + z * stridePartial + nparts * np;
+  const double* th = theta_all + z * strideTheta;
+  double* out = out_all + z * strideOut;
+  const bool precon = (mode == GEGP_MODE_PRECON);
+  const double vk = noisy ? varK[z] : 1.0;
+  const double SK = tot[d], DV = tot[d + 1];
+  double sdg = 0.0, sdg_th = 0.0;
+  for (int m = 0; m < d; m++) {
+    const double DG = tot[d + 2 + m];
+    sdg += DG;
+    sdg_th += 2.0 * th[m] * DG;
+    out[GEGP_OUT_GRAD + m] = vk * (tot[m] + (precon ? 2.0 * eta * DG : 0.0));
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const double* th = theta_all + z * strideTheta;
-    double* out = out_all + z * strideOut;
-    const bool precon = (mode == GEGP_MODE_PRECON);
-    const double vk = noisy ? varK[z] : 1.0;
-    const double SK = tot[d], DV = tot[d + 1];
-    double sdg = 0.0, sdg_th = 0.0;
-    for (int m = 0; m < d; m++) {
-      const double DG = tot[d + 2 + m];
-      sdg += DG;
-      sdg_th += 2.0 * th[m] * DG;
-      out[GEGP_OUT_GRAD + m] = vk * (tot[m] + (precon ? 2.0 * eta * DG : 0.0));
-    }
-    if (noisy) {
-      out[GEGP_OUT_DVARK] = SK + eta * (precon ? (DV + sdg_th) : (DV + sdg));
-      out[GEGP_OUT_DVARF] = (precon ? 1.0 + eta : 1.0) * DV;
-      out[GEGP_OUT_DVARG] = (precon ? 1.0 + eta : 1.0) * sdg;
-    }
+  if (noisy) {
+    out[GEGP_OUT_DVARK] = SK + eta * (precon ? (DV + sdg_th) : (DV + sdg));
+    out[GEGP_OUT_DVARF] = (precon ? 1.0 + eta : 1.0) * DV;
+    out[GEGP_OUT_DVARG] = (precon ? 1.0 + eta : 1.0) * sdg;
   }
 }
 
-size_t lml_grad_partial_doubles(int n, int d) {
-  return (size_t)n * ((n + GB - 1) / GB) * (2 * d + 2);
+size_t lml_grad_partial_doubles(int n, int d) {   // per-CTA partials followed by the 2d+2 column sums
+  return (size_t)n * ((n + GB - 1) / GB) * (2 * d + 2) + (size_t)(2 * d + 2);
 }
 
 int launch_lml_grad(const Ctx& ctx, const Geom& gm, const double* theta, int64_t strideTheta, const double* Kinv,
@@ -286,8 +290,12 @@ int launch_lml_grad(const Ctx& ctx, const Geom& gm, const double* theta, int64_t
                                                   quad);
   GEGP_CHECK_LAUNCH();
   const int64_t nparts = (int64_t)grid.x * grid.y;
-  lml_grad_finalize_kernel<<<ctx.batch, 256, (2 * d + 2) * sizeof(double), ctx.stream>>>(
-      d, nparts, partial, stridePartial, theta, strideTheta, mode, eta, noisy, varK, out, strideOut);
+  const int np = 2 * d + 2;
+  lml_grad_colsum_kernel<<<dim3(np, ctx.batch), 256, 0, ctx.stream>>>(np, nparts, partial, stridePartial);
+  GEGP_CHECK_LAUNCH();
+  lml_grad_finalize_kernel<<<(ctx.batch + 63) / 64, 64, 0, ctx.stream>>>(d, nparts, partial, stridePartial, theta,
+                                                                        strideTheta, mode, eta, noisy, varK, out,
+                                                                        strideOut, ctx.batch);
   GEGP_CHECK_LAUNCH();
   return 0;
 }
