@@ -301,6 +301,10 @@ int gemm_f64(const Ctx& ctx, GemmArgs g) {
       t64 -= sq * (sq - 1) / 2 + (c64 > r64 ? (c64 - r64) * r64 : 0);
     }
     if (t64 * g.inner * g.outer <= small_tile_max()) return launch_cfg<32, 32, 16, 16, 4, true>(ctx, g);
+    // skinny and deep (one block column updated by a long panel: the just-in-time pieces of the factorisation that the
+    // critical path reaches first): less than one 64 x 64 tile per SM, each walking a long K -- 32 x 32 tiles again
+    if (g.N <= 128 && g.K >= 512 && t64 * g.inner * g.outer <= 148 && exp_cfg != 5)
+      return launch_cfg<32, 32, 16, 16, 4, true>(ctx, g);
     // 64 x 64 tiles: with enough CTAs to give every SM several, a 2-stage ring (41 KB, 4 CTAs = 16 warps per SM)
     // beats the 4-stage one (82 KB, 2 CTAs per SM) by 10-15 % (measured: 2048^3 32.5 vs 28.2 TFLOP/s, the batched
     // N=1200 scan +12 %); with few CTAs the deeper prefetch of the 4-stage ring wins.  Same arithmetic either way.

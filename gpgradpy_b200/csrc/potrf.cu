@@ -58,7 +58,7 @@ int split_max_tiles() {
   return v;
 }
 constexpr int MAX_PIECES = 256;
-struct Piece { int c0, c1; cudaEvent_t done; bool live; };   // global column range a queued bulk GEMM writes
+struct Piece { int c0, c1; cudaEvent_t done; cudaStream_t stream; bool live; };   // global column range a queued bulk GEMM writes
 struct LookAhead {
   static constexpr int NBULK = 16;
   cudaStream_t hi = nullptr, col = nullptr, bulk[NBULK] = {};   // one bulk stream per recursion depth (FIFO each)
@@ -107,100 +107,139 @@ LookAhead* look_ahead() {
   return (la.ok && lookahead_enabled()) ? &la : nullptr;
 }
 
-int chol_node(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t lda, int64_t strideA, int m, int k, int row0,
-              int* info, double* Dinv, int64_t strideD) {
+// Single-stream recursion (look-ahead off): factor the left half, one trailing update, factor the right half.
+int chol_node(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, int k, int row0, int* info, double* Dinv,
+              int64_t strideD) {
   if (k <= 0) return 0;
   if (k <= LEAF) {
-    int rc = 0;
-    if (la && (rc = la->join_columns(ctx.stream, row0, row0 + k))) return rc;   // (never pending in practice)
+    int rc = leaf_potf2_inv(ctx, A, lda, strideA, k, row0, info, Dinv + (int64_t)(row0 / LEAF) * LEAF * LEAF, strideD);
+    if (rc) return rc;
+    return trsm_right_rec(ctx, A, lda, strideA, Dinv, strideD, row0, A + (int64_t)k * lda, lda, strideA, m - k, k);
+  }
+  const int k1 = split_point(k);
+  int rc = chol_node(ctx, A, lda, strideA, m, k1, row0, info, Dinv, strideD);
+  if (rc) return rc;
+  // trailing update: C = A[k1:, k1:k] -= A[k1:, :k1] * A[k1:k, :k1]^T  (lower part of the square region)
+  double* C = A + (int64_t)k1 * lda + k1;
+  const double* P = A + (int64_t)k1 * lda;
+  GemmArgs g = gemm_args(P, lda, P, lda, C, lda, m - k1, k - k1, k1, -1.0, 1.0, true);
+  g.cmode = C_LOWER;
+  rc = gemm_f64(ctx, batched(ctx, g, strideA, strideA, strideA));
+  if (rc) return rc;
+  return chol_node(ctx, C, lda, strideA, m - k1, k - k1, row0 + k1, info, Dinv, strideD);
+}
+
+// Look-ahead recursion.  `ext` is the width of the leaf that FOLLOWS this node's columns (0: none).  After the left
+// child (k1 columns, a multiple of LEAF) the trailing update is dealt out as
+//   chain : diagonal block of the next leaf f = [k1, k1+w)        -= last leaf's panel only (K = LEAF)
+//   col   : the rows below it in f's block column                 -= last leaf's panel only (K = LEAF)
+//   bulk  : columns [k1+w, k) in just-in-time pieces              -= the whole left child's panel (K = k1)
+//   bulk  : the block column of the following leaf, [k, k+ext)    -= the whole left child's panel (K = k1)
+// so that every update on the chain has K = LEAF.  f's block column has already received the other leaves of the
+// left child through the `ext` pieces queued inside that child (by induction every (source leaf, target block
+// column) pair is applied exactly once: by the chain when the source is the leaf right before the target, by the
+// bulk piece of their lowest common ancestor X when the target lies in right(X) behind its first leaf or follows X,
+// ...).  A piece is joined when the chain reaches a fork or leaf that touches its columns.
+int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t lda, int64_t strideA, int m, int k,
+                 int row0, int ext, int* info, double* Dinv, int64_t strideD) {
+  if (k <= 0) return 0;
+  int rc = 0;
+  if (k <= LEAF) {
+    if ((rc = la->join_columns(ctx.stream, row0, row0 + k))) return rc;
     rc = leaf_potf2_inv(ctx, A, lda, strideA, k, row0, info, Dinv + (int64_t)(row0 / LEAF) * LEAF * LEAF, strideD);
     if (rc) return rc;
-    if (la && la->col_pending) {   // the rows below the diagonal block were updated beside the leaf factor
+    if (la->col_pending) {   // the rows below the diagonal block were updated beside the leaf factor
       if (cudaStreamWaitEvent(ctx.stream, la->col_done, 0) != cudaSuccess) return -1104;
       la->col_pending = false;
     }
     return trsm_right_rec(ctx, A, lda, strideA, Dinv, strideD, row0, A + (int64_t)k * lda, lda, strideA, m - k, k);
   }
   const int k1 = split_point(k);
-  int rc = chol_node(ctx, la, depth + 1, A, lda, strideA, m, k1, row0, info, Dinv, strideD);
-  if (rc) return rc;
-  // trailing update: C = A[k1:, k1:k] -= A[k1:, :k1] * A[k1:k, :k1]^T  (lower part of the square region)
-  double* C = A + (int64_t)k1 * lda + k1;
-  const double* P = A + (int64_t)k1 * lda;
   const int mc = m - k1, kc = k - k1;
   const int w = kc < LEAF ? kc : LEAF;
-  if (la && depth < 40 && mc > w) {
-    // every queued bulk piece that writes the columns this update touches must have finished
-    if ((rc = la->join_columns(ctx.stream, row0 + k1, row0 + k))) return rc;
-    if (cudaEventRecord(la->fork[depth], ctx.stream) != cudaSuccess) return -1101;
-    // (a) the next leaf's diagonal block, on the chain
-    GemmArgs g0 = gemm_args(P, lda, P, lda, C, lda, w, w, k1, -1.0, 1.0, true);
+  rc = chol_node_la(ctx, la, depth + 1, A, lda, strideA, m, k1, row0, w, info, Dinv, strideD);
+  if (rc) return rc;
+  double* C = A + (int64_t)k1 * lda + k1;
+  const double* P = A + (int64_t)k1 * lda;        // rows k1.., all k1 columns of the left child
+  const double* Pl = P + (k1 - LEAF);              // ... its last leaf only
+  const int dq = depth < 40 ? depth : 39;
+  // every queued piece that writes the columns of the right child must have finished
+  if ((rc = la->join_columns(ctx.stream, row0 + k1, row0 + k))) return rc;
+  if (cudaEventRecord(la->fork[dq], ctx.stream) != cudaSuccess) return -1101;
+  {
+    GemmArgs g0 = gemm_args(Pl, lda, Pl, lda, C, lda, w, w, LEAF, -1.0, 1.0, true);
     g0.cmode = C_LOWER;
     rc = gemm_f64(ctx, batched(ctx, g0, strideA, strideA, strideA));
     if (rc) return rc;
-    // (b) the rest of its block column, beside the leaf factor
-    {
-      if (cudaStreamWaitEvent(la->col, la->fork[depth], 0) != cudaSuccess) return -1105;
-      const double* P1 = P + (int64_t)w * lda;
-      GemmArgs g1 = gemm_args(P1, lda, P, lda, C + (int64_t)w * lda, lda, mc - w, w, k1, -1.0, 1.0, true);
-      Ctx cc{la->col, ctx.batch};
-      rc = gemm_f64(cc, batched(cc, g1, strideA, strideA, strideA));
-      if (rc) return rc;
-      if (cudaEventRecord(la->col_done, la->col) != cudaSuccess) return -1106;
-      la->col_pending = true;
-    }
-    // (c) everything right of that block column, lowest priority.  A bulk that is itself latency-bound (too small
-    // for the TMA kernel) is cut along the left spine of the right child -- the sibling of the first leaf, then the
-    // sibling of that pair, ... -- and queued smallest first: each piece is joined only when the recursion reaches
-    // the columns it writes, so the chain keeps running beside the large pieces.
-    if (kc > w) {
-      cudaStream_t bs = la->bulk[depth < LookAhead::NBULK ? depth : LookAhead::NBULK - 1];
-      if (cudaStreamWaitEvent(bs, la->fork[depth], 0) != cudaSuccess) return -1102;
-      int cut[40];
-      int ncut = 0;
-      cut[ncut++] = kc;
-      const long big_tiles = ((long)(mc - w + 127) / 128) * ((kc - w + 127) / 128);
-      if (big_tiles < split_max_tiles()) {
-        int sz = kc;
-        while (sz > LEAF && ncut < 39) { sz = split_point(sz); cut[ncut++] = sz; }   // sizes along the left spine
-      } else {
-        cut[ncut++] = w;
-      }
-      // cut[] is decreasing: kc = cut[0] > cut[1] > ... > cut[ncut-1] = w; pieces [cut[i+1], cut[i]) , smallest first
-      Ctx bc{bs, ctx.batch};
-      for (int i = ncut - 2; i >= 0; i--) {
-        const int a = cut[i + 1], b = cut[i];
-        const double* Pa = P + (int64_t)a * lda;
-        GemmArgs g2 = gemm_args(Pa, lda, Pa, lda, C + (int64_t)a * lda + a, lda, mc - a, b - a, k1, -1.0, 1.0, true);
-        g2.cmode = C_LOWER;
-        rc = gemm_f64(bc, batched(bc, g2, strideA, strideA, strideA));
-        if (rc) return rc;
-        Piece* pc = la->free_piece();
-        if (!pc) return -1111;
-        if (cudaEventRecord(pc->done, bs) != cudaSuccess) return -1103;
-        pc->c0 = row0 + k1 + a; pc->c1 = row0 + k1 + b; pc->live = true;
-      }
-    }
-  } else {
-    GemmArgs g = gemm_args(P, lda, P, lda, C, lda, mc, kc, k1, -1.0, 1.0, true);
-    g.cmode = C_LOWER;
-    rc = gemm_f64(ctx, batched(ctx, g, strideA, strideA, strideA));
-    if (rc) return rc;
   }
-  return chol_node(ctx, la, depth + 1, C, lda, strideA, mc, kc, row0 + k1, info, Dinv, strideD);
+  if (mc > w) {
+    if (cudaStreamWaitEvent(la->col, la->fork[dq], 0) != cudaSuccess) return -1105;
+    GemmArgs g1 = gemm_args(Pl + (int64_t)w * lda, lda, Pl, lda, C + (int64_t)w * lda, lda, mc - w, w, LEAF, -1.0, 1.0,
+                            true);
+    Ctx cc{la->col, ctx.batch};
+    rc = gemm_f64(cc, batched(cc, g1, strideA, strideA, strideA));
+    if (rc) return rc;
+    if (cudaEventRecord(la->col_done, la->col) != cudaSuccess) return -1106;
+    la->col_pending = true;
+  }
+  cudaStream_t bs = la->bulk[depth < LookAhead::NBULK ? depth : LookAhead::NBULK - 1];
+  bool forked = false;
+  auto queue_piece = [&](cudaStream_t st, int a, int b) -> int {   // columns [a, b) of the right child's frame
+    if (cudaStreamWaitEvent(st, la->fork[dq], 0) != cudaSuccess) return -1102;
+    const double* Pa = P + (int64_t)a * lda;
+    GemmArgs g2 = gemm_args(Pa, lda, Pa, lda, C + (int64_t)a * lda + a, lda, mc - a, b - a, k1, -1.0, 1.0, true);
+    g2.cmode = C_LOWER;
+    Ctx bc{st, ctx.batch};
+    int r = gemm_f64(bc, batched(bc, g2, strideA, strideA, strideA));
+    if (r) return r;
+    Piece* pc = la->free_piece();
+    if (!pc) return -1111;
+    if (cudaEventRecord(pc->done, st) != cudaSuccess) return -1103;
+    pc->c0 = row0 + k1 + a; pc->c1 = row0 + k1 + b; pc->stream = st; pc->live = true;
+    return 0;
+  };
+  (void)forked;
+  if (kc > w) {
+    // A bulk that is itself latency-bound (too small for the TMA kernel) is cut along the left spine of the right
+    // child -- the sibling of the first leaf, then the sibling of that pair, ... -- and queued smallest first.
+    int cut[40];
+    int ncut = 0;
+    cut[ncut++] = kc;
+    const long big_tiles = ((long)(mc - w + 127) / 128) * ((kc - w + 127) / 128);
+    if (big_tiles < split_max_tiles()) {
+      int sz = kc;
+      while (sz > LEAF && ncut < 39) { sz = split_point(sz); cut[ncut++] = sz; }
+    } else {
+      cut[ncut++] = w;
+    }
+    for (int i = ncut - 2; i >= 0; i--)
+      if ((rc = queue_piece(bs, cut[i + 1], cut[i]))) return rc;
+  }
+  if (ext > 0 && mc > kc) {
+    // the following leaf's block column.  Older pieces for the same columns (queued by ancestors) may still be
+    // running on other streams: this node's bulk stream waits for them, the chain does not.
+    cudaStream_t es = bs;
+    for (int i = 0; i < MAX_PIECES; i++) {
+      const Piece& p = la->piece[i];
+      if (p.live && p.stream != es && p.c1 > row0 + k && p.c0 < row0 + k + ext)
+        if (cudaStreamWaitEvent(es, p.done, 0) != cudaSuccess) return -1112;
+    }
+    if ((rc = queue_piece(es, kc, kc + ext))) return rc;
+  }
+  return chol_node_la(ctx, la, depth + 1, C, lda, strideA, mc, kc, row0 + k1, ext, info, Dinv, strideD);
 }
 }  // namespace
 
 int chol_trap(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, int k, int row0, int* info, double* Dinv,
               int64_t strideD) {
   LookAhead* la = (k > LEAF) ? look_ahead() : nullptr;
-  if (!la) return chol_node(ctx, nullptr, 0, A, lda, strideA, m, k, row0, info, Dinv, strideD);
+  if (!la) return chol_node(ctx, A, lda, strideA, m, k, row0, info, Dinv, strideD);
   for (int i = 0; i < MAX_PIECES; i++) la->piece[i].live = false;
   la->col_pending = false;
   if (cudaEventRecord(la->begin, ctx.stream) != cudaSuccess) return -1107;
   if (cudaStreamWaitEvent(la->hi, la->begin, 0) != cudaSuccess) return -1108;
   const Ctx chain{la->hi, ctx.batch};
-  const int rc = chol_node(chain, la, 0, A, lda, strideA, m, k, row0, info, Dinv, strideD);
+  const int rc = chol_node_la(chain, la, 0, A, lda, strideA, m, k, row0, 0, info, Dinv, strideD);
   // every fork is followed by a leaf, which re-joins `col` and `bulk`; the waits below are a safety net that also
   // keeps a failed run (rc != 0) from leaving work un-joined inside a stream capture
   if (la->col_pending) cudaStreamWaitEvent(la->hi, la->col_done, 0);
