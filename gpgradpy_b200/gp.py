@@ -62,6 +62,7 @@ class DeviceMatrix:
 
 class GaussianProcess:
     use_cuda_graphs = True      # replay a captured CUDA graph for repeated noise-free evaluations (not in the reference)
+    lockstep_multistart = True  # run the SLSQP instances of a multi-start fit in lock step, objective requests batched
 
     # ---- options (names and defaults of gpgradpy/src/GaussianProcess.py:27-113) ----
     print_txt_data = False
@@ -806,6 +807,8 @@ class GaussianProcess:
         n_cho_fail = n_cond2big = 0
         max_init_cond = np.nan
         nlc = self.condnum_nlc if self.b_use_cond_cstr else []
+        if n_optz > 1 and self.lockstep_multistart and self._can_batch_fit():
+            return self._optz_multistart_lockstep(hp_x0_all, optz_bound, opt)
         for i in range(n_optz):
             x0 = hp_x0_all[i, :]
             self._last_hp_vec = None
@@ -840,6 +843,62 @@ class GaussianProcess:
             cond_val = self.calc_all_K_w_chofac(None, best_vals, calc_chofac=False, calc_cond=True,
                                                 varK=None if self.b_has_noisy_data else 1)[4]
         return best, cond_val, info
+
+    def _can_batch_fit(self):
+        """The batched objective covers the noise-free, unconstrained (precon) fit with a constant nugget."""
+        return (not self.b_has_noisy_data) and (not self.b_use_cond_cstr) and self.cond_eta_is_const \
+            and (not self.lkd_varK_pnlt_use) and self.optz_log_hp_theta
+
+    def _optz_multistart_lockstep(self, hp_x0_all, optz_bound, opt):
+        """Batch point B (optz/OptzLkd.py:249-270): every start row is its own SLSQP instance; their objective requests
+        are evaluated together (multistart.minimize_lockstep), the start rows sharded over the ranks of dist_group.
+        Same trajectories and the same selected optimum as the sequential loop (batched == single, bit for bit)."""
+        import torch
+        from . import multistart
+        hi = self.hp_info_optz_lkd
+        rank, size = parallel.world(self.dist_group)
+        n_optz = hp_x0_all.shape[0]
+        lo, hi_row = parallel.shard_bounds(n_optz, rank, size)
+        d = self.dim
+
+        def batch_val_and_grad(Xlog):
+            th = 10 ** Xlog[:, hi.idx_theta]
+            tab = self._eval_rows(th, want_grad=True).cpu().numpy()
+            ok = tab[:, L.OUT_INFO] == 0
+            vals = np.empty(Xlog.shape[0])
+            grads = np.zeros((Xlog.shape[0], hi.n_hp))
+            for r in range(Xlog.shape[0]):
+                if ok[r]:
+                    vals[r] = -tab[r, L.OUT_LML]
+                    g = tab[r, L.OUT_GRAD:L.OUT_GRAD + d].copy()
+                    g *= 10 ** Xlog[r, hi.idx_theta] * np.log(10)     # same expression as calc_store_likelihood
+                    grads[r, hi.idx_theta] = -g
+                else:   # failed Cholesky: the condition number becomes the objective (optz/OptzLkd.py:75-77)
+                    hp_vals = self.hp_vec2dataclass(hi, Xlog[r])
+                    vals[r] = self._cond_on_failure(hp_vals, False)[0]
+            return vals, grads
+
+        local = np.full((max(hi_row - lo, 0), hi.n_hp + 3), np.nan)
+        self._lockstep_stats = None
+        if hi_row > lo:
+            res, ev = multistart.minimize_lockstep(batch_val_and_grad, hp_x0_all[lo:hi_row], optz_bound, opt)
+            self._lockstep_stats = dict(n_batches=ev.n_batches, n_evals=ev.n_evals, batch_sizes=ev.batch_sizes)
+            for i, r in enumerate(res):
+                local[i, :hi.n_hp], local[i, hi.n_hp:] = r.x, (r.fun, float(r.success), r.nit)
+        if size > 1:
+            if hi_row <= lo:
+                raise RuntimeError("more ranks than start rows; shrink the process group")
+            t = torch.as_tensor(local)
+            t = t.to(bk.device()) if torch.cuda.is_available() else t
+            table = parallel.gather_rows(t, n_optz, self.dist_group).cpu().numpy()
+        else:
+            table = local
+        sol, obj, ok, nit = table[:, :hi.n_hp], table[:, hi.n_hp], table[:, hi.n_hp + 1], table[:, hi.n_hp + 2]
+        best = sol[np.nanargmin(obj), :]
+        info = {"hp_optz_success": float(np.mean(ok)), "hp_optz_iter_mean": float(np.mean(nit)),
+                "hp_optz_iter_max": float(np.max(nit)), "hp_optz_con_good": 1.0, "optz_n_cho_fail": 0,
+                "optz_n_cond2big": 0, "optz_max_init_cond": np.nan}
+        return best, np.nan, info
 
     def rescaling_data_w_theta_sol(self, X_scl_v1, xvec_scale_v1, hp_theta, tol_min_dist_x=1e-15):
         """base/GpWellCond.py:42-76: anisotropic re-scaling of x by sqrt(theta / geometric-mean theta), corrected so

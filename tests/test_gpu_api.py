@@ -202,3 +202,25 @@ def test_eval_model_hessians(golden_dir, name):
         assert np.max(np.abs((sp_[0] - sm_[0]) / (2 * eps) - h_sig[0][:, j])) < 1e-4 * np.max(np.abs(h_sig))
     out = GP.eval_model(xt, calc_grad=True, calc_hess=True, squeeze_nx=True)
     assert out[4].shape == (d, d) and out[5].shape == (d, d)
+
+
+def test_multistart_lockstep_equals_sequential_loop():
+    """lkd_optz_start_mtd='lhs' (5 SLSQP starts, optz/OptzLkd.py:249-270): the lock-step batched driver selects
+    exactly the optimum of the sequential loop (a batched candidate is evaluated bit-identically to a lone one)."""
+    from gpgradpy_b200.gp import GaussianProcess
+    from oracle import gegp_oracle as O
+    x, f, g = O.synthetic_problem(40, 3, 4)
+    out = []
+    for lock in (True, False):
+        GP = GaussianProcess(3, True, "SqExp", "precon")
+        GP.lkd_optz_start_mtd = "lhs"
+        GP.lockstep_multistart = lock
+        GP.init_optz_surr(3)
+        GP.set_data(x[:1], f[:1], np.zeros(1), g[:1], np.zeros((1, 3)))
+        GP.set_hpara("optz", 0)
+        GP.set_data(x, f, np.zeros(40), g, np.zeros((40, 3)))
+        GP.set_hpara("optz", 1)
+        out.append((GP.hp_vals.theta.copy(), GP.hp_vals.varK, GP.hp_optz_iter_mean[1], getattr(GP, "_lockstep_stats", None)))
+    assert np.array_equal(out[0][0], out[1][0]) and out[0][1] == out[1][1] and out[0][2] == out[1][2]
+    st = out[0][3]
+    assert st is not None and st["batch_sizes"][0] == 5 and st["n_batches"] < st["n_evals"]
