@@ -33,7 +33,10 @@ gemm_f64_kernel(const GemmArgs g) {
   double* sA = smem;
   double* sB = smem + STAGES * Cfg::A_STAGE;
 
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // k range clipped above by the column tile (KHI_N0): the long tiles are the LAST columns -- walk them first so the
+  // tail of the grid is made of short tiles
+  const int bx = (g.khi_mode == KHI_N0) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = bx * BN;
   if (g.cmode != C_FULL && n0 >= m0 + BM) return;  // tile entirely above the diagonal
 
   const int zo = blockIdx.z / g.inner, zi = blockIdx.z - zo * g.inner;
