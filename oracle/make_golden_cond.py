@@ -127,6 +127,42 @@ def case_surr_hess(name, n, d, mode, seed=0, npts=4):
         print(name, "stored", flush=True)
 
 
+def case_ref_unit_lkd():
+    """The scenarios of the reference's own unit test gpgradpy/unit_test/test_grad_lkd.py:26-147 (2 points in 1-D,
+    last point without gradient, theta = 1.5e-3, varK penalty on; noise-free with zero std, and noisy with UNKNOWN
+    noise so that varK, var_fval, var_fgrad are hyper-parameters), run through the reference for every conditioning
+    mode.  (The test module itself does not import as shipped: trailing module-level script)"""
+    x = 3 * np.array([[0.0], [1.0]])
+    f = np.sum(x ** 2, axis=1)
+    g_all = 2 * x
+    mask = np.array([True, False])
+    g = g_all[mask, :]
+    th = 0.001 * np.linspace(1.5, 3, 1)
+    out = dict(x=x, fval=f, grad=g, mask=mask, theta=th, varK=4.0, var_fval=3.0, var_fgrad=4.0)
+    for mode in ("base", "rescale_origin", "rescale_eta_vary", "precon"):
+        for noisy in (False, True):
+            if noisy and "rescale" in mode:
+                continue                      # test_grad_lkd.py:253-254
+            GP = GaussianProcess(1, True, "SqExp", mode)
+            GP.lkd_varK_pnlt_use = True
+            if noisy:
+                GP.set_data(x, f, None, g, None, mask)
+                hp = GP.make_hp_class(None, th.copy(), np.nan, 4.0, 3.0, 4.0)
+            else:
+                GP.set_data(x, f, np.zeros(2), g, np.zeros(g.shape), mask)
+                hp = GP.make_hp_class(None, th.copy(), np.nan, None, None, None)
+            GP.cond_max_target = 1e5
+            GP.cond_eta_is_const = True
+            info = GP.calc_lkd_all(hp, calc_cond=(mode != "precon"), calc_grad=True, lkd_use_adj_mtd=True)[0]
+            key = f"{mode}_{'noisy' if noisy else 'clean'}"
+            out[key + "_lkd"], out[key + "_grad"] = info.ln_lkd, info.ln_lkd_grad
+            out[key + "_beta"] = info.hp_beta
+            if mode != "precon":
+                out[key + "_cond"], out[key + "_cond_grad"] = info.cond, info.cond_grad
+            print("unit_lkd", key, info.ln_lkd, info.ln_lkd_grad, info.cond, flush=True)
+    np.savez_compressed(os.path.join(OUT, "ref_unit_test_grad_lkd.npz"), **out)
+
+
 def case_fit(name, n, d, mode, seed=1):
     """set_hpara('optz') with the history protocol of SURVEY appendix B.12; stores the start point the reference's
     40-candidate scan picked, so that both implementations can be started from the same x0."""
@@ -161,6 +197,7 @@ if __name__ == "__main__":
     case_surr_grad("surrgrad_d3_n14_mask", 14, 3, "precon", seed=2, mask=m)
     case_surr_hess("surrhess_d3_n16_precon", 16, 3, "precon")
     case_surr_hess("surrhess_d2_n12_rescale_origin", 12, 2, "rescale_origin", seed=1)
+    case_ref_unit_lkd()
     if "--no-fit" in sys.argv:
         sys.exit(0)
     case_fit("fit_d2_n20_base", 20, 2, "base")
