@@ -793,8 +793,13 @@ class GaussianProcess:
     def optz_hp_max_lkd(self, hp_x0_all, optz_bound):
         """optz/OptzLkd.py:185-333: SLSQP from every start row, with the condition-number constraint
         kappa_2 <= cond_max outside precon mode; the best feasible solution wins."""
-        assert self.optz_mtd == "SLSQP", "the reference recommends SLSQP; trust-constr is not wired here"
-        opt = {"ftol": self.optz_tol_obj, "eps": self.optz_tol_x, "maxiter": self.optz_iter_max, "disp": False}
+        if self.optz_mtd == "SLSQP":        # recommended by the reference (optz/OptzLkd.py:209)
+            opt = {"ftol": self.optz_tol_obj, "eps": self.optz_tol_x, "maxiter": self.optz_iter_max, "disp": False}
+        elif self.optz_mtd == "trust-constr":   # optz/OptzLkd.py:216-221
+            opt = {"initial_tr_radius": 0.1, "xtol": self.optz_tol_x, "gtol": self.optz_tol_obj,
+                   "maxiter": self.optz_iter_max, "disp": False}
+        else:
+            raise Exception(f"Unknown optz_mtd = {self.optz_mtd}")
         if hp_x0_all.ndim == 1:
             hp_x0_all = hp_x0_all[None, :]
         n_optz = hp_x0_all.shape[0]
@@ -807,7 +812,7 @@ class GaussianProcess:
         n_cho_fail = n_cond2big = 0
         max_init_cond = np.nan
         nlc = self.condnum_nlc if self.b_use_cond_cstr else []
-        if n_optz > 1 and self.lockstep_multistart and self._can_batch_fit():
+        if n_optz > 1 and self.lockstep_multistart and self.optz_mtd == "SLSQP" and self._can_batch_fit():
             return self._optz_multistart_lockstep(hp_x0_all, optz_bound, opt)
         for i in range(n_optz):
             x0 = hp_x0_all[i, :]
@@ -820,7 +825,7 @@ class GaussianProcess:
                 if cond_val > self.cond_max:
                     n_cond2big += 1
             self._last_hp_vec = None
-            res = minimize(self.return_optz_val, x0, method="SLSQP", jac=self.return_optz_grad, bounds=optz_bound,
+            res = minimize(self.return_optz_val, x0, method=self.optz_mtd, jac=self.return_optz_grad, bounds=optz_bound,
                            constraints=nlc, options=opt)
             sol[i, :], obj[i], ok[i], nit[i] = res.x, res.fun, res.success, res.nit
             if self.b_use_cond_cstr:

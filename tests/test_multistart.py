@@ -120,3 +120,18 @@ def test_multistart_sharded_world2():
         assert np.array_equal(best, best1)
         assert info["hp_optz_iter_mean"] == info1["hp_optz_iter_mean"]
         assert stats["batch_sizes"][0] == (3 if rank == 0 else 2)
+
+
+def test_trust_constr_option_reaches_the_same_optimum():
+    """optz_mtd='trust-constr' (optz/OptzLkd.py:216-221) through the same callbacks: same optimum as SLSQP."""
+    x0 = np.array([[-1.0, -0.5]])
+    bound = Bounds(-5 * np.ones(2), 1 * np.ones(2), keep_feasible=True)
+    GP = _make_gp()
+    b1 = GP.optz_hp_max_lkd(x0, bound)[0]
+    GP.optz_mtd = "trust-constr"
+    b2 = GP.optz_hp_max_lkd(x0, bound)[0]
+    f1, f2 = GP.return_optz_val(b1), GP.return_optz_val(b2)
+    assert abs(f1 - f2) < 1e-6 * max(1.0, abs(f1))
+    GP.optz_mtd = "nope"
+    with pytest.raises(Exception):
+        GP.optz_hp_max_lkd(x0, bound)
