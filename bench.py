@@ -332,6 +332,19 @@ def run_b200(args):
                               "frac": ph["build_full_gbs"] / hbm_peak, "bytes": 8.0 * N * N,
                               "lower_only_gbs": ph["build_lower_gbs"]}}
     extra = {}
+    if world == 1:
+        # batch point B (multi-start rows in lock step): several candidates per device call fill the GPU where one
+        # N ~ 5000 evaluation is bound by the latency of its leaf chain.  Reported beside the headline, never instead.
+        try:
+            Bc = 4
+            thb = torch.stack([bk.to_dev(step_theta(theta, 1000 + s, rank)) for s in range(Bc)])
+            runb = lambda: bk.lml_eval(X_dev, y_dev, thb, mode=L.MODE_PRECON, eta=eta, want_grad=True)  # noqa: E731
+            runb()
+            msb = ev_ms(runb, 3)
+            extra["batched"] = {"candidates_per_call": Bc, "ms_per_call": msb, "evals_per_s": Bc / (msb * 1e-3),
+                                "note": "same workload, 4 candidate thetas per gegp_lml_eval call (lock-step multi-start)"}
+        except Exception as exc:
+            extra["batched"] = {"error": repr(exc)}
     if args.workload != "c3" and not args.no_c3 and world == 1:
         try:
             extra["c3"] = phase_numbers(*WORKLOADS["c3"], reps=2)
