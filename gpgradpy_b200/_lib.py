@@ -23,7 +23,7 @@ OPT_SMALL_TILE_MAX = 3
 EXPORTS = (
     "gegp_abi_version", "gegp_set_option", "gegp_workspace_bytes", "gegp_ld", "gegp_build_cov", "gegp_cross_cov", "gegp_potrf",
     "gegp_trsm_rows", "gegp_dinv_doubles", "gegp_potri", "gegp_dgemm", "gegp_lml_eval", "gegp_predict_setup", "gegp_predict", "gegp_profile_begin", "gegp_profile_end",
-    "gegp_predict_grad", "gegp_predict_hess", "gegp_lml_layout", "gegp_symv", "gegp_row_abs_sum", "gegp_lanczos_step", "gegp_lincomb", "gegp_quad_grad_work_bytes", "gegp_quad_grad",
+    "gegp_predict_grad", "gegp_predict_hess", "gegp_lml_layout", "gegp_symv", "gegp_row_abs_sum", "gegp_row_sq_sum", "gegp_weighted_grad", "gegp_lanczos_step", "gegp_lincomb", "gegp_quad_grad_work_bytes", "gegp_quad_grad",
 )
 
 
@@ -86,6 +86,10 @@ def load():
     lib.gegp_symv.argtypes = [i, dp, i64, dp, dp, vp]
     lib.gegp_row_abs_sum.restype = i
     lib.gegp_row_abs_sum.argtypes = [i, dp, i64, dp, vp]
+    lib.gegp_row_sq_sum.restype = i
+    lib.gegp_row_sq_sum.argtypes = [i, dp, i64, dp, vp]
+    lib.gegp_weighted_grad.restype = i
+    lib.gegp_weighted_grad.argtypes = [i, i, i, dp, ip, dp, dp, i64, i, dbl, i, dp, dp, vp, sz, vp]
     lib.gegp_lanczos_step.restype = i
     lib.gegp_lanczos_step.argtypes = [i, i, dp, i64, dp, dp, dp, vp]
     lib.gegp_lincomb.restype = i

@@ -390,6 +390,49 @@ def row_abs_sum(M: torch.Tensor, N: int) -> torch.Tensor:
     return out
 
 
+def fro_norm(M: torch.Tensor, N: int) -> float:
+    """Frobenius norm of M[:N, :N] (gegp_row_sq_sum, the N row sums added on the host)."""
+    out = torch.empty(N, dtype=F64, device=M.device)
+    rc = L.load().gegp_row_sq_sum(N, _p(M), M.stride(0), _p(out), _stream())
+    _check(rc, "gegp_row_sq_sum")
+    return float(np.sqrt(np.sum(out.cpu().numpy())))
+
+
+def weighted_grad(X, theta, W: torch.Tensor, *, n_g=None, slot=None, eta=0.0, noisy=False, varK=1.0):
+    """gegp_weighted_grad: sum(W .* dKcov/dhp) for every hyper-parameter (base mode) -> device row (GEGP_OUT_* layout)."""
+    lib = L.load()
+    X, theta = to_dev(X), to_dev(theta)
+    n, d = X.shape
+    n_g = n if n_g is None else n_g
+    N = n + n_g * d
+    out = torch.zeros(L.out_len(d), dtype=F64, device=device())
+    vk = to_dev(np.array([float(varK)]))
+    nbytes = int(lib.gegp_quad_grad_work_bytes(n, n_g, d)) + 8 * (N + 2)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=device())
+    rc = lib.gegp_weighted_grad(n, n_g, d, _p(X), _p(slot), _p(theta), _p(W), W.stride(0), L.MODE_BASE, float(eta),
+                                int(bool(noisy)), _p(vk), _p(out), _p(ws), nbytes, _stream())
+    _check(rc, "gegp_weighted_grad")
+    return out
+
+
+def cond_fro(Kfull: torch.Tensor, Kinv: torch.Tensor, N: int, want_weight: bool):
+    """Frobenius condition number |K|_F |K^-1|_F and, if asked, the weight matrix of its gradient
+    d cond / dK = frac K - K^-3 / frac, frac = |K^-1|_F / |K|_F  (optz/GpHparaCon.py:237-261); the two matrix
+    products run on the DMMA GEMM engine (K^-1 is symmetric, so K^-1 K^-1 = K^-1 (K^-1)^T)."""
+    nk, ni = fro_norm(Kfull, N), fro_norm(Kinv, N)
+    cond = nk * ni
+    if not want_weight:
+        return cond, None
+    ld = ld_of(N)
+    K2 = torch.empty((N, ld), dtype=F64, device=Kinv.device)
+    K3 = torch.empty((N, ld), dtype=F64, device=Kinv.device)
+    dgemm(Kinv[:, :N], Kinv[:, :N], K2[:, :N], transb=True)
+    frac = ni / nk
+    K3[:, :N].copy_(Kfull[:, :N])                                            # W = frac K - (K^-2 K^-1) / frac, in one GEMM
+    dgemm(K2[:, :N], Kinv[:, :N], K3[:, :N], transb=True, alpha=-1.0 / frac, beta=frac)
+    return cond, K3
+
+
 def extreme_eig(M: torch.Tensor, N: int, *, k: int = 40, tol: float = 1e-12, max_cycles: int = 12, v0=None):
     """Largest eigenpair of the symmetric device matrix M[:N, :N]: restarted Lanczos with full re-orthogonalisation.
 
@@ -479,6 +522,18 @@ def lml_views(n: int, n_g: int, d: int):
     N = n + n_g * d
     return dict(A=dbl[offA:offA + (N + 2) * ld].view(N + 2, ld), U=dbl[offU:offU + N * ld].view(N, ld),
                 Kinv=dbl[offK:offK + N * ld].view(N, ld), p=dbl[offP:offP + N], pinv=dbl[offP + ld:offP + ld + N], ld=ld)
+
+
+def cond_fro_of_matrix(K: torch.Tensor, N: int) -> float:
+    """Frobenius condition number of an explicit SPD device matrix (factor a copy, explicit inverse, two norms)."""
+    ld = ld_of(N)
+    A = torch.empty((N, ld), dtype=F64, device=K.device)
+    A[:, :N] = K[:, :N]
+    info, dinv = potrf(A, N, 0)
+    if int(info.item()) != 0:
+        return 1e18
+    _, Kinv = potri(A, dinv, N)
+    return cond_fro(K, Kinv, N, False)[0]
 
 
 def cond2_of_matrix(K: torch.Tensor, N: int, *, tol: float = 1e-12):

@@ -385,6 +385,15 @@ int gegp_row_abs_sum(int N, const double* M, int64_t ld, double* out, void* stre
   return row_abs_sum(ctx, N, M, ld, out);
 }
 
+int gegp_row_sq_sum(int N, const double* M, int64_t ld, double* out, void* stream) {
+  if (N <= 0) return -1;
+  if (!M || (reinterpret_cast<uintptr_t>(M) & 15)) return -2;
+  if (ld < N || (ld & 1)) return -3;
+  if (!out) return -4;
+  Ctx ctx{(cudaStream_t)stream, 1};
+  return row_abs_sum(ctx, N, M, ld, out, true);
+}
+
 int gegp_lanczos_step(int N, int j, double* V, int64_t ldv, double* w, double* alpha, double* beta, void* stream) {
   if (N <= 0) return -1;
   if (j < 0 || j >= 255) return -2;
@@ -437,6 +446,35 @@ int gegp_quad_grad(int n, int n_g, int d, const double* X, const int32_t* grad_s
   if (rc) return rc;
   return launch_lml_grad(ctx, gm, theta, 0, nullptr, 0, 0, v, 0, ones, 0, mode, eta, noisy, varK_dev, 0.0, partial, 0, out,
                          0, 1);
+}
+
+int gegp_weighted_grad(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+                       const double* W, int64_t ldw, int mode, double eta, int noisy, const double* varK_dev, double* out,
+                       void* work, size_t work_bytes, void* stream) {
+  if (bad_geom(n, n_g, d)) return -1;
+  if (!X) return -4;
+  if (n_g != n && !grad_slot) return -5;
+  if (!theta) return -6;
+  if (!W) return -7;
+  const int N = n + n_g * d;
+  if (ldw < N) return -8;
+  if (mode != GEGP_MODE_BASE) return -9;
+  if (noisy && !varK_dev) return -12;
+  if (!out) return -13;
+  if (!work || (reinterpret_cast<uintptr_t>(work) & 15)) return -14;
+  if (work_bytes < gegp_quad_grad_work_bytes(n, n_g, d) + (size_t)round_up(N, 2) * sizeof(double)) return -15;
+  Ctx ctx{(cudaStream_t)stream, 1};
+  Geom gm{n, n_g, d, N, X, (n_g == n) ? nullptr : grad_slot};
+  double* ones = reinterpret_cast<double*>(work);
+  double* zeros = ones + round_up(N, 2);                     // alpha := 0 (no rank-one part)
+  double* partial = zeros + round_up(N, 2);
+  NoiseSpec ns{nullptr, 0, nullptr, 1.0, 0};
+  int rc = launch_prep_p(ctx, gm, theta, 0, ns, GEGP_MODE_BASE, nullptr, ones, 0);
+  if (rc) return rc;
+  cudaError_t e = cudaMemsetAsync(zeros, 0, (size_t)round_up(N, 2) * sizeof(double), ctx.stream);
+  if (e != cudaSuccess) return -1000 - (int)e;
+  return launch_lml_grad(ctx, gm, theta, 0, W, ldw, 0, zeros, 0, ones, 0, mode, eta, noisy, varK_dev, 0.0, partial, 0, out,
+                         0, 2);
 }
 
 int gegp_predict_setup(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,

@@ -34,6 +34,7 @@ symv_kernel(int N, const double* __restrict__ M, int64_t ld, const double* __res
 
 // out[row] = sum_c |M[row, c]| : the Gershgorin row sums behind the variable nugget
 // eta = max_row sum|K| / (cond_max_target - 1)  (kernel/Kernel.py:229-234, 269-274).
+template <bool SQ>
 __global__ void __launch_bounds__(SYMV_ROWS * 32)
 row_abs_sum_kernel(int N, const double* __restrict__ M, int64_t ld, double* __restrict__ out) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -44,10 +45,10 @@ row_abs_sum_kernel(int N, const double* __restrict__ M, int64_t ld, double* __re
   const int N2 = N & ~1;
   for (int c = 2 * lane; c < N2; c += 64) {
     const double2 m = *reinterpret_cast<const double2*>(mr + c);
-    s0 += fabs(m.x);
-    s1 += fabs(m.y);
+    s0 += SQ ? m.x * m.x : fabs(m.x);
+    s1 += SQ ? m.y * m.y : fabs(m.y);
   }
-  if ((N & 1) && lane == 0) s0 += fabs(mr[N - 1]);
+  if ((N & 1) && lane == 0) s0 += SQ ? mr[N - 1] * mr[N - 1] : fabs(mr[N - 1]);
   const double s = warp_sum(s0 + s1);
   if (lane == 0) out[row] = s;
 }
@@ -130,9 +131,10 @@ int symv_full(const Ctx& ctx, int N, const double* M, int64_t ld, const double* 
   return 0;
 }
 
-int row_abs_sum(const Ctx& ctx, int N, const double* M, int64_t ld, double* out) {
+int row_abs_sum(const Ctx& ctx, int N, const double* M, int64_t ld, double* out, bool squares) {
   if (N <= 0) return 0;
-  row_abs_sum_kernel<<<(N + SYMV_ROWS - 1) / SYMV_ROWS, SYMV_ROWS * 32, 0, ctx.stream>>>(N, M, ld, out);
+  if (squares) row_abs_sum_kernel<true><<<(N + SYMV_ROWS - 1) / SYMV_ROWS, SYMV_ROWS * 32, 0, ctx.stream>>>(N, M, ld, out);
+  else row_abs_sum_kernel<false><<<(N + SYMV_ROWS - 1) / SYMV_ROWS, SYMV_ROWS * 32, 0, ctx.stream>>>(N, M, ld, out);
   GEGP_CHECK_LAUNCH();
   return 0;
 }

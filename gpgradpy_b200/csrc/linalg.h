@@ -92,8 +92,8 @@ int trmv_upper(const Ctx& ctx, const double* U, int64_t ldu, int64_t strideU, co
 // --- extreme eigenpairs (Lanczos building blocks, csrc/eig.cu) ---
 // y = M x for a dense row-major N x ld matrix.
 int symv_full(const Ctx& ctx, int N, const double* M, int64_t ld, const double* x, double* y);
-// out[row] = sum_c |M[row, c]| (Gershgorin row sums for the variable nugget).
-int row_abs_sum(const Ctx& ctx, int N, const double* M, int64_t ld, double* out);
+// out[row] = sum_c |M[row, c]| (Gershgorin row sums for the variable nugget) or sum_c M[row, c]^2 (Frobenius norm).
+int row_abs_sum(const Ctx& ctx, int N, const double* M, int64_t ld, double* out, bool squares = false);
 // One Lanczos step with full re-orthogonalisation: V rows 0..j orthonormal, w = M v_j on entry; writes alpha[j],
 // beta[j] (device) and V row j+1 (j < 255).
 int lanczos_step(const Ctx& ctx, int N, int j, double* V, int64_t ldv, double* w, double* alpha, double* beta);

@@ -133,8 +133,9 @@ lml_grad_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideThe
   __syncthreads();
 
   // quad: W = alpha alpha^T only (quadratic forms v^T dK/dhp v for the condition-number gradient); Kinv is not read
-  const double c1 = quad ? 1.0 : (noisy ? 0.5 : (pnlt_grad / N + 1.0 / (2.0 * outz[GEGP_OUT_SIGMA2])));
-  const double c2 = quad ? 0.0 : 0.5;
+  // quad == 2: W = the symmetric matrix passed in place of Kinv (general weighted sum  sum(W .* dK/dhp))
+  const double c1 = quad == 2 ? 0.0 : quad ? 1.0 : (noisy ? 0.5 : (pnlt_grad / N + 1.0 / (2.0 * outz[GEGP_OUT_SIGMA2])));
+  const double c2 = quad == 2 ? -1.0 : quad ? 0.0 : 0.5;
   const int sa = gm.slot ? gm.slot[a] : a;
   const bool valid = (b < n);
   const int sb = valid ? (gm.slot ? gm.slot[b] : b) : -1;
@@ -158,7 +159,7 @@ lml_grad_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideThe
     }
     kk = exp(e);
     const double pa0 = pinv[a], pb0 = pinv[b];
-    const double W00 = pa0 * pb0 * (c1 * alpha[a] * alpha[b] - (quad ? 0.0 : c2 * Kinv[(int64_t)a * ldk + b]));
+    const double W00 = pa0 * pb0 * (c1 * alpha[a] * alpha[b] - (quad == 1 ? 0.0 : c2 * Kinv[(int64_t)a * ldk + b]));
     S = W00;
     if (same) dv = W00;
   } else {
@@ -178,11 +179,11 @@ lml_grad_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideThe
       const double* krow = Kinv + (int64_t)row * ldk;
       const double rb = gm.X[(int64_t)b * d + i];
       const double ri = xa[i] - rb, ui = th[i] * ri;
-      const double Wi0 = pr * pinv[b] * (c1 * ar * alpha[b] - (quad ? 0.0 : c2 * krow[b]));
+      const double Wi0 = pr * pinv[b] * (c1 * ar * alpha[b] - (quad == 1 ? 0.0 : c2 * krow[b]));
       double rowdot = 0.0, Wii = 0.0;
       if (sb >= 0) {
         double dot = 0.0, kii = 0.0;
-        if (!quad) {
+        if (quad != 1) {
           for (int j = 0; j < d; j++) {
             const double kv = krow[n + j * ng + sb];
             dot += vs[j * GB + tid] * kv;

@@ -455,10 +455,14 @@ class GaussianProcess:
             Kc, _ = bk.build_cov(X, theta, noise=noise, mode=L.MODE_BASE, eta=etaK, varK=varK, **kw)
             Kcor, Kcov, fac_src, pvec = None, DeviceMatrix(Kc), Kc, None
         condK = None
-        if calc_cond:   # kappa_2 of the matrix that is factored (kernel/Kernel.py:240,280), device Lanczos
-            assert self.cond_norm == 2, "the CUDA path implements the recommended 2-norm condition number"
-            self._last_cond = bk.cond2_of_matrix(fac_src, N)
-            condK = float(self._last_cond["cond"])
+        if calc_cond:   # condition number of the matrix that is factored (kernel/Kernel.py:240,280)
+            if self.cond_norm == 2:       # device Lanczos
+                self._last_cond = bk.cond2_of_matrix(fac_src, N)
+                condK = float(self._last_cond["cond"])
+            elif self.cond_norm == "fro":
+                condK = bk.cond_fro_of_matrix(fac_src, N)
+            else:
+                raise Exception(f'cond_norm must be either 2 or "fro" but it is {self.cond_norm}')
             if (not precon) and condK > self.cond_max_abs:
                 calc_chofac = False
         Kcov_chofac = None
@@ -598,10 +602,15 @@ class GaussianProcess:
         qa = bk.quad_grad(self._X_dev, theta, res["v_max"], **kw).cpu().numpy()
         qi = bk.quad_grad(self._X_dev, theta, res["v_min"], **kw).cpu().numpy()
         q = (qa - res["cond"] * qi) / max(res["lam_min"], 1e-16)     # lam_min of Kcov (varK included)
+        return self._hp_row_to_grad(q)
+
+    def _hp_row_to_grad(self, q):
+        """GEGP_OUT_* row of per-hyper-parameter sums -> vector in the optimiser's hyper-parameter order."""
+        hi, d = self.hp_info_optz_lkd, self.dim
         g = np.zeros(hi.n_hp)
         if hi.has_theta:
             g[hi.idx_theta] = q[L.OUT_GRAD:L.OUT_GRAD + d]
-        if noisy:
+        if self.b_has_noisy_data:
             if hi.has_varK:
                 g[hi.idx_varK] = q[L.OUT_DVARK]
             if hi.has_var_fval:
@@ -614,7 +623,6 @@ class GaussianProcess:
         """Condition number (+ gradient) of the matrix whose factor L, L^-T and explicit inverse the likelihood
         evaluation that has just run left in the workspace: the matrix itself is rebuilt into the (no longer needed)
         L^-T buffer for the lambda_max products, lambda_min comes from products with the inverse."""
-        assert self.cond_norm == 2, "the CUDA path implements the recommended 2-norm condition number"
         theta, noise, varK = self._cond_matrix_args(hp_vals)
         v = bk.lml_views(self.n_eval, self.n_grad, self.dim)
         mode, N = self._mode, self.n_data
@@ -625,6 +633,17 @@ class GaussianProcess:
             v["Kinv"][:, :N].mul_(v["pinv"][:, None]).mul_(v["pinv"][None, :])
         bk.build_cov(self._X_dev, theta, n_g=self.n_grad, slot=self._slot_dev, noise=noise, mode=mode,
                      eta=getattr(self, "_eta_used", self._etaK), varK=varK, out=v["U"])
+        if self.cond_norm == "fro":   # optz/GpHparaCon.py:237-261
+            want_w = calc_grad and self.wellcond_mtd != "precon"
+            cond, W = bk.cond_fro(v["U"], v["Kinv"], N, want_w)
+            if not want_w:
+                return cond, None
+            q = bk.weighted_grad(self._X_dev, theta, W, n_g=self.n_grad, slot=self._slot_dev,
+                                 eta=getattr(self, "_eta_used", self._etaK), noisy=self.b_has_noisy_data,
+                                 varK=varK).cpu().numpy()
+            return cond, self._hp_row_to_grad(q)
+        if self.cond_norm != 2:
+            raise Exception(f'cond_norm must be either 2 or "fro" but it is {self.cond_norm}')
         res = bk.cond2(v["U"], v["Kinv"], N)
         self._last_cond = res
         return float(res["cond"]), (self._cond_grad_from_vectors(hp_vals, res, varK) if calc_grad else None)

@@ -192,6 +192,14 @@ int gegp_symv(int N, const double* M, int64_t ld, const double* x, double* y, vo
 /* out[row] = sum_c |M[row, c]|: Gershgorin row sums of the built matrix for the variable nugget
  * eta = max_row / (cond_max_target - 1) of wellcond_mtd = 'rescale_eta_vary' (kernel/Kernel.py:229-234, 269-274). */
 int gegp_row_abs_sum(int N, const double* M, int64_t ld, double* out, void* stream);
+/* out[row] = sum_c M[row, c]^2 (Frobenius norms for cond_norm = 'fro', optz/GpHparaCon.py:237-261). */
+int gegp_row_sq_sum(int N, const double* M, int64_t ld, double* out, void* stream);
+/* sum(W .* dKcov/dhp) for a symmetric device matrix W (N x ldw) and every hyper-parameter, dKcov/dhp generated on the
+ * fly; layout of `out` as gegp_quad_grad.  The Frobenius condition-number gradient contracts
+ * W = frac K - K^-3 / frac this way (optz/GpHparaCon.py:252-259).  work >= gegp_quad_grad_work_bytes + 8 (N + 1). */
+int gegp_weighted_grad(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+                       const double* W, int64_t ldw, int mode, double eta, int noisy, const double* varK_dev,
+                       double* out, void* work, size_t work_bytes, void* stream);
 int gegp_lanczos_step(int N, int j, double* V, int64_t ldv, double* w, double* alpha, double* beta, void* stream);
 int gegp_lincomb(int N, int k, const double* V, int64_t ldv, const double* coef, double* out, void* stream);
 size_t gegp_quad_grad_work_bytes(int n, int n_g, int d);

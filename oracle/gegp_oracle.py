@@ -474,6 +474,18 @@ def cond_l2_w_grad(Kmat, Kgrad_hp=None):
     return cond, np.array([np.sum(diff * Kgrad_hp[i]) / emin for i in range(Kgrad_hp.shape[0])])
 
 
+def cond_fro_w_grad(Kmat, Kgrad_hp=None):
+    """Frobenius condition number |K|_F |K^-1|_F and its gradient sum((frac K - K^-3 / frac) * dK/dhp),
+    frac = |K^-1|_F / |K|_F  (optz/GpHparaCon.py:237-261)."""
+    Kinv = np.linalg.inv(Kmat)
+    nk, ni = np.linalg.norm(Kmat, "fro"), np.linalg.norm(Kinv, "fro")
+    if Kgrad_hp is None:
+        return nk * ni, None
+    frac = ni / nk
+    W = frac * Kmat - (Kinv @ Kinv @ Kinv) / frac
+    return nk * ni, np.sum(W[None, :, :] * Kgrad_hp, axis=(1, 2))
+
+
 def cond_wo_noise(X, theta, mode, eta, mask=None, calc_grad=True):
     """Condition number of the matrix calc_lkd_all factors for noise-free data (K + eta-term, varK := 1) and its
     theta-gradient (optz/CalcLkd.py:322-343).  The reference has no gradient in precon mode (:171-173)."""

@@ -73,6 +73,29 @@ def case_eta_vary(name, n, d, theta, seed=0):
     print(name, "eta", eta, "idx", idx, "lml", info.ln_lkd, "cond", info.cond, flush=True)
 
 
+def case_cond_fro(name, n, d, theta, seed=0, std_f=0.0, std_g=0.0, varK=None):
+    """cond_norm = 'fro' (optz/GpHparaCon.py:237-261) through calc_lkd_all(calc_cond=True, calc_grad=True), base mode."""
+    x, f, g = O.synthetic_problem(n, d, seed)
+    GP = GaussianProcess(d, True, "SqExp", "base")
+    GP.cond_norm = "fro"
+    GP.set_data(x, f, std_f * np.ones(n), g, std_g * np.ones(g.shape))
+    th = np.asarray(theta, float)
+    hp = GP.make_hp_class(theta=th, varK=varK)
+    info, ok = GP.calc_lkd_all(hp, calc_cond=True, calc_grad=True)
+    c0 = GP.calc_lkd_all(hp, calc_cond=True, calc_grad=False)[0].cond
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), x=x, fval=f, grad=g, theta=th, eta=GP._etaK, cond=info.cond,
+                        cond_grad=info.cond_grad, cond_nograd=c0, std_f=std_f, std_g=std_g,
+                        varK=np.nan if varK is None else varK, ln_lkd=info.ln_lkd)
+    if varK is None:
+        ka = O.all_K_w_chofac(x, th, "base", GP._etaK, None, 1.0, None, calc_chofac=False)
+        c, cg = O.cond_fro_w_grad(ka.Kcov, O.kerngrad_hp(x, th, "base", GP._etaK))
+    else:
+        nv = GP.calc_noise_vec(hp)
+        ka = O.all_K_w_chofac(x, th, "base", GP._etaK, nv, varK, None, calc_chofac=False)
+        c, cg = O.cond_fro_w_grad(ka.Kcov, O.kcov_grad_hp_noisy(x, th, ka.Kern, "base", GP._etaK, varK, False, False))
+    print(name, f"cond {info.cond:.6e} oracle rel {rel(c, info.cond):.2e} grad rel {rel(cg, info.cond_grad):.2e}", flush=True)
+
+
 def case_surr_grad(name, n, d, mode, seed=0, mask=None):
     """eval_model(calc_grad=True): d mu / d x and d sig / d x (eval/GpEvalModel.py:170-173, 319-354)."""
     x, f, g = O.synthetic_problem(n, d, seed)
@@ -197,6 +220,8 @@ if __name__ == "__main__":
     case_surr_grad("surrgrad_d3_n14_mask", 14, 3, "precon", seed=2, mask=m)
     case_surr_hess("surrhess_d3_n16_precon", 16, 3, "precon")
     case_surr_hess("surrhess_d2_n12_rescale_origin", 12, 2, "rescale_origin", seed=1)
+    case_cond_fro("condfro_d2_n12_base", 12, 2, [0.6, 1.4])
+    case_cond_fro("condfro_d2_n14_noisy_base", 14, 2, [0.7, 1.1], seed=4, std_f=1e-2, std_g=5e-2, varK=40.0)
     case_ref_unit_lkd()
     if "--no-fit" in sys.argv:
         sys.exit(0)

@@ -192,3 +192,24 @@ def test_variable_nugget_mode(golden_dir):
     mu, sig = GP.eval_model(g["x_test"])[:2]
     assert np.max(np.abs(mu - g["mu"])) < 1e-8 * np.max(np.abs(g["mu"]))
     assert np.max(np.abs(sig - g["sig"])) < 1e-6 * np.max(np.abs(g["sig"]))
+
+
+@pytest.mark.parametrize("name", ["condfro_d2_n12_base", "condfro_d2_n14_noisy_base"])
+def test_frobenius_cond_through_the_api(golden_dir, name):
+    """GP.cond_norm = 'fro' (optz/GpHparaCon.py:237-261): |K|_F |K^-1|_F from two device reductions and its gradient from
+    sum((frac K - K^-3 / frac) .* dKcov/dhp) with dKcov/dhp generated on the fly (gegp_weighted_grad)."""
+    g = _load(golden_dir, name)
+    from gpgradpy_b200.gp import GaussianProcess
+    x = g["x"]
+    n, d = x.shape
+    GP = GaussianProcess(d, True, "SqExp", "base")
+    GP.cond_norm = "fro"
+    GP.set_data(x, g["fval"], float(g["std_f"]) * np.ones(n), g["grad"], float(g["std_g"]) * np.ones((n, d)))
+    varK = None if np.isnan(g["varK"]) else float(g["varK"])
+    hp = GP.make_hp_class(theta=g["theta"], varK=varK)
+    info, ok = GP.calc_lkd_all(hp, calc_cond=True, calc_grad=True)
+    assert ok and abs(info.ln_lkd - g["ln_lkd"]) < 1e-8 * abs(g["ln_lkd"])
+    assert abs(info.cond - g["cond"]) < 1e-7 * g["cond"]
+    assert np.max(np.abs(info.cond_grad - g["cond_grad"])) < 1e-6 * np.max(np.abs(g["cond_grad"]))
+    c = GP.calc_all_K_w_chofac(None, hp, calc_chofac=False, calc_cond=True, varK=varK if varK else 1)[4]
+    assert abs(c - g["cond_nograd"]) < 1e-7 * g["cond_nograd"]

@@ -196,3 +196,21 @@ def test_surrogate_hessians(golden_dir):
                               g["x_test"][p], "precon", float(g["eta"]))
         assert np.max(np.abs(o[4][0] - g["d2mudx2"][p])) < 1e-8 * np.max(np.abs(g["d2mudx2"][p]))
         assert np.max(np.abs(o[5][0] - g["d2sigdx2"][p])) < 1e-6 * np.max(np.abs(g["d2sigdx2"][p]))
+
+
+@pytest.mark.parametrize("name", ["condfro_d2_n12_base", "condfro_d2_n14_noisy_base"])
+def test_frobenius_condition_number(golden_dir, name):
+    """cond_norm = 'fro': |K|_F |K^-1|_F and its gradient (optz/GpHparaCon.py:237-261)."""
+    g = _load(golden_dir, name)
+    x, th, eta = g["x"], g["theta"], float(g["eta"])
+    if np.isnan(g["varK"]):
+        ka = O.all_K_w_chofac(x, th, "base", eta, None, 1.0, None, calc_chofac=False)
+        D = O.kerngrad_hp(x, th, "base", eta)
+    else:
+        n, d = x.shape
+        nv = np.hstack((np.full(n, float(g["std_f"]) ** 2), np.full(n * d, float(g["std_g"]) ** 2)))
+        ka = O.all_K_w_chofac(x, th, "base", eta, nv, float(g["varK"]), None, calc_chofac=False)
+        D = O.kcov_grad_hp_noisy(x, th, ka.Kern, "base", eta, float(g["varK"]), False, False)
+    c, cg = O.cond_fro_w_grad(ka.Kcov, D)
+    assert abs(c - g["cond"]) < 1e-9 * g["cond"] and abs(c - g["cond_nograd"]) < 1e-9 * g["cond"]
+    assert np.max(np.abs(cg - g["cond_grad"])) < 1e-8 * np.max(np.abs(g["cond_grad"]))
