@@ -42,14 +42,17 @@ int trsm_right_rec(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL
 // Look-ahead.  The factorisation's critical path is the chain  leaf factor -> leaf solve -> update of the next
 // leaf's diagonal block -> next leaf factor  (one CTA, then a few: latency bound).  It runs on its own
 // HIGHEST-priority stream (`hi`, forked from and re-joined to the caller's stream), so that its CTAs take the next
-// free SM ahead of queued GEMM tiles.  The trailing update of a recursion node,  C -= P P^T,  is split three ways:
-//   * the next leaf's diagonal block (LEAF x LEAF)                      -> on the chain (`hi`);
-//   * the rest of the next leaf's block column ((mc - LEAF) x LEAF)     -> stream `col` (high priority): only the
-//     leaf SOLVE needs it, so it runs beside the leaf factor;
-//   * everything right of that block column                            -> stream `bulk` (lowest priority): re-joined
-//     right after the next leaf, before anything touches the rest of C.
-// Every output element is still produced by exactly one GEMM with the same k order, so results do not change.
-// One event pair per recursion depth and device; fork/join is capturable in a CUDA graph.
+// free SM ahead of queued GEMM tiles.  Everything else is dealt out so that the chain only ever does K = LEAF work:
+//   * the next leaf's diagonal block, updated with the LAST leaf's panel only          -> on the chain (`hi`);
+//   * the rows below it in that block column, same K = LEAF                            -> stream `col` (high
+//     priority): only the leaf SOLVE needs them, so they are updated beside the leaf factor;
+//   * the columns right of it, updated with the whole left child's panel, cut into pieces along the left spine of
+//     the right child, plus the block column of the leaf that FOLLOWS the node       -> streams `bulk[depth]` (lowest
+//     priority); a piece is joined only when the chain reaches a fork or leaf that touches its columns.
+// See chol_node_la for the induction that every (source leaf, target block column) pair is applied exactly once.
+// The summation order of an element differs from the single-stream schedule (same terms, grouped by update), so the
+// two schedules agree to rounding, not bit for bit; within one schedule results are reproducible and independent of
+// the batch size.  Fork/join is by events only and is capturable in a CUDA graph.
 // ------------------------------------------------------------------------------------------------
 namespace {
 // a trailing update with fewer 128 x 128 tiles than this is cut into just-in-time pieces (env GEGP_SPLIT_TILES)
@@ -183,7 +186,6 @@ int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t ld
     la->col_pending = true;
   }
   cudaStream_t bs = la->bulk[depth < LookAhead::NBULK ? depth : LookAhead::NBULK - 1];
-  bool forked = false;
   auto queue_piece = [&](cudaStream_t st, int a, int b) -> int {   // columns [a, b) of the right child's frame
     if (cudaStreamWaitEvent(st, la->fork[dq], 0) != cudaSuccess) return -1102;
     const double* Pa = P + (int64_t)a * lda;
@@ -198,7 +200,6 @@ int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t ld
     pc->c0 = row0 + k1 + a; pc->c1 = row0 + k1 + b; pc->stream = st; pc->live = true;
     return 0;
   };
-  (void)forked;
   if (kc > w) {
     // A bulk that is itself latency-bound (too small for the TMA kernel) is cut along the left spine of the right
     // child -- the sibling of the first leaf, then the sibling of that pair, ... -- and queued smallest first.
