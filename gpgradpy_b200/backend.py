@@ -433,12 +433,16 @@ def cond_fro(Kfull: torch.Tensor, Kinv: torch.Tensor, N: int, want_weight: bool)
     return cond, K3
 
 
-def extreme_eig(M: torch.Tensor, N: int, *, k: int = 40, tol: float = 1e-12, max_cycles: int = 12, v0=None):
+def extreme_eig(M: torch.Tensor, N: int, *, k: int = 40, tol: float = 1e-12, max_cycles: int = 12, v0=None,
+                chunk: int = 8):
     """Largest eigenpair of the symmetric device matrix M[:N, :N]: restarted Lanczos with full re-orthogonalisation.
 
     The matrix-vector products and the orthogonalisation run on the device (gegp_symv, gegp_lanczos_step,
-    gegp_lincomb); the k x k tridiagonal eigenproblem of each cycle is host work.  Returns (lambda, v [N] device
-    tensor with |v| = 1, relative residual estimate, cycles)."""
+    gegp_lincomb); every `chunk` steps the small tridiagonal eigenproblem is solved on the host and the iteration
+    stops as soon as the residual estimate |beta_j s_j| <= tol |lambda| (or an invariant subspace is hit); after k steps
+    it restarts from the Ritz vector.  `v0` (device vector) warm-starts the iteration -- e.g. the eigenvector of the
+    previous optimiser iterate; it is mixed with the fixed pseudo-random start vector so that no eigen-direction is
+    ever excluded.  Returns (lambda, v [N] device tensor with |v| = 1, relative residual estimate, matvecs)."""
     from scipy.linalg import eigh_tridiagonal
     lib = L.load()
     k = int(max(2, min(k, N, 200)))
@@ -450,46 +454,59 @@ def extreme_eig(M: torch.Tensor, N: int, *, k: int = 40, tol: float = 1e-12, max
     ab = torch.zeros((2, k), dtype=F64, device=dev)
     coef = torch.zeros(k, dtype=F64, device=dev)
     one = torch.ones(1, dtype=F64, device=dev)
-    if v0 is None:   # fixed start vector (deterministic results): not orthogonal to any smooth or oscillating mode
-        v0 = to_dev(np.random.default_rng(12345).standard_normal(N))
-    V[0, :N] = v0[:N]
+    rnd = to_dev(np.random.default_rng(12345).standard_normal(N))   # fixed: deterministic results
+    if v0 is None:
+        V[0, :N] = rnd
+    else:
+        V[0, :N] = v0[:N] + (1e-3 / np.sqrt(N)) * rnd
     rc = lib.gegp_lincomb(N, 1, _p(V), ld, _p(one), _p(r), _stream())      # normalise
     _check(rc, "gegp_lincomb")
     V[0].copy_(r)
-    lam, resid, cycles = float("nan"), float("inf"), 0
-    for cycles in range(1, max_cycles + 1):
-        for j in range(k):
-            rc = lib.gegp_symv(N, _p(M), M.stride(0), _p(V[j]), _p(w), _stream())
-            _check(rc, "gegp_symv")
-            rc = lib.gegp_lanczos_step(N, j, _p(V), ld, _p(w), _p(ab[0]), _p(ab[1]), _stream())
-            _check(rc, "gegp_lanczos_step")
-        h = ab.cpu().numpy()
-        a, b = h[0], h[1]
-        scale = max(float(np.max(np.abs(a))), 1e-300)
-        m = k
-        for j in range(k):            # breakdown: an invariant subspace was found after j + 1 steps
-            if not (b[j] > 1e-14 * scale):
-                m = j + 1
-                break
-        evals, evecs = eigh_tridiagonal(a[:m], b[:m - 1]) if m > 1 else (a[:1], np.ones((1, 1)))
-        lam, s = float(evals[-1]), evecs[:, -1]
-        resid = abs(float(b[m - 1]) * float(s[-1])) / max(abs(lam), 1e-300)
-        coef[:m] = to_dev(np.ascontiguousarray(s))
+    lam, resid, matvecs = float("nan"), float("inf"), 0
+    for _cycle in range(max_cycles):
+        j, done, m = 0, False, k
+        while j < k and not done:
+            jn = min(k, j + chunk)
+            for jj in range(j, jn):
+                rc = lib.gegp_symv(N, _p(M), M.stride(0), _p(V[jj]), _p(w), _stream())
+                _check(rc, "gegp_symv")
+                rc = lib.gegp_lanczos_step(N, jj, _p(V), ld, _p(w), _p(ab[0]), _p(ab[1]), _stream())
+                _check(rc, "gegp_lanczos_step")
+            matvecs += jn - j
+            j = jn
+            h = ab.cpu().numpy()
+            a, b = h[0], h[1]
+            scale = max(float(np.max(np.abs(a[:j]))), 1e-300)
+            m = j
+            for q in range(j):            # breakdown: an invariant subspace was found after q + 1 steps
+                if not (b[q] > 1e-14 * scale):
+                    m = q + 1
+                    break
+            evals, evecs = eigh_tridiagonal(a[:m], b[:m - 1]) if m > 1 else (a[:1], np.ones((1, 1)))
+            lam, s_vec = float(evals[-1]), evecs[:, -1]
+            resid = abs(float(b[m - 1]) * float(s_vec[-1])) / max(abs(lam), 1e-300)
+            done = resid <= tol or m < j
+        coef[:m] = to_dev(np.ascontiguousarray(s_vec))
         rc = lib.gegp_lincomb(N, m, _p(V), ld, _p(coef), _p(r), _stream())
         _check(rc, "gegp_lincomb")
         V[0].copy_(r)
-        if resid <= tol or m < k:
+        if done:
             break
-    return lam, r[:N].clone(), resid, cycles
+    return lam, r[:N].clone(), resid, matvecs
 
 
-def cond2(Kfull: torch.Tensor, Kinv: torch.Tensor, N: int, *, tol: float = 1e-12):
-    """kappa_2 = lambda_max(K) * lambda_max(K^-1) with both extreme eigenvectors.
-    -> dict(cond, lam_max, lam_min, v_max, v_min, resid_max, resid_min)."""
-    lmax, vmax, r1, _ = extreme_eig(Kfull, N, tol=tol)
-    imax, vmin, r2, _ = extreme_eig(Kinv, N, tol=tol)
+def cond2(Kfull: torch.Tensor, Kinv: torch.Tensor, N: int, *, tol: float = 1e-12, warm=None):
+    """kappa_2 = lambda_max(K) * lambda_max(K^-1) with both extreme eigenvectors.  `warm`: a previous result of this
+    function for a nearby matrix of the same order (its eigenvectors warm-start the two iterations).
+    -> dict(cond, lam_max, lam_min, v_max, v_min, resid_max, resid_min, cycles = matvecs of the two iterations)."""
+    w1 = w2 = None
+    if warm is not None and warm.get("v_max") is not None and warm["v_max"].numel() == N:
+        w1, w2 = warm["v_max"], warm["v_min"]
+    lmax, vmax, r1, c1 = extreme_eig(Kfull, N, tol=tol, v0=w1)
+    imax, vmin, r2, c2 = extreme_eig(Kinv, N, tol=tol, v0=w2)
     lmin = 1.0 / imax
-    return dict(cond=lmax * imax, lam_max=lmax, lam_min=lmin, v_max=vmax, v_min=vmin, resid_max=r1, resid_min=r2)
+    return dict(cond=lmax * imax, lam_max=lmax, lam_min=lmin, v_max=vmax, v_min=vmin, resid_max=r1, resid_min=r2,
+                cycles=(c1, c2))
 
 
 def quad_grad(X, theta, v, *, n_g=None, slot=None, eta=0.0, noisy=False, varK=1.0):

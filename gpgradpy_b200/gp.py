@@ -62,6 +62,7 @@ class DeviceMatrix:
 
 class GaussianProcess:
     use_cuda_graphs = True      # replay a captured CUDA graph for repeated noise-free evaluations (not in the reference)
+    cond_warm_start = True      # start the Lanczos iterations of the condition number from the previous eigenvectors
     lockstep_multistart = True  # run the SLSQP instances of a multi-start fit in lock step, objective requests batched
 
     # ---- options (names and defaults of gpgradpy/src/GaussianProcess.py:27-113) ----
@@ -644,7 +645,7 @@ class GaussianProcess:
             return cond, self._hp_row_to_grad(q)
         if self.cond_norm != 2:
             raise Exception(f'cond_norm must be either 2 or "fro" but it is {self.cond_norm}')
-        res = bk.cond2(v["U"], v["Kinv"], N)
+        res = bk.cond2(v["U"], v["Kinv"], N, warm=getattr(self, "_last_cond", None) if self.cond_warm_start else None)
         self._last_cond = res
         return float(res["cond"]), (self._cond_grad_from_vectors(hp_vals, res, varK) if calc_grad else None)
 
