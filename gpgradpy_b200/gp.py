@@ -344,9 +344,16 @@ class GaussianProcess:
                 raise Exception(f"Unknown method wellcond_mtd = {self.wellcond_mtd}")
             self.DataScl = Rescaling(x_eval, x_scl_method=mtd, dist_set=dist_set)
             self.DataScl.set_obj_data(fval, std_fval, grad, std_grad)
+            self.Rtensor_init = None
+        else:
+            # the reference caches the [d, n, n] distance tensor here (GaussianProcess.py:363) and scripts pass it back
+            # into calc_all_K_w_chofac (plt/plt_nugget_1d.py:174-175); the CUDA builder reads X directly, so a
+            # placeholder stands in for it (accepted and ignored wherever an Rtensor argument is taken)
+            self.Rtensor_init = _DeviceRtensor(n_eval, self.dim)
         self._dev_ready = False
         self._pred = None
         self._last_hp_vec = None
+        self._last_cond = None
 
     def _ensure_device(self):
         """Put the (scaled) training data on the device (lazily): X[n,d], y[N], gradient-slot map."""
@@ -561,6 +568,8 @@ class GaussianProcess:
                 info.ln_lkd_grad = g
             if calc_cond:
                 info.cond, info.cond_grad = self._cond_from_workspace(hp_vals, calc_grad)
+                if self.wellcond_mtd != "precon" and info.cond > self.cond_max_abs:
+                    return LkdInfo(cond=info.cond, cond_grad=info.cond_grad), False      # kernel/Kernel.py:282-283
             return info, True
         pn_val = pn_grad = 0.0
         if self.lkd_varK_pnlt_use:   # the penalty slope depends on sigma^2: one value-only pass first
@@ -577,6 +586,9 @@ class GaussianProcess:
                 info.ln_lkd_grad = o[L.OUT_GRAD:L.OUT_GRAD + d].copy()
         if calc_cond:
             info.cond, info.cond_grad = self._cond_from_workspace(hp_vals, calc_grad)
+            if self.wellcond_mtd != "precon" and info.cond > self.cond_max_abs:
+                # the reference does not attempt the factorisation then (kernel/Kernel.py:282-283): no likelihood
+                return LkdInfo(cond=info.cond, cond_grad=info.cond_grad), False
         return info, True
 
     # ------------------------------------------------------------------ condition number (optz/GpHparaCon.py:139-235)
@@ -1154,6 +1166,16 @@ class GaussianProcess:
             if calc_grad:
                 dsig2dx = dsig2dx[0, :]
         return sig2, dsig2dx, None
+
+
+class _DeviceRtensor:
+    """Stand-in for the reference's cached distance tensor R[d, n, n] (never materialised on the CUDA path)."""
+
+    def __init__(self, n, d):
+        self.shape = (d, n, n)
+
+    def __repr__(self):
+        return f"<Rtensor placeholder {self.shape}: the CUDA builder reads X directly>"
 
 
 def _pdist(x):

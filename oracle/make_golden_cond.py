@@ -186,6 +186,38 @@ def case_ref_unit_lkd():
     np.savez_compressed(os.path.join(OUT, "ref_unit_test_grad_lkd.npz"), **out)
 
 
+def case_c1_grid():
+    """BASELINE configs[0] = the recipe of gpgradpy/plt/plt_cond.py:19-207 (the script itself needs matplotlib): 2-D
+    Rosenbrock, n = 20 points in [0.9, 1.1]^2, a grid of (gamma_1, gamma_2) = sqrt(2 theta) over [1e-4, 1e8], nugget of
+    the preconditioned SqExp kernel used for every mode (:98-99,176-177), varK = 0.1; LML and condition number per grid
+    point through calc_lkd_all(calc_lkd=True, calc_cond=True, calc_grad=False) (:189)."""
+    n_eval, dim, n_gamma, varK = 20, 2, 6, 0.1
+    x, f, g = O.synthetic_problem(n_eval, dim, 2, 0.9, 1.1)
+    GP0 = GaussianProcess(dim, use_grad=True, kernel_type="SqExp", wellcond_mtd="precon")
+    nugget = GP0.calc_nugget(n_eval)[1]
+    theta_vec = np.logspace(np.log10(0.5 * 1e-4 ** 2), np.log10(0.5 * 1e8 ** 2), n_gamma)
+    out = dict(x=x, fval=f, grad=g, theta_vec=theta_vec, nugget=nugget, varK=varK)
+    for mode in ("base", "precon", "rescale_origin"):
+        GP = GaussianProcess(dim, True, "SqExp", mode)
+        GP.cond_eta_is_const = True
+        GP.set_data(x, f, np.zeros(n_eval), g, np.zeros(g.shape))
+        GP._etaK = nugget
+        GP._eta_Kgrad = nugget
+        GP.cond_max = 1e10
+        lkd = np.full((n_gamma, n_gamma), np.nan)
+        cond = np.full((n_gamma, n_gamma), np.nan)
+        for i in range(n_gamma):
+            for j in range(n_gamma):
+                hp = GP.make_hp_class(varK=varK, theta=np.array([theta_vec[i], theta_vec[j]]), kernel=GP.hp_kernel_default)
+                info = GP.calc_lkd_all(hp, calc_lkd=True, calc_cond=True, calc_grad=False)[0]
+                lkd[i, j] = np.nan if info.ln_lkd is None else info.ln_lkd
+                cond[i, j] = info.cond
+        out[mode + "_lkd"], out[mode + "_cond"] = lkd, cond
+        print("c1_grid", mode, "n_ok", int(np.sum(np.isfinite(lkd))), "log10 cond range",
+              np.round(np.log10(np.nanmin(cond)), 2), np.round(np.log10(np.nanmax(cond)), 2), flush=True)
+    np.savez_compressed(os.path.join(OUT, "c1_plt_cond_grid.npz"), **out)
+
+
 def case_fit(name, n, d, mode, seed=1):
     """set_hpara('optz') with the history protocol of SURVEY appendix B.12; stores the start point the reference's
     40-candidate scan picked, so that both implementations can be started from the same x0."""
@@ -223,6 +255,7 @@ if __name__ == "__main__":
     case_cond_fro("condfro_d2_n12_base", 12, 2, [0.6, 1.4])
     case_cond_fro("condfro_d2_n14_noisy_base", 14, 2, [0.7, 1.1], seed=4, std_f=1e-2, std_g=5e-2, varK=40.0)
     case_ref_unit_lkd()
+    case_c1_grid()
     if "--no-fit" in sys.argv:
         sys.exit(0)
     case_fit("fit_d2_n20_base", 20, 2, "base")

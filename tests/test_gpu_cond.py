@@ -213,3 +213,43 @@ def test_frobenius_cond_through_the_api(golden_dir, name):
     assert np.max(np.abs(info.cond_grad - g["cond_grad"])) < 1e-6 * np.max(np.abs(g["cond_grad"]))
     c = GP.calc_all_K_w_chofac(None, hp, calc_chofac=False, calc_cond=True, varK=varK if varK else 1)[4]
     assert abs(c - g["cond_nograd"]) < 1e-7 * g["cond_nograd"]
+
+
+@pytest.mark.parametrize("mode", ["base", "precon", "rescale_origin"])
+def test_config1_plt_cond_grid(golden_dir, mode):
+    """BASELINE configs[0]: the loop of gpgradpy/plt/plt_cond.py:154-207 (2-D Rosenbrock, n = 20, grid over the length
+    scales, one nugget for every mode, LML and condition number per grid point through
+    calc_lkd_all(calc_lkd=True, calc_cond=True, calc_grad=False)) against the values the reference produces."""
+    from gpgradpy_b200.gp import GaussianProcess
+    g = _load(golden_dir, "c1_plt_cond_grid")
+    x, f, gr, tv = g["x"], g["fval"], g["grad"], g["theta_vec"]
+    GP = GaussianProcess(2, True, "SqExp", mode)
+    GP.cond_eta_is_const = True
+    GP.set_data(x, f, np.zeros(20), gr, np.zeros(gr.shape))
+    GP._etaK = float(g["nugget"])
+    GP._eta_Kgrad = float(g["nugget"])
+    GP.cond_max = 1e10
+    assert GP.Rtensor_init is not None or mode == "rescale_origin"
+    n_cmp = 0
+    for i in range(tv.size):
+        for j in range(tv.size):
+            hp = GP.make_hp_class(varK=float(g["varK"]), theta=np.array([tv[i], tv[j]]), kernel=GP.hp_kernel_default)
+            info, ok = GP.calc_lkd_all(hp, calc_lkd=True, calc_cond=True, calc_grad=False)
+            ref_l, ref_c = g[mode + "_lkd"][i, j], g[mode + "_cond"][i, j]
+            if ref_c > 1e13:
+                # numerically singular: whether cond passes cond_max_abs = 1e16 (kernel/Kernel.py:282-283) or the
+                # Cholesky survives is decided by rounding noise in either implementation
+                assert (not ok) or np.isfinite(info.ln_lkd)
+                assert info.cond > 1e11
+                continue
+            assert ok == bool(np.isfinite(ref_l)), (i, j, ok, ref_l, ref_c)
+            if not ok:
+                assert info.ln_lkd is None and info.cond > 1e12          # "numerically singular" either way
+                continue
+            # LML: relative 1e-8 where cond(K) allows it (two LAPACK runs differ by ~eps * cond)
+            tol = max(1e-8, 1e-15 * ref_c)
+            assert abs(info.ln_lkd - ref_l) < tol * max(1.0, abs(ref_l)), (i, j, info.ln_lkd, ref_l, ref_c)
+            if ref_c < 1e12:
+                assert abs(info.cond - ref_c) < max(1e-8, 1e-15 * ref_c) * ref_c, (i, j, info.cond, ref_c)
+                n_cmp += 1
+    assert n_cmp >= 10
