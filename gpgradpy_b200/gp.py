@@ -918,7 +918,10 @@ class GaussianProcess:
         local = np.full((max(hi_row - lo, 0), hi.n_hp + 3), np.nan)
         self._lockstep_stats = None
         if hi_row > lo:
-            res, ev = multistart.minimize_lockstep(batch_val_and_grad, hp_x0_all[lo:hi_row], optz_bound, opt)
+            cur_dev = torch.cuda.current_device() if torch.cuda.is_available() else None
+            init = (lambda: torch.cuda.set_device(cur_dev)) if cur_dev is not None else None
+            res, ev = multistart.minimize_lockstep(batch_val_and_grad, hp_x0_all[lo:hi_row], optz_bound, opt,
+                                                   thread_init=init)
             self._lockstep_stats = dict(n_batches=ev.n_batches, n_evals=ev.n_evals, batch_sizes=ev.batch_sizes)
             for i, r in enumerate(res):
                 local[i, :hi.n_hp], local[i, hi.n_hp:] = r.x, (r.fun, float(r.success), r.nit)
@@ -930,6 +933,7 @@ class GaussianProcess:
             table = parallel.gather_rows(t, n_optz, self.dist_group).cpu().numpy()
         else:
             table = local
+        self._multistart_table = table          # per start row: solution, objective, success, iterations
         sol, obj, ok, nit = table[:, :hi.n_hp], table[:, hi.n_hp], table[:, hi.n_hp + 1], table[:, hi.n_hp + 2]
         best = sol[np.nanargmin(obj), :]
         info = {"hp_optz_success": float(np.mean(ok)), "hp_optz_iter_mean": float(np.mean(nit)),

@@ -66,10 +66,12 @@ class LockstepEvaluator:
                 self._flush_locked()
 
 
-def minimize_lockstep(batch_val_and_grad, x0_rows, bounds, options, constraints=()):
+def minimize_lockstep(batch_val_and_grad, x0_rows, bounds, options, constraints=(), thread_init=None):
     """SLSQP from every row of x0_rows, objective/gradient requests batched across the rows.
 
     batch_val_and_grad(X [b, n_hp]) -> (vals [b], grads [b, n_hp]) of the function to MINIMISE.
+    thread_init: called first in every worker thread (the CUDA device is per-thread state: a worker that ends up
+    running the batched device call must select the caller's device).
     Returns (list of scipy OptimizeResult in row order, LockstepEvaluator with its statistics)."""
     x0_rows = np.atleast_2d(np.asarray(x0_rows, dtype=float))
     n = x0_rows.shape[0]
@@ -97,6 +99,8 @@ def minimize_lockstep(batch_val_and_grad, x0_rows, bounds, options, constraints=
             return last["grad"]
 
         try:
+            if thread_init is not None:
+                thread_init()
             results[i] = minimize(fun, x0_rows[i], method="SLSQP", jac=jac, bounds=bounds, constraints=constraints,
                                   options=options)
         except BaseException as exc:   # noqa: BLE001
