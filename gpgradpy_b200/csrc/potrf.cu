@@ -57,7 +57,7 @@ int trsm_right_rec(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL
 namespace {
 // a trailing update with fewer 128 x 128 tiles than this is cut into just-in-time pieces (env GEGP_SPLIT_TILES)
 int split_max_tiles() {
-  static const int v = getenv("GEGP_SPLIT_TILES") ? atoi(getenv("GEGP_SPLIT_TILES")) : 1000;
+  static const int v = getenv("GEGP_SPLIT_TILES") ? atoi(getenv("GEGP_SPLIT_TILES")) : 2500;
   return v;
 }
 constexpr int MAX_PIECES = 256;
