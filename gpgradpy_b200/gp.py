@@ -181,6 +181,29 @@ class GaussianProcess:
         return 0.5 * np.asarray(gamma) ** 2            # kernel/KernelSqExp.py:586-588
 
     @staticmethod
+    def calc_Kern_precon(n_eval, n_grad, theta, calc_grad=False, b_return_vec=False):
+        """Analytic preconditioner of the Gaussian kernel (kernel/KernelSqExp.py:591-605 with
+        kernel/KernelCommon.py:14-49): p = [1_n, gamma_i (x) 1_ng], gamma = sqrt(2 theta), d gamma_i / d theta_i =
+        1 / gamma_i.  Host helper kept for API parity (the kernels form p themselves, csrc/build.cu prep_p_kernel);
+        like the reference it always returns the derivative, as an [N, d] array or a stack of diagonal matrices."""
+        theta = np.asarray(theta, dtype=float)
+        gamma = np.sqrt(2 * theta)
+        pvec = np.hstack((np.ones(n_eval), np.kron(gamma, np.ones(n_grad))))
+        dim, n_data = theta.size, n_eval + n_grad * theta.size
+        dgam = 1 / gamma
+        if b_return_vec:
+            grad = np.zeros((n_data, dim))
+            for i in range(dim):
+                grad[n_eval + i * n_grad: n_eval + (i + 1) * n_grad, i] = dgam[i]
+            return pvec, 1 / pvec, grad
+        grad = np.zeros((dim, n_data, n_data))
+        for i in range(dim):
+            v = np.zeros(n_data)
+            v[n_eval + i * n_grad: n_eval + (i + 1) * n_grad] = dgam[i]
+            grad[i] = np.diag(v)
+        return np.diag(pvec), np.diag(1 / pvec), grad
+
+    @staticmethod
     def make_data_vec(fval, fgrad=None):
         """base/CommonFun.py:152-173."""
         if fgrad is None:

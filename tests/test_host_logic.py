@@ -129,3 +129,27 @@ def test_chain_rule_cache_and_failure_contract(monkeypatch):
     monkeypatch.setattr(GP, "calc_lkd_all", lambda *a, **k: (H.LkdInfo(cond=123.0), False))
     GP._last_hp_vec = None
     assert GP.return_optz_val(v) == 123.0                    # objective = -(-cond)
+
+
+@pytest.mark.parametrize("b_return_vec", [True, False])
+def test_reference_unit_test_precon_grad(b_return_vec):
+    """gpgradpy/unit_test/test_precon_grad.py:22-95 (the one reference test module that passes as shipped): analytic
+    dP/dtheta of the preconditioner against a forward finite difference, vector and matrix form."""
+    from gpgradpy_b200.gp import GaussianProcess
+    eps, dim, n_eval = 1e-6, 2, 1
+    theta = np.linspace(2.5, 3, dim)
+    GP = GaussianProcess(dim, True, "SqExp", "precon")
+    pvec, pvec_inv, grad = GP.calc_Kern_precon(n_eval, n_eval, theta, calc_grad=True, b_return_vec=b_return_vec)
+    n_data = n_eval * (dim + 1)
+    fd = np.zeros((n_data, dim)) if b_return_vec else np.zeros((dim, n_data, n_data))
+    for i in range(dim):
+        tp = theta.copy()
+        tp[i] += eps
+        pe = GP.calc_Kern_precon(n_eval, n_eval, tp, calc_grad=False, b_return_vec=b_return_vec)[0]
+        if b_return_vec:
+            fd[:, i] = (pe - pvec) / eps
+        else:
+            fd[i] = (pe - pvec) / eps
+    np.testing.assert_allclose(grad, fd, rtol=1e-4, atol=1e-8)
+    np.testing.assert_allclose(pvec @ pvec_inv if not b_return_vec else pvec * pvec_inv,
+                               np.eye(n_data) if not b_return_vec else np.ones(n_data))
