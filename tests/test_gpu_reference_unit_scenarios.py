@@ -135,3 +135,33 @@ def test_reference_unit_test_grad_Kmat(noisy, masked):
             np.testing.assert_allclose(q[L.OUT_DVARK], fd, rtol=1e-5, atol=1e-7 * max(1.0, abs(fd)))
             np.testing.assert_allclose(q[L.OUT_DVARF], np.sum(v[:n] ** 2), rtol=1e-12)
             np.testing.assert_allclose(q[L.OUT_DVARG], np.sum(v[n:] ** 2), rtol=1e-12)
+
+
+@pytest.mark.parametrize("mode", ["base", "rescale_origin", "precon"])
+def test_reference_unit_test_grad_surr(mode):
+    """gpgradpy/unit_test/test_grad_surr.py:16-31,101-244: x-derivatives and Hessians of the surrogate against central
+    finite differences (2 points in 1-D at 0 and 2, test point at 0.8, theta = 0.1, varK = 1e3, beta = mean(f),
+    eps 1e-4, rtol 1e-4, atol 1e-8), in the three modes the shipped test names stand for
+    (None -> base, 'req_vmin' -> rescale_origin, precon)."""
+    from gpgradpy_b200.gp import GaussianProcess
+    x = np.array([[0.0], [2.0]])
+    f = np.sum(x ** 2, axis=1)
+    g = 2 * x
+    GP = GaussianProcess(1, True, "SqExp", mode)
+    GP.init_optz_surr(2)
+    GP.set_data(x, f, np.zeros(2), g, np.zeros((2, 1)))
+    GP.set_hpara("set", 0, hp_vals=GP.make_hp_class(beta=np.atleast_1d(np.mean(f)), kernel=np.nan,
+                                                    theta=0.1 * np.linspace(1, 2, 1), varK=1e3))
+    GP.setup_eval_model()
+    xt = np.array([[0.8]])
+    eps, rtol, atol = 1e-4, 1e-4, 1e-8
+    mu, sig, dmu, dsig, h_mu, h_sig = GP.eval_model(xt, calc_grad=True, calc_hess=True)
+    mp, sp, dmp, dsp = GP.eval_model(xt + eps, calc_grad=True)[:4]
+    mm, sm, dmm, dsm = GP.eval_model(xt - eps, calc_grad=True)[:4]
+    np.testing.assert_allclose(dmu[0, 0], (mp[0] - mm[0]) / (2 * eps), rtol=rtol, atol=atol)
+    np.testing.assert_allclose(dsig[0, 0], (sp[0] - sm[0]) / (2 * eps), rtol=rtol, atol=atol)
+    np.testing.assert_allclose(h_mu[0, 0, 0], (dmp[0, 0] - dmm[0, 0]) / (2 * eps), rtol=rtol, atol=atol)
+    np.testing.assert_allclose(h_sig[0, 0, 0], (dsp[0, 0] - dsm[0, 0]) / (2 * eps), rtol=rtol, atol=atol)
+    # the surrogate interpolates values and gradients at the data (up to the nugget)
+    m0, s0, d0 = GP.eval_model(x, calc_grad=True)[:3]
+    assert np.max(np.abs(m0 - f)) < 1e-5 and np.max(np.abs(d0 - g)) < 1e-4
