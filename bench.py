@@ -315,9 +315,11 @@ def run_b200(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r01", "dominant_kernel_ncu.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"kernel": "fp64 DMMA.8x8x4 GEMM engine = all O(N^3) work of one evaluation: gemm_f64_kernel<64,64,32,32,4> "
-                          "(cp.async ring) carries this workload's products (< 1000 tiles of 128x128 each); "
-                          "gemm_tma_nt_kernel<128,64,4,2> (TMA + mbarrier ring) takes over above that (the c3 numbers)",
+    roofline = {"kernel": "fp64 DMMA.8x8x4 GEMM engine = all O(N^3) work of one evaluation: gemm_f64_kernel<64,64,32,32,{4|2}> "
+                          "(cp.async ring; 2 stages when the launch has >= 4 CTAs per SM) carries most of this workload's "
+                          "products (< 400 tiles of 128x128 each), gemm_f64_kernel<32,32,16,16,4> the K=128 updates on the "
+                          "factorisation's critical path, gemm_tma_nt_kernel<128,64,4,2> (TMA + mbarrier ring) the final "
+                          "U U^T product and everything at the c3 size",
                 "bound": "tensor", "achieved": N ** 3 / ph["gemm_ms_per_eval"] * 1e-9, "peak": FP64_DMMA_PEAK_TFLOPS,
                 "unit": "TFLOP/s", "frac": N ** 3 / ph["gemm_ms_per_eval"] * 1e-9 / FP64_DMMA_PEAK_TFLOPS,
                 "traffic": traffic,
