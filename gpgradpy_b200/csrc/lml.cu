@@ -106,12 +106,16 @@ int launch_scale_vec(const Ctx& ctx, int N, const double* a, int64_t strideA, co
 // ------------------------------------------------------------------------------------------------
 constexpr int GB = 128;
 
-__global__ void __launch_bounds__(GB)
+// quad 0: LML gradient weights; 1: W = alpha alpha^T (Kinv not read); 2: W = the matrix passed as Kinv.
+// WIDE (d >= 8): four independent Kinv loads in flight per thread, 72 registers; otherwise the plain loop (63
+// registers, 8 CTAs per SM) -- measured: the wide form is 1.5x faster at d = 10 and 20, the narrow one at d = 5.
+template <int quad, bool WIDE>
+__global__ void __launch_bounds__(GB, WIDE ? 7 : 8)
 lml_grad_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideTheta, const double* __restrict__ Kinv_all,
                 int64_t ldk, int64_t strideK, const double* __restrict__ alpha_all, int64_t strideAlpha,
                 const double* __restrict__ pinv_all, int64_t strideP, const double* __restrict__ out_all,
                 int64_t strideOut, int noisy, double pnlt_grad, double* __restrict__ partial_all,
-                int64_t stridePartial, int quad) {
+                int64_t stridePartial) {
   extern __shared__ double sm[];
   const int d = gm.d, n = gm.n, ng = gm.ng, N = gm.N;
   double* vs = sm;              // [d][GB]  v_j = pinv[col_j] * u_j
@@ -184,22 +188,30 @@ lml_grad_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideThe
       if (sb >= 0) {
         double dot = 0.0, kii = 0.0;
         if (quad != 1) {
-          // four independent loads in flight per thread (the kernel is HBM-read bound: 8 N^2 bytes of Kinv; eight
-          // cost more in occupancy than they gain: measured 82 us with four, 112 us with eight at N = 5500)
           const double* kp = krow + n + sb;
-          double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
-          int j = 0;
-          for (; j + 3 < d; j += 4) {
-            const double k0 = kp[(int64_t)j * ng], k1 = kp[(int64_t)(j + 1) * ng], k2 = kp[(int64_t)(j + 2) * ng],
-                         k3 = kp[(int64_t)(j + 3) * ng];
-            d0 += vs[j * GB + tid] * k0;
-            d1 += vs[(j + 1) * GB + tid] * k1;
-            d2 += vs[(j + 2) * GB + tid] * k2;
-            d3 += vs[(j + 3) * GB + tid] * k3;
+          if (WIDE) {
+            // four independent loads in flight per thread (the kernel is HBM-read bound: 8 N^2 bytes of Kinv; eight
+            // cost more in occupancy than they gain: measured 82 us with four, 112 us with eight at N = 5500)
+            double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+            int j = 0;
+            for (; j + 3 < d; j += 4) {
+              const double k0 = kp[(int64_t)j * ng], k1 = kp[(int64_t)(j + 1) * ng], k2 = kp[(int64_t)(j + 2) * ng],
+                           k3 = kp[(int64_t)(j + 3) * ng];
+              d0 += vs[j * GB + tid] * k0;
+              d1 += vs[(j + 1) * GB + tid] * k1;
+              d2 += vs[(j + 2) * GB + tid] * k2;
+              d3 += vs[(j + 3) * GB + tid] * k3;
+            }
+            for (; j < d; j++) d0 += vs[j * GB + tid] * kp[(int64_t)j * ng];
+            dot = (d0 + d1) + (d2 + d3);
+            kii = kp[(int64_t)i * ng];
+          } else {   // few dimensions: the plain loop (one pass, no extra load for the diagonal entry) is faster
+            for (int j = 0; j < d; j++) {
+              const double kv = krow[n + j * ng + sb];
+              dot += vs[j * GB + tid] * kv;
+              if (j == i) kii = kv;
+            }
           }
-          for (; j < d; j++) d0 += vs[j * GB + tid] * kp[(int64_t)j * ng];
-          dot = (d0 + d1) + (d2 + d3);
-          kii = kp[(int64_t)i * ng];
         }
         rowdot = pr * (c1 * ar * Ab - c2 * dot);
         const int coli = n + i * ng + sb;
@@ -291,15 +303,24 @@ int launch_lml_grad(const Ctx& ctx, const Geom& gm, const double* theta, int64_t
                     double* partial, int64_t stridePartial, double* out, int64_t strideOut, int quad) {
   const int d = gm.d;
   const size_t smem = (size_t)(d * GB + (d + 1) * GB + 2 * d) * sizeof(double);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    GEGP_SET_SMEM(lml_grad_kernel, smem);
-    smem_set = smem;
+  static size_t smem_set[3] = {0, 0, 0};
+  if (quad < 0 || quad > 2) return -906;
+  const bool wide = d >= 8;
+  if (smem > 48 * 1024 && smem > smem_set[quad]) {   // (only reached with d > 20: the wide kernels)
+    if (quad == 0) GEGP_SET_SMEM((lml_grad_kernel<0, true>), smem);
+    else if (quad == 1) GEGP_SET_SMEM((lml_grad_kernel<1, true>), smem);
+    else GEGP_SET_SMEM((lml_grad_kernel<2, true>), smem);
+    smem_set[quad] = smem;
   }
   dim3 grid((gm.n + GB - 1) / GB, gm.n, ctx.batch);
-  lml_grad_kernel<<<grid, GB, smem, ctx.stream>>>(gm, theta, strideTheta, Kinv, ldk, strideK, alpha_t, strideAlpha, pinv,
-                                                  strideP, out, strideOut, noisy, pnlt_grad, partial, stridePartial,
-                                                  quad);
+#define GEGP_LAUNCH_LML_GRAD(Q, W)                                                                                       \
+  lml_grad_kernel<Q, W><<<grid, GB, smem, ctx.stream>>>(gm, theta, strideTheta, Kinv, ldk, strideK, alpha_t,             \
+                                                        strideAlpha, pinv, strideP, out, strideOut, noisy, pnlt_grad,    \
+                                                        partial, stridePartial)
+  if (quad == 0) { if (wide) GEGP_LAUNCH_LML_GRAD(0, true); else GEGP_LAUNCH_LML_GRAD(0, false); }
+  else if (quad == 1) { if (wide) GEGP_LAUNCH_LML_GRAD(1, true); else GEGP_LAUNCH_LML_GRAD(1, false); }
+  else { if (wide) GEGP_LAUNCH_LML_GRAD(2, true); else GEGP_LAUNCH_LML_GRAD(2, false); }
+#undef GEGP_LAUNCH_LML_GRAD
   GEGP_CHECK_LAUNCH();
   const int64_t nparts = (int64_t)grid.x * grid.y;
   const int np = 2 * d + 2;
