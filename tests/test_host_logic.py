@@ -153,3 +153,28 @@ def test_reference_unit_test_precon_grad(b_return_vec):
     np.testing.assert_allclose(grad, fd, rtol=1e-4, atol=1e-8)
     np.testing.assert_allclose(pvec @ pvec_inv if not b_return_vec else pvec * pvec_inv,
                                np.eye(n_data) if not b_return_vec else np.ones(n_data))
+
+
+def test_host_bookkeeping_table_vs_reference(golden_dir):
+    """Every conditioning mode x noise model x use_grad: the flags set_data derives, nuggets, hyper-parameter index
+    maps, scaled data, noise vectors, vector <-> dataclass maps, initial hyper-parameters, LHS start points and box
+    bounds must equal what the reference produces (tests/golden/host_logic_table.npz, oracle/make_golden_host.py walks
+    both classes with the same function).  The LHS sampler is scipy's here and in the reference run (its `smt` import
+    is shimmed), so start points are comparable."""
+    import os
+    from oracle.make_golden_host import collect
+    from gpgradpy_b200.gp import GaussianProcess
+    z = np.load(os.path.join(golden_dir, "host_logic_table.npz"))
+    x, f, g = O.synthetic_problem(14, 3, 0)
+    mine = collect(GaussianProcess, x, f, g)
+    assert set(mine) == set(z.files)
+    bad = []
+    for k in z.files:
+        a, b = z[k], mine[k]
+        if a.dtype.kind in "US" or b.dtype.kind in "US":
+            ok = str(a) == str(b)
+        else:
+            ok = a.shape == b.shape and np.allclose(a, b, rtol=1e-13, atol=0, equal_nan=True)
+        if not ok:
+            bad.append(k)
+    assert not bad, bad[:10]
