@@ -224,3 +224,33 @@ def test_multistart_lockstep_equals_sequential_loop():
     assert np.array_equal(out[0][0], out[1][0]) and out[0][1] == out[1][1] and out[0][2] == out[1][2]
     st = out[0][3]
     assert st is not None and st["batch_sizes"][0] == 5 and st["n_batches"] < st["n_evals"]
+
+
+def test_gradient_free_gp_posterior_and_x_gradients():
+    """use_grad=False: posterior mean / std and their x-gradients (the gradient-enhanced kernels with n_g = 0)
+    against the oracle with an all-False mask and against central finite differences."""
+    from gpgradpy_b200.gp import GaussianProcess
+    from oracle import gegp_oracle as O
+    x, f, g = O.synthetic_problem(30, 3, 2)
+    GP = GaussianProcess(3, False, "SqExp", "precon")
+    GP.set_data(x, f, np.zeros(30))
+    th = O.bench_theta(3) * 4
+    info, ok = GP.calc_lkd_all(GP.make_hp_class(theta=th), calc_grad=True)
+    assert ok
+    GP.set_hpara("set", 1, GP.make_hp_class(theta=th, varK=info.hp_varK, beta=info.hp_beta))
+    xs = np.random.default_rng(4).uniform(-2, 2, (9, 3))
+    mu, sig, dmu, dsig = GP.eval_model(xs, calc_grad=True)[:4]
+    mask = np.zeros(30, bool)
+    mu_r, sig_r, dmu_r, dsig_r = O.eval_model_grad(x, f, np.zeros((0, 3)), th, info.hp_varK, info.hp_beta, xs, "base",
+                                                   GP._etaK, mask=mask)
+    assert np.max(np.abs(mu - mu_r)) < 1e-8 * np.max(np.abs(mu_r))
+    assert np.max(np.abs(sig - sig_r)) < 1e-6 * np.max(np.abs(sig_r))
+    assert np.max(np.abs(dmu - dmu_r)) < 1e-8 * np.max(np.abs(dmu_r))
+    assert np.max(np.abs(dsig - dsig_r)) < 1e-6 * np.max(np.abs(dsig_r))
+    eps = 1e-5
+    for j in range(3):
+        e = np.zeros(3); e[j] = eps
+        mp, sp = GP.eval_model(xs + e)[:2]
+        mm, sm = GP.eval_model(xs - e)[:2]
+        assert np.max(np.abs((mp - mm) / (2 * eps) - dmu[:, j])) < 1e-5 * np.max(np.abs(dmu))
+        assert np.max(np.abs((sp - sm) / (2 * eps) - dsig[:, j])) < 1e-4 * np.max(np.abs(dsig))
