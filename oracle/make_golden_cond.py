@@ -218,20 +218,21 @@ def case_c1_grid():
     np.savez_compressed(os.path.join(OUT, "c1_plt_cond_grid.npz"), **out)
 
 
-def case_fit(name, n, d, mode, seed=1):
+def case_fit(name, n, d, mode, seed=1, std_f=0.0, std_g=0.0):
     """set_hpara('optz') with the history protocol of SURVEY appendix B.12; stores the start point the reference's
     40-candidate scan picked, so that both implementations can be started from the same x0."""
     x, f, g = O.synthetic_problem(n, d, seed)
     GP = GaussianProcess(d, True, "SqExp", mode)
     GP.init_optz_surr(3)
-    GP.set_data(x[:1], f[:1], np.zeros(1), g[:1], np.zeros((1, d)))
+    GP.set_data(x[:1], f[:1], std_f * np.ones(1), g[:1], std_g * np.ones((1, d)))
     GP.set_hpara("optz", 0)
-    GP.set_data(x, f, np.zeros(n), g, np.zeros((n, d)))
+    GP.set_data(x, f, std_f * np.ones(n), g, std_g * np.ones((n, d)))
     hp_x0, bound, _ = GP.select_hp_optz_x0(1, GP.hp_info_optz_lkd)
     GP.set_hpara("optz", 1)
     hp = GP.hp_vals
     info, ok = GP.calc_lkd_all(hp, calc_cond=True, calc_grad=False)
     out = dict(x=x, fval=f, grad=g, mode=mode, hp_x0=hp_x0, lb=bound.lb, ub=bound.ub, theta=hp.theta, varK=hp.varK,
+               std_f=std_f, std_g=std_g,
                beta=hp.beta, ln_lkd=info.ln_lkd, cond=info.cond, eta=GP._etaK,
                xvec_scale=GP.DataScl.xvec_scale if GP.b_use_data_scl else np.ones(d))
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
@@ -260,3 +261,4 @@ if __name__ == "__main__":
         sys.exit(0)
     case_fit("fit_d2_n20_base", 20, 2, "base")
     case_fit("fit_d2_n20_rescale_origin", 20, 2, "rescale_origin")
+    case_fit("fit_d2_n20_noisy_precon", 20, 2, "precon", std_f=5.0, std_g=20.0)

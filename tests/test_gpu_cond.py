@@ -253,3 +253,30 @@ def test_config1_plt_cond_grid(golden_dir, mode):
                 assert abs(info.cond - ref_c) < max(1e-8, 1e-15 * ref_c) * ref_c, (i, j, info.cond, ref_c)
                 n_cmp += 1
     assert n_cmp >= 10
+
+
+def test_noisy_fit_vs_reference(golden_dir):
+    """Fit with known observation noise (varK becomes a numerically optimised hyper-parameter, optz/CalcLkd.py:185-251):
+    from the start point the reference's scan picked, the optimum must be as good as the reference's."""
+    g = _load(golden_dir, "fit_d2_n20_noisy_precon")
+    from gpgradpy_b200.gp import GaussianProcess
+    from scipy.optimize import Bounds
+    x, f, gr = g["x"], g["fval"], g["grad"]
+    n, d = x.shape
+    sf, sg = float(g["std_f"]), float(g["std_g"])
+    GP = GaussianProcess(d, True, "SqExp", "precon")
+    GP.init_optz_surr(3)
+    GP.set_data(x[:1], f[:1], sf * np.ones(1), gr[:1], sg * np.ones((1, d)))
+    GP.set_hpara("optz", 0)
+    GP.set_data(x, f, sf * np.ones(n), gr, sg * np.ones((n, d)))
+    assert GP.b_has_noisy_data and GP.hp_info_optz_lkd.has_varK
+    best, _, info = GP.optz_hp_max_lkd(g["hp_x0"], Bounds(g["lb"], g["ub"], keep_feasible=True))
+    hp = GP.optz_closed_form_hp(GP.hp_vec2dataclass(GP.hp_info_optz_lkd, best))
+    res, ok = GP.calc_lkd_all(hp, calc_grad=True)
+    assert ok
+    assert res.ln_lkd > float(g["ln_lkd"]) - 1e-4 * abs(float(g["ln_lkd"]))
+    glog = res.ln_lkd_grad * np.hstack((hp.theta, [hp.varK])) * np.log(10)
+    assert np.max(np.abs(glog)) < 1e-2 * abs(res.ln_lkd)
+    assert np.allclose(hp.theta, g["theta"], rtol=5e-2) and abs(hp.varK - float(g["varK"])) < 5e-2 * float(g["varK"])
+    GP.set_hpara("optz", 1)                       # the whole public path, incl. the candidate scan
+    assert GP.hp_vals.varK > 0
