@@ -182,6 +182,10 @@ def _lml_workspace(lib, op, n, n_g, d, B, max_ws_bytes):
     if max_ws_bytes is None:
         free, _total = torch.cuda.mem_get_info()
         max_ws_bytes = int(0.6 * (free + (cached.numel() if cached is not None else 0)))
+    if per1 + 4096 + 4 * B > max_ws_bytes:
+        raise MemoryError(f"one candidate of this size needs a {per1 / 2**30:.1f} GiB workspace (N = {n + n_g * d}, "
+                          f"{'with' if op == L.OP_LML_GRAD else 'without'} gradient) but only {max_ws_bytes / 2**30:.1f} GiB "
+                          "may be used on this device")
     chunk = max(1, min(B, (max_ws_bytes - 4096 - 4 * B) // per1))
     return workspace(int(lib.gegp_workspace_bytes(op, n, n_g, d, chunk)) + 4 * B + 256)
 
