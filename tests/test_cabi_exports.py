@@ -57,6 +57,23 @@ def test_argument_checks_return_negative_codes_without_touching_the_gpu():
     assert lib.gegp_dgemm(0, 4, 4, 4, 1.0, 0, 4, 0, 4, 0.0, 0, 4, 0) == -6
     assert lib.gegp_dinv_doubles(129) == 2 * 128 * 128
     assert lib.gegp_set_option(99, 1) == -1 and lib.gegp_set_option(_lib.OPT_TMA_MIN_TILES, 0) == -2
+    # condition-number / surrogate-derivative entry points
+    import ctypes as C
+    assert lib.gegp_symv(0, 0, 0, 0, 0, 0) == -1 and lib.gegp_symv(8, 0, 8, 0, 0, 0) == -2
+    assert lib.gegp_row_abs_sum(8, 0, 8, 0, 0) == -2 and lib.gegp_row_sq_sum(8, 16, 7, 0, 0) == -3
+    assert lib.gegp_lanczos_step(8, 300, 0, 8, 0, 0, 0, 0) == -2 and lib.gegp_lanczos_step(8, 0, 0, 8, 0, 0, 0, 0) == -3
+    assert lib.gegp_lincomb(8, 0, 0, 8, 0, 0, 0) == -2
+    assert lib.gegp_quad_grad(4, 4, 3, 16, 0, 16, 16, _lib.MODE_PRECON, 0.0, 0, 0, 16, 16, 1 << 20, 0) == -8   # base only
+    assert lib.gegp_weighted_grad(4, 4, 3, 16, 0, 16, 0, 16, _lib.MODE_BASE, 0.0, 0, 0, 16, 16, 1 << 20, 0) == -7  # W NULL
+    assert lib.gegp_quad_grad_work_bytes(4, 4, 3) > 0 and lib.gegp_quad_grad_work_bytes(0, 0, 3) == 0
+    assert lib.gegp_predict_grad(4, 4, 3, 0, 0, 0, 0, 16, 0, 0, 1, 0.0, 1.0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0) == -4
+    assert lib.gegp_predict_hess(4, 4, 3, 16, 0, 16, 16, 16, 16, 16, 0, 1, 0.0, 1.0, 16, 16, 16, 0, 16, 16, 16, 0, 0, 0, 0) == -11
+    out8 = (C.c_int64 * 8)()
+    assert lib.gegp_lml_layout(500, 500, 10, 1, 1, out8) == 0
+    header, ld, per, offA, offP, offD, offU, offK = (int(v) for v in out8)
+    assert header == 256 and ld == 5504 and offA == 0 and offU > offD > offP > offA and offK == offU + 5500 * ld
+    assert 8 * per + header == lib.gegp_workspace_bytes(_lib.OP_LML_GRAD, 500, 500, 10, 1)
+    assert lib.gegp_lml_layout(500, 500, 10, 0, 1, out8) == 0 and out8[6] == -1 and out8[7] == -1
 
 
 def test_no_cpu_fallback_when_library_is_missing(monkeypatch):
