@@ -94,8 +94,13 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   constexpr int TBM = Cfg::TBM, TBN = Cfg::TBN, TSTAGES = Cfg::TSTAGES, TCONSUMERS = Cfg::CONSUMERS;
   constexpr uint32_t TILE_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
-  const int bx = (g.khi_mode == KHI_N0) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;   // long tiles first
-  const int m0 = blockIdx.y * TBM, n0 = bx * TBN;
+  int bx = blockIdx.x, by = blockIdx.y;
+  if (g.khi_mode == KHI_N0) {   // longest tiles (last columns) first over the whole grid: see gemm.cu
+    const int lin = blockIdx.y * gridDim.x + blockIdx.x;
+    bx = (int)gridDim.x - 1 - lin / (int)gridDim.y;
+    by = lin % (int)gridDim.y;
+  }
+  const int m0 = by * TBM, n0 = bx * TBN;
   if (g.cmode != C_FULL && n0 >= m0 + TBM) return;  // tile entirely above the diagonal
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B-swizzled TMA tiles need 1024-byte alignment
