@@ -296,6 +296,7 @@ class Lkd:
     alpha: np.ndarray | None = None
     chofac_good: bool = True
     eta: float | None = None
+    post: tuple | None = None   # (mu, sig, sig2) at the test points handed to lkd_wo_noise_lean
 
 
 def gls_beta(chofac, H, y):
@@ -336,10 +337,26 @@ def lkd_wo_noise(X, fval, grad, theta, mode="precon", eta=None, mask=None, calc_
     return out
 
 
-def lkd_wo_noise_lean(X, fval, grad, theta, mode="precon", eta=None, calc_grad=True, tile=256):
+def cross_cov_values(X, Xs, theta):
+    """Value columns of calc_KernGrad(Rtensor(X, X*)): Kyx[N, nx] with rows [k ; -2 theta_i r_i k], r = x_train - x_test
+    (eval/GpEvalModel.py:133-139, kernel/KernelSqExp.py:392) -- without the nx*d test-gradient columns the reference
+    builds and drops."""
+    n, d = X.shape
+    R = X[:, None, :] - Xs[None, :, :]
+    k = np.exp(-np.einsum("abi,i->ab", R ** 2, theta))
+    out = np.empty((n * (d + 1), Xs.shape[0]))
+    out[:n] = k
+    for i in range(d):
+        out[n + i * n: n + (i + 1) * n] = -2.0 * theta[i] * R[:, :, i] * k
+    return out
+
+
+def lkd_wo_noise_lean(X, fval, grad, theta, mode="precon", eta=None, calc_grad=True, tile=256, Xs=None):
     """Same quantities as lkd_wo_noise for sizes where the reference cannot run (its dK/dtheta
     tensor is d*N*N*8 bytes).  In-place LAPACK potrf/potri; dK/dtheta contracted tile by tile.
-    All gradients used (mask=None).  Must agree with lkd_wo_noise (checked in tests)."""
+    All gradients used (mask=None).  Must agree with lkd_wo_noise (checked in tests).
+    With Xs [nx, d] the posterior of eval_model (eval/GpEvalModel.py:154-168) at the closed-form (beta, varK)
+    is taken from the same factor and returned as out.post = (mu, sig, sig2)."""
     n, d = X.shape
     theta = np.asarray(theta, dtype=float)
     if eta is None:
@@ -367,6 +384,15 @@ def lkd_wo_noise_lean(X, fval, grad, theta, mode="precon", eta=None, calc_grad=T
     ln_det = 2.0 * np.sum(np.log(np.diag(c) * p))
     lml = -(N * np.log(varK) + ln_det) / 2.0
     out = Lkd(lml, None, varK, np.array([beta]), ln_det, alpha_t / p, True, eta)
+    if Xs is not None:
+        # mu = beta + K*^T K^-1 (y - H beta); sig2 = 1 - diag(K*^T K^-1 K*) with the varK := 1 factor, in chunks
+        mu, sig2 = np.empty(Xs.shape[0]), np.empty(Xs.shape[0])
+        for s0 in range(0, Xs.shape[0], 512):
+            Kyx = cross_cov_values(X, Xs[s0:s0 + 512], theta)
+            mu[s0:s0 + 512] = beta + Kyx.T @ (alpha_t / p)
+            Z = linalg.solve_triangular(c, Kyx / p[:, None], lower=True, check_finite=False)
+            sig2[s0:s0 + 512] = 1.0 - np.einsum("ij,ij->j", Z, Z)
+        out.post = (mu, np.sqrt(np.maximum(sig2, 0.0)) * np.sqrt(varK), sig2)
     if not calc_grad:
         return out
     Kinv, info = linalg.lapack.dpotri(c, lower=1, overwrite_c=1)

@@ -94,6 +94,20 @@ def test_posterior(golden_dir, name):
     assert np.max(np.abs(sig ** 2 - g["sig"] ** 2)) / varK < 1e-8
 
 
+@pytest.mark.parametrize("name", ["d4_n37_precon", "d5_n64_precon_seed1", "d3_n30_base"])
+def test_lean_posterior(golden_dir, name):
+    """The memory-lean form (the only one that fits N = 21000) gives the reference's posterior from the same factor
+    it takes the LML from: mu / sig of the golden files were computed by the reference at ITS closed-form (beta, varK)."""
+    g = _load(golden_dir, name)
+    mode = "precon" if str(g["mode"]) == "precon" else "base"
+    o = O.lkd_wo_noise_lean(g["x_scl"], g["fval_scl"], g["grad_scl"], g["theta"], mode, float(g["eta"]),
+                            calc_grad=False, Xs=g["x_test"])
+    mu, sig, sig2 = o.post
+    assert _rel(o.hp_varK, g["hp_varK"]) < 1e-8 and _rel(o.hp_beta[0], g["hp_beta"][0]) < 1e-8
+    assert np.max(np.abs(mu - g["mu"])) / np.max(np.abs(g["mu"])) < 1e-8
+    assert np.max(np.abs(sig ** 2 - g["sig"] ** 2)) / float(g["hp_varK"]) < 1e-8
+
+
 def test_candidate_scan(golden_dir):
     g = _load(golden_dir, "c4_d5_n200_cand8")
     th = 10.0 ** g["log10_theta"]
