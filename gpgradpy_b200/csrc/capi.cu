@@ -115,7 +115,9 @@ extern "C" {
 int gegp_abi_version(void) { return GEGP_ABI_VERSION; }
 
 void gegp_profile_begin(int time_gemm) {
-  g_prof = Prof{};
+  g_prof.launches = 0;
+  g_prof.gemm_flops = 0.0;
+  g_prof.gemm_launches = 0;
   g_prof.on = (time_gemm != 0);
   g_ev_used = 0;
 }
@@ -153,6 +155,12 @@ int gegp_set_option(int key, int value) {
     if (value < 0) return -2;
     const int old = small_tile_max();
     small_tile_max() = value;
+    return old;
+  }
+  if (key == GEGP_OPT_CHAIN_CLUSTER) {
+    if (value != 0 && value != 1 && value != 2 && value != 4) return -2;
+    const int old = chain_cluster();
+    chain_cluster() = value;
     return old;
   }
   if (key == GEGP_OPT_LOOKAHEAD) {

@@ -1,6 +1,7 @@
 // Common device helpers for the gradient-enhanced GP kernels (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 
@@ -8,7 +9,7 @@
 namespace gegp {
 struct Prof {
   bool on = false;
-  long launches = 0;        // every kernel launch of the library since the last reset
+  std::atomic<long> launches{0};   // every kernel launch of the library since the last reset
   double gemm_flops = 0.0;  // useful flops of the DMMA GEMM launches (2*M*N*K with triangular clipping)
   long gemm_launches = 0;
 };
@@ -46,13 +47,22 @@ struct Ctx {
     }                                                                                            \
   } while (0)
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory, once per (kernel instantiation, device): the attribute
+// is per device, so the flag is a per-device bit, not a process-wide bool (thread-safe: the worst case is a repeat).
 #define GEGP_SET_SMEM(kern, bytes)                                                               \
   do {                                                                                           \
-    cudaError_t e__ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
-    if (e__ != cudaSuccess) {                                                                    \
-      fprintf(stderr, "[gegp] cannot set %d bytes of dynamic shared memory: %s (%s:%d)\n", (int)(bytes), \
-              cudaGetErrorString(e__), __FILE__, __LINE__);                                      \
-      return -1000 - (int)e__;                                                                   \
+    static std::atomic<unsigned long long> done__{0ull};                                         \
+    int dev__ = 0;                                                                               \
+    cudaGetDevice(&dev__);                                                                       \
+    const unsigned long long bit__ = 1ull << (dev__ & 63);                                       \
+    if (!(done__.load(std::memory_order_acquire) & bit__)) {                                     \
+      cudaError_t e__ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+      if (e__ != cudaSuccess) {                                                                  \
+        fprintf(stderr, "[gegp] cannot set %d bytes of dynamic shared memory: %s (%s:%d)\n", (int)(bytes), \
+                cudaGetErrorString(e__), __FILE__, __LINE__);                                    \
+        return -1000 - (int)e__;                                                                 \
+      }                                                                                          \
+      done__.fetch_or(bit__, std::memory_order_release);                                         \
     }                                                                                            \
   } while (0)
 

@@ -228,11 +228,7 @@ template <int BM, int BN, int WM, int WN, int STAGES, bool B_KCONT>
 static int launch_cfg(const Ctx& ctx, const GemmArgs& g) {
   using Cfg = GemmCfg<BM, BN, WM, WN, STAGES, B_KCONT>;
   auto kern = gemm_f64_kernel<BM, BN, WM, WN, STAGES, B_KCONT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GEGP_SET_SMEM(kern, Cfg::SMEM);
-    attr_set = true;
-  }
+  GEGP_SET_SMEM(kern, Cfg::SMEM);
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.outer * g.inner);
   prof_gemm_begin(ctx.stream);
   timeline_begin(ctx.stream, "gemm", g.M, g.N, g.K);

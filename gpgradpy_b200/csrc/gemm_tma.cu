@@ -295,11 +295,7 @@ static int launch_tma(const Ctx& ctx, const GemmArgs& g, uint64_t a_d0, uint64_t
   t.klo_mode = g.klo_mode; t.khi_mode = g.khi_mode; t.cmode = g.cmode;
   t.inner = g.inner; t.iAr = g.iAr; t.iAc = g.iAc; t.iBr = g.iBr; t.iBc = g.iBc;
   t.Ct = g.Ct; t.ldct = g.ldct; t.sCto = g.sCto; t.sCti = g.sCti;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GEGP_SET_SMEM(gemm_tma_nt_kernel<Cfg>, Cfg::SMEM);
-    attr_set = true;
-  }
+  GEGP_SET_SMEM(gemm_tma_nt_kernel<Cfg>, Cfg::SMEM);
   dim3 grid((g.N + Cfg::TBN - 1) / Cfg::TBN, (g.M + Cfg::TBM - 1) / Cfg::TBM, g.outer * g.inner);
   prof_gemm_begin(ctx.stream);
   timeline_begin(ctx.stream, "gemm_tma", g.M, g.N, g.K);

@@ -402,9 +402,8 @@ dinv_assemble_kernel(const double* __restrict__ L, int64_t ldl, int64_t strideL,
 int leaf_dinv_assemble(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, double* Dinv, int64_t strideD,
                        int N) {
   if (N <= 0) return 0;
-  static bool attr = false;
   const int smem = NB * PLD * (int)sizeof(double);
-  if (!attr) { GEGP_SET_SMEM(dinv_assemble_kernel, smem); attr = true; }
+  GEGP_SET_SMEM(dinv_assemble_kernel, smem);
   dinv_assemble_kernel<<<dim3((N + NB - 1) / NB, 1, ctx.batch), LT, smem, ctx.stream>>>(L, ldl, strideL, Dinv, strideD, N);
   GEGP_CHECK_LAUNCH();
   return 0;
@@ -420,9 +419,8 @@ int leaf_potf2_inv(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int 
                    int64_t strideD) {
   if (k <= 0) return 0;
   if (k > NB) return -901;
-  static bool attr = false;
   const int smem = NB * PLD * (int)sizeof(double);
-  if (!attr) { GEGP_SET_SMEM(potf2_inv_kernel, smem); attr = true; }
+  GEGP_SET_SMEM(potf2_inv_kernel, smem);
   timeline_begin(ctx.stream, "potf2", row0, k);
   potf2_inv_kernel<<<dim3(1, 1, ctx.batch), LT, smem, ctx.stream>>>(A, lda, strideA, k, row0, info, Dinv, strideD);
   timeline_end(ctx.stream);
@@ -456,6 +454,222 @@ __device__ __forceinline__ void frag_c_to_a(double* scr, const double (&c)[4][2]
   for (int kq = 0; kq < 8; kq++) a[kq] = sign * scr[lr * SLD + 4 * kq + lk];
 }
 
+// One 8-row strip of the leaf solve.  `s` is the shared tile with L (lower) and the shifted 32 x 32 diagonal blocks of
+// U = L^-T, `scr` this warp's 8 x SLD scratch strip.  On entry x[j][ct] holds the strip's right-hand side as C fragments
+// (32-column block j, 8-column tile ct); on exit it holds the solution.  Blocks j >= nb32 are left untouched.
+__device__ __forceinline__ void solve_strip(const double* s, double* scr, double (&x)[4][4][2], int nb32, int lr, int lk) {
+  double xneg[3][8];  // -X_i as A fragments, i = 0..2
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    if (j < nb32) {
+      const int j0 = j * 32;
+      double (&acc)[4][2] = x[j];
+      // C_j = B_j - sum_{i<j} X_i L_ji^T
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        if (i < j) {
+#pragma unroll
+          for (int ct = 0; ct < 4; ct++) {
+            const double* lrow = s + (j0 + ct * 8 + lr) * PLD + i * 32 + lk;
+#pragma unroll
+            for (int kq = 0; kq < 8; kq++) dmma884(acc[ct][0], acc[ct][1], xneg[i][kq], lrow[4 * kq]);
+          }
+        }
+      }
+      // X1 = C_j U_jj
+      double af[8], x1[4][2];
+      frag_c_to_a(scr, acc, af, lr, lk, 1.0);
+#pragma unroll
+      for (int ct = 0; ct < 4; ct++) {
+        x1[ct][0] = x1[ct][1] = 0.0;
+        const int c = ct * 8 + lr;
+#pragma unroll
+        for (int kq = 0; kq <= 2 * ct + 1; kq++) {
+          const int kx = 4 * kq + lk;
+          const double b = (kx <= c) ? s[(j0 + kx) * PLD + j0 + c + 1] : 0.0;
+          dmma884(x1[ct][0], x1[ct][1], af[kq], b);
+        }
+      }
+      // R = C_j - X1 L_jj^T
+      frag_c_to_a(scr, x1, af, lr, lk, -1.0);
+#pragma unroll
+      for (int ct = 0; ct < 4; ct++) {
+        const int nn = ct * 8 + lr;
+#pragma unroll
+        for (int kq = 0; kq <= 2 * ct + 1; kq++) {
+          const int kx = 4 * kq + lk;
+          const double b = (kx <= nn) ? s[(j0 + nn) * PLD + j0 + kx] : 0.0;
+          dmma884(acc[ct][0], acc[ct][1], af[kq], b);
+        }
+      }
+      // X_j = X1 + R U_jj
+      frag_c_to_a(scr, acc, af, lr, lk, 1.0);
+#pragma unroll
+      for (int ct = 0; ct < 4; ct++) {
+        const int c = ct * 8 + lr;
+#pragma unroll
+        for (int kq = 0; kq <= 2 * ct + 1; kq++) {
+          const int kx = 4 * kq + lk;
+          const double b = (kx <= c) ? s[(j0 + kx) * PLD + j0 + c + 1] : 0.0;
+          dmma884(x1[ct][0], x1[ct][1], af[kq], b);
+        }
+      }
+#pragma unroll
+      for (int ct = 0; ct < 4; ct++) { acc[ct][0] = x1[ct][0]; acc[ct][1] = x1[ct][1]; }
+      if (j < 3) frag_c_to_a(scr, x1, xneg[j], lr, lk, -1.0);
+    }
+  }
+}
+
+// One 8-row strip of the leaf solve, streamed: each 32-column block of the strip is read from / written back to global
+// memory (row pointer brow) as it is reached, so only one block of the strip is ever held in registers.  Performs
+// exactly the arithmetic of solve_strip (same DMMA sequence): the two give bit-identical results.
+__device__ __forceinline__ void solve_strip_streamed(const double* s, double* scr, double* brow, bool rok, int k, int nb32,
+                                                     bool vec, int lr, int lk) {
+  double xneg[3][8];  // -X_i as A fragments, i = 0..2
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    if (j < nb32) {
+      const int j0 = j * 32;
+      double acc[4][2];
+#pragma unroll
+      for (int ct = 0; ct < 4; ct++) {
+        const int c = j0 + ct * 8 + 2 * lk;
+        acc[ct][0] = acc[ct][1] = 0.0;
+        if (rok) {
+          if (vec) {
+            if (c < k) {
+              const double2 v = *reinterpret_cast<const double2*>(brow + c);
+              acc[ct][0] = v.x;
+              acc[ct][1] = v.y;
+            }
+          } else {
+            if (c < k) acc[ct][0] = brow[c];
+            if (c + 1 < k) acc[ct][1] = brow[c + 1];
+          }
+        }
+      }
+      // C_j = B_j - sum_{i<j} X_i L_ji^T
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        if (i < j) {
+#pragma unroll
+          for (int ct = 0; ct < 4; ct++) {
+            const double* lrow = s + (j0 + ct * 8 + lr) * PLD + i * 32 + lk;
+#pragma unroll
+            for (int kq = 0; kq < 8; kq++) dmma884(acc[ct][0], acc[ct][1], xneg[i][kq], lrow[4 * kq]);
+          }
+        }
+      }
+      // X1 = C_j U_jj
+      double af[8], x1[4][2];
+      frag_c_to_a(scr, acc, af, lr, lk, 1.0);
+#pragma unroll
+      for (int ct = 0; ct < 4; ct++) {
+        x1[ct][0] = x1[ct][1] = 0.0;
+        const int c = ct * 8 + lr;
+#pragma unroll
+        for (int kq = 0; kq <= 2 * ct + 1; kq++) {
+          const int kx = 4 * kq + lk;
+          const double b = (kx <= c) ? s[(j0 + kx) * PLD + j0 + c + 1] : 0.0;
+          dmma884(x1[ct][0], x1[ct][1], af[kq], b);
+        }
+      }
+      // R = C_j - X1 L_jj^T
+      frag_c_to_a(scr, x1, af, lr, lk, -1.0);
+#pragma unroll
+      for (int ct = 0; ct < 4; ct++) {
+        const int nn = ct * 8 + lr;
+#pragma unroll
+        for (int kq = 0; kq <= 2 * ct + 1; kq++) {
+          const int kx = 4 * kq + lk;
+          const double b = (kx <= nn) ? s[(j0 + nn) * PLD + j0 + kx] : 0.0;
+          dmma884(acc[ct][0], acc[ct][1], af[kq], b);
+        }
+      }
+      // X_j = X1 + R U_jj
+      frag_c_to_a(scr, acc, af, lr, lk, 1.0);
+#pragma unroll
+      for (int ct = 0; ct < 4; ct++) {
+        const int c = ct * 8 + lr;
+#pragma unroll
+        for (int kq = 0; kq <= 2 * ct + 1; kq++) {
+          const int kx = 4 * kq + lk;
+          const double b = (kx <= c) ? s[(j0 + kx) * PLD + j0 + c + 1] : 0.0;
+          dmma884(x1[ct][0], x1[ct][1], af[kq], b);
+        }
+      }
+      if (rok) {
+#pragma unroll
+        for (int ct = 0; ct < 4; ct++) {
+          const int c = j0 + ct * 8 + 2 * lk;
+          if (vec) {
+            if (c < k) *reinterpret_cast<double2*>(brow + c) = make_double2(x1[ct][0], x1[ct][1]);
+          } else {
+            if (c < k) brow[c] = x1[ct][0];
+            if (c + 1 < k) brow[c + 1] = x1[ct][1];
+          }
+        }
+      }
+      if (j < 3) frag_c_to_a(scr, x1, xneg[j], lr, lk, -1.0);
+    }
+  }
+}
+
+// Strip rows <-> global memory (C-fragment layout): all loads of a strip are issued up front so that only one L2
+// round trip is exposed per strip.
+__device__ __forceinline__ void load_strip(const double* brow, bool rok, int k, bool vec, int lk, double (&x)[4][4][2]) {
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int ct = 0; ct < 4; ct++) {
+      const int c = j * 32 + ct * 8 + 2 * lk;
+      x[j][ct][0] = x[j][ct][1] = 0.0;
+      if (rok) {
+        if (vec) {
+          if (c < k) {
+            const double2 v = *reinterpret_cast<const double2*>(brow + c);
+            x[j][ct][0] = v.x;
+            x[j][ct][1] = v.y;
+          }
+        } else {
+          if (c < k) x[j][ct][0] = brow[c];
+          if (c + 1 < k) x[j][ct][1] = brow[c + 1];
+        }
+      }
+    }
+}
+__device__ __forceinline__ void store_strip(double* brow, bool rok, int k, bool vec, int lk, const double (&x)[4][4][2]) {
+  if (!rok) return;
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int ct = 0; ct < 4; ct++) {
+      const int c = j * 32 + ct * 8 + 2 * lk;
+      if (vec) {
+        if (c < k) *reinterpret_cast<double2*>(brow + c) = make_double2(x[j][ct][0], x[j][ct][1]);
+      } else {
+        if (c < k) brow[c] = x[j][ct][0];
+        if (c + 1 < k) brow[c + 1] = x[j][ct][1];
+      }
+    }
+}
+
+// Stage a factored leaf for solves: L (lower, identity padded to kk) and the 32 x 32 diagonal blocks of U = L^-T
+// (shifted one column right) into the shared tile.
+__device__ __forceinline__ void stage_factor(double* s, const double* __restrict__ L, int64_t ldl,
+                                             const double* __restrict__ Dinv, int k, int kk, int tid, int nthreads) {
+  stage_lower(s, L, ldl, k, kk, tid, nthreads);
+  __syncthreads();
+  for (int e = tid; e < kk * 32; e += nthreads) {   // 8-byte copies: odd offsets
+    const int i = e >> 5, c = (i & ~31) + (e & 31);
+    if (c >= i) cp_async8(s + i * PLD + c + 1, Dinv + i * NB + c);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+}
+
 template <int TW>
 __global__ void __launch_bounds__(TW * 32, 1)
 leaf_trsm_kernel(const double* __restrict__ L, int64_t ldl, int64_t strideL, const double* __restrict__ Dinv,
@@ -467,110 +681,142 @@ leaf_trsm_kernel(const double* __restrict__ L, int64_t ldl, int64_t strideL, con
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lk = lane & 3;
   const int kk = (k + 31) & ~31;
-  stage_lower(s, L, ldl, k, kk, tid, TW * 32);
-  __syncthreads();
-  // ... then the 32 x 32 diagonal blocks of U = L^-T, shifted one column right (8-byte copies: odd offsets)
-  for (int e = tid; e < kk * 32; e += TW * 32) {
-    const int i = e >> 5, c = (i & ~31) + (e & 31);
-    if (c >= i) cp_async8(s + i * PLD + c + 1, Dinv + i * NB + c);
-  }
-  cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
+  stage_factor(s, L, ldl, Dinv, k, kk, tid, TW * 32);
   double* scr = s + NB * PLD + warp * 8 * SLD;
   const int nb32 = kk >> 5;
   const bool vec = ((k & 1) == 0);
-
   for (int st = blockIdx.x * TW + warp; st * 8 < r; st += gridDim.x * TW) {
     const int row = st * 8 + lr;
     const bool rok = row < r;
     double* brow = B + (int64_t)row * ldb;
-    double xneg[3][8];  // -X_i as A fragments, i = 0..2
+    solve_strip_streamed(s, scr, brow, rok, k, nb32, vec, lr, lk);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Chain step, first half (everything between two leaf factorisations that the NEXT leaf factorisation waits for):
+//   X  = B L_p^-T          the 128 rows right below the previous leaf p (the next leaf's block row), solved in place
+//   E -= X X^T             the next leaf's diagonal block (lower triangle), K = 128
+// One thread-block cluster of CS CTAs: the 16 row strips of the solve are dealt out over the CTAs, every CTA then
+// receives all of X in its shared tile (distributed shared memory stores), and the 8 x 8 output tiles of the update
+// are dealt out over all CS x 8 warps.  The rows further down are solved off the critical path by leaf_trsm_kernel.
+// Same arithmetic per strip / per output element for every CS, so results do not depend on the cluster size.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_f64x2(const void* local_ptr, uint32_t rank, double a, double b) {
+  const uint32_t la = (uint32_t)__cvta_generic_to_shared(local_ptr);
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(ra), "d"(a), "d"(b) : "memory");
+}
+
+constexpr int SYRK_UNITS = 40;   // (row tile rt, group of four column tiles cg <= rt / 4) units of the 128 x 128 lower update
+
+template <int CS>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(LT, 1)
+chain_prep_kernel(const double* __restrict__ Lp, int64_t lda, int64_t strideA, const double* __restrict__ Dinv,
+                  int64_t strideD, double* __restrict__ B, double* __restrict__ E, int kc) {
+  extern __shared__ __align__(16) double s[];  // NB x PLD tile, then NW x 8 x SLD scratch strips
+  Lp += (int64_t)blockIdx.z * strideA;
+  B += (int64_t)blockIdx.z * strideA;
+  E += (int64_t)blockIdx.z * strideA;
+  Dinv += (int64_t)blockIdx.z * strideD;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lk = lane & 3;
+  const uint32_t rank = (CS > 1) ? cluster_rank() : 0u;
+  constexpr int SPC = 16 / CS;                 // strips per CTA
+  constexpr int WTOT = CS * NW;                // warps of the whole cluster
+  constexpr int MAXU = (SYRK_UNITS + WTOT - 1) / WTOT;
+  const int gw = (int)rank * NW + warp;        // cluster-wide warp index: owner of update units gw, gw + WTOT, ...
+  double* scr = s + NB * PLD + warp * 8 * SLD;
+
+  if (CS == 1) {
+    // ---- one CTA per problem (batches that fill the machine): streamed solve, then X comes back from L2
+    stage_factor(s, Lp, lda, Dinv, NB, NB, tid, LT);
+    for (int st = warp; st * 8 < kc; st += NW) {
+      const int row = st * 8 + lr;
+      solve_strip_streamed(s, scr, B + (int64_t)row * lda, row < kc, NB, 4, true, lr, lk);
+    }
+    __syncthreads();
+    for (int e = tid; e < NB * (NB / 2); e += LT) {
+      const int r = e >> 6, c = (e & 63) * 2;
+      cp_async16(s + r * PLD + c, B + (int64_t)(r < kc ? r : 0) * lda + c, r < kc ? 16 : 0);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+  } else {
+    // ---- solve: strip rank * SPC + warp of the block row (one per warp), kept in registers
+    static_assert(CS == 1 || SPC <= NW, "one strip per warp");
+    const int st = (int)rank * SPC + warp;
+    const bool mine = (warp < SPC) && st * 8 < kc;            // warp-uniform
+    const int row = st * 8 + lr;
+    double x[4][4][2];
+    load_strip(B + (int64_t)row * lda, mine && row < kc, NB, true, lk, x);
+    stage_factor(s, Lp, lda, Dinv, NB, NB, tid, LT);
+    if (mine) {
+      solve_strip(s, scr, x, 4, lr, lk);
+      store_strip(B + (int64_t)row * lda, row < kc, NB, true, lk, x);
+    }
+    // ---- every CTA gets all of X (rows beyond kc are zero) in its tile, plain layout s[r][c]
+    cluster_sync();                                            // everybody is done reading L_p
+    if (warp < SPC) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      if (j < nb32) {
-        const int j0 = j * 32;
-        double acc[4][2];
+      for (int j = 0; j < 4; j++)
 #pragma unroll
         for (int ct = 0; ct < 4; ct++) {
-          const int c = j0 + ct * 8 + 2 * lk;
-          acc[ct][0] = acc[ct][1] = 0.0;
-          if (rok) {
-            if (vec) {
-              if (c < k) {
-                const double2 v = *reinterpret_cast<const double2*>(brow + c);
-                acc[ct][0] = v.x;
-                acc[ct][1] = v.y;
-              }
-            } else {
-              if (c < k) acc[ct][0] = brow[c];
-              if (c + 1 < k) acc[ct][1] = brow[c + 1];
-            }
-          }
+          const double* dst = s + row * PLD + j * 32 + ct * 8 + 2 * lk;
+#pragma unroll
+          for (int t = 0; t < CS; t++) st_cluster_f64x2(dst, (uint32_t)t, x[j][ct][0], x[j][ct][1]);
         }
-        // C_j = B_j - sum_{i<j} X_i L_ji^T
+    }
+    cluster_sync();
+  }
+  // ---- E -= X X^T on this warp's units (accumulate X X^T from zero, then subtract: the arithmetic of the GEMM engine
+  //      with alpha = -1, beta = 1)
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-          if (i < j) {
+  for (int q = 0; q < MAXU; q++) {
+    const int u = gw + q * WTOT;
+    if (u >= SYRK_UNITS) continue;
+    // unit u -> (rt, cg): row tiles 4g .. 4g+3 have g + 1 groups of four column tiles each
+    int g = 0, first = 0;
+    while (u >= first + 4 * (g + 1)) { first += 4 * (g + 1); g++; }
+    const int rt = 4 * g + (u - first) / (g + 1), cg = (u - first) % (g + 1);
+    if (rt * 8 >= kc) continue;                // warp-uniform
+    const int r0 = rt * 8, r = r0 + lr;
+    double e[4][2], acc[4][2];
 #pragma unroll
-            for (int ct = 0; ct < 4; ct++) {
-              const double* lrow = s + (j0 + ct * 8 + lr) * PLD + i * 32 + lk;
+    for (int t = 0; t < 4; t++) {
+      const int ct = cg * 4 + t, c = ct * 8 + 2 * lk;
+      e[t][0] = e[t][1] = acc[t][0] = acc[t][1] = 0.0;
+      if (ct <= rt && r < kc) {
+        if (c <= r) e[t][0] = E[(int64_t)r * lda + c];
+        if (c + 1 <= r) e[t][1] = E[(int64_t)r * lda + c + 1];
+      }
+    }
+#pragma unroll 8
+    for (int kq = 0; kq < 32; kq++) {
+      const double a = s[r * PLD + 4 * kq + lk];
 #pragma unroll
-              for (int kq = 0; kq < 8; kq++) dmma884(acc[ct][0], acc[ct][1], xneg[i][kq], lrow[4 * kq]);
-            }
-          }
-        }
-        // X1 = C_j U_jj
-        double af[8], x1[4][2];
-        frag_c_to_a(scr, acc, af, lr, lk, 1.0);
+      for (int t = 0; t < 4; t++) {
+        const int ct = min(cg * 4 + t, rt);
+        const double b = s[(ct * 8 + lr) * PLD + 4 * kq + lk];
+        dmma884(acc[t][0], acc[t][1], a, b);
+      }
+    }
 #pragma unroll
-        for (int ct = 0; ct < 4; ct++) {
-          x1[ct][0] = x1[ct][1] = 0.0;
-          const int c = ct * 8 + lr;
-#pragma unroll
-          for (int kq = 0; kq <= 2 * ct + 1; kq++) {
-            const int kx = 4 * kq + lk;
-            const double b = (kx <= c) ? s[(j0 + kx) * PLD + j0 + c + 1] : 0.0;
-            dmma884(x1[ct][0], x1[ct][1], af[kq], b);
-          }
-        }
-        // R = C_j - X1 L_jj^T
-        frag_c_to_a(scr, x1, af, lr, lk, -1.0);
-#pragma unroll
-        for (int ct = 0; ct < 4; ct++) {
-          const int nn = ct * 8 + lr;
-#pragma unroll
-          for (int kq = 0; kq <= 2 * ct + 1; kq++) {
-            const int kx = 4 * kq + lk;
-            const double b = (kx <= nn) ? s[(j0 + nn) * PLD + j0 + kx] : 0.0;
-            dmma884(acc[ct][0], acc[ct][1], af[kq], b);
-          }
-        }
-        // X_j = X1 + R U_jj
-        frag_c_to_a(scr, acc, af, lr, lk, 1.0);
-#pragma unroll
-        for (int ct = 0; ct < 4; ct++) {
-          const int c = ct * 8 + lr;
-#pragma unroll
-          for (int kq = 0; kq <= 2 * ct + 1; kq++) {
-            const int kx = 4 * kq + lk;
-            const double b = (kx <= c) ? s[(j0 + kx) * PLD + j0 + c + 1] : 0.0;
-            dmma884(x1[ct][0], x1[ct][1], af[kq], b);
-          }
-        }
-        if (rok) {
-#pragma unroll
-          for (int ct = 0; ct < 4; ct++) {
-            const int c = j0 + ct * 8 + 2 * lk;
-            if (vec) {
-              if (c < k) *reinterpret_cast<double2*>(brow + c) = make_double2(x1[ct][0], x1[ct][1]);
-            } else {
-              if (c < k) brow[c] = x1[ct][0];
-              if (c + 1 < k) brow[c + 1] = x1[ct][1];
-            }
-          }
-        }
-        if (j < 3) frag_c_to_a(scr, x1, xneg[j], lr, lk, -1.0);
+    for (int t = 0; t < 4; t++) {
+      const int ct = cg * 4 + t, c = ct * 8 + 2 * lk;
+      if (ct <= rt && r < kc) {
+        if (c <= r) E[(int64_t)r * lda + c] = e[t][0] - acc[t][0];
+        if (c + 1 <= r) E[(int64_t)r * lda + c + 1] = e[t][1] - acc[t][1];
       }
     }
   }
@@ -579,9 +825,8 @@ leaf_trsm_kernel(const double* __restrict__ L, int64_t ldl, int64_t strideL, con
 template <int TW>
 static int launch_leaf_trsm(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv,
                             int64_t strideD, double* B, int64_t ldb, int64_t strideB, int r, int k) {
-  static bool attr = false;
   const int smem = (NB * PLD + TW * 8 * SLD) * (int)sizeof(double);
-  if (!attr) { GEGP_SET_SMEM(leaf_trsm_kernel<TW>, smem); attr = true; }
+  GEGP_SET_SMEM(leaf_trsm_kernel<TW>, smem);
   const int nctas = (r + TW * 8 - 1) / (TW * 8);
   timeline_begin(ctx.stream, "ltrsm", r, k);
   leaf_trsm_kernel<TW><<<dim3(nctas, 1, ctx.batch), TW * 32, smem, ctx.stream>>>(L, ldl, strideL, Dinv, strideD, B, ldb,
@@ -589,6 +834,37 @@ static int launch_leaf_trsm(const Ctx& ctx, const double* L, int64_t ldl, int64_
   timeline_end(ctx.stream);
   GEGP_CHECK_LAUNCH();
   return 0;
+}
+
+template <int CS>
+static int launch_chain_prep(const Ctx& ctx, const double* Lp, int64_t lda, int64_t strideA, const double* Dinv,
+                             int64_t strideD, double* B, double* E, int kc) {
+  const int smem = (NB * PLD + NW * 8 * SLD) * (int)sizeof(double);
+  GEGP_SET_SMEM(chain_prep_kernel<CS>, smem);
+  timeline_begin(ctx.stream, "cprep", kc, CS);
+  chain_prep_kernel<CS><<<dim3(CS, 1, ctx.batch), LT, smem, ctx.stream>>>(Lp, lda, strideA, Dinv, strideD, B, E, kc);
+  timeline_end(ctx.stream);
+  GEGP_CHECK_LAUNCH();
+  return 0;
+}
+
+static int g_chain_cluster = -1;
+int& chain_cluster() {
+  if (g_chain_cluster < 0) g_chain_cluster = getenv("GEGP_CHAIN_CLUSTER") ? atoi(getenv("GEGP_CHAIN_CLUSTER")) : 0;
+  return g_chain_cluster;
+}
+
+int leaf_chain_prep(const Ctx& ctx, const double* Lp, int64_t lda, int64_t strideA, const double* Dinv, int64_t strideD,
+                    double* B, double* E, int kc) {
+  if (kc <= 0) return 0;
+  if (kc > NB) return -905;
+  // a lone problem is latency-bound: spread the chain step over a cluster of four SMs; a batch that fills the machine
+  // with one CTA per problem runs the same arithmetic in a single CTA each (bit-identical either way)
+  int cs = chain_cluster();
+  if (cs != 1 && cs != 2 && cs != 4) cs = (ctx.batch * 4 <= 148) ? 4 : (ctx.batch * 2 <= 148 ? 2 : 1);
+  if (cs == 4) return launch_chain_prep<4>(ctx, Lp, lda, strideA, Dinv, strideD, B, E, kc);
+  if (cs == 2) return launch_chain_prep<2>(ctx, Lp, lda, strideA, Dinv, strideD, B, E, kc);
+  return launch_chain_prep<1>(ctx, Lp, lda, strideA, Dinv, strideD, B, E, kc);
 }
 
 int leaf_trsm(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv, int64_t strideD,

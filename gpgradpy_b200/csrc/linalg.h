@@ -62,6 +62,12 @@ int leaf_dinv_assemble(const Ctx& ctx, const double* L, int64_t ldl, int64_t str
 // the 32 x 32 diagonal inverses taken from Dinv and one refinement step each (as accurate as a substitution).
 int leaf_trsm(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv, int64_t strideD,
               double* B, int64_t ldb, int64_t strideB, int r, int k);
+// Chain step between two leaf factorisations: B (kc x LEAF, the block row right below the factored leaf Lp) <- B Lp^-T
+// in place, then E (kc x kc, lower: the next leaf's diagonal block) -= B B^T.  One small thread-block cluster.
+int leaf_chain_prep(const Ctx& ctx, const double* Lp, int64_t lda, int64_t strideA, const double* Dinv, int64_t strideD,
+                    double* B, double* E, int kc);
+// cluster size of that step (0: automatic; 1, 2, 4) -- tuning knob, same results for every value
+int& chain_cluster();
 // Diagonal blocks of the N x N buffer U <- Dinv blocks (upper triangular), diagonal blocks of W <- their transposes
 // (lower triangular); the rest of both buffers is left untouched.
 int leaf_scatter_dinv(const Ctx& ctx, const double* Dinv, int64_t strideD, double* U, int64_t ldu, int64_t strideU,

@@ -4,6 +4,8 @@
 // optz/CalcLkd.py:154,174).
 #include "linalg.h"
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 
 namespace gegp {
 
@@ -39,13 +41,16 @@ int trsm_right_rec(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL
 }
 
 // ------------------------------------------------------------------------------------------------
-// Look-ahead.  The factorisation's critical path is the chain  leaf factor -> leaf solve -> update of the next
-// leaf's diagonal block -> next leaf factor  (one CTA, then a few: latency bound).  It runs on its own
-// HIGHEST-priority stream (`hi`, forked from and re-joined to the caller's stream), so that its CTAs take the next
-// free SM ahead of queued GEMM tiles.  Everything else is dealt out so that the chain only ever does K = LEAF work:
-//   * the next leaf's diagonal block, updated with the LAST leaf's panel only          -> on the chain (`hi`);
-//   * the rows below it in that block column, same K = LEAF                            -> stream `col` (high
-//     priority): only the leaf SOLVE needs them, so they are updated beside the leaf factor;
+// Look-ahead.  The factorisation's critical path is the chain
+//     leaf factor (one CTA)  ->  solve of the NEXT leaf's 128-row block row + K = 128 update of its diagonal block
+//                                (chain_prep_kernel, one small cluster)  ->  next leaf factor  -> ...
+// It runs on its own HIGHEST-priority stream (`hi`, forked from and re-joined to the caller's stream), so that its
+// CTAs take the next free SM ahead of queued GEMM tiles.  Everything else is dealt out so that the chain never does
+// more than that:
+//   * the rows below the next leaf's block row are solved against a leaf on stream `col` (high priority), beside the
+//     next chain step: nothing on the chain reads them;
+//   * the rows below the diagonal block in the next leaf's block column, updated with the LAST leaf's panel only
+//     (K = LEAF)                                                                     -> stream `col` as well;
 //   * the columns right of it, updated with the whole left child's panel, cut into pieces along the left spine of
 //     the right child, plus the block column of the leaf that FOLLOWS the node       -> streams `bulk[depth]` (lowest
 //     priority); a piece is joined only when the chain reaches a fork or leaf that touches its columns.
@@ -53,6 +58,10 @@ int trsm_right_rec(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL
 // The summation order of an element differs from the single-stream schedule (same terms, grouped by update), so the
 // two schedules agree to rounding, not bit for bit; within one schedule results are reproducible and independent of
 // the batch size.  Fork/join is by events only and is capturable in a CUDA graph.
+//
+// Re-entrancy: the streams, events and piece table of one factorisation live in a LookAhead object taken from a
+// per-device pool for the duration of the (host-side, asynchronous) call, so concurrent calls from several host
+// threads or on several caller streams never share mutable state.
 // ------------------------------------------------------------------------------------------------
 namespace {
 // a trailing update with fewer 128 x 128 tiles than this is cut into just-in-time pieces (env GEGP_SPLIT_TILES)
@@ -61,13 +70,16 @@ int split_max_tiles() {
   return v;
 }
 constexpr int MAX_PIECES = 256;
+constexpr int MAX_DEV = 32;
 struct Piece { int c0, c1; cudaEvent_t done; cudaStream_t stream; bool live; };   // global column range a queued bulk GEMM writes
 struct LookAhead {
   static constexpr int NBULK = 16;
+  int dev = 0;
   cudaStream_t hi = nullptr, col = nullptr, bulk[NBULK] = {};   // one bulk stream per recursion depth (FIFO each)
-  cudaEvent_t fork[40], col_done, begin, end;
+  cudaEvent_t fork[40], ev_prep, ev_fac, ev_colupd, ev_solve, begin, end;
   Piece piece[MAX_PIECES];
-  bool col_pending = false;
+  bool colupd_pending = false;   // a K = LEAF block-column update is in flight on `col` (the next chain step reads its top rows)
+  bool solve_pending = false;    // a leaf solve is in flight on `col` (bulk pieces read its rows)
   bool ok = false;
   // the chain must not touch columns [c0, c1) before every queued bulk piece that writes them has finished
   int join_columns(cudaStream_t chain, int c0, int c1) {
@@ -84,30 +96,53 @@ struct LookAhead {
       if (!piece[i].live) return &piece[i];
     return nullptr;
   }
+  bool create() {
+    int lo = 0, hip = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hip);   // lo: numerically largest = lowest priority; hip: greatest
+    const int mid = hip < lo ? hip + 1 : hip;
+    ok = cudaStreamCreateWithPriority(&hi, cudaStreamNonBlocking, hip) == cudaSuccess &&
+         cudaStreamCreateWithPriority(&col, cudaStreamNonBlocking, mid) == cudaSuccess;
+    for (int i = 0; i < NBULK && ok; i++) ok = cudaStreamCreateWithPriority(&bulk[i], cudaStreamNonBlocking, lo) == cudaSuccess;
+    auto mk = [&](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
+    for (int i = 0; i < 40 && ok; i++) ok = mk(&fork[i]);
+    for (int i = 0; i < MAX_PIECES && ok; i++) { ok = mk(&piece[i].done); piece[i].live = false; }
+    ok = ok && mk(&ev_prep) && mk(&ev_fac) && mk(&ev_colupd) && mk(&ev_solve) && mk(&begin) && mk(&end);
+    return ok;
+  }
 };
 
-LookAhead* look_ahead() {
-  static LookAhead per_dev[16];
-  static bool init[16] = {false};
+struct LaPool {
+  std::mutex mu;
+  std::vector<LookAhead*> idle[MAX_DEV];
+};
+LaPool& la_pool() {
+  static LaPool* p = new LaPool();   // leaked on purpose: streams must outlive static destruction order
+  return *p;
+}
+// One LookAhead per factorisation in flight on the host side; returned to the pool when the call has been enqueued
+// (re-using its streams and events for a later call only adds stream-order dependencies).
+LookAhead* la_acquire() {
+  if (!lookahead_enabled()) return nullptr;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-  LookAhead& la = per_dev[dev];
-  if (!init[dev]) {
-    init[dev] = true;
-    int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo: numerically largest = lowest priority; hi: greatest
-    const int mid = hi < lo ? hi + 1 : hi;
-    la.ok = cudaStreamCreateWithPriority(&la.hi, cudaStreamNonBlocking, hi) == cudaSuccess &&
-            cudaStreamCreateWithPriority(&la.col, cudaStreamNonBlocking, mid) == cudaSuccess &&
-            true;
-    for (int i = 0; i < LookAhead::NBULK && la.ok; i++)
-      la.ok = cudaStreamCreateWithPriority(&la.bulk[i], cudaStreamNonBlocking, lo) == cudaSuccess;
-    auto mk = [&](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
-    for (int i = 0; i < 40 && la.ok; i++) la.ok = mk(&la.fork[i]);
-    for (int i = 0; i < MAX_PIECES && la.ok; i++) { la.ok = mk(&la.piece[i].done); la.piece[i].live = false; }
-    la.ok = la.ok && mk(&la.col_done) && mk(&la.begin) && mk(&la.end);
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
+  LaPool& pool = la_pool();
+  {
+    std::lock_guard<std::mutex> lock(pool.mu);
+    if (!pool.idle[dev].empty()) {
+      LookAhead* la = pool.idle[dev].back();
+      pool.idle[dev].pop_back();
+      return la;
+    }
   }
-  return (la.ok && lookahead_enabled()) ? &la : nullptr;
+  LookAhead* la = new LookAhead();
+  la->dev = dev;
+  if (!la->create()) { delete la; return nullptr; }   // (partially created handles are leaked: this never happens in practice)
+  return la;
+}
+void la_release(LookAhead* la) {
+  LaPool& pool = la_pool();
+  std::lock_guard<std::mutex> lock(pool.mu);
+  pool.idle[la->dev].push_back(la);
 }
 
 // Single-stream recursion (look-ahead off): factor the left half, one trailing update, factor the right half.
@@ -133,16 +168,20 @@ int chol_node(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, in
 }
 
 // Look-ahead recursion.  `ext` is the width of the leaf that FOLLOWS this node's columns (0: none).  After the left
-// child (k1 columns, a multiple of LEAF) the trailing update is dealt out as
-//   chain : diagonal block of the next leaf f = [k1, k1+w)        -= last leaf's panel only (K = LEAF)
-//   col   : the rows below it in f's block column                 -= last leaf's panel only (K = LEAF)
-//   bulk  : columns [k1+w, k) in just-in-time pieces              -= the whole left child's panel (K = k1)
-//   bulk  : the block column of the following leaf, [k, k+ext)    -= the whole left child's panel (K = k1)
-// so that every update on the chain has K = LEAF.  f's block column has already received the other leaves of the
-// left child through the `ext` pieces queued inside that child (by induction every (source leaf, target block
-// column) pair is applied exactly once: by the chain when the source is the leaf right before the target, by the
-// bulk piece of their lowest common ancestor X when the target lies in right(X) behind its first leaf or follows X,
-// ...).  A piece is joined when the chain reaches a fork or leaf that touches its columns.
+// child (k1 columns, a multiple of LEAF; its last leaf is l) the work that involves the next leaf f = [k1, k1+w) is
+// dealt out as
+//   chain : block row f of l's panel solved against l, then the diagonal block of f -= that block row's square
+//           (one chain_prep launch, K = LEAF)
+//   col   : the rows below f in l's panel solved against l (queued by leaf l itself, beside the chain step)
+//   col   : the rows below the diagonal block in f's block column   -= last leaf's panel only (K = LEAF)
+//   bulk  : columns [k1+w, k) in just-in-time pieces                -= the whole left child's panel (K = k1)
+//   bulk  : the block column of the following leaf, [k, k+ext)      -= the whole left child's panel (K = k1)
+// so that every update on the chain has K = LEAF and 128 rows.  f's block column has already received the other
+// leaves of the left child through the `ext` pieces queued inside that child (by induction every (source leaf, target
+// block column) pair is applied exactly once: by chain + col when the source is the leaf right before the target, by
+// the bulk piece of their lowest common ancestor X when the target lies in right(X) behind its first leaf or follows
+// X, ...).  A piece is joined when the chain reaches a fork or leaf that touches its columns.  The bulk pieces read
+// panel rows from k1+w on only (never block row f), all of which are produced on `col`: they wait for its last solve.
 int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t lda, int64_t strideA, int m, int k,
                  int row0, int ext, int* info, double* Dinv, int64_t strideD) {
   if (k <= 0) return 0;
@@ -151,11 +190,17 @@ int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t ld
     if ((rc = la->join_columns(ctx.stream, row0, row0 + k))) return rc;
     rc = leaf_potf2_inv(ctx, A, lda, strideA, k, row0, info, Dinv + (int64_t)(row0 / LEAF) * LEAF * LEAF, strideD);
     if (rc) return rc;
-    if (la->col_pending) {   // the rows below the diagonal block were updated beside the leaf factor
-      if (cudaStreamWaitEvent(ctx.stream, la->col_done, 0) != cudaSuccess) return -1104;
-      la->col_pending = false;
+    const int below = m - k - ext;   // rows under the next leaf's block row (that one is solved by the next chain step)
+    if (below > 0) {
+      if (cudaEventRecord(la->ev_fac, ctx.stream) != cudaSuccess) return -1104;
+      if (cudaStreamWaitEvent(la->col, la->ev_fac, 0) != cudaSuccess) return -1104;
+      const Ctx cc{la->col, ctx.batch};
+      rc = trsm_right_rec(cc, A, lda, strideA, Dinv, strideD, row0, A + (int64_t)(k + ext) * lda, lda, strideA, below, k);
+      if (rc) return rc;
+      if (cudaEventRecord(la->ev_solve, la->col) != cudaSuccess) return -1104;
+      la->solve_pending = true;
     }
-    return trsm_right_rec(ctx, A, lda, strideA, Dinv, strideD, row0, A + (int64_t)k * lda, lda, strideA, m - k, k);
+    return 0;
   }
   const int k1 = split_point(k);
   const int mc = m - k1, kc = k - k1;
@@ -164,30 +209,36 @@ int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t ld
   if (rc) return rc;
   double* C = A + (int64_t)k1 * lda + k1;
   const double* P = A + (int64_t)k1 * lda;        // rows k1.., all k1 columns of the left child
-  const double* Pl = P + (k1 - LEAF);              // ... its last leaf only
+  double* Pl = A + (int64_t)k1 * lda + (k1 - LEAF);   // ... its last leaf only
   const int dq = depth < 40 ? depth : 39;
   // every queued piece that writes the columns of the right child must have finished
   if ((rc = la->join_columns(ctx.stream, row0 + k1, row0 + k))) return rc;
   if (cudaEventRecord(la->fork[dq], ctx.stream) != cudaSuccess) return -1101;
   {
-    GemmArgs g0 = gemm_args(Pl, lda, Pl, lda, C, lda, w, w, LEAF, -1.0, 1.0, true);
-    g0.cmode = C_LOWER;
-    rc = gemm_f64(ctx, batched(ctx, g0, strideA, strideA, strideA));
+    // block row f of the last leaf's panel has received that leaf's own K = LEAF column update on `col`
+    if (la->colupd_pending) {
+      if (cudaStreamWaitEvent(ctx.stream, la->ev_colupd, 0) != cudaSuccess) return -1105;
+      la->colupd_pending = false;
+    }
+    const double* Lp = A + (int64_t)(k1 - LEAF) * (lda + 1);
+    rc = leaf_chain_prep(ctx, Lp, lda, strideA, Dinv + (int64_t)((row0 + k1 - LEAF) / LEAF) * LEAF * LEAF, strideD, Pl, C, w);
     if (rc) return rc;
   }
   if (mc > w) {
-    if (cudaStreamWaitEvent(la->col, la->fork[dq], 0) != cudaSuccess) return -1105;
+    if (cudaEventRecord(la->ev_prep, ctx.stream) != cudaSuccess) return -1105;
+    if (cudaStreamWaitEvent(la->col, la->ev_prep, 0) != cudaSuccess) return -1105;
     GemmArgs g1 = gemm_args(Pl + (int64_t)w * lda, lda, Pl, lda, C + (int64_t)w * lda, lda, mc - w, w, LEAF, -1.0, 1.0,
                             true);
     Ctx cc{la->col, ctx.batch};
     rc = gemm_f64(cc, batched(cc, g1, strideA, strideA, strideA));
     if (rc) return rc;
-    if (cudaEventRecord(la->col_done, la->col) != cudaSuccess) return -1106;
-    la->col_pending = true;
+    if (cudaEventRecord(la->ev_colupd, la->col) != cudaSuccess) return -1106;
+    la->colupd_pending = true;
   }
   cudaStream_t bs = la->bulk[depth < LookAhead::NBULK ? depth : LookAhead::NBULK - 1];
   auto queue_piece = [&](cudaStream_t st, int a, int b) -> int {   // columns [a, b) of the right child's frame
     if (cudaStreamWaitEvent(st, la->fork[dq], 0) != cudaSuccess) return -1102;
+    if (la->solve_pending && cudaStreamWaitEvent(st, la->ev_solve, 0) != cudaSuccess) return -1102;
     const double* Pa = P + (int64_t)a * lda;
     GemmArgs g2 = gemm_args(Pa, lda, Pa, lda, C + (int64_t)a * lda + a, lda, mc - a, b - a, k1, -1.0, 1.0, true);
     g2.cmode = C_LOWER;
@@ -233,21 +284,27 @@ int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t ld
 
 int chol_trap(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, int k, int row0, int* info, double* Dinv,
               int64_t strideD) {
-  LookAhead* la = (k > LEAF) ? look_ahead() : nullptr;
+  LookAhead* la = (k > LEAF) ? la_acquire() : nullptr;
   if (!la) return chol_node(ctx, A, lda, strideA, m, k, row0, info, Dinv, strideD);
   for (int i = 0; i < MAX_PIECES; i++) la->piece[i].live = false;
-  la->col_pending = false;
-  if (cudaEventRecord(la->begin, ctx.stream) != cudaSuccess) return -1107;
-  if (cudaStreamWaitEvent(la->hi, la->begin, 0) != cudaSuccess) return -1108;
-  const Ctx chain{la->hi, ctx.batch};
-  const int rc = chol_node_la(chain, la, 0, A, lda, strideA, m, k, row0, 0, info, Dinv, strideD);
-  // every fork is followed by a leaf, which re-joins `col` and `bulk`; the waits below are a safety net that also
-  // keeps a failed run (rc != 0) from leaving work un-joined inside a stream capture
-  if (la->col_pending) cudaStreamWaitEvent(la->hi, la->col_done, 0);
+  la->colupd_pending = la->solve_pending = false;
+  int rc = 0;
+  if (cudaEventRecord(la->begin, ctx.stream) != cudaSuccess) rc = -1107;
+  if (!rc && (cudaStreamWaitEvent(la->hi, la->begin, 0) != cudaSuccess ||
+              cudaStreamWaitEvent(la->col, la->begin, 0) != cudaSuccess)) rc = -1108;
+  if (!rc) {
+    const Ctx chain{la->hi, ctx.batch};
+    rc = chol_node_la(chain, la, 0, A, lda, strideA, m, k, row0, 0, info, Dinv, strideD);
+  }
+  // join everything back into the chain, then into the caller's stream (also after a failure, so that no work is left
+  // un-joined inside a stream capture)
+  cudaEventRecord(la->ev_solve, la->col);   // the tail of `col`: covers its last solve and column update
+  cudaStreamWaitEvent(la->hi, la->ev_solve, 0);
   la->join_columns(la->hi, 0, 1 << 30);
-  la->col_pending = false;
-  if (cudaEventRecord(la->end, la->hi) != cudaSuccess) return -1109;
-  if (cudaStreamWaitEvent(ctx.stream, la->end, 0) != cudaSuccess) return -1110;
+  la->colupd_pending = la->solve_pending = false;
+  if (cudaEventRecord(la->end, la->hi) != cudaSuccess && !rc) rc = -1109;
+  if (cudaStreamWaitEvent(ctx.stream, la->end, 0) != cudaSuccess && !rc) rc = -1110;
+  la_release(la);
   return rc;
 }
 

@@ -75,6 +75,7 @@ int gegp_abi_version(void);
 #define GEGP_OPT_TMA_MIN_TILES 1
 #define GEGP_OPT_LOOKAHEAD 2       /* 0: single-stream factorisation; 1 (default): look-ahead on priority streams */
 #define GEGP_OPT_SMALL_TILE_MAX 3  /* products with at most this many 64 x 64 tiles in total use 32 x 32 tiles (36) */
+#define GEGP_OPT_CHAIN_CLUSTER 4   /* CTAs per cluster of the factorisation's chain step: 0 automatic (default), 1, 2, 4 */
 int gegp_set_option(int key, int value);
 
 size_t gegp_workspace_bytes(int op, int n, int n_g, int d, int arg);
