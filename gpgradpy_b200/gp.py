@@ -711,7 +711,8 @@ class GaussianProcess:
         if self.optz_log_hp_theta:
             th = 10 ** th
         cand = bk.to_dev(th)
-        table = parallel.sharded_eval(lambda c: self._eval_rows(c, want_grad=calc_grad), cand, self.dist_group)
+        table = parallel.sharded_eval(lambda c: self._eval_rows(c, want_grad=calc_grad), cand, self.dist_group,
+                                      width=L.out_len(self.dim))
         return table.cpu().numpy()
 
     # ------------------------------------------------------------------ optimiser callbacks (optz/OptzLkd.py:16-113)
@@ -949,11 +950,10 @@ class GaussianProcess:
             for i, r in enumerate(res):
                 local[i, :hi.n_hp], local[i, hi.n_hp:] = r.x, (r.fun, float(r.success), r.nit)
         if size > 1:
-            if hi_row <= lo:
-                raise RuntimeError("more ranks than start rows; shrink the process group")
+            # a rank without start rows (more ranks than rows) contributes an empty block but enters the collective
             t = torch.as_tensor(local)
             t = t.to(bk.device()) if torch.cuda.is_available() else t
-            table = parallel.gather_rows(t, n_optz, self.dist_group).cpu().numpy()
+            table = parallel.gather_rows(t, n_optz, self.dist_group, width=hi.n_hp + 3).cpu().numpy()
         else:
             table = local
         self._multistart_table = table          # per start row: solution, objective, success, iterations

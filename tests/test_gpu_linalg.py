@@ -213,3 +213,89 @@ def test_small_and_regular_tiles_agree_bit_for_bit(M, N, K):
         lib.gegp_set_option(_lib.OPT_SMALL_TILE_MAX, old)
     assert torch.equal(C1, C2)
     assert (C1 - (C0 - A @ B.T)).abs().max().item() < 1e-11
+
+
+def test_potrf_reentrant_two_host_threads():
+    """include/gegp.h promises re-entrancy: two host threads factoring different matrices on their own streams of the
+    same device at the same time must not share look-ahead state.  Each concurrent result is compared bit for bit with
+    the same factorisation run alone (reference call sites: kernel/Kernel.py:251,291, one cho_factor per thread)."""
+    import threading
+    import torch
+    from gpgradpy_b200 import backend as bk
+    Ns = (1500, 1100)
+    Ks = [_spd(N, 40 + i) for i, N in enumerate(Ns)]
+
+    def stage(i):
+        N = Ns[i]
+        A = torch.zeros((N + 1, bk.ld_of(N)), dtype=torch.float64, device="cuda")
+        A[:N, :N] = torch.as_tensor(np.tril(Ks[i])).cuda()
+        A[N, :N] = 1.0
+        return A
+
+    serial = []
+    for i in range(2):
+        A = stage(i)
+        info, dinv = bk.potrf(A, Ns[i], 1)
+        torch.cuda.synchronize()
+        assert int(info.item()) == 0
+        serial.append((A.clone(), dinv.clone()))
+    for rep in range(3):
+        bufs = [stage(i) for i in range(2)]
+        streams = [torch.cuda.Stream() for _ in range(2)]
+        torch.cuda.synchronize()
+        out, errs = [None, None], []
+        gate = threading.Barrier(2)
+
+        def work(i):
+            try:
+                torch.cuda.set_device(0)
+                with torch.cuda.stream(streams[i]):
+                    gate.wait()
+                    for _ in range(4):                      # several back-to-back calls per thread widen the overlap window
+                        bufs[i].copy_(stage(i))
+                        out[i] = bk.potrf(bufs[i], Ns[i], 1)
+                streams[i].synchronize()
+            except Exception as exc:                        # noqa: BLE001
+                errs.append(exc)
+
+        th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert not errs, errs
+        torch.cuda.synchronize()
+        for i in range(2):
+            N = Ns[i]
+            assert int(out[i][0].item()) == 0
+            assert torch.equal(torch.tril(bufs[i][:N, :N]), torch.tril(serial[i][0][:N, :N]))
+            assert torch.equal(bufs[i][N, :N], serial[i][0][N, :N])
+            assert torch.equal(out[i][1], serial[i][1])
+
+
+def test_chain_cluster_size_does_not_change_results():
+    """The factorisation's chain step runs on a cluster of 1, 2 or 4 CTAs depending on the batch count; every size does
+    the same arithmetic per strip / per element, so the factor must be bit-identical (a candidate evaluated alone, inside
+    a batch or on another rank gives the same bits)."""
+    import torch
+    from gpgradpy_b200 import backend as bk, _lib as L
+    N = 1000
+    K = _spd(N, 5)
+    lib = L.load()
+    res = []
+    for cs in (1, 2, 4, 0):
+        old = lib.gegp_set_option(L.OPT_CHAIN_CLUSTER, cs)
+        try:
+            A = torch.zeros((N + 2, bk.ld_of(N)), dtype=torch.float64, device="cuda")
+            A[:N, :N] = torch.as_tensor(np.tril(K)).cuda()
+            A[N:, :N] = torch.as_tensor(np.random.default_rng(1).standard_normal((2, N))).cuda()
+            info, dinv = bk.potrf(A, N, 2)
+            torch.cuda.synchronize()
+            assert int(info.item()) == 0
+            res.append((torch.tril(A[:N, :N]).clone(), A[N:, :N].clone(), dinv.clone()))
+        finally:
+            lib.gegp_set_option(L.OPT_CHAIN_CLUSTER, old)
+    for r in res[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(r, res[0]))
+    Lr = np.linalg.cholesky(K)
+    assert np.abs(res[0][0].cpu().numpy() - Lr).max() / np.abs(Lr).max() < 1e-11

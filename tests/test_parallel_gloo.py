@@ -41,14 +41,14 @@ def _worker(rank, world, port, B, q):
             out.append(np.hstack(([o.ln_lkd, o.hp_varK], o.ln_lkd_grad)))
         return torch.as_tensor(np.array(out))
 
-    table = parallel.sharded_eval(eval_rows, cand)
+    table = parallel.sharded_eval(eval_rows, cand, width=4)
     lo, hi = parallel.shard_bounds(B, rank, world)
     q.put((rank, table.numpy(), len(seen), (lo, hi)))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("B", [7, 8])
+@pytest.mark.parametrize("B", [7, 8, 1])   # B = 1: more ranks than rows (the surplus rank still enters the collective)
 def test_sharded_candidate_scan_world2(B):
     from oracle import gegp_oracle as O
     world, port = 2, _free_port()
@@ -69,6 +69,7 @@ def test_sharded_candidate_scan_world2(B):
                     (O.lkd_wo_noise_lean(x, f, g, th, "precon", eta) for th in cand)])
     assert res[0][2] + res[1][2] == B                       # every row evaluated exactly once
     assert abs(res[0][2] - res[1][2]) <= 1
+    assert all(t[1].shape[0] == B for t in res)
     for _, table, _, _ in res:
         assert table.shape == seq.shape
         assert np.array_equal(table, seq)                   # same arithmetic, same order: bit-identical
