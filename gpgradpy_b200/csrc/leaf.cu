@@ -286,10 +286,30 @@ __device__ __forceinline__ void pair_phase2(double* s, int a0, int sza, int b0, 
 }  // namespace
 
 #ifdef GEGP_LEAF_CLOCKS
-__device__ long long g_leaf_clk[16];
+__device__ long long g_leaf_clk[32];
 #define LEAF_CLK(i) do { if (threadIdx.x == 0) g_leaf_clk[i] = clock64(); } while (0)
+#define PREP_CLK(i) do { if (threadIdx.x == 0 && rank == 0) g_leaf_clk[16 + (i)] = clock64(); } while (0)
+// wall-clock (globaltimer, ns) begin / end of every chain kernel, in launch order: [kind (0 factor, 1 chain step), t0, t1]
+__device__ unsigned long long g_chain_ts[3 * 1024];
+__device__ unsigned int g_chain_n;
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define CHAIN_TS_BEGIN(kind, lead)                                                         \
+  unsigned int ts_slot__ = 0xffffffffu;                                                    \
+  if ((lead) && threadIdx.x == 0 && blockIdx.z == 0) {                                     \
+    ts_slot__ = atomicAdd(&g_chain_n, 1u);                                                 \
+    if (ts_slot__ < 1024) { g_chain_ts[3 * ts_slot__] = (kind); g_chain_ts[3 * ts_slot__ + 1] = gtimer(); } \
+  }
+#define CHAIN_TS_END()                                                                     \
+  do { if (ts_slot__ < 1024) g_chain_ts[3 * ts_slot__ + 2] = gtimer(); } while (0)
 #else
 #define LEAF_CLK(i) do { } while (0)
+#define PREP_CLK(i) do { } while (0)
+#define CHAIN_TS_BEGIN(kind, lead) do { } while (0)
+#define CHAIN_TS_END() do { } while (0)
 #endif
 
 // One CTA per problem: A (k x k lower, k <= 128) -> L in place; Dinv (128 x 128, ld 128) <- L^-T (upper
@@ -297,21 +317,24 @@ __device__ long long g_leaf_clk[16];
 // (1-based global index row0 + i + 1) if info[z] was 0.
 // Stage the lower triangle of a leaf block (k x k, identity padded to kk) into the shared tile with cp.async.
 __device__ __forceinline__ void stage_lower(double* s, const double* __restrict__ A, int64_t lda, int k, int kk, int tid,
-                                            int nthreads) {
-  // 16-byte chunks, all in flight at once (A is 16-byte aligned, lda even).  A chunk that crosses the diagonal
-  // also drops one element into the shifted upper part, which is (re)written later.
+                                            int nthreads, bool wait = true) {
+  // 16-byte chunks, all in flight at once (A is 16-byte aligned, lda even).  The chunk that starts ON the diagonal is
+  // an 8-byte copy, so nothing is ever written into the shifted upper part (other copies may fill that concurrently).
   for (int e = tid; e < kk * (NB / 2); e += nthreads) {
     const int r = e >> 6, c = (e & 63) * 2;
     if (c > r) continue;
     if (r < k) {
-      cp_async16(s + r * PLD + c, A + (int64_t)r * lda + c, (c + 1 < k) ? 16 : 8);
+      if (c == r) cp_async8(s + r * PLD + c, A + (int64_t)r * lda + c);
+      else cp_async16(s + r * PLD + c, A + (int64_t)r * lda + c, (c + 1 < k) ? 16 : 8);
     } else {   // identity padding
       s[r * PLD + c] = (r == c) ? 1.0 : 0.0;
       if (c + 1 <= r) s[r * PLD + c + 1] = (r == c + 1) ? 1.0 : 0.0;
     }
   }
-  cp_async_commit();
-  cp_async_wait<0>();
+  if (wait) {
+    cp_async_commit();
+    cp_async_wait<0>();
+  }
 }
 
 __global__ void __launch_bounds__(LT, 1)
@@ -328,6 +351,7 @@ potf2_inv_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int k, in
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int kk = (k + 31) & ~31;  // padded with an identity block up to a multiple of 32
   if (tid == 0) bad_sh = 0x7fffffff;
+  CHAIN_TS_BEGIN(0, true);
   LEAF_CLK(0);
   stage_lower(s, A, lda, k, kk, tid, LT);
   __syncthreads();
@@ -345,6 +369,7 @@ potf2_inv_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int k, in
   }
   if (tid == 0 && bad_sh <= k) atomicCAS(info + blockIdx.z, 0, row0 + bad_sh);
   LEAF_CLK(10);
+  CHAIN_TS_END();
 }
 
 // Complete the Dinv blocks of a factor: the leaf kernel leaves only the 32 x 32 diagonal inverses there; this
@@ -411,7 +436,18 @@ int leaf_dinv_assemble(const Ctx& ctx, const double* L, int64_t ldl, int64_t str
 
 #ifdef GEGP_LEAF_CLOCKS
 extern "C" int gegp_debug_leaf_clocks(long long* out16) {
-  return (int)cudaMemcpyFromSymbol(out16, g_leaf_clk, sizeof(long long) * 16);
+  return (int)cudaMemcpyFromSymbol(out16, g_leaf_clk, sizeof(long long) * 32);
+}
+// copies the chain time stamps (n records of 3 uint64) and resets the counter; returns n
+extern "C" int gegp_debug_chain_ts(unsigned long long* out, int max_records) {
+  unsigned int n = 0;
+  cudaMemcpyFromSymbol(&n, g_chain_n, sizeof(n));
+  if (n > 1024u) n = 1024u;
+  if ((int)n > max_records) n = (unsigned)max_records;
+  cudaMemcpyFromSymbol(out, g_chain_ts, sizeof(unsigned long long) * 3 * n);
+  const unsigned int zero = 0;
+  cudaMemcpyToSymbol(g_chain_n, &zero, sizeof(zero));
+  return (int)n;
 }
 #endif
 
@@ -659,8 +695,7 @@ __device__ __forceinline__ void store_strip(double* brow, bool rok, int k, bool 
 // (shifted one column right) into the shared tile.
 __device__ __forceinline__ void stage_factor(double* s, const double* __restrict__ L, int64_t ldl,
                                              const double* __restrict__ Dinv, int k, int kk, int tid, int nthreads) {
-  stage_lower(s, L, ldl, k, kk, tid, nthreads);
-  __syncthreads();
+  stage_lower(s, L, ldl, k, kk, tid, nthreads, false);   // both sets of copies in flight together: one wait
   for (int e = tid; e < kk * 32; e += nthreads) {   // 8-byte copies: odd offsets
     const int i = e >> 5, c = (i & ~31) + (e & 31);
     if (c >= i) cp_async8(s + i * PLD + c + 1, Dinv + i * NB + c);
@@ -717,7 +752,7 @@ __device__ __forceinline__ void st_cluster_f64x2(const void* local_ptr, uint32_t
   asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(ra), "d"(a), "d"(b) : "memory");
 }
 
-constexpr int SYRK_UNITS = 40;   // (row tile rt, group of four column tiles cg <= rt / 4) units of the 128 x 128 lower update
+constexpr int SYRK_UNITS = 72;   // (row tile rt, pair of column tiles cp <= rt / 2) units of the 128 x 128 lower update
 
 template <int CS>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(LT, 1)
@@ -733,9 +768,8 @@ chain_prep_kernel(const double* __restrict__ Lp, int64_t lda, int64_t strideA, c
   const uint32_t rank = (CS > 1) ? cluster_rank() : 0u;
   constexpr int SPC = 16 / CS;                 // strips per CTA
   constexpr int WTOT = CS * NW;                // warps of the whole cluster
-  constexpr int MAXU = (SYRK_UNITS + WTOT - 1) / WTOT;
-  const int gw = (int)rank * NW + warp;        // cluster-wide warp index: owner of update units gw, gw + WTOT, ...
   double* scr = s + NB * PLD + warp * 8 * SLD;
+  CHAIN_TS_BEGIN(1, rank == 0);
 
   if (CS == 1) {
     // ---- one CTA per problem (batches that fill the machine): streamed solve, then X comes back from L2
@@ -759,14 +793,18 @@ chain_prep_kernel(const double* __restrict__ Lp, int64_t lda, int64_t strideA, c
     const bool mine = (warp < SPC) && st * 8 < kc;            // warp-uniform
     const int row = st * 8 + lr;
     double x[4][4][2];
+    PREP_CLK(0);
     load_strip(B + (int64_t)row * lda, mine && row < kc, NB, true, lk, x);
     stage_factor(s, Lp, lda, Dinv, NB, NB, tid, LT);
+    PREP_CLK(1);
     if (mine) {
       solve_strip(s, scr, x, 4, lr, lk);
       store_strip(B + (int64_t)row * lda, row < kc, NB, true, lk, x);
     }
+    PREP_CLK(2);
     // ---- every CTA gets all of X (rows beyond kc are zero) in its tile, plain layout s[r][c]
     cluster_sync();                                            // everybody is done reading L_p
+    PREP_CLK(3);
     if (warp < SPC) {
 #pragma unroll
       for (int j = 0; j < 4; j++)
@@ -777,49 +815,52 @@ chain_prep_kernel(const double* __restrict__ Lp, int64_t lda, int64_t strideA, c
           for (int t = 0; t < CS; t++) st_cluster_f64x2(dst, (uint32_t)t, x[j][ct][0], x[j][ct][1]);
         }
     }
+    PREP_CLK(4);
     cluster_sync();
+    PREP_CLK(5);
   }
-  // ---- E -= X X^T on this warp's units (accumulate X X^T from zero, then subtract: the arithmetic of the GEMM engine
-  //      with alpha = -1, beta = 1)
-#pragma unroll
-  for (int q = 0; q < MAXU; q++) {
-    const int u = gw + q * WTOT;
-    if (u >= SYRK_UNITS) continue;
-    // unit u -> (rt, cg): row tiles 4g .. 4g+3 have g + 1 groups of four column tiles each
+  // ---- E -= X X^T (accumulate X X^T from zero, then subtract: the arithmetic of the GEMM engine with alpha = -1,
+  //      beta = 1).  Work unit: a row tile times a PAIR of column tiles; the 72 units of the lower triangle are dealt
+  //      round-robin over the CTAs first, then over the warps, so that every SM of the cluster carries the same load.
+#pragma unroll 1
+  for (int u = (int)rank + CS * warp; u < SYRK_UNITS; u += WTOT) {
+    // unit u -> (rt, cp): row tiles 2g and 2g+1 have g + 1 column pairs each
     int g = 0, first = 0;
-    while (u >= first + 4 * (g + 1)) { first += 4 * (g + 1); g++; }
-    const int rt = 4 * g + (u - first) / (g + 1), cg = (u - first) % (g + 1);
+    while (u >= first + 2 * (g + 1)) { first += 2 * (g + 1); g++; }
+    const int rt = 2 * g + (u - first) / (g + 1), cp = (u - first) % (g + 1);
     if (rt * 8 >= kc) continue;                // warp-uniform
-    const int r0 = rt * 8, r = r0 + lr;
-    double e[4][2], acc[4][2];
+    const int r = rt * 8 + lr;
+    double e[2][2], acc[2][2];
 #pragma unroll
-    for (int t = 0; t < 4; t++) {
-      const int ct = cg * 4 + t, c = ct * 8 + 2 * lk;
+    for (int t = 0; t < 2; t++) {
+      const int ct = cp * 2 + t, c = ct * 8 + 2 * lk;
       e[t][0] = e[t][1] = acc[t][0] = acc[t][1] = 0.0;
       if (ct <= rt && r < kc) {
         if (c <= r) e[t][0] = E[(int64_t)r * lda + c];
         if (c + 1 <= r) e[t][1] = E[(int64_t)r * lda + c + 1];
       }
     }
-#pragma unroll 8
+    const double* arow = s + r * PLD + lk;
+    const double* b0 = s + (min(cp * 2, rt) * 8 + lr) * PLD + lk;
+    const double* b1 = s + (min(cp * 2 + 1, rt) * 8 + lr) * PLD + lk;
+#pragma unroll 16
     for (int kq = 0; kq < 32; kq++) {
-      const double a = s[r * PLD + 4 * kq + lk];
-#pragma unroll
-      for (int t = 0; t < 4; t++) {
-        const int ct = min(cg * 4 + t, rt);
-        const double b = s[(ct * 8 + lr) * PLD + 4 * kq + lk];
-        dmma884(acc[t][0], acc[t][1], a, b);
-      }
+      const double a = arow[4 * kq];
+      dmma884(acc[0][0], acc[0][1], a, b0[4 * kq]);
+      dmma884(acc[1][0], acc[1][1], a, b1[4 * kq]);
     }
 #pragma unroll
-    for (int t = 0; t < 4; t++) {
-      const int ct = cg * 4 + t, c = ct * 8 + 2 * lk;
+    for (int t = 0; t < 2; t++) {
+      const int ct = cp * 2 + t, c = ct * 8 + 2 * lk;
       if (ct <= rt && r < kc) {
         if (c <= r) E[(int64_t)r * lda + c] = e[t][0] - acc[t][0];
         if (c + 1 <= r) E[(int64_t)r * lda + c + 1] = e[t][1] - acc[t][1];
       }
     }
   }
+  PREP_CLK(6);
+  PREP_CLK(7);
+  CHAIN_TS_END();
 }
 
 template <int TW>

@@ -3,6 +3,7 @@
 // of the LML gradient (reference: scipy cho_factor / cho_solve at kernel/Kernel.py:251,
 // optz/CalcLkd.py:154,174).
 #include "linalg.h"
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 #include <vector>
@@ -69,13 +70,23 @@ int split_max_tiles() {
   static const int v = getenv("GEGP_SPLIT_TILES") ? atoi(getenv("GEGP_SPLIT_TILES")) : 2500;
   return v;
 }
+// width of the look-ahead window: the columns right behind a node that receive its panels as early as they exist
+// (env GEGP_LA_WINDOW, multiple of LEAF; LEAF = the next leaf only)
+int la_window() {
+  static const int v = [] {
+    int x = getenv("GEGP_LA_WINDOW") ? atoi(getenv("GEGP_LA_WINDOW")) : 256;
+    x = (x / LEAF) * LEAF;
+    return x < LEAF ? LEAF : x;
+  }();
+  return v;
+}
 constexpr int MAX_PIECES = 256;
 constexpr int MAX_DEV = 32;
 struct Piece { int c0, c1; cudaEvent_t done; cudaStream_t stream; bool live; };   // global column range a queued bulk GEMM writes
 struct LookAhead {
   static constexpr int NBULK = 16;
   int dev = 0;
-  cudaStream_t hi = nullptr, col = nullptr, bulk[NBULK] = {};   // one bulk stream per recursion depth (FIFO each)
+  cudaStream_t hi = nullptr, col = nullptr, late = nullptr, bulk[NBULK] = {};   // one bulk stream per recursion depth (FIFO each)
   cudaEvent_t fork[40], ev_prep, ev_fac, ev_colupd, ev_solve, begin, end;
   Piece piece[MAX_PIECES];
   bool colupd_pending = false;   // a K = LEAF block-column update is in flight on `col` (the next chain step reads its top rows)
@@ -101,7 +112,8 @@ struct LookAhead {
     cudaDeviceGetStreamPriorityRange(&lo, &hip);   // lo: numerically largest = lowest priority; hip: greatest
     const int mid = hip < lo ? hip + 1 : hip;
     ok = cudaStreamCreateWithPriority(&hi, cudaStreamNonBlocking, hip) == cudaSuccess &&
-         cudaStreamCreateWithPriority(&col, cudaStreamNonBlocking, mid) == cudaSuccess;
+         cudaStreamCreateWithPriority(&col, cudaStreamNonBlocking, mid) == cudaSuccess &&
+         cudaStreamCreateWithPriority(&late, cudaStreamNonBlocking, mid) == cudaSuccess;
     for (int i = 0; i < NBULK && ok; i++) ok = cudaStreamCreateWithPriority(&bulk[i], cudaStreamNonBlocking, lo) == cudaSuccess;
     auto mk = [&](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
     for (int i = 0; i < 40 && ok; i++) ok = mk(&fork[i]);
@@ -167,21 +179,26 @@ int chol_node(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, in
   return chol_node(ctx, C, lda, strideA, m - k1, k - k1, row0 + k1, info, Dinv, strideD);
 }
 
-// Look-ahead recursion.  `ext` is the width of the leaf that FOLLOWS this node's columns (0: none).  After the left
-// child (k1 columns, a multiple of LEAF; its last leaf is l) the work that involves the next leaf f = [k1, k1+w) is
-// dealt out as
-//   chain : block row f of l's panel solved against l, then the diagonal block of f -= that block row's square
-//           (one chain_prep launch, K = LEAF)
+// Look-ahead recursion.  `ext` is the width of the WINDOW that follows this node's columns (0: none): the node applies
+// all of its leaves except its last one to the window columns [k, k+ext) as early as their panels exist; the caller
+// applies that last leaf.  A window is at most la_window() columns wide and never ends inside a leaf.  After the left
+// child (k1 columns, a multiple of LEAF; its last leaf is l; its window was E_w = the first ext_l = min(window, kc + ext)
+// columns behind it, so E_w lacks nothing of the left child but l) the work is dealt out as
+//   chain : block row f of l's panel solved against l, then the diagonal block of the next leaf f = [k1, k1+w) -= that
+//           block row's square (one chain_prep launch, K = LEAF)
 //   col   : the rows below f in l's panel solved against l (queued by leaf l itself, beside the chain step)
-//   col   : the rows below the diagonal block in f's block column   -= last leaf's panel only (K = LEAF)
-//   bulk  : columns [k1+w, k) in just-in-time pieces                -= the whole left child's panel (K = k1)
-//   bulk  : the block column of the following leaf, [k, k+ext)      -= the whole left child's panel (K = k1)
-// so that every update on the chain has K = LEAF and 128 rows.  f's block column has already received the other
-// leaves of the left child through the `ext` pieces queued inside that child (by induction every (source leaf, target
-// block column) pair is applied exactly once: by chain + col when the source is the leaf right before the target, by
-// the bulk piece of their lowest common ancestor X when the target lies in right(X) behind its first leaf or follows
-// X, ...).  A piece is joined when the chain reaches a fork or leaf that touches its columns.  The bulk pieces read
-// panel rows from k1+w on only (never block row f), all of which are produced on `col`: they wait for its last solve.
+//   col   : the rows below the diagonal block in f's block column     -= l's panel (K = LEAF)
+//   late  : the other window columns, E_w \ f, leaf by leaf           -= l's panel (K = LEAF)
+//   bulk  : columns of the right child behind the window, [ext_l, kc), in just-in-time pieces
+//                                                                     -= the whole left child's panel (K = k1)
+//   bulk  : the part of this node's own window that E_w did not reach -= the whole left child's panel (K = k1)
+// so that every update the chain waits for at a fork has K = LEAF.  By induction every (source leaf, target block
+// column) pair is applied exactly once: by chain + col + late when the source is the last leaf of left(X) and the
+// target lies in the window behind it, by the window pieces of the nodes on the right spine of left(X) for the other
+// sources of such a target, and by the bulk piece of their lowest common ancestor X otherwise.  Pieces that write the
+// same columns from different streams are serialised through their events; a piece is joined by the chain when it
+// reaches a fork or leaf that touches its columns.  The bulk pieces read panel rows from k1+w on only (never block row
+// f), all of which are produced on `col`: they wait for its last solve.
 int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t lda, int64_t strideA, int m, int k,
                  int row0, int ext, int* info, double* Dinv, int64_t strideD) {
   if (k <= 0) return 0;
@@ -190,12 +207,13 @@ int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t ld
     if ((rc = la->join_columns(ctx.stream, row0, row0 + k))) return rc;
     rc = leaf_potf2_inv(ctx, A, lda, strideA, k, row0, info, Dinv + (int64_t)(row0 / LEAF) * LEAF * LEAF, strideD);
     if (rc) return rc;
-    const int below = m - k - ext;   // rows under the next leaf's block row (that one is solved by the next chain step)
+    const int nxt = ext < LEAF ? ext : LEAF;   // the next leaf's block row is solved by the next chain step
+    const int below = m - k - nxt;
     if (below > 0) {
       if (cudaEventRecord(la->ev_fac, ctx.stream) != cudaSuccess) return -1104;
       if (cudaStreamWaitEvent(la->col, la->ev_fac, 0) != cudaSuccess) return -1104;
       const Ctx cc{la->col, ctx.batch};
-      rc = trsm_right_rec(cc, A, lda, strideA, Dinv, strideD, row0, A + (int64_t)(k + ext) * lda, lda, strideA, below, k);
+      rc = trsm_right_rec(cc, A, lda, strideA, Dinv, strideD, row0, A + (int64_t)(k + nxt) * lda, lda, strideA, below, k);
       if (rc) return rc;
       if (cudaEventRecord(la->ev_solve, la->col) != cudaSuccess) return -1104;
       la->solve_pending = true;
@@ -205,14 +223,17 @@ int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t ld
   const int k1 = split_point(k);
   const int mc = m - k1, kc = k - k1;
   const int w = kc < LEAF ? kc : LEAF;
-  rc = chol_node_la(ctx, la, depth + 1, A, lda, strideA, m, k1, row0, w, info, Dinv, strideD);
+  const int ext_l = std::min(la_window(), kc + ext);   // the left child's window, in the right child's frame [0, ext_l)
+  rc = chol_node_la(ctx, la, depth + 1, A, lda, strideA, m, k1, row0, ext_l, info, Dinv, strideD);
   if (rc) return rc;
   double* C = A + (int64_t)k1 * lda + k1;
   const double* P = A + (int64_t)k1 * lda;        // rows k1.., all k1 columns of the left child
   double* Pl = A + (int64_t)k1 * lda + (k1 - LEAF);   // ... its last leaf only
   const int dq = depth < 40 ? depth : 39;
-  // every queued piece that writes the columns of the right child must have finished
-  if ((rc = la->join_columns(ctx.stream, row0 + k1, row0 + k))) return rc;
+  // every queued piece that writes the next leaf's block column must have finished (the chain step and the column
+  // update touch it right away; the other columns of the right child are only written by further pieces, which
+  // order themselves behind the live ones through their events)
+  if ((rc = la->join_columns(ctx.stream, row0 + k1, row0 + k1 + w))) return rc;
   if (cudaEventRecord(la->fork[dq], ctx.stream) != cudaSuccess) return -1101;
   {
     // block row f of the last leaf's panel has received that leaf's own K = LEAF column update on `col`
@@ -236,11 +257,21 @@ int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t ld
     la->colupd_pending = true;
   }
   cudaStream_t bs = la->bulk[depth < LookAhead::NBULK ? depth : LookAhead::NBULK - 1];
-  auto queue_piece = [&](cudaStream_t st, int a, int b) -> int {   // columns [a, b) of the right child's frame
+  // columns [a, b) of the right child's frame (may reach into this node's window) -= the last kk columns of the left
+  // child's panel, on stream st
+  auto queue_piece = [&](cudaStream_t st, int a, int b, int kk) -> int {
+    if (b <= a || mc <= a) return 0;
     if (cudaStreamWaitEvent(st, la->fork[dq], 0) != cudaSuccess) return -1102;
     if (la->solve_pending && cudaStreamWaitEvent(st, la->ev_solve, 0) != cudaSuccess) return -1102;
-    const double* Pa = P + (int64_t)a * lda;
-    GemmArgs g2 = gemm_args(Pa, lda, Pa, lda, C + (int64_t)a * lda + a, lda, mc - a, b - a, k1, -1.0, 1.0, true);
+    // older pieces for the same columns may still be running on other streams: this stream waits for them, the chain
+    // does not (same-stream pieces are ordered anyway)
+    for (int i = 0; i < MAX_PIECES; i++) {
+      const Piece& p = la->piece[i];
+      if (p.live && p.stream != st && p.c1 > row0 + k1 + a && p.c0 < row0 + k1 + b)
+        if (cudaStreamWaitEvent(st, p.done, 0) != cudaSuccess) return -1112;
+    }
+    const double* Pa = P + (int64_t)a * lda + (k1 - kk);
+    GemmArgs g2 = gemm_args(Pa, lda, Pa, lda, C + (int64_t)a * lda + a, lda, mc - a, b - a, kk, -1.0, 1.0, true);
     g2.cmode = C_LOWER;
     Ctx bc{st, ctx.batch};
     int r = gemm_f64(bc, batched(bc, g2, strideA, strideA, strideA));
@@ -251,33 +282,31 @@ int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t ld
     pc->c0 = row0 + k1 + a; pc->c1 = row0 + k1 + b; pc->stream = st; pc->live = true;
     return 0;
   };
-  if (kc > w) {
+  // the rest of the left child's window: only its last leaf is missing there (K = LEAF), leaf by leaf, next leaf first
+  for (int a = w; a < ext_l; a += LEAF)
+    if ((rc = queue_piece(la->late, a, std::min(a + LEAF, ext_l), LEAF))) return rc;
+  if (kc > ext_l) {
     // A bulk that is itself latency-bound (too small for the TMA kernel) is cut along the left spine of the right
     // child -- the sibling of the first leaf, then the sibling of that pair, ... -- and queued smallest first.
     int cut[40];
     int ncut = 0;
     cut[ncut++] = kc;
-    const long big_tiles = ((long)(mc - w + 127) / 128) * ((kc - w + 127) / 128);
+    const long big_tiles = ((long)(mc - ext_l + 127) / 128) * ((kc - ext_l + 127) / 128);
     if (big_tiles < split_max_tiles()) {
       int sz = kc;
-      while (sz > LEAF && ncut < 39) { sz = split_point(sz); cut[ncut++] = sz; }
-    } else {
-      cut[ncut++] = w;
+      while (sz > LEAF && ncut < 39) {
+        sz = split_point(sz);
+        if (sz <= ext_l) break;
+        cut[ncut++] = sz;
+      }
     }
+    cut[ncut++] = ext_l;
     for (int i = ncut - 2; i >= 0; i--)
-      if ((rc = queue_piece(bs, cut[i + 1], cut[i]))) return rc;
+      if ((rc = queue_piece(bs, cut[i + 1], cut[i], k1))) return rc;
   }
-  if (ext > 0 && mc > kc) {
-    // the following leaf's block column.  Older pieces for the same columns (queued by ancestors) may still be
-    // running on other streams: this node's bulk stream waits for them, the chain does not.
-    cudaStream_t es = bs;
-    for (int i = 0; i < MAX_PIECES; i++) {
-      const Piece& p = la->piece[i];
-      if (p.live && p.stream != es && p.c1 > row0 + k && p.c0 < row0 + k + ext)
-        if (cudaStreamWaitEvent(es, p.done, 0) != cudaSuccess) return -1112;
-    }
-    if ((rc = queue_piece(es, kc, kc + ext))) return rc;
-  }
+  // the part of this node's own window that the left child's window did not reach
+  if (ext > 0 && kc + ext > ext_l)
+    if ((rc = queue_piece(bs, std::max(kc, ext_l), kc + ext, k1))) return rc;
   return chol_node_la(ctx, la, depth + 1, C, lda, strideA, mc, kc, row0 + k1, ext, info, Dinv, strideD);
 }
 }  // namespace

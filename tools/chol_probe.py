@@ -26,6 +26,26 @@ for n, d in cfgs:
     ms_b = ev(build)[0]
     def fac():
         build(); bk.potrf(buf, N, 0, dinv)
+    # the product runs the factorisation inside a captured CUDA graph (backend.LmlGraph): no host launch overhead
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    def raw():
+        rc = lib.gegp_potrf(N, 0, buf.data_ptr(), buf.stride(0), dinv.data_ptr(), info.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+    def graphed_ms():
+        side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            build(); raw()
+        torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            build(); raw()
+        gb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gb):
+            build()
+        return ev(gr.replay)[0] - ev(gb.replay)[0]
+    for win in ([None] if os.environ.get("GEGP_LA_WINDOW") else [None]):
+        mg = graphed_ms()
+        print(f"N={N} graph replay: potrf {mg:.3f} ms  {N**3/3/mg*1e-9:.2f} TFLOP/s ({N**3/3/mg*1e-9/37.13*100:.1f}% of DMMA peak), info {int(info.item())}", flush=True)
     for cs in (0, 1, 2, 4):
         lib.gegp_set_option(L.OPT_CHAIN_CLUSTER, cs)
         mn, md = ev(fac)
