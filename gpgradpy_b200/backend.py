@@ -52,6 +52,18 @@ def _check(rc: int, what: str):
         raise RuntimeError(f"{what} failed with code {rc} (negative: bad argument index / -1000-cudaError)")
 
 
+def dmma_peak_tflops(reps: int = 3) -> float:
+    """gegp_dmma_peak: issue peak of DMMA.8x8x4 on the current device in TFLOP/s (the fp64 roofline denominator)."""
+    lib = L.load()
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    scratch = torch.empty(512 * sms, dtype=F64, device=device())
+    out = C.c_double(0.0)
+    torch.cuda.synchronize()
+    rc = lib.gegp_dmma_peak(_p(scratch), scratch.numel(), int(reps), C.byref(out), _stream())
+    _check(rc, "gegp_dmma_peak")
+    return float(out.value)
+
+
 def ld_of(N: int) -> int:
     return int(L.load().gegp_ld(N))
 

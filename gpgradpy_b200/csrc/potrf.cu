@@ -86,7 +86,10 @@ struct Piece { int c0, c1; cudaEvent_t done; cudaStream_t stream; bool live; }; 
 struct LookAhead {
   static constexpr int NBULK = 16;
   int dev = 0;
-  cudaStream_t hi = nullptr, col = nullptr, late = nullptr, bulk[NBULK] = {};   // one bulk stream per recursion depth (FIFO each)
+  static constexpr int NLANE = 3;
+  // bulk[depth][lane]: pieces queued at one fork are needed one after the other; the first two get streams of their
+  // own with a higher priority than the rest, so that they run beside (not behind) each other and ahead of older work
+  cudaStream_t hi = nullptr, col = nullptr, late = nullptr, bulk[NBULK][NLANE] = {};
   cudaEvent_t fork[40], ev_prep, ev_fac, ev_colupd, ev_solve, begin, end;
   Piece piece[MAX_PIECES];
   bool colupd_pending = false;   // a K = LEAF block-column update is in flight on `col` (the next chain step reads its top rows)
@@ -114,7 +117,12 @@ struct LookAhead {
     ok = cudaStreamCreateWithPriority(&hi, cudaStreamNonBlocking, hip) == cudaSuccess &&
          cudaStreamCreateWithPriority(&col, cudaStreamNonBlocking, mid) == cudaSuccess &&
          cudaStreamCreateWithPriority(&late, cudaStreamNonBlocking, mid) == cudaSuccess;
-    for (int i = 0; i < NBULK && ok; i++) ok = cudaStreamCreateWithPriority(&bulk[i], cudaStreamNonBlocking, lo) == cudaSuccess;
+    for (int i = 0; i < NBULK && ok; i++)
+      for (int j = 0; j < NLANE && ok; j++) {
+        int pr = lo - (NLANE - 1 - j);               // lane 0: two levels above the lowest priority
+        if (pr < mid + 1) pr = mid + 1 <= lo ? mid + 1 : lo;
+        ok = cudaStreamCreateWithPriority(&bulk[i][j], cudaStreamNonBlocking, pr) == cudaSuccess;
+      }
     auto mk = [&](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
     for (int i = 0; i < 40 && ok; i++) ok = mk(&fork[i]);
     for (int i = 0; i < MAX_PIECES && ok; i++) { ok = mk(&piece[i].done); piece[i].live = false; }
@@ -256,7 +264,8 @@ int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t ld
     if (cudaEventRecord(la->ev_colupd, la->col) != cudaSuccess) return -1106;
     la->colupd_pending = true;
   }
-  cudaStream_t bs = la->bulk[depth < LookAhead::NBULK ? depth : LookAhead::NBULK - 1];
+  cudaStream_t* lanes = la->bulk[depth < LookAhead::NBULK ? depth : LookAhead::NBULK - 1];
+  cudaStream_t bs = lanes[LookAhead::NLANE - 1];
   // columns [a, b) of the right child's frame (may reach into this node's window) -= the last kk columns of the left
   // child's panel, on stream st
   auto queue_piece = [&](cudaStream_t st, int a, int b, int kk) -> int {
@@ -301,8 +310,8 @@ int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t ld
       }
     }
     cut[ncut++] = ext_l;
-    for (int i = ncut - 2; i >= 0; i--)
-      if ((rc = queue_piece(bs, cut[i + 1], cut[i], k1))) return rc;
+    for (int i = ncut - 2, q = 0; i >= 0; i--, q++)
+      if ((rc = queue_piece(lanes[q < LookAhead::NLANE ? q : LookAhead::NLANE - 1], cut[i + 1], cut[i], k1))) return rc;
   }
   // the part of this node's own window that the left child's window did not reach
   if (ext > 0 && kc + ext > ext_l)

@@ -213,6 +213,12 @@ int gegp_quad_grad(int n, int n_g, int d, const double* X, const int32_t* grad_s
 void gegp_profile_begin(int time_gemm);
 int gegp_profile_end(long* launches, long* gemm_launches, double* gemm_ms, double* gemm_flops);
 
+/* Roofline denominator, measured on the device the caller is about to time: issue peak of the fp64 tensor-core
+ * instruction (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4) with 16 warps per SM, best of `reps` runs, in TFLOP/s.
+ * Synchronous (it times itself with CUDA events).  scratch: device buffer of >= 512 * (number of SMs) doubles.
+ * No reference counterpart: the reference has no device path; bench.py reports every O(N^3) kernel against this. */
+int gegp_dmma_peak(double* scratch, size_t scratch_doubles, int reps, double* tflops_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
