@@ -12,9 +12,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgegp.so")
 
 # mirrors of the #defines in include/gegp.h
-ABI_VERSION = 3
+ABI_VERSION = 4
 MODE_BASE, MODE_PRECON, MODE_PRECON_COV = 0, 1, 2
-OUT_LML, OUT_SIGMA2, OUT_BETA, OUT_LOGDET, OUT_INFO, OUT_QUAD, OUT_DVARK, OUT_DVARF, OUT_DVARG, OUT_GRAD = range(10)
+OUT_LML, OUT_SIGMA2, OUT_BETA, OUT_LOGDET, OUT_INFO, OUT_QUAD, OUT_DVARK, OUT_DVARF, OUT_DVARG, OUT_DKERN, OUT_GRAD = range(11)
+KERNEL_SQEXP, KERNEL_MATERN52, KERNEL_RATQUAD = 0, 1, 2
+KERNEL_IDS = {"SqExp": KERNEL_SQEXP, "Ma5f2": KERNEL_MATERN52, "RatQu": KERNEL_RATQUAD}   # names of kernel/Kernel.py:27-107
 OP_LML, OP_LML_GRAD, OP_PREDICT = 0, 1, 2
 OPT_TMA_MIN_TILES = 1
 OPT_LOOKAHEAD = 2
@@ -56,9 +58,9 @@ def load():
     lib.gegp_ld.restype = i64
     lib.gegp_ld.argtypes = [i]
     lib.gegp_build_cov.restype = i
-    lib.gegp_build_cov.argtypes = [i, i, i, dp, ip, dp, dp, i, dbl, dbl, dp, i64, dp, i, vp]
+    lib.gegp_build_cov.argtypes = [i, i, i, dp, ip, dp, i, dbl, dp, i, dbl, dbl, dp, i64, dp, i, vp]
     lib.gegp_cross_cov.restype = i
-    lib.gegp_cross_cov.argtypes = [i, i, i, dp, ip, dp, i, dp, dp, dp, i64, vp]
+    lib.gegp_cross_cov.argtypes = [i, i, i, dp, ip, dp, i, dp, i, dbl, dp, dp, i64, vp]
     lib.gegp_potrf.restype = i
     lib.gegp_potrf.argtypes = [i, i, dp, i64, dp, ip, vp]
     lib.gegp_dinv_doubles.restype = i64
@@ -70,16 +72,16 @@ def load():
     lib.gegp_dgemm.restype = i
     lib.gegp_dgemm.argtypes = [i, i, i, i, dbl, dp, i64, dp, i64, dbl, dp, i64, vp]
     lib.gegp_lml_eval.restype = i
-    lib.gegp_lml_eval.argtypes = [i, dp, dp, i, i, i, dp, ip, dp, dp, i, dbl, i, dbl, i, dp, dp, vp, sz, vp]
+    lib.gegp_lml_eval.argtypes = [i, dp, dp, i, dp, i, i, i, dp, ip, dp, dp, i, dbl, i, dbl, i, dp, dp, vp, sz, vp]
     lib.gegp_predict_setup.restype = i
-    lib.gegp_predict_setup.argtypes = [i, i, i, dp, ip, dp, dp, i, dbl, dp, dbl, dp, i64, dp, dp, dp, ip, vp]
+    lib.gegp_predict_setup.argtypes = [i, i, i, dp, ip, dp, i, dbl, dp, i, dbl, dp, dbl, dp, i64, dp, dp, dp, ip, vp]
     lib.gegp_predict.restype = i
-    lib.gegp_predict.argtypes = [i, i, i, dp, ip, dp, dp, i64, dp, dp, i, dbl, dbl, dp, i, dp, dp, dp, ip, vp, sz, vp]
+    lib.gegp_predict.argtypes = [i, i, i, dp, ip, dp, i, dbl, dp, i64, dp, dp, i, dbl, dbl, dp, i, dp, dp, dp, ip, vp, sz, vp]
     lib.gegp_predict_grad.restype = i
-    lib.gegp_predict_grad.argtypes = [i, i, i, dp, ip, dp, dp, i64, dp, dp, i, dbl, dbl, dp, i, dp, dp, dp, dp, dp, ip, vp,
+    lib.gegp_predict_grad.argtypes = [i, i, i, dp, ip, dp, i, dbl, dp, i64, dp, dp, i, dbl, dbl, dp, i, dp, dp, dp, dp, dp, ip, vp,
                                       sz, vp]
     lib.gegp_predict_hess.restype = i
-    lib.gegp_predict_hess.argtypes = [i, i, i, dp, ip, dp, dp, i64, dp, dp, dp, i, dbl, dbl, dp, dp, dp, dp, dp, dp, dp, ip,
+    lib.gegp_predict_hess.argtypes = [i, i, i, dp, ip, dp, i, dbl, dp, i64, dp, dp, dp, i, dbl, dbl, dp, dp, dp, dp, dp, dp, dp, ip,
                                       vp, sz, vp]
     lib.gegp_lml_layout.restype = i
     lib.gegp_lml_layout.argtypes = [i, i, i, i, i, C.POINTER(i64)]
@@ -90,7 +92,7 @@ def load():
     lib.gegp_row_sq_sum.restype = i
     lib.gegp_row_sq_sum.argtypes = [i, dp, i64, dp, vp]
     lib.gegp_weighted_grad.restype = i
-    lib.gegp_weighted_grad.argtypes = [i, i, i, dp, ip, dp, dp, i64, i, dbl, i, dp, dp, vp, sz, vp]
+    lib.gegp_weighted_grad.argtypes = [i, i, i, dp, ip, dp, i, dbl, dp, i64, i, dbl, i, dp, dp, vp, sz, vp]
     lib.gegp_lanczos_step.restype = i
     lib.gegp_lanczos_step.argtypes = [i, i, dp, i64, dp, dp, dp, vp]
     lib.gegp_lincomb.restype = i
@@ -98,7 +100,7 @@ def load():
     lib.gegp_quad_grad_work_bytes.restype = sz
     lib.gegp_quad_grad_work_bytes.argtypes = [i, i, i]
     lib.gegp_quad_grad.restype = i
-    lib.gegp_quad_grad.argtypes = [i, i, i, dp, ip, dp, dp, i, dbl, i, dp, dp, vp, sz, vp]
+    lib.gegp_quad_grad.argtypes = [i, i, i, dp, ip, dp, i, dbl, dp, i, dbl, i, dp, dp, vp, sz, vp]
     lib.gegp_dmma_peak.restype = i
     lib.gegp_dmma_peak.argtypes = [dp, sz, i, C.POINTER(dbl), vp]
     lib.gegp_profile_begin.restype = None

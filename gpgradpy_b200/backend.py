@@ -64,6 +64,17 @@ def dmma_peak_tflops(reps: int = 3) -> float:
     return float(out.value)
 
 
+def _kern(kernel):
+    """kernel = None | name | id | (name-or-id, hp)  ->  (GEGP_KERNEL_* id, hp float)."""
+    if kernel is None:
+        return L.KERNEL_SQEXP, 0.0
+    hp = 0.0
+    if isinstance(kernel, (tuple, list)):
+        kernel, hp = kernel[0], (0.0 if kernel[1] is None else float(np.ravel(kernel[1])[0]))
+    kid = L.KERNEL_IDS[kernel] if isinstance(kernel, str) else int(kernel)
+    return kid, hp
+
+
 def ld_of(N: int) -> int:
     return int(L.load().gegp_ld(N))
 
@@ -101,7 +112,8 @@ def free_workspace():
     _ws_cache.clear()
 
 
-def build_cov(X, theta, *, n_g=None, slot=None, noise=None, mode=L.MODE_BASE, eta=0.0, varK=1.0, uplo=0, out=None):
+def build_cov(X, theta, *, n_g=None, slot=None, noise=None, mode=L.MODE_BASE, eta=0.0, varK=1.0, uplo=0, out=None,
+              kernel=None):
     """gegp_build_cov -> (K [N, N] strided view over an [N, ld] buffer, p [2N] or None)."""
     lib = L.load()
     X = to_dev(X)
@@ -114,13 +126,14 @@ def build_cov(X, theta, *, n_g=None, slot=None, noise=None, mode=L.MODE_BASE, et
     if out is None:
         out = torch.empty((N, ld), dtype=F64, device=device())
     p = torch.empty(2 * N, dtype=F64, device=device()) if mode == L.MODE_PRECON else None
-    rc = lib.gegp_build_cov(n, n_g, d, _p(X), _p(slot), _p(theta), _p(noise), mode, float(eta), float(varK), _p(out),
-                            out.stride(0), _p(p), int(uplo), _stream())
+    kid, khp = _kern(kernel)
+    rc = lib.gegp_build_cov(n, n_g, d, _p(X), _p(slot), _p(theta), kid, khp, _p(noise), mode, float(eta), float(varK),
+                            _p(out), out.stride(0), _p(p), int(uplo), _stream())
     _check(rc, "gegp_build_cov")
     return out[:, :N], p
 
 
-def cross_cov(X, Xs, theta, *, n_g=None, slot=None, pinv=None):
+def cross_cov(X, Xs, theta, *, n_g=None, slot=None, pinv=None, kernel=None):
     lib = L.load()
     X, Xs, theta, pinv = to_dev(X), to_dev(Xs), to_dev(theta), to_dev(pinv)
     n, d = X.shape
@@ -129,7 +142,8 @@ def cross_cov(X, Xs, theta, *, n_g=None, slot=None, pinv=None):
     nx = Xs.shape[0]
     ld = ld_of(N)
     out = torch.empty((nx, ld), dtype=F64, device=device())
-    rc = lib.gegp_cross_cov(n, n_g, d, _p(X), _p(slot), _p(Xs), nx, _p(theta), _p(pinv), _p(out), ld, _stream())
+    kid, khp = _kern(kernel)
+    rc = lib.gegp_cross_cov(n, n_g, d, _p(X), _p(slot), _p(Xs), nx, _p(theta), kid, khp, _p(pinv), _p(out), ld, _stream())
     _check(rc, "gegp_cross_cov")
     return out[:, :N]
 
@@ -203,7 +217,7 @@ def _lml_workspace(lib, op, n, n_g, d, B, max_ws_bytes):
 
 
 def lml_eval(X, y, theta_batch, *, n_g=None, slot=None, mode=L.MODE_PRECON, eta=0.0, noise=None, varK_batch=None,
-             pnlt_grad=0.0, want_grad=True, want_alpha=False, max_ws_bytes=None, out=None):
+             pnlt_grad=0.0, want_grad=True, want_alpha=False, max_ws_bytes=None, out=None, kernel=None, kernel_hp_batch=None):
     """gegp_lml_eval for B candidate rows -> (out [B, 9+d] device tensor, alpha [B, N] or None)."""
     lib = L.load()
     X, y = to_dev(X), to_dev(y)
@@ -222,9 +236,15 @@ def lml_eval(X, y, theta_batch, *, n_g=None, slot=None, mode=L.MODE_PRECON, eta=
     alpha = torch.empty((B, N), dtype=F64, device=device()) if want_alpha else None
     op = L.OP_LML_GRAD if want_grad else L.OP_LML
     ws = _lml_workspace(lib, op, n, n_g, d, B, max_ws_bytes)
-    rc = lib.gegp_lml_eval(B, _p(th), _p(vk), n, n_g, d, _p(X), _p(slot), _p(y), _p(noise), int(mode), float(eta),
-                           int(noisy), float(pnlt_grad), int(bool(want_grad)), _p(out), _p(alpha), _p(ws), ws.numel(),
-                           _stream())
+    kid, khp = _kern(kernel)
+    khp_dev = None
+    if kid == L.KERNEL_RATQUAD:      # one alpha per candidate row (a scalar is broadcast)
+        khp_dev = to_dev(kernel_hp_batch).reshape(-1) if kernel_hp_batch is not None else torch.full(
+            (B,), khp, dtype=F64, device=device())
+        assert khp_dev.numel() == B
+    rc = lib.gegp_lml_eval(B, _p(th), _p(vk), kid, _p(khp_dev), n, n_g, d, _p(X), _p(slot), _p(y), _p(noise), int(mode),
+                           float(eta), int(noisy), float(pnlt_grad), int(bool(want_grad)), _p(out), _p(alpha), _p(ws),
+                           ws.numel(), _stream())
     _check(rc, "gegp_lml_eval")
     return out, alpha
 
@@ -237,14 +257,16 @@ class LmlGraph:
     same-shaped evaluation is repeated hundreds of times (optz/OptzLkd.py:249-270).
     """
 
-    def __init__(self, X, y, B, *, n_g, slot, mode, eta, noise, noisy, pnlt_grad, want_grad):
+    def __init__(self, X, y, B, *, n_g, slot, mode, eta, noise, noisy, pnlt_grad, want_grad, kernel=None):
         n, d = X.shape
         self.key_tensors = (X, y, slot, noise)          # keep the captured buffers alive
         self.theta = torch.empty((B, d), dtype=F64, device=device())
         self.varK = torch.ones(B, dtype=F64, device=device()) if noisy else None
+        kid = _kern(kernel)[0]
+        self.khp = torch.full((B,), 2.0, dtype=F64, device=device()) if kid == L.KERNEL_RATQUAD else None
         self.out = torch.empty((B, L.out_len(d)), dtype=F64, device=device())
         kw = dict(n_g=n_g, slot=slot, mode=mode, eta=eta, noise=noise if noisy else None, varK_batch=self.varK,
-                  pnlt_grad=pnlt_grad, want_grad=want_grad, out=self.out)
+                  pnlt_grad=pnlt_grad, want_grad=want_grad, out=self.out, kernel=kid, kernel_hp_batch=self.khp)
         self.theta.fill_(1.0)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -259,12 +281,14 @@ class LmlGraph:
         self.n_launches = L.profile_end()["launches"]          # kernels recorded in the graph
         self.ws = _ws_cache.get(torch.cuda.current_device())   # the captured workspace must stay allocated
 
-    def __call__(self, theta_rows, varK_rows=None):
+    def __call__(self, theta_rows, varK_rows=None, khp_rows=None):
         src = theta_rows if isinstance(theta_rows, torch.Tensor) else torch.as_tensor(
             np.ascontiguousarray(theta_rows, dtype=np.float64))
         self.theta.copy_(src.reshape(self.theta.shape), non_blocking=True)
         if self.varK is not None:
             self.varK.copy_(torch.as_tensor(np.ascontiguousarray(varK_rows, dtype=np.float64)).reshape(-1))
+        if self.khp is not None:
+            self.khp.copy_(torch.as_tensor(np.ascontiguousarray(khp_rows, dtype=np.float64)).reshape(-1))
         self.graph.replay()
         replay_stats["replays"] += 1
         replay_stats["kernel_launches"] += self.n_launches
@@ -276,7 +300,7 @@ replay_stats = {"replays": 0, "kernel_launches": 0}   # kernels launched through
 
 
 def lml_eval_graphed(X, y, theta_batch, *, n_g=None, slot=None, mode=L.MODE_PRECON, eta=0.0, noise=None,
-                     varK_batch=None, pnlt_grad=0.0, want_grad=True):
+                     varK_batch=None, pnlt_grad=0.0, want_grad=True, kernel=None, kernel_hp_batch=None):
     """Same result as lml_eval(...)[0], through a cached CUDA graph.  X, y, slot, noise must be device tensors that
     stay alive and unchanged in place between calls (the graph holds their addresses)."""
     n, d = X.shape
@@ -284,7 +308,7 @@ def lml_eval_graphed(X, y, theta_batch, *, n_g=None, slot=None, mode=L.MODE_PREC
     B = int(np.prod(theta_batch.shape)) // d
     noisy = noise is not None
     key = (torch.cuda.current_device(), X.data_ptr(), y.data_ptr(), _p(slot), _p(noise), n, n_g, d, B, int(mode),
-           float(eta), float(pnlt_grad), bool(want_grad), noisy)
+           float(eta), float(pnlt_grad), bool(want_grad), noisy, _kern(kernel)[0])
     g = _graph_cache.get(key)
     ws_now = _ws_cache.get(torch.cuda.current_device())
     if g is not None and g.ws is not ws_now:   # the workspace was re-allocated since the capture
@@ -293,9 +317,12 @@ def lml_eval_graphed(X, y, theta_batch, *, n_g=None, slot=None, mode=L.MODE_PREC
         if len(_graph_cache) >= 8:
             _graph_cache.clear()
         g = LmlGraph(X, y, B, n_g=n_g, slot=slot, mode=mode, eta=eta, noise=noise, noisy=noisy, pnlt_grad=pnlt_grad,
-                     want_grad=want_grad)
+                     want_grad=want_grad, kernel=kernel)
         _graph_cache[key] = g
-    return g(theta_batch, varK_batch)
+    khp = kernel_hp_batch
+    if g.khp is not None and khp is None:
+        khp = np.full(B, _kern(kernel)[1])
+    return g(theta_batch, varK_batch, khp)
 
 
 def free_graphs():
@@ -305,14 +332,15 @@ def free_graphs():
 class PredictState:
     """Factor + solved residual row kept on the device between setup_eval_model and eval_model."""
 
-    def __init__(self, A, dinv, p, info, alpha, n, n_g, d, N, X, slot, theta, mode, beta):
+    def __init__(self, A, dinv, p, info, alpha, n, n_g, d, N, X, slot, theta, mode, beta, kernel=(0, 0.0)):
         self.A, self.dinv, self.p, self.info, self.alpha = A, dinv, p, info, alpha
         self.n, self.n_g, self.d, self.N = n, n_g, d, N
         self.X, self.slot, self.theta, self.mode, self.beta = X, slot, theta, mode, beta
+        self.kid, self.khp = kernel
 
 
 def predict_setup(X, y, theta, beta, *, n_g=None, slot=None, noise=None, mode=L.MODE_PRECON, eta=0.0,
-                  want_alpha=True) -> PredictState:
+                  want_alpha=True, kernel=None) -> PredictState:
     lib = L.load()
     X, y, theta, noise = to_dev(X), to_dev(y), to_dev(theta), to_dev(noise)
     n, d = X.shape
@@ -324,10 +352,11 @@ def predict_setup(X, y, theta, beta, *, n_g=None, slot=None, noise=None, mode=L.
     p = torch.empty(2 * N, dtype=F64, device=device())
     info = torch.zeros(1, dtype=torch.int32, device=device())
     alpha = torch.empty(N, dtype=F64, device=device()) if want_alpha else None
-    rc = lib.gegp_predict_setup(n, n_g, d, _p(X), _p(slot), _p(theta), _p(noise), int(mode), float(eta), _p(y),
+    kid, khp = _kern(kernel)
+    rc = lib.gegp_predict_setup(n, n_g, d, _p(X), _p(slot), _p(theta), kid, khp, _p(noise), int(mode), float(eta), _p(y),
                                 float(beta), _p(A), ld, _p(dinv), _p(p), _p(alpha), _p(info), _stream())
     _check(rc, "gegp_predict_setup")
-    return PredictState(A, dinv, p, info, alpha, n, n_g, d, N, X, slot, theta, mode, float(beta))
+    return PredictState(A, dinv, p, info, alpha, n, n_g, d, N, X, slot, theta, mode, float(beta), (kid, khp))
 
 
 def predict(st: PredictState, Xs, varK: float, *, chunk_bytes: int = 1 << 30):
@@ -342,7 +371,7 @@ def predict(st: PredictState, Xs, varK: float, *, chunk_bytes: int = 1 << 30):
     row_bytes = ld_of(st.N) * 8
     cx = max(1, min(nx, chunk_bytes // row_bytes))
     ws = workspace(cx * row_bytes)
-    rc = lib.gegp_predict(st.n, st.n_g, st.d, _p(st.X), _p(st.slot), _p(st.theta), _p(st.A), st.A.stride(0), _p(st.dinv),
+    rc = lib.gegp_predict(st.n, st.n_g, st.d, _p(st.X), _p(st.slot), _p(st.theta), st.kid, st.khp, _p(st.A), st.A.stride(0), _p(st.dinv),
                           _p(st.p), int(st.mode), st.beta, float(varK), _p(Xs), nx, _p(mu), _p(sig), _p(sig2), _p(nneg), _p(ws),
                           cx * row_bytes, _stream())
     _check(rc, "gegp_predict")
@@ -361,7 +390,7 @@ def predict_grad(st: PredictState, Xs, varK: float, *, chunk_bytes: int = 1 << 3
     per_x = (d + 1) * ld_of(st.N) * 8
     cx = max(1, min(nx, chunk_bytes // per_x))
     ws = workspace(cx * per_x)
-    rc = lib.gegp_predict_grad(st.n, st.n_g, st.d, _p(st.X), _p(st.slot), _p(st.theta), _p(st.A), st.A.stride(0),
+    rc = lib.gegp_predict_grad(st.n, st.n_g, st.d, _p(st.X), _p(st.slot), _p(st.theta), st.kid, st.khp, _p(st.A), st.A.stride(0),
                                _p(st.dinv), _p(st.p), int(st.mode), st.beta, float(varK), _p(Xs), nx, _p(mu), _p(sig),
                                _p(sig2), _p(dmu), _p(dsg), _p(nneg), _p(ws), cx * per_x, _stream())
     _check(rc, "gegp_predict_grad")
@@ -381,7 +410,7 @@ def predict_hess(st: PredictState, xs, varK: float):
     nneg = torch.zeros(1, dtype=torch.int32, device=dev)
     nbytes = (d + 2) * ld_of(st.N) * 8
     ws = workspace(nbytes)
-    rc = lib.gegp_predict_hess(st.n, st.n_g, st.d, _p(st.X), _p(st.slot), _p(st.theta), _p(st.A), st.A.stride(0),
+    rc = lib.gegp_predict_hess(st.n, st.n_g, st.d, _p(st.X), _p(st.slot), _p(st.theta), st.kid, st.khp, _p(st.A), st.A.stride(0),
                                _p(st.dinv), _p(st.p), _p(st.alpha), int(st.mode), st.beta, float(varK), _p(xs), _p(mu),
                                _p(sig), _p(sig2), _p(dmu), _p(dsg), _p(h3), _p(nneg), _p(ws), nbytes, _stream())
     _check(rc, "gegp_predict_hess")
@@ -414,7 +443,7 @@ def fro_norm(M: torch.Tensor, N: int) -> float:
     return float(np.sqrt(np.sum(out.cpu().numpy())))
 
 
-def weighted_grad(X, theta, W: torch.Tensor, *, n_g=None, slot=None, eta=0.0, noisy=False, varK=1.0):
+def weighted_grad(X, theta, W: torch.Tensor, *, n_g=None, slot=None, eta=0.0, noisy=False, varK=1.0, kernel=None):
     """gegp_weighted_grad: sum(W .* dKcov/dhp) for every hyper-parameter (base mode) -> device row (GEGP_OUT_* layout)."""
     lib = L.load()
     X, theta = to_dev(X), to_dev(theta)
@@ -425,7 +454,8 @@ def weighted_grad(X, theta, W: torch.Tensor, *, n_g=None, slot=None, eta=0.0, no
     vk = to_dev(np.array([float(varK)]))
     nbytes = int(lib.gegp_quad_grad_work_bytes(n, n_g, d)) + 8 * (N + 2)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=device())
-    rc = lib.gegp_weighted_grad(n, n_g, d, _p(X), _p(slot), _p(theta), _p(W), W.stride(0), L.MODE_BASE, float(eta),
+    kid, khp = _kern(kernel)
+    rc = lib.gegp_weighted_grad(n, n_g, d, _p(X), _p(slot), _p(theta), kid, khp, _p(W), W.stride(0), L.MODE_BASE, float(eta),
                                 int(bool(noisy)), _p(vk), _p(out), _p(ws), nbytes, _stream())
     _check(rc, "gegp_weighted_grad")
     return out
@@ -525,7 +555,7 @@ def cond2(Kfull: torch.Tensor, Kinv: torch.Tensor, N: int, *, tol: float = 1e-12
                 cycles=(c1, c2))
 
 
-def quad_grad(X, theta, v, *, n_g=None, slot=None, eta=0.0, noisy=False, varK=1.0):
+def quad_grad(X, theta, v, *, n_g=None, slot=None, eta=0.0, noisy=False, varK=1.0, kernel=None):
     """gegp_quad_grad: v^T (dKcov/dhp) v for every hyper-parameter (base mode) -> device row laid out as GEGP_OUT_*."""
     lib = L.load()
     X, theta, v = to_dev(X), to_dev(theta), to_dev(v)
@@ -535,7 +565,8 @@ def quad_grad(X, theta, v, *, n_g=None, slot=None, eta=0.0, noisy=False, varK=1.
     vk = to_dev(np.array([float(varK)]))
     nbytes = int(lib.gegp_quad_grad_work_bytes(n, n_g, d))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=device())
-    rc = lib.gegp_quad_grad(n, n_g, d, _p(X), _p(slot), _p(theta), _p(v), L.MODE_BASE, float(eta), int(bool(noisy)),
+    kid, khp = _kern(kernel)
+    rc = lib.gegp_quad_grad(n, n_g, d, _p(X), _p(slot), _p(theta), kid, khp, _p(v), L.MODE_BASE, float(eta), int(bool(noisy)),
                             _p(vk), _p(out), _p(ws), nbytes, _stream())
     _check(rc, "gegp_quad_grad")
     return out

@@ -1,4 +1,5 @@
-// K1: fused Gaussian-kernel covariance builder for the gradient-enhanced GP.
+// K1: fused covariance builder for the gradient-enhanced GP (Gaussian kernel: specialised fast path; Matern-5/2 and
+// rational-quadratic kernels: the generic tile kernel with the radial profiles of kernels.h).
 //
 // Writes the N x N matrix (N = n + n_g*d, dimension-major order) in ONE pass: value block, dK/dx
 // blocks, d2K/dxdx' blocks, observation noise, diagonal preconditioner P^-1 . P^-1 and nugget.
@@ -16,7 +17,8 @@ constexpr int TA = 16;   // a-points per CTA
 constexpr int TB = 64;   // b-points per CTA (2 warps wide)
 constexpr int BUILD_THREADS = 256;
 
-// p[row] = sqrt(diag(K) + noise[row]), pinv = 1/p.  diag(K) = 1 (value rows), 2*theta_i (gradient rows).
+// p[row] = sqrt(diag(K) + noise[row]), pinv = 1/p.  diag(K) = 1 (value rows), c theta_i (gradient rows; c = 2, or 5/3
+// for Matern-5/2: kernel_diag_coef).
 __device__ __forceinline__ double noise_at(const NoiseSpec& ns, int z, int row) {
   const double v = ns.noise[z * ns.stride + row];
   if (!ns.divide) return v;
@@ -32,7 +34,7 @@ __global__ void prep_p_kernel(Geom gm, const double* __restrict__ theta, int64_t
   if (mode == GEGP_MODE_PRECON) {
     const double* th = theta + z * strideTheta;
     double dg = 1.0;
-    if (row >= gm.n) dg = 2.0 * th[(row - gm.n) / gm.ng];
+    if (row >= gm.n) dg = kernel_diag_coef(gm.ktype) * th[(row - gm.n) / gm.ng];
     if (ns.noise) dg += noise_at(ns, z, row);
     pv = sqrt(dg);
     pi = 1.0 / pv;
@@ -75,9 +77,11 @@ build_cov_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideTh
     xb[i * TB + b] = (b0 + b < n) ? gm.X[(int64_t)(b0 + b) * d + i] : 0.0;
   }
   const bool precon = (mode == GEGP_MODE_PRECON);
+  const int ktype = gm.ktype;
+  const double kalpha = gm.kernel_hp(z), cdiag = kernel_diag_coef(ktype);
   for (int e = tid; e < d; e += BUILD_THREADS) {
     th[e] = theta[e];
-    sg[e] = precon ? 1.0 / sqrt(2.0 * theta[e]) : 1.0;
+    sg[e] = precon ? 1.0 / sqrt(cdiag * theta[e]) : 1.0;
   }
   for (int e = tid; e < TA; e += BUILD_THREADS) slot_a[e] = (a0 + e < n) ? (gm.slot ? gm.slot[a0 + e] : a0 + e) : -1;
   for (int e = tid; e < TB; e += BUILD_THREADS) slot_b[e] = (b0 + e < n) ? (gm.slot ? gm.slot[b0 + e] : b0 + e) : -1;
@@ -99,9 +103,10 @@ build_cov_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideTh
     double e = 0.0;
     for (int i = 0; i < d; i++) {
       const double r = xav[i] - xb[i * TB + tb];
-      e -= th[i] * (r * r);
+      e += th[i] * (r * r);
     }
-    const double k = exp(e);
+    const RadialProfile ph = radial_profile(ktype, kalpha, e);
+    const double k = ph.f0, k1 = ph.f1, k2 = ph.f2;
     const bool same = (a == b);
     // ---- value-value entry
     {
@@ -113,14 +118,14 @@ build_cov_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideTh
       v = (v * sr) * sc + dadd;
       if (!lower_only || a >= b) out[(int64_t)a * ld + b] = varK * v;
     }
-    // ---- value row, gradient columns: K_0j = +2 th_j r_j k   (upper part: skipped when lower_only)
+    // ---- value row, gradient columns: K_0j = -2 th_j r_j f1  (SqExp: +2 th_j r_j k; upper part: skipped when lower_only)
     if (sb >= 0 && !lower_only) {
       const double sr = use_pvec ? pinv[a] : 1.0;
       for (int j = 0; j < d; j++) {
         const int col = n + j * ng + sb;
         const double r = xav[j] - xb[j * TB + tb];
         const double sc = use_pvec ? pinv[col] : sg[j];
-        out[(int64_t)a * ld + col] = varK * (((2.0 * th[j] * r * k) * sr) * sc);
+        out[(int64_t)a * ld + col] = varK * (((-2.0 * th[j] * r * k1) * sr) * sc);
       }
     }
     if (sa < 0) continue;
@@ -131,10 +136,10 @@ build_cov_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideTh
       const double sr = use_pvec ? pinv[row] : sg[i];
       const double ui = th[i] * ri;
       double* orow = out + (int64_t)row * ld;
-      // gradient-value: K_i0 = -2 th_i r_i k
+      // gradient-value: K_i0 = 2 th_i r_i f1  (SqExp: -2 th_i r_i k)
       {
         const double sc = use_pvec ? pinv[b] : 1.0;
-        orow[b] = varK * (((-2.0 * ui * k) * sr) * sc);
+        orow[b] = varK * (((2.0 * ui * k1) * sr) * sc);
       }
       if (sb < 0) continue;
       const int jmax = lower_only ? i : d - 1;
@@ -143,8 +148,8 @@ build_cov_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideTh
         const int col = n + j * ng + sb;
         const double rj = xav[j] - xb[j * TB + tb];
         double v;
-        if (j == i) v = (2.0 * th[i] - 4.0 * (ui * ui)) * k;   // (2 th_i - 4 th_i^2 r_i^2) k
-        else v = -4.0 * (ui * (th[j] * rj)) * k;              // -4 th_i th_j r_i r_j k
+        if (j == i) v = -2.0 * th[i] * k1 - 4.0 * (ui * ui) * k2;   // SqExp: (2 th_i - 4 th_i^2 r_i^2) k
+        else v = -4.0 * (ui * (th[j] * rj)) * k2;                   // SqExp: -4 th_i th_j r_i r_j k
         const double sc = use_pvec ? pinv[col] : sg[j];
         double dadd = 0.0;
         if (same && j == i) {
@@ -305,7 +310,7 @@ build_cov_fast_kernel(Geom gm, const double* __restrict__ theta_all, int64_t str
 }
 
 // Cross covariance rows for prediction: Kx[x][col] = K(x*_x ; training datum col) * pinv[col]
-// value columns: k ; gradient column (j, slot): -2 th_j r_j k with r = x_train - x_test
+// value columns: k ; gradient column (j, slot): 2 th_j r_j f1 (SqExp: -2 th_j r_j k) with r = x_train - x_test
 // (eval/GpEvalModel.py:133-139 builds K(X, X*) and keeps its value columns; this is its transpose).
 __global__ void __launch_bounds__(256)
 cross_cov_kernel(Geom gm, const double* __restrict__ theta, const double* __restrict__ pinv,
@@ -332,16 +337,16 @@ cross_cov_kernel(Geom gm, const double* __restrict__ theta, const double* __rest
     double e = 0.0;
     for (int i = 0; i < d; i++) {
       const double r = xb[i] - xv[i];
-      e -= th[i] * (r * r);
+      e += th[i] * (r * r);
     }
-    const double k = exp(e);
+    const RadialProfile ph = radial_profile(gm.ktype, gm.khp, e);
     double* orow = out + (int64_t)(x0 + x) * ld;
-    orow[b] = k * (pinv ? pinv[b] : 1.0);
+    orow[b] = ph.f0 * (pinv ? pinv[b] : 1.0);
     if (sb >= 0) {
       for (int j = 0; j < d; j++) {
         const int col = n + j * ng + sb;
         const double r = xb[j] - xv[j];
-        orow[col] = (-2.0 * th[j] * r * k) * (pinv ? pinv[col] : 1.0);
+        orow[col] = (2.0 * th[j] * r * ph.f1) * (pinv ? pinv[col] : 1.0);
       }
     }
   }
@@ -350,8 +355,8 @@ cross_cov_kernel(Geom gm, const double* __restrict__ theta, const double* __rest
 // Cross covariance WITH its derivatives with respect to the test point (eval/GpEvalModel.py:133-139 keeps the
 // test-gradient columns of K(X, X*) for calc_grad; kernel/KernelSqExp.py:392-408 gives the blocks).  Per test point
 // x the output holds d + 1 consecutive rows: row 0 = k*(x) as cross_cov_kernel writes it, row 1 + j = d k*(x) / d x*_j:
-//   value entry a      :  +2 th_j r_j k                         (r = x_train - x_test)
-//   gradient entry (i,a): (2 th_i delta_ij - 4 th_i th_j r_i r_j) k
+//   value entry a      :  -2 th_j r_j f1                        (r = x_train - x_test; SqExp: +2 th_j r_j k)
+//   gradient entry (i,a): -2 th_i delta_ij f1 - 4 th_i th_j r_i r_j f2   (SqExp: (2 th_i delta_ij - 4 th_i th_j r_i r_j) k)
 // every entry scaled by pinv of its training row.
 __global__ void __launch_bounds__(256)
 cross_cov_dx_kernel(Geom gm, const double* __restrict__ theta, const double* __restrict__ pinv,
@@ -370,15 +375,16 @@ cross_cov_dx_kernel(Geom gm, const double* __restrict__ theta, const double* __r
   double e = 0.0;
   for (int i = 0; i < d; i++) {
     const double r = xb[i] - xv[i];
-    e -= th[i] * (r * r);
+    e += th[i] * (r * r);
   }
-  const double k = exp(e);
+  const RadialProfile ph = radial_profile(gm.ktype, gm.khp, e);
+  const double k = ph.f0, k1 = ph.f1, k2 = ph.f2;
   double* base = out + (int64_t)x * (d + 1) * ld;
   const double pb = pinv ? pinv[b] : 1.0;
   base[b] = k * pb;
   for (int j = 0; j < d; j++) {
     const double rj = xb[j] - xv[j];
-    base[(int64_t)(1 + j) * ld + b] = (2.0 * th[j] * rj * k) * pb;
+    base[(int64_t)(1 + j) * ld + b] = (-2.0 * th[j] * rj * k1) * pb;
   }
   if (sb >= 0) {
     for (int i = 0; i < d; i++) {
@@ -386,11 +392,11 @@ cross_cov_dx_kernel(Geom gm, const double* __restrict__ theta, const double* __r
       const double pc = pinv ? pinv[col] : 1.0;
       const double ri = xb[i] - xv[i];
       const double ui = th[i] * ri;
-      base[col] = (-2.0 * ui * k) * pc;
+      base[col] = (2.0 * ui * k1) * pc;
       for (int j = 0; j < d; j++) {
         const double rj = xb[j] - xv[j];
-        const double v = ((i == j) ? 2.0 * th[i] : 0.0) - 4.0 * ui * th[j] * rj;
-        base[(int64_t)(1 + j) * ld + col] = (v * k) * pc;
+        const double v = ((i == j) ? -2.0 * th[i] * k1 : 0.0) - 4.0 * ui * th[j] * rj * k2;
+        base[(int64_t)(1 + j) * ld + col] = v * pc;
       }
     }
   }
@@ -435,14 +441,13 @@ int launch_build_cov(const Ctx& ctx, const Geom& gm, const double* theta, int64_
   // fast path: all points carry gradients, even n (16-byte aligned column blocks), aligned even-stride output
   const size_t fsmem = (size_t)(FTA * gm.d + gm.d * FTB + 3 * gm.d) * sizeof(double);
   const bool use_pvec = (mode == GEGP_MODE_PRECON) && ns.noise != nullptr;
-  if (gm.slot == nullptr && gm.ng == gm.n && (gm.n & 1) == 0 && (ld & 1) == 0 && (strideOut & 1) == 0 &&
+  if (gm.ktype == GEGP_KERNEL_SQEXP && gm.slot == nullptr && gm.ng == gm.n && (gm.n & 1) == 0 && (ld & 1) == 0 &&
+      (strideOut & 1) == 0 &&
       (reinterpret_cast<uintptr_t>(out) & 15) == 0 && fsmem <= 200 * 1024 &&
       (!use_pvec || ((strideP & 1) == 0 && (reinterpret_cast<uintptr_t>(pinv) & 15) == 0))) {
-    static size_t fsmem_set[2] = {0, 0};
-    if (fsmem > 48 * 1024 && fsmem > fsmem_set[use_pvec]) {
-      if (use_pvec) GEGP_SET_SMEM(build_cov_fast_kernel<true>, fsmem);
-      else GEGP_SET_SMEM(build_cov_fast_kernel<false>, fsmem);
-      fsmem_set[use_pvec] = fsmem;
+    if (fsmem > 48 * 1024) {   // opt in once per device to the largest size any d can ask for
+      if (use_pvec) GEGP_SET_SMEM(build_cov_fast_kernel<true>, GEGP_MAX_DYN_SMEM);
+      else GEGP_SET_SMEM(build_cov_fast_kernel<false>, GEGP_MAX_DYN_SMEM);
     }
     dim3 grid((gm.n + FTB - 1) / FTB, (gm.n + FTA - 1) / FTA, ctx.batch);
     if (use_pvec)
@@ -455,11 +460,8 @@ int launch_build_cov(const Ctx& ctx, const Geom& gm, const double* theta, int64_
     return 0;
   }
   const size_t smem = (size_t)(TA * gm.d + gm.d * TB + 2 * gm.d) * sizeof(double) + (TA + TB) * sizeof(int);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    GEGP_SET_SMEM(build_cov_kernel, smem);
-    smem_set = smem;
-  }
+  if (smem > GEGP_MAX_DYN_SMEM) return -907;
+  if (smem > 48 * 1024) GEGP_SET_SMEM(build_cov_kernel, GEGP_MAX_DYN_SMEM);
   dim3 grid((gm.n + TB - 1) / TB, (gm.n + TA - 1) / TA, ctx.batch);
   build_cov_kernel<<<grid, BUILD_THREADS, smem, ctx.stream>>>(gm, theta, strideTheta, ns, pinv, strideP, mode, eta, out,
                                                               ld, strideOut, lower_only);

@@ -108,6 +108,17 @@ size_t info_header_bytes(int B) { return (size_t)round_up((int64_t)B * (int64_t)
 
 bool bad_geom(int n, int n_g, int d) { return n <= 0 || d <= 0 || n_g < 0 || n_g > n; }
 
+// kernel family + extra hyper-parameter: the rational-quadratic alpha must be positive, the others ignore it
+bool bad_kernel(int kernel, double kernel_hp) {
+  if (kernel < GEGP_KERNEL_SQEXP || kernel > GEGP_KERNEL_RATQUAD) return true;
+  return kernel == GEGP_KERNEL_RATQUAD && !(kernel_hp > 0.0);
+}
+
+Geom make_geom(int n, int n_g, int d, const double* X, const int32_t* grad_slot, int kernel, double kernel_hp,
+               const double* kernel_hp_batch = nullptr) {
+  return Geom{n, n_g, d, n + n_g * d, X, (n_g == n) ? nullptr : grad_slot, kernel, kernel_hp, kernel_hp_batch};
+}
+
 }  // namespace
 
 extern "C" {
@@ -182,10 +193,11 @@ size_t gegp_workspace_bytes(int op, int n, int n_g, int d, int arg) {
   return 0;
 }
 
-int gegp_build_cov(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+int gegp_build_cov(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta, int kernel, double kernel_hp,
                    const double* noise, int mode, double eta, double varK, double* K_out, int64_t ldk, double* p_out,
                    int uplo, void* stream) {
   if (bad_geom(n, n_g, d)) return -1;
+  if (bad_kernel(kernel, kernel_hp)) return -50;
   if (!X) return -4;
   if (!theta) return -6;
   if (mode < GEGP_MODE_BASE || mode > GEGP_MODE_PRECON_COV) return -8;
@@ -195,7 +207,7 @@ int gegp_build_cov(int n, int n_g, int d, const double* X, const int32_t* grad_s
   if (mode == GEGP_MODE_PRECON && !p_out) return -13;
   if (n_g != n && !grad_slot) return -5;  // gradient-free GP (n_g == 0): pass a slot array of -1
   Ctx ctx{(cudaStream_t)stream, 1};
-  Geom gm{n, n_g, d, N, X, (n_g == n) ? nullptr : grad_slot};
+  const Geom gm = make_geom(n, n_g, d, X, grad_slot, kernel, kernel_hp);
   NoiseSpec ns{noise, 0, nullptr, varK, 0};
   int rc = 0;
   if (p_out) {
@@ -206,8 +218,9 @@ int gegp_build_cov(int n, int n_g, int d, const double* X, const int32_t* grad_s
 }
 
 int gegp_cross_cov(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* Xs, int nx,
-                   const double* theta, const double* pinv, double* Kx, int64_t ld, void* stream) {
+                   const double* theta, int kernel, double kernel_hp, const double* pinv, double* Kx, int64_t ld, void* stream) {
   if (bad_geom(n, n_g, d)) return -1;
+  if (bad_kernel(kernel, kernel_hp)) return -50;
   if (!X) return -4;
   if (!Xs || nx < 0) return -6;
   if (!theta) return -8;
@@ -217,7 +230,7 @@ int gegp_cross_cov(int n, int n_g, int d, const double* X, const int32_t* grad_s
   if (n_g != n && !grad_slot) return -5;
   if (nx == 0) return 0;
   Ctx ctx{(cudaStream_t)stream, 1};
-  Geom gm{n, n_g, d, N, X, (n_g == n) ? nullptr : grad_slot};
+  const Geom gm = make_geom(n, n_g, d, X, grad_slot, kernel, kernel_hp);
   return launch_cross_cov(ctx, gm, theta, pinv, Xs, nx, Kx, ld);
 }
 
@@ -275,13 +288,16 @@ int gegp_dgemm(int transb, int M, int N, int K, double alpha, const double* A, i
   return gemm_f64(ctx, gemm_args(A, lda, B, ldb, C, ldc, M, N, K, alpha, beta, transb != 0));
 }
 
-int gegp_lml_eval(int B, const double* theta_batch, const double* varK_batch, int n, int n_g, int d, const double* X,
+int gegp_lml_eval(int B, const double* theta_batch, const double* varK_batch, int kernel,
+                  const double* kernel_hp_batch, int n, int n_g, int d, const double* X,
                   const int32_t* grad_slot, const double* y, const double* noise, int mode, double eta, int noisy,
                   double pnlt_grad, int want_grad, double* out, double* alpha_out, void* work, size_t work_bytes,
                   void* stream) {
   if (B <= 0) return -1;
   if (!theta_batch) return -2;
   if (noisy && !varK_batch) return -3;
+  if (kernel < GEGP_KERNEL_SQEXP || kernel > GEGP_KERNEL_RATQUAD) return -50;
+  if (kernel == GEGP_KERNEL_RATQUAD && !kernel_hp_batch) return -50;
   if (bad_geom(n, n_g, d)) return -4;
   if (!X) return -7;
   if (n_g != n && !grad_slot) return -8;
@@ -301,11 +317,11 @@ int gegp_lml_eval(int B, const double* theta_batch, const double* varK_batch, in
   double* wk = reinterpret_cast<double*>(reinterpret_cast<char*>(work) + header);
   const int64_t sC = (int64_t)L.per_cand_doubles;  // candidate stride of every workspace array
   const int outlen = GEGP_OUT_LEN(d);
-  Geom gm{n, n_g, d, N, X, (n_g == n) ? nullptr : grad_slot};
 
   for (int b0 = 0; b0 < B; b0 += chunk) {
     const int nb = std::min(chunk, B - b0);
     Ctx ctx{st, nb};
+    const Geom gm = make_geom(n, n_g, d, X, grad_slot, kernel, 0.0, kernel_hp_batch ? kernel_hp_batch + b0 : nullptr);
     const double* theta = theta_batch + (int64_t)b0 * d;
     const double* varK = noisy ? varK_batch + b0 : nullptr;
     double* A = wk + L.A;
@@ -431,10 +447,11 @@ size_t gegp_quad_grad_work_bytes(int n, int n_g, int d) {
   return ((size_t)round_up(N, 2) + (size_t)round_up((int64_t)lml_grad_partial_doubles(n, d), 2)) * sizeof(double);
 }
 
-int gegp_quad_grad(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+int gegp_quad_grad(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta, int kernel, double kernel_hp,
                    const double* v, int mode, double eta, int noisy, const double* varK_dev, double* out, void* work,
                    size_t work_bytes, void* stream) {
   if (bad_geom(n, n_g, d)) return -1;
+  if (bad_kernel(kernel, kernel_hp)) return -50;
   if (!X) return -4;
   if (n_g != n && !grad_slot) return -5;
   if (!theta) return -6;
@@ -446,7 +463,7 @@ int gegp_quad_grad(int n, int n_g, int d, const double* X, const int32_t* grad_s
   if (work_bytes < gegp_quad_grad_work_bytes(n, n_g, d)) return -14;
   const int N = n + n_g * d;
   Ctx ctx{(cudaStream_t)stream, 1};
-  Geom gm{n, n_g, d, N, X, (n_g == n) ? nullptr : grad_slot};
+  const Geom gm = make_geom(n, n_g, d, X, grad_slot, kernel, kernel_hp);
   double* ones = reinterpret_cast<double*>(work);           // p^-1 = 1 in base mode
   double* partial = ones + round_up(N, 2);
   NoiseSpec ns{nullptr, 0, nullptr, 1.0, 0};
@@ -456,10 +473,11 @@ int gegp_quad_grad(int n, int n_g, int d, const double* X, const int32_t* grad_s
                          0, 1);
 }
 
-int gegp_weighted_grad(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+int gegp_weighted_grad(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta, int kernel, double kernel_hp,
                        const double* W, int64_t ldw, int mode, double eta, int noisy, const double* varK_dev, double* out,
                        void* work, size_t work_bytes, void* stream) {
   if (bad_geom(n, n_g, d)) return -1;
+  if (bad_kernel(kernel, kernel_hp)) return -50;
   if (!X) return -4;
   if (n_g != n && !grad_slot) return -5;
   if (!theta) return -6;
@@ -472,7 +490,7 @@ int gegp_weighted_grad(int n, int n_g, int d, const double* X, const int32_t* gr
   if (!work || (reinterpret_cast<uintptr_t>(work) & 15)) return -14;
   if (work_bytes < gegp_quad_grad_work_bytes(n, n_g, d) + (size_t)round_up(N, 2) * sizeof(double)) return -15;
   Ctx ctx{(cudaStream_t)stream, 1};
-  Geom gm{n, n_g, d, N, X, (n_g == n) ? nullptr : grad_slot};
+  const Geom gm = make_geom(n, n_g, d, X, grad_slot, kernel, kernel_hp);
   double* ones = reinterpret_cast<double*>(work);
   double* zeros = ones + round_up(N, 2);                     // alpha := 0 (no rank-one part)
   double* partial = zeros + round_up(N, 2);
@@ -485,10 +503,11 @@ int gegp_weighted_grad(int n, int n_g, int d, const double* X, const int32_t* gr
                          0, 2);
 }
 
-int gegp_predict_setup(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+int gegp_predict_setup(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta, int kernel, double kernel_hp,
                        const double* noise, int mode, double eta, const double* y, double beta, double* A, int64_t lda,
                        double* dinv, double* p_out, double* alpha_out, int* info_dev, void* stream) {
   if (bad_geom(n, n_g, d)) return -1;
+  if (bad_kernel(kernel, kernel_hp)) return -50;
   if (!X) return -4;
   if (n_g != n && !grad_slot) return -5;
   if (!theta) return -6;
@@ -501,7 +520,7 @@ int gegp_predict_setup(int n, int n_g, int d, const double* X, const int32_t* gr
   if (!p_out) return -15;
   if (!info_dev) return -17;
   Ctx ctx{(cudaStream_t)stream, 1};
-  Geom gm{n, n_g, d, N, X, (n_g == n) ? nullptr : grad_slot};
+  const Geom gm = make_geom(n, n_g, d, X, grad_slot, kernel, kernel_hp);
   NoiseSpec ns{noise, 0, nullptr, 1.0, 0};
   double* pinv = p_out + N;
   int rc = launch_prep_p(ctx, gm, theta, 0, ns, mode, p_out, pinv, 0);
@@ -526,11 +545,12 @@ int gegp_predict_setup(int n, int n_g, int d, const double* X, const int32_t* gr
   return 0;
 }
 
-int gegp_predict(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta, const double* A,
+int gegp_predict(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta, int kernel, double kernel_hp, const double* A,
                  int64_t lda, const double* dinv, const double* p, int mode, double beta, double varK, const double* Xs,
                  int nx, double* mu,
                  double* sig, double* sig2_out, int* n_negative_dev, void* work, size_t work_bytes, void* stream) {
   if (bad_geom(n, n_g, d)) return -1;
+  if (bad_kernel(kernel, kernel_hp)) return -50;
   if (!X) return -4;
   if (n_g != n && !grad_slot) return -5;
   if (!theta) return -6;
@@ -548,7 +568,7 @@ int gegp_predict(int n, int n_g, int d, const double* X, const int32_t* grad_slo
   const int chunk = (int)std::min<size_t>((size_t)nx, work_bytes / (ldz * sizeof(double)));
   if (nx > 0 && chunk < 1) return -21;
   Ctx ctx{(cudaStream_t)stream, 1};
-  Geom gm{n, n_g, d, N, X, (n_g == n) ? nullptr : grad_slot};
+  const Geom gm = make_geom(n, n_g, d, X, grad_slot, kernel, kernel_hp);
   const double* pinv = p + N;
   const double* w = A + (int64_t)N * lda;
   double* Z = reinterpret_cast<double*>(work);
@@ -565,11 +585,12 @@ int gegp_predict(int n, int n_g, int d, const double* X, const int32_t* grad_slo
   return 0;
 }
 
-int gegp_predict_grad(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+int gegp_predict_grad(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta, int kernel, double kernel_hp,
                       const double* A, int64_t lda, const double* dinv, const double* p, int mode, double beta,
                       double varK, const double* Xs, int nx, double* mu, double* sig, double* sig2_out, double* dmudx,
                       double* dsigdx, int* n_negative_dev, void* work, size_t work_bytes, void* stream) {
   if (bad_geom(n, n_g, d)) return -1;
+  if (bad_kernel(kernel, kernel_hp)) return -50;
   if (!X) return -4;
   if (n_g != n && !grad_slot) return -5;
   if (!theta) return -6;
@@ -590,7 +611,7 @@ int gegp_predict_grad(int n, int n_g, int d, const double* X, const int32_t* gra
   const int chunk = (int)std::min<size_t>((size_t)nx, work_bytes / per_x);
   if (nx > 0 && chunk < 1) return -23;
   Ctx ctx{(cudaStream_t)stream, 1};
-  Geom gm{n, n_g, d, N, X, (n_g == n) ? nullptr : grad_slot};
+  const Geom gm = make_geom(n, n_g, d, X, grad_slot, kernel, kernel_hp);
   const double* pinv = p + N;
   const double* w = A + (int64_t)N * lda;
   double* Z = reinterpret_cast<double*>(work);
@@ -608,12 +629,13 @@ int gegp_predict_grad(int n, int n_g, int d, const double* X, const int32_t* gra
   return 0;
 }
 
-int gegp_predict_hess(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+int gegp_predict_hess(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta, int kernel, double kernel_hp,
                       const double* A, int64_t lda, const double* dinv, const double* p, const double* alpha, int mode,
                       double beta, double varK, const double* xs, double* mu, double* sig, double* sig2_out,
                       double* dmudx, double* dsigdx, double* hess3, int* n_negative_dev, void* work, size_t work_bytes,
                       void* stream) {
   if (bad_geom(n, n_g, d)) return -1;
+  if (bad_kernel(kernel, kernel_hp)) return -50;
   if (!X) return -4;
   if (n_g != n && !grad_slot) return -5;
   if (!theta) return -6;
@@ -634,7 +656,7 @@ int gegp_predict_hess(int n, int n_g, int d, const double* X, const int32_t* gra
   const int64_t ldz = gegp_ld(N);
   if (work_bytes < (size_t)(d + 2) * ldz * sizeof(double)) return -24;
   Ctx ctx{(cudaStream_t)stream, 1};
-  Geom gm{n, n_g, d, N, X, (n_g == n) ? nullptr : grad_slot};
+  const Geom gm = make_geom(n, n_g, d, X, grad_slot, kernel, kernel_hp);
   const double* pinv = p + N;
   const double* w = A + (int64_t)N * lda;
   double* Z = reinterpret_cast<double*>(work);

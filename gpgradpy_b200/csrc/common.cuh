@@ -28,6 +28,7 @@ int& lookahead_enabled();
 namespace gegp {
 
 constexpr int LEAF = 128;  // blocking quantum of the recursive factorisation / inverse
+constexpr int GEGP_MAX_DYN_SMEM = 227 * 1024;  // largest dynamic shared memory a CTA can opt in to on sm_100
 
 // Launch context: every kernel of one C-ABI call goes to this stream; `batch` independent problems
 // (multi-start candidates) are laid out with a fixed element stride and mapped to blockIdx.z.

@@ -66,6 +66,7 @@ lml_finalize_kernel(int N, const double* __restrict__ A_all, int64_t lda, int64_
     out[GEGP_OUT_DVARK] = 0.0;
     out[GEGP_OUT_DVARF] = 0.0;
     out[GEGP_OUT_DVARG] = 0.0;
+    out[GEGP_OUT_DKERN] = 0.0;
     for (int m = 0; m < zero_grad_d; m++) out[GEGP_OUT_GRAD + m] = 0.0;   // gradient not requested: defined zeros
   }
 }
@@ -99,9 +100,12 @@ int launch_scale_vec(const Ctx& ctx, int N, const double* a, int64_t strideA, co
 // (a = preconditioned alpha, Kinv = inverse of the factored matrix).  One CTA per (point a, 128 points b);
 // each thread owns one pair and walks the (d+1) x (d+1) block of W that belongs to it, reading Kinv
 // coalesced along b.  Using the symmetry of W and K, only rows i of the pair block are needed:
-//   S   = W00 - 4 sum_i u_i W_i0 + 2 sum_i th_i W_ii - 4 sum_i u_i (W u)_i          (u_i = th_i r_i)
-//   t_m = -4 r_m W_m0 + 2 W_mm - 8 r_m (W u)_m
-//   g_m = sum_pairs k (t_m - r_m^2 S) ;  sum(K .* W) = sum_pairs k S
+//   A0 = W00,  A1 = 4 sum_i u_i W_i0 - 2 sum_i th_i W_ii,  A2 = -4 sum_i u_i (W u)_i      (u_i = th_i r_i)
+//   sum(K .* W)        = sum_pairs  f0 A0 + f1 A1 + f2 A2        (f0..f3: radial profile and its s-derivatives, kernels.h)
+//   g_m                = sum_pairs  r_m^2 (f1 A0 + f2 A1 + f3 A2) + f1 (4 r_m W_m0 - 2 W_mm) - 8 f2 r_m (W u)_m
+//   g_alpha (RatQuad)  = sum_pairs  (df0 A0 + df1 A1 + df2 A2) / dalpha
+// For the Gaussian kernel (f1 = f3 = -k, f0 = f2 = k) this is  g_m = sum_pairs k (t_m - r_m^2 S)  with
+//   S = W00 - 4 sum u_i W_i0 + 2 sum th_i W_ii - 4 sum u_i (W u)_i,  t_m = -4 r_m W_m0 + 2 W_mm - 8 r_m (W u)_m.
 // Per-CTA partial sums are written to `partial` and reduced in a fixed order by the finalize kernel.
 // ------------------------------------------------------------------------------------------------
 constexpr int GB = 128;
@@ -130,7 +134,7 @@ lml_grad_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideThe
   const double* alpha = alpha_all + z * strideAlpha;
   const double* pinv = pinv_all + z * strideP;
   const double* outz = out_all + z * strideOut;
-  const int np = 2 * d + 2;
+  const int np = 2 * d + 3;
   double* part = partial_all + z * stridePartial + ((int64_t)a * gridDim.x + blockIdx.x) * np;
 
   for (int e = tid; e < d; e += GB) { xa[e] = gm.X[(int64_t)a * d + e]; th[e] = theta[e]; }
@@ -145,14 +149,19 @@ lml_grad_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideThe
   const int sb = valid ? (gm.slot ? gm.slot[b] : b) : -1;
   const bool same = valid && (a == b);
 
-  double kk = 0.0, S = 0.0, Ab = 0.0;
+  double A0 = 0.0, A1 = 0.0, A2 = 0.0, Ab = 0.0;
   double dv = 0.0;
+  RadialProfile ph;
+  ph.f0 = ph.f1 = ph.f2 = ph.f3 = 0.0;
+  const int ktype = gm.ktype;
+  const double kalpha = gm.kernel_hp(z);
+  double ssum = 0.0;
   if (valid) {
     double e = 0.0;
     for (int j = 0; j < d; j++) {
       const double r = xa[j] - gm.X[(int64_t)b * d + j];
       const double u = th[j] * r;
-      e -= u * r;
+      e += u * r;
       double v = 0.0;
       if (sb >= 0) {
         const int col = n + j * ng + sb;
@@ -161,10 +170,11 @@ lml_grad_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideThe
       }
       vs[j * GB + tid] = v;
     }
-    kk = exp(e);
+    ssum = e;
+    ph = radial_profile(ktype, kalpha, e);
     const double pa0 = pinv[a], pb0 = pinv[b];
     const double W00 = pa0 * pb0 * (c1 * alpha[a] * alpha[b] - (quad == 1 ? 0.0 : c2 * Kinv[(int64_t)a * ldk + b]));
-    S = W00;
+    A0 = W00;
     if (same) dv = W00;
   } else {
     for (int j = 0; j < d; j++) vs[j * GB + tid] = 0.0;
@@ -217,22 +227,43 @@ lml_grad_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideThe
         const int coli = n + i * ng + sb;
         Wii = pr * pinv[coli] * (c1 * ar * alpha[coli] - c2 * kii);
       }
-      S += -4.0 * ui * Wi0 + 2.0 * th[i] * Wii - 4.0 * ui * rowdot;
-      t = -4.0 * ri * Wi0 + 2.0 * Wii - 8.0 * ri * rowdot;
+      A1 += 4.0 * ui * Wi0 - 2.0 * th[i] * Wii;
+      A2 -= 4.0 * ui * rowdot;
+      t = ph.f1 * (4.0 * ri * Wi0 - 2.0 * Wii) - 8.0 * ph.f2 * (ri * rowdot);
       if (same) part[d + 2 + i] = Wii;
     }
     gs[i * GB + tid] = t;
   }
-  // g_m = k (t_m - r_m^2 S)
+  // g_m = t_m + r_m^2 (f1 A0 + f2 A1 + f3 A2)
+  const double Sth = ph.f1 * A0 + ph.f2 * A1 + ph.f3 * A2;
   for (int m = 0; m < d; m++) {
     double g = 0.0;
     if (valid) {
       const double r = xa[m] - gm.X[(int64_t)b * d + m];
-      g = kk * (gs[m * GB + tid] - r * r * S);
+      g = gs[m * GB + tid] + (r * r) * Sth;
     }
     gs[m * GB + tid] = g;
   }
-  gs[d * GB + tid] = valid ? kk * S : 0.0;
+  gs[d * GB + tid] = valid ? (ph.f0 * A0 + ph.f1 * A1 + ph.f2 * A2) : 0.0;
+  // the kernel hyper-parameter (one block-wide sum more; only the rational-quadratic kernel has one)
+  if (ktype == GEGP_KERNEL_RATQUAD) {
+    double ga = 0.0;
+    if (valid) {
+      const RadialProfile da = radial_profile_dalpha(ktype, kalpha, ssum, ph);
+      ga = da.f0 * A0 + da.f1 * A1 + da.f2 * A2;
+    }
+    ga = warp_sum(ga);
+    __shared__ double ga_sh[GB / 32];
+    if ((tid & 31) == 0) ga_sh[tid >> 5] = ga;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int q = 0; q < GB / 32; q++) t += ga_sh[q];
+      part[2 * d + 2] = t;
+    }
+  } else if (tid == 0) {
+    part[2 * d + 2] = 0.0;
+  }
   __syncthreads();
   // reduce d+1 rows of GB values: warp w handles rows w, w+4, ...
   const int lane = tid & 31, w = tid >> 5;
@@ -249,9 +280,10 @@ lml_grad_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideThe
 }
 
 // Sum the per-CTA partials in a fixed order and assemble the gradient entries of `out`.
-//   noise-free: dLML/dtheta_m = G_m + [precon] 2 eta DG_m
-//   noisy     : dLML/dtheta_m = varK (G_m + [precon] 2 eta DG_m)
-//               dLML/dvarK    = SK + eta (DV + sum_m 2 th_m DG_m) [precon]  |  SK + eta (DV + sum DG_m) [base]
+//   noise-free: dLML/dtheta_m = G_m + [precon] c eta DG_m          (c = kernel_diag_coef: 2, Matern-5/2: 5/3)
+//   noisy     : dLML/dtheta_m = varK (G_m + [precon] c eta DG_m)
+//               dLML/dvarK    = SK + eta (DV + sum_m c th_m DG_m) [precon]  |  SK + eta (DV + sum DG_m) [base]
+//               dLML/dalpha   = [varK] G_alpha                      (rational-quadratic kernel only)
 //               dLML/dvar_f   = (1 + eta) DV [precon] | DV [base] ; dLML/dvar_g likewise with sum_m DG_m
 // stage 1: one CTA per (column c of the partial table, problem z): fixed-order sum over the CTAs' partials
 __global__ void __launch_bounds__(256)
@@ -269,10 +301,12 @@ lml_grad_colsum_kernel(int np, int64_t nparts, double* __restrict__ partial_all,
 __global__ void __launch_bounds__(64)
 lml_grad_finalize_kernel(int d, int64_t nparts, const double* __restrict__ partial_all, int64_t stridePartial,
                          const double* __restrict__ theta_all, int64_t strideTheta, int mode, double eta, int noisy,
-                         const double* __restrict__ varK, double* __restrict__ out_all, int64_t strideOut, int B) {
+                         const double* __restrict__ varK, double* __restrict__ out_all, int64_t strideOut, int B,
+                         int ktype) {
   const int z = blockIdx.x * blockDim.x + threadIdx.x;
   if (z >= B) return;
-  const int np = 2 * d + 2;
+  const int np = 2 * d + 3;
+  const double cd = kernel_diag_coef(ktype);   // d diag(K) / d theta_m on gradient block m (optz/GpHparaGrad.py:40-50)
   const double* tot = partial_all + z * stridePartial + nparts * np;
   const double* th = theta_all + z * strideTheta;
   double* out = out_all + z * strideOut;
@@ -283,9 +317,11 @@ lml_grad_finalize_kernel(int d, int64_t nparts, const double* __restrict__ parti
   for (int m = 0; m < d; m++) {
     const double DG = tot[d + 2 + m];
     sdg += DG;
-    sdg_th += 2.0 * th[m] * DG;
-    out[GEGP_OUT_GRAD + m] = vk * (tot[m] + (precon ? 2.0 * eta * DG : 0.0));
+    sdg_th += cd * th[m] * DG;
+    out[GEGP_OUT_GRAD + m] = vk * (tot[m] + (precon ? cd * eta * DG : 0.0));
   }
+  // diag(K) does not depend on the kernel hyper-parameter: no nugget term (optz/GpHparaGrad.py:52-55, 111-123)
+  out[GEGP_OUT_DKERN] = vk * tot[2 * d + 2];
   if (noisy) {
     out[GEGP_OUT_DVARK] = SK + eta * (precon ? (DV + sdg_th) : (DV + sdg));
     out[GEGP_OUT_DVARF] = (precon ? 1.0 + eta : 1.0) * DV;
@@ -293,8 +329,8 @@ lml_grad_finalize_kernel(int d, int64_t nparts, const double* __restrict__ parti
   }
 }
 
-size_t lml_grad_partial_doubles(int n, int d) {   // per-CTA partials followed by the 2d+2 column sums
-  return (size_t)n * ((n + GB - 1) / GB) * (2 * d + 2) + (size_t)(2 * d + 2);
+size_t lml_grad_partial_doubles(int n, int d) {   // per-CTA partials followed by the 2d+3 column sums
+  return (size_t)n * ((n + GB - 1) / GB) * (2 * d + 3) + (size_t)(2 * d + 3);
 }
 
 int launch_lml_grad(const Ctx& ctx, const Geom& gm, const double* theta, int64_t strideTheta, const double* Kinv,
@@ -303,14 +339,13 @@ int launch_lml_grad(const Ctx& ctx, const Geom& gm, const double* theta, int64_t
                     double* partial, int64_t stridePartial, double* out, int64_t strideOut, int quad) {
   const int d = gm.d;
   const size_t smem = (size_t)(d * GB + (d + 1) * GB + 2 * d) * sizeof(double);
-  static size_t smem_set[3] = {0, 0, 0};
   if (quad < 0 || quad > 2) return -906;
+  if (smem > (size_t)GEGP_MAX_DYN_SMEM) return -907;
   const bool wide = d >= 8;
-  if (smem > 48 * 1024 && smem > smem_set[quad]) {   // (only reached with d > 20: the wide kernels)
-    if (quad == 0) GEGP_SET_SMEM((lml_grad_kernel<0, true>), smem);
-    else if (quad == 1) GEGP_SET_SMEM((lml_grad_kernel<1, true>), smem);
-    else GEGP_SET_SMEM((lml_grad_kernel<2, true>), smem);
-    smem_set[quad] = smem;
+  if (smem > 48 * 1024) {   // (only reached with d > 20: the wide kernels); once per device, largest size
+    if (quad == 0) GEGP_SET_SMEM((lml_grad_kernel<0, true>), GEGP_MAX_DYN_SMEM);
+    else if (quad == 1) GEGP_SET_SMEM((lml_grad_kernel<1, true>), GEGP_MAX_DYN_SMEM);
+    else GEGP_SET_SMEM((lml_grad_kernel<2, true>), GEGP_MAX_DYN_SMEM);
   }
   dim3 grid((gm.n + GB - 1) / GB, gm.n, ctx.batch);
 #define GEGP_LAUNCH_LML_GRAD(Q, W)                                                                                       \
@@ -323,12 +358,12 @@ int launch_lml_grad(const Ctx& ctx, const Geom& gm, const double* theta, int64_t
 #undef GEGP_LAUNCH_LML_GRAD
   GEGP_CHECK_LAUNCH();
   const int64_t nparts = (int64_t)grid.x * grid.y;
-  const int np = 2 * d + 2;
+  const int np = 2 * d + 3;
   lml_grad_colsum_kernel<<<dim3(np, ctx.batch), 256, 0, ctx.stream>>>(np, nparts, partial, stridePartial);
   GEGP_CHECK_LAUNCH();
   lml_grad_finalize_kernel<<<(ctx.batch + 63) / 64, 64, 0, ctx.stream>>>(d, nparts, partial, stridePartial, theta,
                                                                         strideTheta, mode, eta, noisy, varK, out,
-                                                                        strideOut, ctx.batch);
+                                                                        strideOut, ctx.batch, gm.ktype);
   GEGP_CHECK_LAUNCH();
   return 0;
 }
@@ -421,9 +456,11 @@ int launch_predict_grad_rows(const Ctx& ctx, int N, int d, const double* Z, int6
 // CTA (i, k):  out[0][i,k] = sum_col d2k*[i,k,col] a[col]    (a = K^-1 (y - H beta)      -> d2mu/dx2)
 //              out[1][i,k] = sum_col d2k*[i,k,col] b[col]    (b = K^-1 k*                -> term1 of d2sig2/dx2)
 //              out[2][i,k] = z_i . z_k                        (forward-solved derivative rows -> term2)
-// with r = x_train - x*:  value entry a      : (4 th_i th_k r_i r_k - 2 th_i delta_ik) k
-//   gradient entry (j, a): (4 th_i th_j (delta_ik r_j + delta_jk r_i) + 4 delta_ij th_i th_k r_k
-//                           - 8 th_i th_j th_k r_i r_j r_k) k
+// with r = x_train - x* and the radial profile f1, f2, f3 (kernels.h; Gaussian kernel: f2 = k, f1 = f3 = -k):
+//   value entry a        : 4 th_i th_k r_i r_k f2 + 2 th_i delta_ik f1
+//   gradient entry (j, a): (4 th_i th_j (delta_ik r_j + delta_jk r_i) + 4 delta_ij th_i th_k r_k) f2
+//                           + 8 th_i th_j th_k r_i r_j r_k f3
+// (kernel/KernelMatern5f2.py:54-96, 272-331 and kernel/KernelRatQuad.py:54-97, 556-633 for the other two families)
 __global__ void __launch_bounds__(256)
 predict_hess_kernel(Geom gm, const double* __restrict__ theta, const double* __restrict__ xs,
                     const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ Z,
@@ -438,22 +475,22 @@ predict_hess_kernel(Geom gm, const double* __restrict__ theta, const double* __r
     double e = 0.0;
     for (int q = 0; q < d; q++) {
       const double r = xp[q] - xs[q];
-      e -= theta[q] * (r * r);
+      e += theta[q] * (r * r);
     }
-    const double kk = exp(e);
+    const RadialProfile ph = radial_profile(gm.ktype, gm.khp, e);
     const double ri = xp[i] - xs[i], rk = xp[k] - xs[k];
-    const double hv = (4.0 * thi * thk * ri * rk - ((i == k) ? 2.0 * thi : 0.0)) * kk;
+    const double hv = 4.0 * thi * thk * ri * rk * ph.f2 + ((i == k) ? 2.0 * thi * ph.f1 : 0.0);
     s0 += hv * a[p];
     s1 += hv * b[p];
     const int sp = gm.slot ? gm.slot[p] : p;
     if (sp >= 0) {
       for (int j = 0; j < d; j++) {
         const double thj = theta[j], rj = xp[j] - xs[j];
-        double v = -8.0 * thi * thj * thk * ri * rj * rk;
+        double v = 0.0;
         if (i == k) v += 4.0 * thi * thj * rj;
         if (j == k) v += 4.0 * thi * thj * ri;
         if (i == j) v += 4.0 * thi * thk * rk;
-        v *= kk;
+        v = v * ph.f2 + 8.0 * thi * thj * thk * ri * rj * rk * ph.f3;
         const int col = n + j * ng + sp;
         s0 += v * a[col];
         s1 += v * b[col];

@@ -141,16 +141,34 @@ class GaussianProcess:
         assert isinstance(dim, int), "dim must be an integer"
         assert isinstance(use_grad, bool), "use_grad must be of type bool"
         assert isinstance(kernel_type, str), "kernel_type must be of type str"
-        if kernel_type != "SqExp":
-            raise Exception("Kernel type is not available (the B200 path implements the Gaussian kernel 'SqExp')")
+        if kernel_type not in L.KERNEL_IDS:
+            raise Exception("Kernel type is not available")                  # kernel/Kernel.py:105-107
         if mean_fun_type != "poly_ord_0":
             raise Exception(f"mean_fun_type = {mean_fun_type} not available")
         self.dim, self.use_grad, self.kernel_type = dim, use_grad, kernel_type
         self.mean_fun_type, self.n_beta_coeff, self.beta_var_npara = mean_fun_type, 1, 1
         self.set_wellcond_mtd(wellcond_mtd)
         self.path_data_surr, self.surr_name = path_data_surr, surr_name
-        self.hp_kernel = None
+        # kernel family (kernel/Kernel.py:27-113): extra hyper-parameter and its range per kernel file
+        # (kernel/KernelSqExp.py:577-578, kernel/KernelMatern5f2.py:649-650: none; kernel/KernelRatQuad.py:849-850: alpha)
+        self._kid = L.KERNEL_IDS[kernel_type]
+        if kernel_type == "RatQu":
+            self.hp_kernel_default, self.hp_kernel_range = 2, [1e-3, 10]
+        else:
+            self.hp_kernel_default, self.hp_kernel_range = None, [np.nan, np.nan]
+        self.kernel_has_hp = self.hp_kernel_default is not None
+        self.hp_kernel = self.hp_kernel_default
+        self._diag_coef = 5.0 / 3.0 if kernel_type == "Ma5f2" else 2.0      # gamma_i^2 = c theta_i
+        self.theta2gamma = lambda theta: np.sqrt(self._diag_coef * np.asarray(theta))
+        self.gamma2theta = lambda gamma: np.asarray(gamma) ** 2 / self._diag_coef
+        self.calc_Kern_precon = lambda n_eval, n_grad, theta, calc_grad=False, b_return_vec=False: \
+            GaussianProcess.calc_Kern_precon(n_eval, n_grad, theta, calc_grad, b_return_vec, diag_coef=self._diag_coef)
         self._pred = None
+
+    def _kern(self, hp_vals=None):
+        """(GEGP_KERNEL_* id, kernel hyper-parameter) handed to every device call."""
+        hp = self.hp_kernel_default if (hp_vals is None or hp_vals.kernel is None) else hp_vals.kernel
+        return self._kid, (0.0 if hp is None else float(np.ravel(hp)[0]))
 
     # ------------------------------------------------------------------ configuration
     def set_wellcond_mtd(self, wellcond_mtd):
@@ -181,16 +199,18 @@ class GaussianProcess:
         return 0.5 * np.asarray(gamma) ** 2            # kernel/KernelSqExp.py:586-588
 
     @staticmethod
-    def calc_Kern_precon(n_eval, n_grad, theta, calc_grad=False, b_return_vec=False):
-        """Analytic preconditioner of the Gaussian kernel (kernel/KernelSqExp.py:591-605 with
-        kernel/KernelCommon.py:14-49): p = [1_n, gamma_i (x) 1_ng], gamma = sqrt(2 theta), d gamma_i / d theta_i =
-        1 / gamma_i.  Host helper kept for API parity (the kernels form p themselves, csrc/build.cu prep_p_kernel);
-        like the reference it always returns the derivative, as an [N, d] array or a stack of diagonal matrices."""
+    def calc_Kern_precon(n_eval, n_grad, theta, calc_grad=False, b_return_vec=False, diag_coef=2.0):
+        """Analytic preconditioner (kernel/KernelSqExp.py:591-605, kernel/KernelMatern5f2.py:665-680,
+        kernel/KernelRatQuad.py:863-877 with kernel/KernelCommon.py:14-49): p = [1_n, gamma_i (x) 1_ng],
+        gamma = sqrt(c theta) with c = 2 (Gaussian, rational quadratic) or 5/3 (Matern-5/2), d gamma_i / d theta_i =
+        c / (2 gamma_i).  Host helper kept for API parity (the kernels form p themselves, csrc/build.cu prep_p_kernel);
+        like the reference it always returns the derivative, as an [N, d] array or a stack of diagonal matrices.
+        Called on the class it is the Gaussian kernel's; instances bind their own kernel's coefficient."""
         theta = np.asarray(theta, dtype=float)
-        gamma = np.sqrt(2 * theta)
+        gamma = np.sqrt(diag_coef * theta)
         pvec = np.hstack((np.ones(n_eval), np.kron(gamma, np.ones(n_grad))))
         dim, n_data = theta.size, n_eval + n_grad * theta.size
-        dgam = 1 / gamma
+        dgam = diag_coef / (2 * gamma)
         if b_return_vec:
             grad = np.zeros((n_data, dim))
             for i in range(dim):
@@ -229,7 +249,9 @@ class GaussianProcess:
         if n_eval == 1:
             return eta_Kbase, eta_Kbase
         if self.wellcond_mtd == "precon":
-            return eta_Kbase, H.nugget_precon_sqexp(n_eval, self.dim, self.cond_max_target)
+            if self.kernel_type == "Ma5f2":
+                return eta_Kbase, H.nugget_precon_matern52(n_eval, self.dim, self.cond_max_target)
+            return eta_Kbase, H.nugget_precon_sqexp(n_eval, self.dim, self.cond_max_target)   # SqExp and RatQu share it
         if "rescale" in self.wellcond_mtd:
             return eta_Kbase, self.calc_nugget_Kfull_vreq(n_eval)
         if self.cond_eta_set_mtd == "Kbase_eta":
@@ -253,15 +275,15 @@ class GaussianProcess:
         b = hp_optz_info.bvec_log_optz
         v[b] = 10 ** v[b]
         theta = v[hp_optz_info.idx_theta] if hp_optz_info.has_theta else None
+        kernel = float(v[hp_optz_info.idx_kernel][0]) if hp_optz_info.has_kernel else None
         varK = float(v[hp_optz_info.idx_varK]) if hp_optz_info.has_varK else None
         var_fval = float(v[hp_optz_info.idx_var_fval]) if hp_optz_info.has_var_fval else None
         var_fgrad = float(v[hp_optz_info.idx_var_fgrad]) if hp_optz_info.has_var_fgrad else None
-        return self.make_hp_class(None, theta, None, varK, var_fval, var_fgrad)
+        return self.make_hp_class(None, theta, kernel, varK, var_fval, var_fgrad)
 
     def set_hp_optz_info(self, has_theta, has_kernel=False, has_varK=False, has_var_fval=False, has_var_fgrad=False):
         """optz/GpHparaOptz.py:44-138."""
-        assert not has_kernel, "the Gaussian kernel has no extra hyper-parameter"
-        n_hp = has_theta * self.dim + has_varK + has_var_fval + has_var_fgrad
+        n_hp = has_theta * self.dim + has_kernel + has_varK + has_var_fval + has_var_fgrad
         blog = np.zeros(n_hp, dtype=bool)
         cnt = 0
         empty = np.array([], dtype=int)
@@ -270,6 +292,12 @@ class GaussianProcess:
             idx_theta = np.arange(cnt, cnt + self.dim, dtype=int)
             cnt += self.dim
             blog[idx_theta] = self.optz_log_hp_theta
+        idx_kernel = empty
+        if has_kernel:
+            assert self.kernel_has_hp, "Kernel must have hyperaparamters if b_optz_hp_kernel is set to True"
+            idx_kernel = np.array([cnt])
+            cnt += 1
+            blog[idx_kernel] = self.optz_log_hp_kernel
         idx_varK = idx_vf = idx_vg = empty
         if has_varK:
             idx_varK, cnt = cnt, cnt + 1
@@ -280,13 +308,14 @@ class GaussianProcess:
         if has_var_fgrad:
             idx_vg, cnt = cnt, cnt + 1
             blog[idx_vg] = self.optz_log_hp_var
-        return HparaOptzInfo(n_hp=n_hp, has_theta=has_theta, idx_theta=idx_theta, has_kernel=False, idx_kernel=empty,
+        return HparaOptzInfo(n_hp=n_hp, has_theta=has_theta, idx_theta=idx_theta, has_kernel=bool(has_kernel),
+                             idx_kernel=idx_kernel,
                              has_varK=has_varK, idx_varK=idx_varK, has_var_fval=has_var_fval, idx_var_fval=idx_vf,
                              has_var_fgrad=has_var_fgrad, idx_var_fgrad=idx_vg, bvec_log_optz=blog)
 
     def setup_hp_idx4optz(self):
-        self.hp_info_optz_lkd = self.set_hp_optz_info(True, False, self.b_has_noisy_data, self.b_optz_var_fval,
-                                                      self.b_optz_var_fgrad)
+        self.hp_info_optz_lkd = self.set_hp_optz_info(True, self.b_optz_hp_kernel and self.kernel_has_hp,
+                                                      self.b_has_noisy_data, self.b_optz_var_fval, self.b_optz_var_fgrad)
 
     # ------------------------------------------------------------------ data
     def set_data(self, x_eval, fval, std_fval, grad=None, std_grad=None, bvec_use_grad=None):
@@ -467,7 +496,7 @@ class GaussianProcess:
             noise_vec = self.calc_noise_vec(hp_vals)
         noise = None if not np.any(noise_vec) else bk.to_dev(np.asarray(noise_vec, dtype=float) / varK)
         X, slot, ng, N = self._X_dev, self._slot_dev, self.n_grad, self.n_data
-        kw = dict(n_g=ng, slot=slot)
+        kw = dict(n_g=ng, slot=slot, kernel=self._kern(hp_vals))
         Kern, _ = bk.build_cov(X, theta, mode=L.MODE_BASE, eta=0.0, **kw)
         idx_etaK_argmax = None
         precon = self.wellcond_mtd == "precon"
@@ -476,7 +505,7 @@ class GaussianProcess:
         if self.cond_eta_is_const:
             etaK = self._etaK
         else:
-            etaK, idx_etaK_argmax = self._variable_eta(theta, noise, Kern)
+            etaK, idx_etaK_argmax = self._variable_eta(theta, noise, Kern, kernel=self._kern(hp_vals))
         if precon:
             Kt, p = bk.build_cov(X, theta, noise=noise, mode=L.MODE_PRECON, eta=etaK, varK=varK, **kw)
             Kcor = DeviceMatrix(Kt / varK - etaK * torch.eye(N, dtype=Kt.dtype, device=Kt.device))
@@ -512,11 +541,11 @@ class GaussianProcess:
         self._time_chofac += time.time() - t0
         return DeviceMatrix(Kern), Kcor, Kcov, Kcov_chofac, condK, etaK, idx_etaK_argmax
 
-    def _variable_eta(self, theta, noise_div, Kern=None):
+    def _variable_eta(self, theta, noise_div, Kern=None, kernel=None):
         """Variable nugget from the Gershgorin row sums of Kcor (precon) or of the noise-free Kern (otherwise):
         eta = max_row sum|.| / (cond_max_target - 1)  (kernel/Kernel.py:229-234, 269-274) -> (eta, argmax row)."""
         self._ensure_device()
-        kw = dict(n_g=self.n_grad, slot=self._slot_dev)
+        kw = dict(n_g=self.n_grad, slot=self._slot_dev, kernel=kernel if kernel is not None else self._kern())
         if self.wellcond_mtd == "precon":
             M = bk.build_cov(self._X_dev, theta, noise=noise_div, mode=L.MODE_PRECON, eta=0.0, **kw)[0]
         else:
@@ -530,7 +559,7 @@ class GaussianProcess:
         if self.cond_eta_is_const:
             return self._etaK
         theta, noise_div, _ = self._cond_matrix_args(hp_vals)
-        return self._variable_eta(theta, noise_div)[0]
+        return self._variable_eta(theta, noise_div, kernel=self._kern(hp_vals))[0]
 
     # ------------------------------------------------------------------ likelihood
     def calc_lkd_varK_pnlt(self, varK, fval_vec):
@@ -541,14 +570,19 @@ class GaussianProcess:
         mx = max(varK - self.lkd_varK_pnlt_c2 * var_fval, 0)
         return self.lkd_varK_pnlt_c1 * var_fval * mx ** 2, 2 * self.lkd_varK_pnlt_c1 * var_fval * mx
 
-    def _eval_rows(self, theta_rows, *, want_grad, varK_rows=None, noise_vec=None, pnlt_grad=0.0, eta=None):
+    def _eval_rows(self, theta_rows, *, want_grad, varK_rows=None, noise_vec=None, pnlt_grad=0.0, eta=None,
+                   khp_rows=None):
         """Device evaluation of B candidate rows -> torch [B, 9+d] (see GEGP_OUT_* in include/gegp.h).
 
         Noise-free evaluations of a fixed data set replay a captured CUDA graph (the optimiser repeats the same-shaped
         evaluation hundreds of times); everything else goes through the plain stream path."""
         self._ensure_device()
         kw = dict(n_g=self.n_grad, slot=self._slot_dev, mode=self._mode, eta=self._etaK if eta is None else eta,
-                  pnlt_grad=pnlt_grad, want_grad=want_grad)
+                  pnlt_grad=pnlt_grad, want_grad=want_grad, kernel=self._kern())
+        if self.kernel_has_hp:        # one kernel hyper-parameter per candidate row (default: the kernel's default value)
+            nrow = int(np.prod(tuple(theta_rows.shape))) // self.dim
+            kw["kernel_hp_batch"] = (np.full(nrow, float(self.hp_kernel_default)) if khp_rows is None
+                                     else np.asarray(khp_rows, dtype=float).reshape(-1))
         single = int(np.prod(tuple(theta_rows.shape))) == self.dim   # one candidate: the optimiser's inner loop
         if self.use_cuda_graphs and single and noise_vec is None and pnlt_grad == 0.0 and eta is None:
             th = theta_rows if hasattr(theta_rows, "is_cuda") else np.asarray(theta_rows, dtype=float)
@@ -570,10 +604,11 @@ class GaussianProcess:
         eta = None if self.cond_eta_is_const else self._eta_for(hp_vals)
         self._eta_used = self._etaK if eta is None else eta
         hi = self.hp_info_optz_lkd
+        khp = np.array([self._kern(hp_vals)[1]]) if self.kernel_has_hp else None
         if self.b_has_noisy_data:
             noise = self.calc_noise_vec(hp_vals)
             o = self._eval_rows(theta[None, :], want_grad=need_inv, varK_rows=np.array([hp_vals.varK]),
-                                noise_vec=noise, eta=eta).cpu().numpy()[0]
+                                noise_vec=noise, eta=eta, khp_rows=khp).cpu().numpy()[0]
             if o[L.OUT_INFO] != 0:
                 cond, cond_grad = self._cond_on_failure(hp_vals, calc_grad)
                 return LkdInfo(cond=cond, cond_grad=cond_grad), False
@@ -582,6 +617,8 @@ class GaussianProcess:
             if calc_grad:
                 g = np.zeros(hi.n_hp)
                 g[hi.idx_theta] = o[L.OUT_GRAD:L.OUT_GRAD + d]
+                if hi.has_kernel:
+                    g[hi.idx_kernel] = o[L.OUT_DKERN]
                 if hi.has_varK:
                     g[hi.idx_varK] = o[L.OUT_DVARK]
                 if hi.has_var_fval:
@@ -596,17 +633,21 @@ class GaussianProcess:
             return info, True
         pn_val = pn_grad = 0.0
         if self.lkd_varK_pnlt_use:   # the penalty slope depends on sigma^2: one value-only pass first
-            o0 = self._eval_rows(theta[None, :], want_grad=False, eta=eta).cpu().numpy()[0]
+            o0 = self._eval_rows(theta[None, :], want_grad=False, eta=eta, khp_rows=khp).cpu().numpy()[0]
             pn_val, pn_grad = self.calc_lkd_varK_pnlt(o0[L.OUT_SIGMA2], self.get_scl_eval_data()[0])
-        o = self._eval_rows(theta[None, :], want_grad=need_inv, pnlt_grad=pn_grad, eta=eta).cpu().numpy()[0]
+        o = self._eval_rows(theta[None, :], want_grad=need_inv, pnlt_grad=pn_grad, eta=eta, khp_rows=khp).cpu().numpy()[0]
         if o[L.OUT_INFO] != 0:
             cond, cond_grad = self._cond_on_failure(hp_vals, calc_grad)
             return LkdInfo(cond=cond, cond_grad=cond_grad), False
         info = LkdInfo(hp_beta=np.array([o[L.OUT_BETA]]), hp_varK=o[L.OUT_SIGMA2], ln_det_Kmat=o[L.OUT_LOGDET])
         if calc_lkd:
             info.ln_lkd = o[L.OUT_LML] - pn_val
-            if calc_grad:
-                info.ln_lkd_grad = o[L.OUT_GRAD:L.OUT_GRAD + d].copy()
+            if calc_grad:       # hyper-parameter order of the optimiser: theta_1..d, then the kernel's own (RatQu alpha)
+                g = np.zeros(hi.n_hp)
+                g[hi.idx_theta] = o[L.OUT_GRAD:L.OUT_GRAD + d]
+                if hi.has_kernel:
+                    g[hi.idx_kernel] = o[L.OUT_DKERN]
+                info.ln_lkd_grad = g
         if calc_cond:
             info.cond, info.cond_grad = self._cond_from_workspace(hp_vals, calc_grad)
             if self.wellcond_mtd != "precon" and info.cond > self.cond_max_abs:
@@ -634,7 +675,8 @@ class GaussianProcess:
         hi, d = self.hp_info_optz_lkd, self.dim
         theta = np.asarray(hp_vals.theta, dtype=float)
         noisy = self.b_has_noisy_data
-        kw = dict(n_g=self.n_grad, slot=self._slot_dev, eta=getattr(self, "_eta_used", self._etaK), noisy=noisy, varK=varK)
+        kw = dict(n_g=self.n_grad, slot=self._slot_dev, eta=getattr(self, "_eta_used", self._etaK), noisy=noisy, varK=varK,
+                  kernel=self._kern(hp_vals))
         qa = bk.quad_grad(self._X_dev, theta, res["v_max"], **kw).cpu().numpy()
         qi = bk.quad_grad(self._X_dev, theta, res["v_min"], **kw).cpu().numpy()
         q = (qa - res["cond"] * qi) / max(res["lam_min"], 1e-16)     # lam_min of Kcov (varK included)
@@ -646,6 +688,8 @@ class GaussianProcess:
         g = np.zeros(hi.n_hp)
         if hi.has_theta:
             g[hi.idx_theta] = q[L.OUT_GRAD:L.OUT_GRAD + d]
+        if hi.has_kernel:
+            g[hi.idx_kernel] = q[L.OUT_DKERN]
         if self.b_has_noisy_data:
             if hi.has_varK:
                 g[hi.idx_varK] = q[L.OUT_DVARK]
@@ -668,7 +712,7 @@ class GaussianProcess:
             mode = L.MODE_PRECON_COV
             v["Kinv"][:, :N].mul_(v["pinv"][:, None]).mul_(v["pinv"][None, :])
         bk.build_cov(self._X_dev, theta, n_g=self.n_grad, slot=self._slot_dev, noise=noise, mode=mode,
-                     eta=getattr(self, "_eta_used", self._etaK), varK=varK, out=v["U"])
+                     eta=getattr(self, "_eta_used", self._etaK), varK=varK, out=v["U"], kernel=self._kern(hp_vals))
         if self.cond_norm == "fro":   # optz/GpHparaCon.py:237-261
             want_w = calc_grad and self.wellcond_mtd != "precon"
             cond, W = bk.cond_fro(v["U"], v["Kinv"], N, want_w)
@@ -676,7 +720,7 @@ class GaussianProcess:
                 return cond, None
             q = bk.weighted_grad(self._X_dev, theta, W, n_g=self.n_grad, slot=self._slot_dev,
                                  eta=getattr(self, "_eta_used", self._etaK), noisy=self.b_has_noisy_data,
-                                 varK=varK).cpu().numpy()
+                                 varK=varK, kernel=self._kern(hp_vals)).cpu().numpy()
             return cond, self._hp_row_to_grad(q)
         if self.cond_norm != 2:
             raise Exception(f'cond_norm must be either 2 or "fro" but it is {self.cond_norm}')
@@ -690,7 +734,7 @@ class GaussianProcess:
         try:
             theta, noise, varK = self._cond_matrix_args(hp_vals)
             K = bk.build_cov(self._X_dev, theta, n_g=self.n_grad, slot=self._slot_dev, noise=noise, mode=self._mode,
-                             eta=getattr(self, "_eta_used", self._etaK), varK=varK)[0]
+                             eta=getattr(self, "_eta_used", self._etaK), varK=varK, kernel=self._kern(hp_vals))[0]
             res = bk.cond2_of_matrix(K, self.n_data)
             self._last_cond = res
             return float(res["cond"]), (self._cond_grad_from_vectors(hp_vals, res, varK) if calc_grad else None)
@@ -710,9 +754,19 @@ class GaussianProcess:
         th = rows[:, hi.idx_theta].copy()
         if self.optz_log_hp_theta:
             th = 10 ** th
-        cand = bk.to_dev(th)
-        table = parallel.sharded_eval(lambda c: self._eval_rows(c, want_grad=calc_grad), cand, self.dist_group,
-                                      width=L.out_len(self.dim))
+        cols = [th]
+        if self.kernel_has_hp:      # the kernel's own hyper-parameter rides along as one more candidate column
+            kh = rows[:, hi.idx_kernel[0]].copy() if hi.has_kernel else np.full(rows.shape[0], float(self.hp_kernel_default))
+            if hi.has_kernel and self.optz_log_hp_kernel:
+                kh = 10 ** kh
+            cols.append(kh[:, None])
+        cand = bk.to_dev(np.hstack(cols))
+        d = self.dim
+
+        def eval_shard(c):
+            return self._eval_rows(c[:, :d].contiguous(), want_grad=calc_grad,
+                                   khp_rows=c[:, d].cpu().numpy() if self.kernel_has_hp else None)
+        table = parallel.sharded_eval(eval_shard, cand, self.dist_group, width=L.out_len(self.dim))
         return table.cpu().numpy()
 
     # ------------------------------------------------------------------ optimiser callbacks (optz/OptzLkd.py:16-113)
@@ -769,6 +823,8 @@ class GaussianProcess:
 
         if hp_optz_info.has_theta:
             fill(hp_optz_info.idx_theta, self.hp_theta_all[lo_i:hi_i, :], self.hp_theta_range)
+        if hp_optz_info.has_kernel:     # optz/GpHparaX0.py:100-111
+            fill(hp_optz_info.idx_kernel, self.hp_kernel_all[lo_i:hi_i], self.hp_kernel_range)
         if hp_optz_info.has_varK:
             fill(hp_optz_info.idx_varK, self.hp_varK_all[lo_i:hi_i], self.hp_varK_range)
         if hp_optz_info.has_var_fval:
@@ -837,7 +893,8 @@ class GaussianProcess:
         beta = np.array([np.mean(fval)])
         vf = None if self.known_eps_fval else self.hp_var_fval_init
         vg = None if ((self.use_grad is False) or self.known_eps_fgrad) else self.hp_var_fgrad_init
-        return self.make_hp_class(beta, self.hp_theta_init * np.ones(self.dim), None, self.hp_varK_init, vf, vg)
+        return self.make_hp_class(beta, self.hp_theta_init * np.ones(self.dim), self.hp_kernel_default, self.hp_varK_init,
+                                  vf, vg)
 
     def optz_closed_form_hp(self, hp_vals):
         info, _ = self.calc_lkd_all(hp_vals, calc_lkd=False, calc_cond=False, calc_grad=False)
@@ -908,7 +965,7 @@ class GaussianProcess:
     def _can_batch_fit(self):
         """The batched objective covers the noise-free, unconstrained (precon) fit with a constant nugget."""
         return (not self.b_has_noisy_data) and (not self.b_use_cond_cstr) and self.cond_eta_is_const \
-            and (not self.lkd_varK_pnlt_use) and self.optz_log_hp_theta
+            and (not self.lkd_varK_pnlt_use) and self.optz_log_hp_theta and (not self.kernel_has_hp)
 
     def _optz_multistart_lockstep(self, hp_x0_all, optz_bound, opt):
         """Batch point B (optz/OptzLkd.py:249-270): every start row is its own SLSQP instance; their objective requests
@@ -1051,6 +1108,7 @@ class GaussianProcess:
         self.time_hp_optz_all[i], self.time_chofac_all[i], self.time_pick_hp0_all[i] = time_hp_optz, time_chofac, time_pick_hp0
         self.hp_beta_all[i, :], self.hp_theta_all[i, :] = hp_vals.beta, hp_vals.theta
         self.hp_varK_all[i] = hp_vals.varK
+        self.hp_kernel_all[i] = np.nan if hp_vals.kernel is None else hp_vals.kernel
         self.hp_var_fval_all[i] = np.nan if hp_vals.var_fval is None else hp_vals.var_fval
         self.hp_var_fgrad_all[i] = np.nan if hp_vals.var_fgrad is None else hp_vals.var_fgrad
         self.min_nugget_all[i] = self._eta_Kgrad if self.use_grad else self._eta_Kbase
@@ -1067,7 +1125,8 @@ class GaussianProcess:
     def set_hp_from_idx(self, i_optz):
         vf = None if np.isnan(self.hp_var_fval_all[i_optz]) else self.hp_var_fval_all[i_optz]
         vg = None if np.isnan(self.hp_var_fgrad_all[i_optz]) else self.hp_var_fgrad_all[i_optz]
-        self.hp_vals = self.make_hp_class(self.hp_beta_all[i_optz, :], self.hp_theta_all[i_optz, :], None,
+        kh = None if np.isnan(self.hp_kernel_all[i_optz]) else self.hp_kernel_all[i_optz]
+        self.hp_vals = self.make_hp_class(self.hp_beta_all[i_optz, :], self.hp_theta_all[i_optz, :], kh,
                                           self.hp_varK_all[i_optz], vf, vg)
 
     def set_hpara(self, method2set_hp, i_optz, hp_vals=None, calc_cond=False):
@@ -1099,10 +1158,11 @@ class GaussianProcess:
         beta = float(np.atleast_1d(hp.beta)[0])
         eta = self._etaK
         if not self.cond_eta_is_const:   # variable nugget: Gershgorin row sums with varK := 1 (kernel/Kernel.py:196-197)
-            eta = self._variable_eta(np.asarray(hp.theta, dtype=float), None if noise is None else bk.to_dev(noise))[0]
+            eta = self._variable_eta(np.asarray(hp.theta, dtype=float), None if noise is None else bk.to_dev(noise),
+                                     kernel=self._kern(hp))[0]
         self._pred = bk.predict_setup(self._X_dev, self._y_dev, np.asarray(hp.theta, dtype=float), beta,
                                       n_g=self.n_grad, slot=self._slot_dev, noise=noise, mode=self._mode,
-                                      eta=eta)
+                                      eta=eta, kernel=self._kern(hp))
         self.data_vec = self._y_host
         self.etaK_eval = eta
         self.condK = None

@@ -81,3 +81,11 @@ def nugget_precon_sqexp(n_eval: int, dim: int, cond_max: float) -> float:
     root = np.sqrt(1.0 + 4.0 * dim)
     ub = 0.5 * (n_eval - 1) * (1.0 + root) * np.exp(-(1.0 + 2.0 * dim - root) / (4.0 * dim))
     return (1.0 + ub) / (cond_max - 1.0)
+
+
+def nugget_precon_matern52(n_eval: int, dim: int, cond_max: float) -> float:
+    """Gershgorin-bound nugget of the preconditioned Matern-5/2 matrix (base/GpWellCond.py:130-134)."""
+    r3 = np.sqrt(3.0 * dim)
+    al = (r3 - 1.0 + np.sqrt(15.0 * dim + 2.0 * r3 + 1.0)) / (2.0 * (3.0 * dim + r3))
+    ub = (n_eval - 1) * (1.0 + (dim + r3) * al + dim * (1.0 + r3) * al ** 2) * np.exp(-r3 * al)
+    return (1.0 + ub) / (cond_max - 1.0)

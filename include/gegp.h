@@ -26,8 +26,16 @@
  *   - N = n + n_g*d; row/column order is dimension-major: value of point a -> a, d/dx_i at gradient slot g ->
  *     n + i*n_g + g (base/CommonFun.py:170, kernel/Kernel.py:353);
  *   - grad_slot[n] (int32, device) maps a point to its gradient slot or -1; NULL means all points carry gradients;
+ *   - every function that evaluates the kernel takes (int kernel, double kernel_hp) right after theta: the kernel
+ *     family GEGP_KERNEL_* and its extra hyper-parameter (alpha of the rational-quadratic kernel; ignored otherwise);
  *   - every call is asynchronous on `stream` (a cudaStream_t), never allocates, never throws;
- *   - return value: 0 ok; < 0 bad argument (-(index of the argument)) or -1000-cudaError for a launch failure.
+ *   - re-entrant: no call keeps mutable state between or across calls except caches that are keyed and locked
+ *     (tensor maps) and pooled per call (the look-ahead streams of the factorisation); concurrent calls from several
+ *     host threads and on several devices are supported.  gegp_set_option and gegp_profile_* are process-wide tuning /
+ *     instrumentation hooks and must not race with running calls;
+ *   - return value: 0 ok; < 0 bad argument (a small negative code naming the argument: its position in the ABI-3
+ *     argument list, i.e. not counting (kernel, kernel_hp); -50: bad kernel family / kernel hyper-parameter) or
+ *     -1000-cudaError for a launch failure.
  *     Numerical failure (matrix not positive definite) is reported LAPACK-style in a device int / the
  *     GEGP_OUT_INFO slot: 0 ok, k > 0 leading minor of order k is not positive definite.
  */
@@ -40,12 +48,18 @@
 extern "C" {
 #endif
 
-#define GEGP_ABI_VERSION 3
+#define GEGP_ABI_VERSION 4
 
 /* covariance assembly modes (kernel/Kernel.py:220-237 vs :268-277) */
 #define GEGP_MODE_BASE 0       /* varK * (K + diag(noise) + eta*I)                                  */
 #define GEGP_MODE_PRECON 1     /* varK * (P^-1 (K + diag(noise)) P^-1 + eta*I), P = diag sqrt(diag)    */
 #define GEGP_MODE_PRECON_COV 2 /* varK * (K + diag(noise) + eta*diag(K + noise))  (= P * PRECON * P)   */
+
+/* kernel families (kernel/Kernel.py:27-107 binds one of three kernel files); kernel_hp is the extra hyper-parameter
+ * of the family (alpha of the rational-quadratic kernel, kernel/KernelRatQuad.py:849-850; ignored by the others) */
+#define GEGP_KERNEL_SQEXP 0     /* 'SqExp'  kernel/KernelSqExp.py     exp(-s),  s = sum_i theta_i r_i^2            */
+#define GEGP_KERNEL_MATERN52 1  /* 'Ma5f2'  kernel/KernelMatern5f2.py (1 + sqrt5 nu + 5/3 nu^2) exp(-sqrt5 nu)    */
+#define GEGP_KERNEL_RATQUAD 2   /* 'RatQu'  kernel/KernelRatQuad.py   (1 + s / alpha)^-alpha                      */
 
 /* layout of the per-candidate result vector of gegp_lml_eval (doubles) */
 #define GEGP_OUT_LML 0     /* log marginal likelihood (no N/2 ln 2pi term, optz/CalcLkd.py:168,226)      */
@@ -57,7 +71,8 @@ extern "C" {
 #define GEGP_OUT_DVARK 6   /* noisy only: dLML/dvarK                                                    */
 #define GEGP_OUT_DVARF 7   /* noisy only: dLML/dvar_fval                                                */
 #define GEGP_OUT_DVARG 8   /* noisy only: dLML/dvar_fgrad                                               */
-#define GEGP_OUT_GRAD 9    /* dLML/dtheta[0..d-1] (w.r.t. theta, not log10 theta)                        */
+#define GEGP_OUT_DKERN 9   /* dLML/dkernel_hp (rational-quadratic alpha; 0 for the other kernels)        */
+#define GEGP_OUT_GRAD 10   /* dLML/dtheta[0..d-1] (w.r.t. theta, not log10 theta)                        */
 #define GEGP_OUT_LEN(d) (GEGP_OUT_GRAD + (d))
 
 /* operations for gegp_workspace_bytes */
@@ -86,14 +101,14 @@ int64_t gegp_ld(int N);
 /* K1: fused covariance builder.  theta[d]; noise[N] (already divided by varK where the reference divides,
  * kernel/Kernel.py:218) or NULL; p_out[2N] receives p and 1/p (required for GEGP_MODE_PRECON, else may be NULL);
  * uplo 0: full matrix, 1: lower triangle only (strict upper part is left untouched). */
-int gegp_build_cov(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+int gegp_build_cov(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta, int kernel, double kernel_hp,
                    const double* noise, int mode, double eta, double varK, double* K_out, int64_t ldk,
                    double* p_out, int uplo, void* stream);
 
 /* Cross covariance, transposed: Kx[x, c] = cov(test point x, training datum c) * (pinv ? pinv[c] : 1);
  * Kx is [nx, ld]. */
 int gegp_cross_cov(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* Xs, int nx,
-                   const double* theta, const double* pinv, double* Kx, int64_t ld, void* stream);
+                   const double* theta, int kernel, double kernel_hp, const double* pinv, double* Kx, int64_t ld, void* stream);
 
 /* K2: blocked Cholesky on the fp64 tensor cores.  A is (N + n_extra) x lda, lower triangle of the leading
  * N x N block holds the SPD matrix; on exit it holds L (lower) and the n_extra appended rows R are
@@ -126,8 +141,11 @@ int gegp_dgemm(int transb, int M, int N, int K, double alpha, const double* A, i
  * (kernel/Kernel.py:128-138, optz/CalcLkd.py:149-181); noisy = 1: varK_batch[B] given, LML of
  * optz/CalcLkd.py:185-251.  mode is GEGP_MODE_BASE or GEGP_MODE_PRECON.  pnlt_grad is the varK-penalty
  * derivative term of optz/CalcLkd.py:175 (0 when lkd_varK_pnlt_use is False).
+ * kernel: GEGP_KERNEL_*; kernel_hp_batch[B] (device): the kernel's extra hyper-parameter per candidate (alpha of the
+ * rational-quadratic kernel; may be NULL for the kernels without one); dLML/dalpha comes back in GEGP_OUT_DKERN.
  * out[B, GEGP_OUT_LEN(d)].  alpha_out[B, N] (K^-1 (y - H beta), un-preconditioned) or NULL. */
-int gegp_lml_eval(int B, const double* theta_batch, const double* varK_batch, int n, int n_g, int d,
+int gegp_lml_eval(int B, const double* theta_batch, const double* varK_batch, int kernel,
+                  const double* kernel_hp_batch, int n, int n_g, int d,
                   const double* X, const int32_t* grad_slot, const double* y, const double* noise, int mode,
                   double eta, int noisy, double pnlt_grad, int want_grad, double* out, double* alpha_out,
                   void* work, size_t work_bytes, void* stream);
@@ -135,14 +153,14 @@ int gegp_lml_eval(int B, const double* theta_batch, const double* varK_batch, in
 /* K4 setup: build (varK := 1, kernel/Kernel.py:196-197) + factor + forward-solve of P^-1 (y - H beta).
  * A is (N + 1) x lda; dinv[gegp_dinv_doubles(N)]; p_out[2N]; on exit row N of A holds
  * w = L^-1 P^-1 (y - H beta).  alpha_out[N] (optional) receives K^-1 (y - H beta) (eval/GpEvalModel.py:57). */
-int gegp_predict_setup(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+int gegp_predict_setup(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta, int kernel, double kernel_hp,
                        const double* noise, int mode, double eta, const double* y, double beta, double* A,
                        int64_t lda, double* dinv, double* p_out, double* alpha_out, int* info_dev, void* stream);
 
 /* K4: posterior mean and standard deviation at nx test points (eval/GpEvalModel.py:154-168):
  * mu = beta + k*^T K^-1 (y - H beta), sig = sqrt(varK) sqrt(max(0, 1 - k*^T K^-1 k*)); sig2_out (optional)
  * receives the unclipped 1 - k*^T K^-1 k*, n_negative_dev counts entries < 0 (the reference asserts on them). */
-int gegp_predict(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+int gegp_predict(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta, int kernel, double kernel_hp,
                  const double* A, int64_t lda, const double* dinv, const double* p, int mode, double beta, double varK,
                  const double* Xs, int nx, double* mu, double* sig, double* sig2_out, int* n_negative_dev,
                  void* work, size_t work_bytes, void* stream);
@@ -150,7 +168,7 @@ int gegp_predict(int n, int n_g, int d, const double* X, const int32_t* grad_slo
 /* K4 with x-derivatives (eval_model(calc_grad=True), eval/GpEvalModel.py:170-173, 319-354): additionally
  * dmudx[nx, d] = d mu / d x and dsigdx[nx, d] = d sig / d x.  The derivative columns of K(X, X*) are generated on the
  * fly and forward-solved beside k* (d + 1 rows per test point): work >= (d + 1) * gegp_ld(N) * 8 bytes per point. */
-int gegp_predict_grad(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+int gegp_predict_grad(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta, int kernel, double kernel_hp,
                       const double* A, int64_t lda, const double* dinv, const double* p, int mode, double beta,
                       double varK, const double* Xs, int nx, double* mu, double* sig, double* sig2_out, double* dmudx,
                       double* dsigdx, int* n_negative_dev, void* work, size_t work_bytes, void* stream);
@@ -162,7 +180,7 @@ int gegp_predict_grad(int n, int n_g, int d, const double* X, const int32_t* gra
  *   hess3[2] = (d kstar / dx) K^-1 (d kstar / dx)^T  (term2), kstar = K(X, xs);
  * the caller forms d2sig2/dx2 = -2 varK (term1 + term2) and d2sig/dx2 = (d2sig2/dx2 - 2 dsig dsig^T) / (2 sig).
  * work >= (d + 2) * gegp_ld(N) * 8 bytes. */
-int gegp_predict_hess(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+int gegp_predict_hess(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta, int kernel, double kernel_hp,
                       const double* A, int64_t lda, const double* dinv, const double* p, const double* alpha, int mode,
                       double beta, double varK, const double* xs, double* mu, double* sig, double* sig2_out,
                       double* dmudx, double* dsigdx, double* hess3, int* n_negative_dev, void* work, size_t work_bytes,
@@ -198,13 +216,13 @@ int gegp_row_sq_sum(int N, const double* M, int64_t ld, double* out, void* strea
 /* sum(W .* dKcov/dhp) for a symmetric device matrix W (N x ldw) and every hyper-parameter, dKcov/dhp generated on the
  * fly; layout of `out` as gegp_quad_grad.  The Frobenius condition-number gradient contracts
  * W = frac K - K^-3 / frac this way (optz/GpHparaCon.py:252-259).  work >= gegp_quad_grad_work_bytes + 8 (N + 1). */
-int gegp_weighted_grad(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+int gegp_weighted_grad(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta, int kernel, double kernel_hp,
                        const double* W, int64_t ldw, int mode, double eta, int noisy, const double* varK_dev,
                        double* out, void* work, size_t work_bytes, void* stream);
 int gegp_lanczos_step(int N, int j, double* V, int64_t ldv, double* w, double* alpha, double* beta, void* stream);
 int gegp_lincomb(int N, int k, const double* V, int64_t ldv, const double* coef, double* out, void* stream);
 size_t gegp_quad_grad_work_bytes(int n, int n_g, int d);
-int gegp_quad_grad(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+int gegp_quad_grad(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta, int kernel, double kernel_hp,
                    const double* v, int mode, double eta, int noisy, const double* varK_dev, double* out,
                    void* work, size_t work_bytes, void* stream);
 

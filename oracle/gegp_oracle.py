@@ -65,9 +65,12 @@ def calc_rtensor(X, Y):
     return (X[:, None, :] - Y[None, :, :]).transpose(2, 0, 1).copy()
 
 
-def kern_base(X, Y, theta):
-    """k = exp(-sum_i theta_i r_i^2), accumulated i = 0..d-1 (kernel/KernelSqExp.py:18-46)."""
+def kern_base(X, Y, theta, kernel=None):
+    """k = exp(-sum_i theta_i r_i^2), accumulated i = 0..d-1 (kernel/KernelSqExp.py:18-46); the Matern-5/2 and
+    rational-quadratic values through _radial (kernel/KernelMatern5f2.py:17-52, kernel/KernelRatQuad.py:18-51)."""
     R = calc_rtensor(X, Y)
+    if kernel is not None and _kernel_spec(kernel)[0] != "SqExp":
+        return _radial(kernel, _sqdist(R, theta))[0]
     e = np.zeros(R.shape[1:])
     for i in range(R.shape[0]):
         e -= theta[i] * R[i] ** 2
@@ -78,7 +81,110 @@ def _sel(n, mask):
     return np.arange(n) if mask is None else np.flatnonzero(np.asarray(mask, dtype=bool))
 
 
-def kern_grad(X, Y, theta, mask1=None, mask2=None):
+def _kernel_spec(kernel):
+    """kernel = None | 'SqExp' | 'Ma5f2' | ('RatQu', alpha)  ->  (name, alpha-or-None).  Names are the reference's
+    (kernel/Kernel.py:27-107); RatQu defaults to alpha = 2 (kernel/KernelRatQuad.py:849)."""
+    if kernel is None:
+        return "SqExp", None
+    if isinstance(kernel, str):
+        return kernel, (2.0 if kernel == "RatQu" else None)
+    name, hp = kernel
+    return name, (None if hp is None else float(np.ravel(hp)[0]))
+
+
+def kernel_diag_coef(kernel=None):
+    """diag(K) of a gradient row is c * theta_i: gamma_i^2 of theta2gamma (kernel/KernelSqExp.py:581-583 and
+    kernel/KernelRatQuad.py:853-855: 2; kernel/KernelMatern5f2.py:655-657: 5/3)."""
+    return 5.0 / 3.0 if _kernel_spec(kernel)[0] == "Ma5f2" else 2.0
+
+
+def _radial(kernel, s):
+    """(phi, phi', phi'', phi''') of the kernel as a function of s = sum_i theta_i r_i^2, written with the reference's
+    own intermediate quantities:
+      SqExp  kernel/KernelSqExp.py:18-46:        phi = exp(-s)
+      Ma5f2  kernel/KernelMatern5f2.py:38-52, 149-186:  nu = sqrt(s), Abase = exp(-sqrt5 nu), mat1 = 5/3 (1 + sqrt5 nu) Abase;
+             phi = (1 + sqrt5 nu + 5/3 nu^2) Abase, phi' = -mat1 / 2, phi'' = 25/12 Abase,
+             phi''' = -(25 sqrt5 / 24) Abase / max(nu, 1e-16)    (:574 inv_nu_mat clamp)
+      RatQu  kernel/KernelRatQuad.py:18-51, 451-458:    B = 1 + s / alpha; phi = B^-alpha, phi' = -B^(-alpha-1),
+             phi'' = (1 + 1/alpha) B^(-alpha-2), phi''' = -(1 + 1/alpha)(alpha + 2)/alpha B^(-alpha-3)"""
+    name, alpha = _kernel_spec(kernel)
+    if name == "SqExp":
+        k = np.exp(-s)
+        return k, -k, k, -k
+    if name == "Ma5f2":
+        sqrt5 = np.sqrt(5.0)
+        nu = np.sqrt(s)
+        Abase = np.exp(-sqrt5 * nu)
+        mat1 = (5.0 / 3.0) * (1.0 + sqrt5 * nu) * Abase
+        return ((1.0 + sqrt5 * nu + (5.0 / 3.0) * nu ** 2) * Abase, -0.5 * mat1, (25.0 / 12.0) * Abase,
+                -(25.0 * sqrt5 / 24.0) * Abase / np.maximum(nu, 1e-16))
+    if name == "RatQu":
+        B = 1.0 + s / alpha
+        return (B ** (-alpha), -B ** (-alpha - 1.0), (1.0 + 1.0 / alpha) * B ** (-alpha - 2.0),
+                -(1.0 + 1.0 / alpha) * (alpha + 2.0) / alpha * B ** (-alpha - 3.0))
+    raise ValueError(f"unknown kernel {name}")
+
+
+def _radial_dalpha(kernel, s):
+    """d/dalpha of (phi, phi', phi'') for the rational-quadratic kernel, in the reference's T0 / T1 / T2 form
+    (kernel/KernelRatQuad.py:133-163 and :770-782): dphi = B^(-alpha-1) (s/alpha - B ln B), dphi' = T0 / 2,
+    dphi'' = -T2 / 4."""
+    name, alpha = _kernel_spec(kernel)
+    assert name == "RatQu"
+    B = 1.0 + s / alpha
+    B_lnB = B * np.log(B)
+    d0 = B ** (-alpha - 1.0) * (s / alpha - B_lnB)
+    T0 = 2.0 * B ** (-alpha - 2.0) * (((-alpha - 1.0) / alpha ** 2) * s + B_lnB)
+    T2 = 4.0 * B ** (-alpha - 3.0) * (B / alpha ** 2 - ((1.0 + 1.0 / alpha) * (alpha + 2.0) / alpha ** 2) * s
+                                      + (1.0 + 1.0 / alpha) * B_lnB)
+    return d0, 0.5 * T0, -0.25 * T2
+
+
+def _sqdist(R, theta):
+    s = np.zeros(R.shape[1:])
+    for i in range(R.shape[0]):
+        s += theta[i] * R[i] ** 2
+    return s
+
+
+def _blocks_from_profile(X, Y, theta, f0, f1, f2, mask1, mask2):
+    """Assemble [K00 | K0j ; Ki0 | Kij] from profile values: K00 = f0, K_i0 = 2 th_i r_i f1, K_0j = -2 th_j r_j f1,
+    K_ij = -2 th_i delta_ij f1 - 4 th_i th_j r_i r_j f2  (the common structure of kernel/KernelSqExp.py:380-408,
+    kernel/KernelMatern5f2.py:424-449 and kernel/KernelRatQuad.py:520-551)."""
+    n1, d = X.shape
+    n2 = Y.shape[0]
+    s1, s2 = _sel(n1, mask1), _sel(n2, mask2)
+    g1, g2 = s1.size, s2.size
+    R = calc_rtensor(X, Y)
+    K = np.zeros((n1 + g1 * d, n2 + g2 * d))
+    K[:n1, :n2] = f0
+    for i in range(d):
+        ri = slice(n1 + i * g1, n1 + (i + 1) * g1)
+        ci = slice(n2 + i * g2, n2 + (i + 1) * g2)
+        K[ri, :n2] = 2.0 * theta[i] * R[i][s1, :] * f1[s1, :]
+        K[:n1, ci] = -2.0 * theta[i] * R[i][:, s2] * f1[:, s2]
+        Rgg_i = R[i][np.ix_(s1, s2)]
+        f1gg, f2gg = f1[np.ix_(s1, s2)], f2[np.ix_(s1, s2)]
+        K[ri, ci] = -2.0 * theta[i] * f1gg - 4.0 * theta[i] ** 2 * Rgg_i ** 2 * f2gg
+        for j in range(i + 1, d):
+            rj = slice(n1 + j * g1, n1 + (j + 1) * g1)
+            cj = slice(n2 + j * g2, n2 + (j + 1) * g2)
+            term = -4.0 * theta[i] * theta[j] * (Rgg_i * R[j][np.ix_(s1, s2)] * f2gg)
+            K[ri, cj] += term
+            K[rj, ci] += term
+    return K
+
+
+def kern_grad_dalpha(X, theta, kernel, mask=None):
+    """d K / d alpha of the rational-quadratic kernel, [N, N] (kernel/KernelRatQuad.py:752-843): the blocks of K with
+    (phi, phi', phi'') replaced by their alpha-derivatives."""
+    theta = np.asarray(theta, dtype=float)
+    s = _sqdist(calc_rtensor(X, X), theta)
+    d0, d1, d2 = _radial_dalpha(kernel, s)
+    return _blocks_from_profile(X, X, theta, d0, d1, d2, mask, mask)
+
+
+def kern_grad(X, Y, theta, mask1=None, mask2=None, kernel=None):
     """Gradient-enhanced kernel matrix (kernel/KernelSqExp.py:322-410).
 
     Blocks: K00 = k; K_i0 = -2 th_i r_i k (:392); K_0j = +2 th_j r_j k (:393);
@@ -86,6 +192,10 @@ def kern_grad(X, Y, theta, mask1=None, mask2=None):
     Gradient rows/cols are restricted to the masked points (:349-377).
     """
     theta = np.asarray(theta, dtype=float)
+    if kernel is not None and _kernel_spec(kernel)[0] != "SqExp":
+        # kernel/KernelMatern5f2.py:354-451 (KernelMatern5f2GradMod), kernel/KernelRatQuad.py:439-553
+        f0, f1, f2, _ = _radial(kernel, _sqdist(calc_rtensor(X, Y), theta))
+        return _blocks_from_profile(X, Y, theta, f0, f1, f2, mask1, mask2)
     n1, d = X.shape
     n2 = Y.shape[0]
     s1, s2 = _sel(n1, mask1), _sel(n2, mask2)
@@ -111,7 +221,42 @@ def kern_grad(X, Y, theta, mask1=None, mask2=None):
     return K
 
 
-def kern_grad_dtheta(X, theta, mask=None):
+def _kern_grad_dtheta_profile(X, theta, kernel, mask=None):
+    """d K / d theta_m for the Matern-5/2 and rational-quadratic kernels (kernel/KernelMatern5f2.py:534-643,
+    kernel/KernelRatQuad.py:636-749) in profile form: r_m^2 times the blocks one s-derivative up, plus the explicit
+    theta_m dependence:  dK_i0 += 2 d_im r_i f1 ; dK_ij += -2 d_ij d_im f1 - 4 (d_im th_j + d_jm th_i) r_i r_j f2."""
+    theta = np.asarray(theta, dtype=float)
+    n, d = X.shape
+    s = _sel(n, mask)
+    g = s.size
+    N = n + g * d
+    R = calc_rtensor(X, X)
+    _, f1, f2, f3 = _radial(kernel, _sqdist(R, theta))
+    up = _blocks_from_profile(X, X, theta, f1, f2, f3, mask, mask)
+    out = np.zeros((d, N, N))
+
+    def blk(i):
+        return slice(n + i * g, n + (i + 1) * g)
+
+    def rep(r2):    # r_m^2 on the block structure [values | d gradient blocks]
+        row = np.hstack([r2] + [r2[:, s]] * d)
+        return np.vstack([row] + [row[s, :]] * d)
+
+    gg = np.ix_(s, s)
+    for m in range(d):
+        D = out[m]
+        D[:] = rep(R[m] ** 2) * up
+        D[blk(m), :n] += 2.0 * R[m][s, :] * f1[s, :]
+        D[:n, blk(m)] += -2.0 * R[m][:, s] * f1[:, s]
+        D[blk(m), blk(m)] += -2.0 * f1[gg]
+        for j in range(d):
+            t = -4.0 * theta[j] * R[m][gg] * R[j][gg] * f2[gg]
+            D[blk(m), blk(j)] += t
+            D[blk(j), blk(m)] += t
+    return out
+
+
+def kern_grad_dtheta(X, theta, mask=None, kernel=None):
     """d K / d theta_m for all m -> [d, N, N]  (kernel/KernelSqExp.py:471-568).
 
     Restated from the closed form:
@@ -120,6 +265,8 @@ def kern_grad_dtheta(X, theta, mask=None):
     With a mask this is the derivative of K_full[sel, sel] (the semantics the builder has);
     the reference's jit is only right for None/prefix masks.
     """
+    if kernel is not None and _kernel_spec(kernel)[0] != "SqExp":
+        return _kern_grad_dtheta_profile(X, theta, kernel, mask)
     theta = np.asarray(theta, dtype=float)
     n, d = X.shape
     s = _sel(n, mask)
@@ -166,7 +313,7 @@ def vreq_rescale_origin(n, d):
     return min(v, ds)
 
 
-def nugget(n, d, mode, cond_max_target=1e10, use_grad=True, eta_set_mtd="Kbase_eta", eta_dflt=1e-8):
+def nugget(n, d, mode, cond_max_target=1e10, use_grad=True, eta_set_mtd="Kbase_eta", eta_dflt=1e-8, kernel=None):
     """(eta_Kbase, eta_Kgrad) per conditioning mode  (base/GpWellCond.py:116-154, :78-99, :109-114)."""
     if eta_set_mtd == "dflt_eta":
         return eta_dflt, eta_dflt
@@ -176,7 +323,11 @@ def nugget(n, d, mode, cond_max_target=1e10, use_grad=True, eta_set_mtd="Kbase_e
     if n == 1:
         return eta_base, eta_base
     if mode == "precon":
-        u = 0.5 * (n - 1) * (1.0 + np.sqrt(1.0 + 4.0 * d)) * np.exp(-(1.0 + 2.0 * d - np.sqrt(1.0 + 4.0 * d)) / (4.0 * d))
+        if _kernel_spec(kernel)[0] == "Ma5f2":      # base/GpWellCond.py:130-132
+            al = (np.sqrt(3.0 * d) - 1.0 + np.sqrt(15.0 * d + 2.0 * np.sqrt(3.0 * d) + 1.0)) / (2.0 * (3.0 * d + np.sqrt(3.0 * d)))
+            u = (n - 1) * (1.0 + (d + np.sqrt(3.0 * d)) * al + d * (1.0 + np.sqrt(3.0 * d)) * al ** 2) * np.exp(-np.sqrt(3.0 * d) * al)
+        else:                                        # 'SqExp' and 'RatQu' share the bound (:127-129)
+            u = 0.5 * (n - 1) * (1.0 + np.sqrt(1.0 + 4.0 * d)) * np.exp(-(1.0 + 2.0 * d - np.sqrt(1.0 + 4.0 * d)) / (4.0 * d))
         return eta_base, (1.0 + u) / (cond_max_target - 1.0)
     if "rescale" in mode:
         vmin = vreq_rescale_origin(n, d)
@@ -222,14 +373,14 @@ class KAll:
 
 
 def all_K_w_chofac(X, theta, mode="precon", eta=None, noise_vec=None, varK=1.0, mask=None,
-                   cond_max_target=1e10, eta_is_const=True, calc_chofac=True):
+                   cond_max_target=1e10, eta_is_const=True, calc_chofac=True, kernel=None):
     """Faithful restatement of calc_all_K_w_chofac (kernel/Kernel.py:213-302) with use_grad=True.
 
     precon (:220-266): p = sqrt(diag(K + noise/varK)); Kcor = P^-1 (K+noise/varK) P^-1;
     Kt = varK (Kcor + eta I); Kcov = P Kt P; factor returned as (P Lt, lower=True).
     otherwise (:268-302): Kcov = varK (K + noise/varK + eta I); cho_factor default (upper).
     """
-    K = kern_grad(X, X, theta, mask, mask)
+    K = kern_grad(X, X, theta, mask, mask, kernel=kernel)
     N = K.shape[0]
     if noise_vec is None:
         noise_vec = np.zeros(N)
@@ -267,18 +418,21 @@ def all_K_w_chofac(X, theta, mode="precon", eta=None, noise_vec=None, varK=1.0, 
     return KAll(K, None, Kcov, fac, eta, None, None, idx)
 
 
-def kerngrad_hp(X, theta, mode, eta, mask=None):
-    """d(K + eta-term)/d theta stack, noise-free  (optz/GpHparaGrad.py:13-56).
+def kerngrad_hp(X, theta, mode, eta, mask=None, kernel=None):
+    """d(K + eta-term)/d[theta.., alpha?] stack, noise-free  (optz/GpHparaGrad.py:13-56).
 
-    precon adds 2*eta on the diagonal of gradient block m (:40-50): d(eta p^2)/d theta_m.
+    precon adds 2 eta gamma_m dgamma_m/dtheta_m = c eta on the diagonal of gradient block m (:40-50): d(eta p^2)/d theta_m
+    (c = 2; Matern-5/2: 5/3).  A kernel with a hyper-parameter of its own (RatQu) appends dK/dalpha (:52-55).
     """
     n, d = X.shape
     g = _sel(n, mask).size
-    D = kern_grad_dtheta(X, theta, mask)
+    D = kern_grad_dtheta(X, theta, mask, kernel=kernel)
     if mode == "precon":
         for m in range(d):
             idx = np.arange(n + m * g, n + (m + 1) * g)
-            D[m, idx, idx] += 2.0 * eta
+            D[m, idx, idx] += kernel_diag_coef(kernel) * eta
+    if _kernel_spec(kernel)[0] == "RatQu":
+        D = np.concatenate((D, kern_grad_dalpha(X, theta, kernel, mask)[None]), axis=0)
     return D
 
 
@@ -307,14 +461,14 @@ def gls_beta(chofac, H, y):
 
 
 def lkd_wo_noise(X, fval, grad, theta, mode="precon", eta=None, mask=None, calc_grad=True,
-                 pnlt_grad=0.0, pnlt_val=0.0):
+                 pnlt_grad=0.0, pnlt_val=0.0, kernel=None):
     """Noise-free LML + d/dtheta, adjoint form.  Follows calc_lkd_all (optz/CalcLkd.py:322-339),
     calc_lkd_all_wo_noise (:30-95) and calc_lkd_w_Kern_mtd_adjoint (:149-181) with varK := 1 inside
     K (kernel/Kernel.py:128-138).  Materialises everything exactly as the reference does."""
     n, d = X.shape
     if eta is None:
-        eta = nugget(n, d, mode)[1]
-    ka = all_K_w_chofac(X, theta, mode, eta, None, 1.0, mask)
+        eta = nugget(n, d, mode, kernel=kernel)[1]
+    ka = all_K_w_chofac(X, theta, mode, eta, None, 1.0, mask, kernel=kernel)
     if ka.chofac is None:
         return Lkd(chofac_good=False, eta=eta)
     g = _sel(n, mask).size
@@ -329,7 +483,7 @@ def lkd_wo_noise(X, fval, grad, theta, mode="precon", eta=None, mask=None, calc_
     lml = -(N * np.log(varK) + ln_det) / 2.0 - pnlt_val
     out = Lkd(lml, None, varK, beta, ln_det, alpha, True, eta)
     if calc_grad:
-        D = kerngrad_hp(X, theta, mode, eta, mask)
+        D = kerngrad_hp(X, theta, mode, eta, mask, kernel=kernel)     # rows: theta_1..d, then alpha (RatQu)
         adj_varK = np.outer(alpha, -alpha / N)
         Kinv = linalg.cho_solve(ka.chofac, np.eye(N))
         adj = -adj_varK * (pnlt_grad + N / (2.0 * varK)) - 0.5 * Kinv
@@ -432,17 +586,23 @@ def lkd_wo_noise_lean(X, fval, grad, theta, mode="precon", eta=None, calc_grad=T
     return out
 
 
-def kcov_grad_hp_noisy(X, theta, Kern, mode, eta, varK, has_var_fval, has_var_fgrad, mask=None):
-    """dKcov/d[theta.., varK, var_fval?, var_fgrad?]  (optz/GpHparaGrad.py:58-155)."""
+def kcov_grad_hp_noisy(X, theta, Kern, mode, eta, varK, has_var_fval, has_var_fgrad, mask=None, kernel=None):
+    """dKcov/d[theta.., alpha?, varK, var_fval?, var_fgrad?]  (optz/GpHparaGrad.py:58-155; hp order of
+    optz/GpHparaOptz.py:76-126)."""
     n, d = X.shape
     g = _sel(n, mask).size
     N = n + g * d
     stack = []
-    Dth = varK * kern_grad_dtheta(X, theta, mask)
+    Dth = varK * kern_grad_dtheta(X, theta, mask, kernel=kernel)
     if mode == "precon":
         for i in range(d):
             Dth[i] += np.diag(np.diag(Dth[i])) * eta            # :105-109
     stack.extend(list(Dth))
+    if _kernel_spec(kernel)[0] == "RatQu":                      # :111-123 (diag(dK/dalpha) = 0: no nugget term)
+        Da = varK * kern_grad_dalpha(X, theta, kernel, mask)
+        if mode == "precon":
+            Da = Da + np.diag(np.diag(Da)) * eta
+        stack.append(Da)
     if mode == "precon":
         stack.append(Kern + eta * np.diag(np.diag(Kern)))        # :132-133
     else:
@@ -456,13 +616,13 @@ def kcov_grad_hp_noisy(X, theta, Kern, mode, eta, varK, has_var_fval, has_var_fg
 
 
 def lkd_w_noise(X, fval, grad, theta, varK, noise_vec, mode="precon", eta=None, mask=None,
-                calc_grad=True, has_var_fval=False, has_var_fgrad=False):
+                calc_grad=True, has_var_fval=False, has_var_fgrad=False, kernel=None):
     """Noisy-data LML + gradient wrt [theta, varK, (var_fval), (var_fgrad)], adjoint form
     (optz/CalcLkd.py:185-251, :299-320).  LML = -(ln det Kcov + res^T alpha)/2."""
     n, d = X.shape
     if eta is None:
-        eta = nugget(n, d, mode)[1]
-    ka = all_K_w_chofac(X, theta, mode, eta, noise_vec, varK, mask)
+        eta = nugget(n, d, mode, kernel=kernel)[1]
+    ka = all_K_w_chofac(X, theta, mode, eta, noise_vec, varK, mask, kernel=kernel)
     if ka.chofac is None:
         return Lkd(chofac_good=False, eta=eta)
     g = _sel(n, mask).size
@@ -476,7 +636,7 @@ def lkd_w_noise(X, fval, grad, theta, varK, noise_vec, mode="precon", eta=None, 
     lml = -(ln_det + float(res @ alpha)) / 2.0
     out = Lkd(lml, None, varK, beta, ln_det, alpha, True, eta)
     if calc_grad:
-        D = kcov_grad_hp_noisy(X, theta, ka.Kern, mode, eta, varK, has_var_fval, has_var_fgrad, mask)
+        D = kcov_grad_hp_noisy(X, theta, ka.Kern, mode, eta, varK, has_var_fval, has_var_fgrad, mask, kernel=kernel)
         adj = 0.5 * (np.outer(alpha, alpha) - linalg.cho_solve(ka.chofac, np.eye(N)))
         out.ln_lkd_grad = np.einsum("ijk,jk", D, adj)
     return out
@@ -539,19 +699,19 @@ def cond_w_noise(X, theta, varK, noise_vec, mode, eta, has_var_fval=False, has_v
 # posterior  (eval/GpEvalModel.py:17-57, 59-198)
 # ----------------------------------------------------------------------------------------------
 
-def eval_model(X, fval, grad, theta, varK, beta, Xs, mode="precon", eta=None, noise_vec=None, mask=None):
+def eval_model(X, fval, grad, theta, varK, beta, Xs, mode="precon", eta=None, noise_vec=None, mask=None, kernel=None):
     """mu = beta + K*^T K^-1 (y - H beta); sig = sqrt(varK) sqrt(max(0, 1 - diag(K*^T K^-1 K*)))
     with the factor built for varK := 1 (kernel/Kernel.py:196-197)."""
     n, d = X.shape
     if eta is None:
-        eta = nugget(n, d, mode)[1]
-    ka = all_K_w_chofac(X, theta, mode, eta, noise_vec, 1.0, mask)
+        eta = nugget(n, d, mode, kernel=kernel)[1]
+    ka = all_K_w_chofac(X, theta, mode, eta, noise_vec, 1.0, mask, kernel=kernel)
     g = _sel(n, mask).size
     y = make_data_vec(fval, grad)
     H = aug_vand(n, g, d)
     fdiff = y - H @ np.atleast_1d(beta)
     a = linalg.cho_solve(ka.chofac, fdiff)
-    Kyx = kern_grad(X, Xs, theta, mask, None)[:, : Xs.shape[0]]
+    Kyx = kern_grad(X, Xs, theta, mask, None, kernel=kernel)[:, : Xs.shape[0]]
     KinvK = linalg.cho_solve(ka.chofac, Kyx)
     sig2 = 1.0 - np.einsum("ij,ij->j", Kyx, KinvK)
     n_neg = int(np.sum(sig2 < 0))
@@ -560,19 +720,20 @@ def eval_model(X, fval, grad, theta, varK, beta, Xs, mode="precon", eta=None, no
     return mu, sig, sig2, n_neg
 
 
-def eval_model_grad(X, fval, grad, theta, varK, beta, Xs, mode="precon", eta=None, noise_vec=None, mask=None):
+def eval_model_grad(X, fval, grad, theta, varK, beta, Xs, mode="precon", eta=None, noise_vec=None, mask=None,
+                    kernel=None):
     """eval_model(calc_grad=True): additionally d mu / d x and d sig / d x, [nx, d]
     (eval/GpEvalModel.py:134-139 test-gradient columns of K(X, X*); :319-354 calc_dmudx / calc_dsigdx)."""
     n, d = X.shape
     nx = Xs.shape[0]
     if eta is None:
-        eta = nugget(n, d, mode)[1]
-    ka = all_K_w_chofac(X, theta, mode, eta, noise_vec, 1.0, mask)
+        eta = nugget(n, d, mode, kernel=kernel)[1]
+    ka = all_K_w_chofac(X, theta, mode, eta, noise_vec, 1.0, mask, kernel=kernel)
     g = _sel(n, mask).size
     y = make_data_vec(fval, grad)
     H = aug_vand(n, g, d)
     a = linalg.cho_solve(ka.chofac, y - H @ np.atleast_1d(beta))
-    Kg = kern_grad(X, Xs, theta, mask, None)           # [N, nx (1 + d)]
+    Kg = kern_grad(X, Xs, theta, mask, None, kernel=kernel)           # [N, nx (1 + d)]
     Kyx, dKxy = Kg[:, :nx], Kg[:, nx:].T               # dKxy[(j, x), row]
     KinvK = linalg.cho_solve(ka.chofac, Kyx)           # [N, nx]
     sig2 = 1.0 - np.einsum("ij,ij->j", Kyx, KinvK)
@@ -585,12 +746,26 @@ def eval_model_grad(X, fval, grad, theta, varK, beta, Xs, mode="precon", eta=Non
     return mu, sig, dmudx, -inv_sig[:, None] * t2
 
 
-def kern_hess_x(X, xs, theta):
+def kern_hess_x(X, xs, theta, kernel=None):
     """Second derivatives of the cross covariance k*(x) with respect to the test point x, [d, d, N], every training
     point carrying a gradient (kernel/KernelSqExp.py:66-88 value entries, :432-468 gradient entries; the reference
     builds them with R = x_test - x_train)."""
     n, d = X.shape
     rho = xs[None, :] - X                                # [n, d] = x_test - x_train
+    if kernel is not None and _kernel_spec(kernel)[0] != "SqExp":
+        # kernel/KernelMatern5f2.py:54-96, 272-331; kernel/KernelRatQuad.py:54-97, 556-633, in profile form
+        # (rho = -r: the odd powers of r change sign against the training-minus-test convention of the CUDA kernels)
+        _, f1, f2, f3 = _radial(kernel, np.sum(theta[None, :] * rho ** 2, axis=1))
+        H = np.zeros((d, d, n * (d + 1)))
+        for kk in range(d):
+            for i in range(d):
+                H[kk, i, :n] = 2.0 * theta[i] * (i == kk) * f1 + 4.0 * theta[i] * theta[kk] * rho[:, i] * rho[:, kk] * f2
+                for j in range(d):
+                    H[kk, i, n + j * n: n + (j + 1) * n] = (
+                        -4.0 * theta[i] * theta[j] * ((i == kk) * rho[:, j] + (j == kk) * rho[:, i]) * f2
+                        - 4.0 * (i == j) * theta[i] * theta[kk] * rho[:, kk] * f2
+                        - 8.0 * theta[i] * theta[j] * theta[kk] * rho[:, i] * rho[:, j] * rho[:, kk] * f3)
+        return H
     k = np.exp(-np.sum(theta[None, :] * rho ** 2, axis=1))
     H = np.zeros((d, d, n * (d + 1)))
     for kk in range(d):
@@ -604,22 +779,22 @@ def kern_hess_x(X, xs, theta):
     return H
 
 
-def eval_model_hess(X, fval, grad, theta, varK, beta, xs, mode="precon", eta=None):
+def eval_model_hess(X, fval, grad, theta, varK, beta, xs, mode="precon", eta=None, kernel=None):
     """eval_model(calc_grad=True, calc_hess=True) at ONE point: (mu, sig, dmudx, dsigdx, d2mudx2, d2sigdx2)
     (eval/GpEvalModel.py:175-180, 356-382)."""
     n, d = X.shape
     if eta is None:
-        eta = nugget(n, d, mode)[1]
+        eta = nugget(n, d, mode, kernel=kernel)[1]
     xs = np.atleast_2d(xs)
-    mu, sig, dmu, dsig = eval_model_grad(X, fval, grad, theta, varK, beta, xs, mode, eta)
-    ka = all_K_w_chofac(X, theta, mode, eta, None, 1.0, None)
+    mu, sig, dmu, dsig = eval_model_grad(X, fval, grad, theta, varK, beta, xs, mode, eta, kernel=kernel)
+    ka = all_K_w_chofac(X, theta, mode, eta, None, 1.0, None, kernel=kernel)
     y = make_data_vec(fval, grad)
     H = aug_vand(n, n, d)
     a = linalg.cho_solve(ka.chofac, y - H @ np.atleast_1d(beta))
-    Kg = kern_grad(X, xs, theta, None, None)
+    Kg = kern_grad(X, xs, theta, None, None, kernel=kernel)
     Kyx, dKxy = Kg[:, :1], Kg[:, 1:].T
     KinvK = linalg.cho_solve(ka.chofac, Kyx)[:, 0]
-    d2K = kern_hess_x(X, xs[0], theta)
+    d2K = kern_hess_x(X, xs[0], theta, kernel=kernel)
     d2mu = d2K @ a
     term1 = d2K @ KinvK
     term2 = dKxy @ linalg.cho_solve(ka.chofac, dKxy.T)

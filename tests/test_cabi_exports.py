@@ -47,11 +47,15 @@ def test_host_only_entry_points():
 def test_argument_checks_return_negative_codes_without_touching_the_gpu():
     from gpgradpy_b200 import _lib
     lib = _lib.load()
-    assert lib.gegp_build_cov(0, 0, 3, 0, 0, 0, 0, 0, 0.0, 1.0, 0, 0, 0, 0, 0) == -1      # n <= 0
-    assert lib.gegp_build_cov(4, 4, 3, 0, 0, 0, 0, 0, 0.0, 1.0, 0, 0, 0, 0, 0) == -4      # X is NULL
+    assert lib.gegp_build_cov(0, 0, 3, 0, 0, 0, 0, 0.0, 0, 0, 0.0, 1.0, 0, 0, 0, 0, 0) == -1      # n <= 0
+    assert lib.gegp_build_cov(4, 4, 3, 0, 0, 0, 0, 0.0, 0, 0, 0.0, 1.0, 0, 0, 0, 0, 0) == -4      # X is NULL
+    # kernel family / kernel hyper-parameter: -50 (unknown family; rational-quadratic alpha must be positive)
+    assert lib.gegp_build_cov(4, 4, 3, 16, 0, 16, 7, 0.0, 0, 0, 0.0, 1.0, 16, 16, 0, 0, 0) == -50
+    assert lib.gegp_build_cov(4, 4, 3, 16, 0, 16, _lib.KERNEL_RATQUAD, 0.0, 0, 0, 0.0, 1.0, 16, 16, 0, 0, 0) == -50
+    assert lib.gegp_lml_eval(1, 16, 0, _lib.KERNEL_RATQUAD, 0, 4, 4, 3, 16, 0, 16, 0, 1, 0.0, 0, 0.0, 0, 16, 0, 16, 1 << 20, 0) == -50
     assert lib.gegp_potrf(0, 0, 0, 0, 0, 0, 0) == -1
     assert lib.gegp_potrf(8, 0, 0, 8, 0, 0, 0) == -3
-    assert lib.gegp_lml_eval(0, 0, 0, 4, 4, 3, 0, 0, 0, 0, 1, 0.0, 0, 0.0, 0, 0, 0, 0, 0, 0) == -1
+    assert lib.gegp_lml_eval(0, 0, 0, 0, 0, 4, 4, 3, 0, 0, 0, 0, 1, 0.0, 0, 0.0, 0, 0, 0, 0, 0, 0) == -1
     assert lib.gegp_trsm_rows(8, 0, 8, 0, 0, 8, 1, 0) == -2
     assert lib.gegp_potri(8, 0, 8, 0, 0, 8, 0, 8, 0) == -2
     assert lib.gegp_dgemm(0, 4, 4, 4, 1.0, 0, 4, 0, 4, 0.0, 0, 4, 0) == -6
@@ -63,11 +67,11 @@ def test_argument_checks_return_negative_codes_without_touching_the_gpu():
     assert lib.gegp_row_abs_sum(8, 0, 8, 0, 0) == -2 and lib.gegp_row_sq_sum(8, 16, 7, 0, 0) == -3
     assert lib.gegp_lanczos_step(8, 300, 0, 8, 0, 0, 0, 0) == -2 and lib.gegp_lanczos_step(8, 0, 0, 8, 0, 0, 0, 0) == -3
     assert lib.gegp_lincomb(8, 0, 0, 8, 0, 0, 0) == -2
-    assert lib.gegp_quad_grad(4, 4, 3, 16, 0, 16, 16, _lib.MODE_PRECON, 0.0, 0, 0, 16, 16, 1 << 20, 0) == -8   # base only
-    assert lib.gegp_weighted_grad(4, 4, 3, 16, 0, 16, 0, 16, _lib.MODE_BASE, 0.0, 0, 0, 16, 16, 1 << 20, 0) == -7  # W NULL
+    assert lib.gegp_quad_grad(4, 4, 3, 16, 0, 16, 0, 0.0, 16, _lib.MODE_PRECON, 0.0, 0, 0, 16, 16, 1 << 20, 0) == -8   # base only
+    assert lib.gegp_weighted_grad(4, 4, 3, 16, 0, 16, 0, 0.0, 0, 16, _lib.MODE_BASE, 0.0, 0, 0, 16, 16, 1 << 20, 0) == -7  # W NULL
     assert lib.gegp_quad_grad_work_bytes(4, 4, 3) > 0 and lib.gegp_quad_grad_work_bytes(0, 0, 3) == 0
-    assert lib.gegp_predict_grad(4, 4, 3, 0, 0, 0, 0, 16, 0, 0, 1, 0.0, 1.0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0) == -4
-    assert lib.gegp_predict_hess(4, 4, 3, 16, 0, 16, 16, 16, 16, 16, 0, 1, 0.0, 1.0, 16, 16, 16, 0, 16, 16, 16, 0, 0, 0, 0) == -11
+    assert lib.gegp_predict_grad(4, 4, 3, 0, 0, 0, 0, 0.0, 0, 16, 0, 0, 1, 0.0, 1.0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0) == -4
+    assert lib.gegp_predict_hess(4, 4, 3, 16, 0, 16, 0, 0.0, 16, 16, 16, 16, 0, 1, 0.0, 1.0, 16, 16, 16, 0, 16, 16, 16, 0, 0, 0, 0) == -11
     out8 = (C.c_int64 * 8)()
     assert lib.gegp_lml_layout(500, 500, 10, 1, 1, out8) == 0
     header, ld, per, offA, offP, offD, offU, offK = (int(v) for v in out8)

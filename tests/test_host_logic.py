@@ -77,7 +77,10 @@ def test_mode_table():
     with pytest.raises(AssertionError):
         GaussianProcess(2, True, "SqExp", "req_vmin")                              # stale name of the reference tests
     with pytest.raises(Exception):
-        GaussianProcess(2, True, "Ma5f2")
+        GaussianProcess(2, True, "Matern")                                         # kernel/Kernel.py:105-107
+    for kt, has_hp in (("SqExp", False), ("Ma5f2", False), ("RatQu", True)):       # kernel/Kernel.py:109
+        GP = GaussianProcess(2, True, kt)
+        assert GP.kernel_has_hp == has_hp and (GP.hp_kernel_default == 2) == has_hp
 
 
 def test_lhs_bounds_follow_history():
@@ -131,14 +134,19 @@ def test_chain_rule_cache_and_failure_contract(monkeypatch):
     assert GP.return_optz_val(v) == 123.0                    # objective = -(-cond)
 
 
+@pytest.mark.parametrize("kernel_type", ["SqExp", "Ma5f2", "RatQu"])
 @pytest.mark.parametrize("b_return_vec", [True, False])
-def test_reference_unit_test_precon_grad(b_return_vec):
-    """gpgradpy/unit_test/test_precon_grad.py:22-95 (the one reference test module that passes as shipped): analytic
-    dP/dtheta of the preconditioner against a forward finite difference, vector and matrix form."""
+def test_reference_unit_test_precon_grad(b_return_vec, kernel_type):
+    """gpgradpy/unit_test/test_precon_grad.py:22-95 (the one reference test module that passes as shipped; it loops over
+    the three kernels): analytic dP/dtheta of the preconditioner against a forward finite difference, vector and
+    matrix form."""
     from gpgradpy_b200.gp import GaussianProcess
     eps, dim, n_eval = 1e-6, 2, 1
     theta = np.linspace(2.5, 3, dim)
-    GP = GaussianProcess(dim, True, "SqExp", "precon")
+    GP = GaussianProcess(dim, True, kernel_type, "precon")
+    c = 5.0 / 3.0 if kernel_type == "Ma5f2" else 2.0
+    np.testing.assert_allclose(GP.theta2gamma(theta), np.sqrt(c * theta))
+    np.testing.assert_allclose(GP.gamma2theta(GP.theta2gamma(theta)), theta)
     pvec, pvec_inv, grad = GP.calc_Kern_precon(n_eval, n_eval, theta, calc_grad=True, b_return_vec=b_return_vec)
     n_data = n_eval * (dim + 1)
     fd = np.zeros((n_data, dim)) if b_return_vec else np.zeros((dim, n_data, n_data))

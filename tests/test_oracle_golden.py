@@ -228,3 +228,71 @@ def test_frobenius_condition_number(golden_dir, name):
     c, cg = O.cond_fro_w_grad(ka.Kcov, D)
     assert abs(c - g["cond"]) < 1e-9 * g["cond"] and abs(c - g["cond_nograd"]) < 1e-9 * g["cond"]
     assert np.max(np.abs(cg - g["cond_grad"])) < 1e-8 * np.max(np.abs(g["cond_grad"]))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Matern-5/2 and rational-quadratic kernels: fixtures written by oracle/make_golden_kernels.py from the live reference
+# (kernel/KernelMatern5f2.py, kernel/KernelRatQuad.py), all three conditioning modes
+# ---------------------------------------------------------------------------------------------------------------
+KERN_CASES = [f"kern_{k}_d3_n22_{m}" for k in ("ma5f2", "ratqu_a2", "ratqu_a07") for m in ("precon", "base", "rescale_origin")] \
+    + ["kern_ma5f2_d2_n14_mask_prefix", "kern_ratqu_d2_n14_mask_scatter", "kern_ma5f2_d5_n60_precon", "kern_ratqu_d5_n60_precon"]
+
+
+def _kern_of(g):
+    hp = float(g["hp_kernel"])
+    return (str(g["kernel"]), None if np.isnan(hp) else hp)
+
+
+@pytest.mark.parametrize("name", KERN_CASES)
+def test_kernel_families_lml_gradient_posterior(golden_dir, name):
+    g = _load(golden_dir, name)
+    kern = _kern_of(g)
+    mask = g["mask"] if g["mask"].size else None
+    mode = "precon" if str(g["mode"]) == "precon" else "base"
+    x, f, gr, th, eta = g["x_scl"], g["fval_scl"], g["grad_scl"], g["theta"], float(g["eta"])
+    n, d = x.shape
+    assert _rel(O.nugget(n, d, str(g["mode"]), kernel=kern)[1], eta) < 1e-14
+    if "Kern" in g:
+        ka = O.all_K_w_chofac(x, th, mode, eta, None, 1.0, mask, kernel=kern)
+        assert _mat_err(ka.Kern, g["Kern"]) < 1e-12 and _mat_err(ka.Kcov, g["Kcov"]) < 1e-12
+        if mode == "precon":
+            assert _mat_err(ka.Kcor, g["Kcor"]) < 1e-12
+    o = O.lkd_wo_noise(x, f, gr, th, mode, eta, mask, kernel=kern)
+    assert o.ln_lkd_grad.size == int(g["n_hp"]) == d + (kern[0] == "RatQu")       # [theta.., alpha]
+    assert _rel(o.ln_lkd, g["ln_lkd"]) < 1e-9 and _rel(o.hp_varK, g["hp_varK"]) < 1e-8
+    assert np.max(np.abs(o.ln_lkd_grad - g["ln_lkd_grad"])) / np.max(np.abs(g["ln_lkd_grad"])) < 1e-8
+    if "mu" not in g:
+        return
+    # posterior in the (possibly rescaled) coordinates the reference evaluates in
+    xt = g["x_test"]
+    if str(g["mode"]) == "rescale_origin":
+        xs_, fs_, gs_, c, sc, f0 = O.rescale_origin(g["x"], g["fval"], g["grad"], O.vreq_rescale_origin(n, d))
+        xt_s = (xt - g["x"][-1][None, :]) * c
+    else:
+        xt_s, c, sc, f0 = xt, 1.0, 1.0, 0.0
+    mu, sig, dmu, dsig = O.eval_model_grad(x, f, gr, th, float(g["hp_varK"]), g["hp_beta"], xt_s, mode, eta, None, mask,
+                                           kernel=kern)
+    mu, sig, dmu, dsig = mu / sc + f0, sig / sc, dmu * c / sc, dsig * c / sc
+    assert np.max(np.abs(mu - g["mu"])) / np.max(np.abs(g["mu"])) < 1e-8
+    assert np.max(np.abs(sig - g["sig"])) / np.max(np.abs(g["sig"])) < 1e-6
+    assert np.max(np.abs(dmu - g["dmudx"])) / np.max(np.abs(g["dmudx"])) < 1e-8
+    assert np.max(np.abs(dsig - g["dsigdx"])) / np.max(np.abs(g["dsigdx"])) < 1e-5
+    if "d2mudx2" in g and str(g["mode"]) != "rescale_origin":
+        h = O.eval_model_hess(x, f, gr, th, float(g["hp_varK"]), g["hp_beta"], xt[3], mode, eta, kernel=kern)
+        assert np.max(np.abs(h[4] - g["d2mudx2"])) / np.max(np.abs(g["d2mudx2"])) < 1e-8
+        assert np.max(np.abs(h[5] - g["d2sigdx2"])) / np.max(np.abs(g["d2sigdx2"])) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["kern_ma5f2_d3_n20_noisy_precon", "kern_ratqu_d3_n20_noisy_precon",
+                                  "kern_ratqu_d3_n20_noisy_base"])
+def test_kernel_families_noisy(golden_dir, name):
+    g = _load(golden_dir, name)
+    kern, mode = _kern_of(g), str(g["mode"])
+    o = O.lkd_w_noise(g["x"], g["fval"], g["grad"], g["theta"], float(g["varK"]), g["noise_vec"], mode, float(g["eta"]),
+                      kernel=kern)
+    assert _rel(o.ln_lkd, g["ln_lkd"]) < 1e-9
+    assert np.max(np.abs(o.ln_lkd_grad - g["ln_lkd_grad"])) / np.max(np.abs(g["ln_lkd_grad"])) < 1e-8
+    mu, sig, _, _ = O.eval_model(g["x"], g["fval"], g["grad"], g["theta"], float(g["varK"]), g["hp_beta"], g["x_test"],
+                                 mode, float(g["eta"]), g["noise_vec"], kernel=kern)
+    assert np.max(np.abs(mu - g["mu"])) / np.max(np.abs(g["mu"])) < 1e-8
+    assert np.max(np.abs(sig - g["sig"])) / np.max(np.abs(g["sig"])) < 1e-6
