@@ -27,8 +27,8 @@ int& lookahead_enabled();
 
 namespace gegp {
 
+constexpr int GEGP_MAX_DYN_SMEM = 227 * 1024;  // largest shared memory (static + dynamic) a CTA can opt in to on sm_100
 constexpr int LEAF = 128;  // blocking quantum of the recursive factorisation / inverse
-constexpr int GEGP_MAX_DYN_SMEM = 227 * 1024;  // largest dynamic shared memory a CTA can opt in to on sm_100
 
 // Launch context: every kernel of one C-ABI call goes to this stream; `batch` independent problems
 // (multi-start candidates) are laid out with a fixed element stride and mapped to blockIdx.z.
@@ -57,8 +57,14 @@ struct Ctx {
     cudaGetDevice(&dev__);                                                                       \
     const unsigned long long bit__ = 1ull << (dev__ & 63);                                       \
     if (!(done__.load(std::memory_order_acquire) & bit__)) {                                     \
-      cudaError_t e__ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+      int want__ = (int)(bytes);                                                                 \
+      if (want__ >= ::gegp::GEGP_MAX_DYN_SMEM) {   /* "as much as there is": leave room for the static part */ \
+        cudaFuncAttributes fa__;                                                                 \
+        if (cudaFuncGetAttributes(&fa__, kern) == cudaSuccess) want__ = ::gegp::GEGP_MAX_DYN_SMEM - (int)fa__.sharedSizeBytes; \
+      }                                                                                          \
+      cudaError_t e__ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, want__); \
       if (e__ != cudaSuccess) {                                                                  \
+        (void)cudaGetLastError();   /* do not leave the error for the next launch check to find */ \
         fprintf(stderr, "[gegp] cannot set %d bytes of dynamic shared memory: %s (%s:%d)\n", (int)(bytes), \
                 cudaGetErrorString(e__), __FILE__, __LINE__);                                    \
         return -1000 - (int)e__;                                                                 \
