@@ -26,7 +26,7 @@ OPT_CHAIN_CLUSTER = 4
 EXPORTS = (
     "gegp_abi_version", "gegp_set_option", "gegp_workspace_bytes", "gegp_ld", "gegp_build_cov", "gegp_cross_cov", "gegp_potrf",
     "gegp_trsm_rows", "gegp_dinv_doubles", "gegp_potri", "gegp_dgemm", "gegp_lml_eval", "gegp_predict_setup", "gegp_predict", "gegp_profile_begin", "gegp_profile_end",
-    "gegp_predict_grad", "gegp_predict_hess", "gegp_lml_layout", "gegp_symv", "gegp_row_abs_sum", "gegp_row_sq_sum", "gegp_weighted_grad", "gegp_lanczos_step", "gegp_lincomb", "gegp_quad_grad_work_bytes", "gegp_quad_grad", "gegp_dmma_peak",
+    "gegp_predict_grad", "gegp_predict_hess", "gegp_lml_layout", "gegp_symv", "gegp_row_abs_sum", "gegp_row_sq_sum", "gegp_weighted_grad", "gegp_lanczos_step", "gegp_lincomb", "gegp_quad_grad_work_bytes", "gegp_quad_grad", "gegp_dmma_peak", "gegp_lml_direct_terms",
 )
 
 
@@ -101,6 +101,8 @@ def load():
     lib.gegp_quad_grad_work_bytes.argtypes = [i, i, i]
     lib.gegp_quad_grad.restype = i
     lib.gegp_quad_grad.argtypes = [i, i, i, dp, ip, dp, i, dbl, dp, i, dbl, i, dp, dp, vp, sz, vp]
+    lib.gegp_lml_direct_terms.restype = i
+    lib.gegp_lml_direct_terms.argtypes = [i, i, i, dp, ip, dp, i, dbl, i, dbl, i, dp, vp, sz, dp, dp, vp]
     lib.gegp_dmma_peak.restype = i
     lib.gegp_dmma_peak.argtypes = [dp, sz, i, C.POINTER(dbl), vp]
     lib.gegp_profile_begin.restype = None

@@ -572,6 +572,29 @@ def quad_grad(X, theta, v, *, n_g=None, slot=None, eta=0.0, noisy=False, varK=1.
     return out
 
 
+def lml_direct_terms(X, theta, *, n_g=None, slot=None, mode=L.MODE_PRECON, eta=0.0, noisy=False, varK=1.0, kernel=None):
+    """gegp_lml_direct_terms right after a B = 1 lml_eval(want_grad=True) on this device -> dict of per-hyper-parameter
+    rows (GEGP_OUT_* layout, NumPy): aDa = a^T D a, hDa = h^T D a, trKinvD = tr(K^-1 D), and the scalars HKH, Ha."""
+    lib = L.load()
+    X, theta = to_dev(X), to_dev(theta)
+    n, d = X.shape
+    n_g = n if n_g is None else n_g
+    N = n + n_g * d
+    ws = _ws_cache.get(torch.cuda.current_device())
+    assert ws is not None, "no likelihood evaluation has run on this device yet"
+    ol = L.out_len(d)
+    out = torch.zeros(4 * ol + 2, dtype=F64, device=device())
+    scratch = torch.empty(4 * ld_of(N), dtype=F64, device=device())
+    vk = to_dev(np.array([float(varK)]))
+    kid, khp = _kern(kernel)
+    rc = lib.gegp_lml_direct_terms(n, n_g, d, _p(X), _p(slot), _p(theta), kid, khp, int(mode), float(eta), int(bool(noisy)),
+                                   _p(vk), _p(ws), ws.numel(), _p(scratch), _p(out), _stream())
+    _check(rc, "gegp_lml_direct_terms")
+    o = out.cpu().numpy()
+    rows = o[:4 * ol].reshape(4, ol)
+    return dict(aDa=rows[0], hDa=0.25 * (rows[1] - rows[2]), trKinvD=rows[3], HKH=float(o[4 * ol]), Ha=float(o[4 * ol + 1]))
+
+
 def lml_views(n: int, n_g: int, d: int):
     """Views of candidate 0's arrays inside the shared workspace, valid right after a B = 1 lml_eval(want_grad=True)
     (eager or graph replay) on this device: dict(A [N+2, ld] factor, U [N, ld], Kinv [N, ld], ld)."""

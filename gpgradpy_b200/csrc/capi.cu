@@ -677,3 +677,81 @@ int gegp_predict_hess(int n, int n_g, int d, const double* X, const int32_t* gra
 }
 
 }  // extern "C"
+
+namespace {
+// hh = z_h . z_h ( = H^T K^-1 H ) and aH = sum_{i < n} pinv_i alpha~_i ( = H^T K^-1 (y - H beta) ), one CTA
+__global__ void __launch_bounds__(256)
+direct_scalars_kernel(int N, int n, const double* __restrict__ zh, const double* __restrict__ alpha_t,
+                      const double* __restrict__ pinv, double* __restrict__ out2) {
+  __shared__ double sh[32];
+  double hh = 0.0, aH = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double z = zh[i];
+    hh += z * z;
+    if (i < n) aH += pinv[i] * alpha_t[i];
+  }
+  hh = block_sum(hh, sh);
+  aH = block_sum(aH, sh);
+  if (threadIdx.x == 0) { out2[0] = hh; out2[1] = aH; }
+}
+// vp = a + h, vm = a - h, zero = 0
+__global__ void direct_vectors_kernel(int N, const double* __restrict__ a, const double* __restrict__ h,
+                                      double* __restrict__ vp, double* __restrict__ vm, double* __restrict__ zero) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  vp[i] = a[i] + h[i];
+  vm[i] = a[i] - h[i];
+  zero[i] = 0.0;
+}
+}  // namespace
+
+extern "C" int gegp_lml_direct_terms(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+                                     int kernel, double kernel_hp, int mode, double eta, int noisy, const double* varK_dev,
+                                     void* work, size_t work_bytes, double* scratch, double* out, void* stream) {
+  if (bad_geom(n, n_g, d)) return -1;
+  if (bad_kernel(kernel, kernel_hp)) return -50;
+  if (!X) return -4;
+  if (n_g != n && !grad_slot) return -5;
+  if (!theta) return -6;
+  if (mode != GEGP_MODE_BASE && mode != GEGP_MODE_PRECON) return -7;
+  if (noisy && !varK_dev) return -10;
+  if (!work || (reinterpret_cast<uintptr_t>(work) & 15)) return -11;
+  const int N = n + n_g * d;
+  const LmlLayout L = lml_layout(n, d, N, true);
+  const size_t header = info_header_bytes(1);
+  if (work_bytes < header + L.per_cand_doubles * sizeof(double)) return -12;
+  if (!scratch || (reinterpret_cast<uintptr_t>(scratch) & 15)) return -13;
+  if (!out) return -14;
+  double* wk = reinterpret_cast<double*>(reinterpret_cast<char*>(work) + header);
+  const double* A = wk + L.A;
+  const double* pinv = wk + L.P + L.ld;
+  const double* alpha_t = wk + L.W + L.ld;          // preconditioned alpha = L^-T w of the evaluation
+  const double* U = wk + L.U;
+  const double* Kinv = wk + L.Kinv;
+  double* part = wk + L.Part;
+  const double* zh = A + (int64_t)(N + 1) * L.ld;   // L^-1 P^-1 H, second appended row of the trapezoid
+  double* h_t = scratch;                             // preconditioned h = L^-T z_h  (K^-1 H = P^-1 h_t)
+  double* vp = scratch + L.ld, *vm = scratch + 2 * L.ld, *zero = scratch + 3 * L.ld;
+  const int outlen = GEGP_OUT_LEN(d);
+  Ctx ctx{(cudaStream_t)stream, 1};
+  const Geom gm = make_geom(n, n_g, d, X, grad_slot, kernel, kernel_hp);
+  int rc = trmv_upper(ctx, U, L.ld, 0, zh, 0, h_t, 0, N);
+  if (rc) return rc;
+  direct_vectors_kernel<<<(N + 255) / 256, 256, 0, ctx.stream>>>(N, alpha_t, h_t, vp, vm, zero);
+  GEGP_CHECK_LAUNCH();
+  direct_scalars_kernel<<<1, 256, 0, ctx.stream>>>(N, n, zh, alpha_t, pinv, out + 4 * (int64_t)outlen);
+  GEGP_CHECK_LAUNCH();
+  {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double) * 4 * (size_t)outlen, ctx.stream);
+    if (e != cudaSuccess) return -1000 - (int)e;
+  }
+  const double* vecs[3] = {alpha_t, vp, vm};
+  for (int q = 0; q < 3; q++) {      // rows 0..2: v^T (dKcov/dhp) v for v = alpha, alpha + h, alpha - h
+    rc = launch_lml_grad(ctx, gm, theta, 0, nullptr, 0, 0, vecs[q], 0, pinv, 0, mode, eta, noisy, varK_dev, 0.0, part, 0,
+                         out + (int64_t)q * outlen, 0, 1);
+    if (rc) return rc;
+  }
+  // row 3: sum(K^-1 .* dKcov/dhp) = tr(K^-1 dKcov/dhp)
+  return launch_lml_grad(ctx, gm, theta, 0, Kinv, L.ld, 0, zero, 0, pinv, 0, mode, eta, noisy, varK_dev, 0.0, part, 0,
+                         out + 3 * (int64_t)outlen, 0, 2);
+}

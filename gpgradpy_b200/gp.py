@@ -590,8 +590,31 @@ class GaussianProcess:
         out, _ = bk.lml_eval(self._X_dev, self._y_dev, theta_rows, noise=noise_vec, varK_batch=varK_rows, **kw)
         return out
 
+    def _direct_form(self, hp_vals, info, varK_scale, pn_grad=0.0):
+        """lkd_use_adj_mtd = False (optz/CalcLkd.py:64-85 noise-free, :238-241 noisy): fill hp_beta_grad, hp_varK_grad,
+        ln_det_Kmat_grad and the direct-form ln_lkd_grad from three on-the-fly contractions over dKcov/dhp
+        (gegp_lml_direct_terms) of the evaluation that has just run."""
+        noisy = self.b_has_noisy_data
+        t = bk.lml_direct_terms(self._X_dev, np.asarray(hp_vals.theta, dtype=float), n_g=self.n_grad, slot=self._slot_dev,
+                                mode=self._mode, eta=getattr(self, "_eta_used", self._etaK), noisy=noisy,
+                                varK=float(hp_vals.varK) if noisy else 1.0, kernel=self._kern(hp_vals))
+        aDa, hDa, tr = (self._hp_row_to_grad(t[k]) for k in ("aDa", "hDa", "trKinvD"))
+        N = self.n_data
+        beta_grad = -hDa / t["HKH"]                              # eval/GpMeanFun.py:110-117 (term2 = -alpha)
+        info.hp_beta_grad = beta_grad[None, :]
+        info.ln_det_Kmat_grad = tr                               # optz/CalcLkd.py:349-367
+        if noisy:                                                # optz/CalcLkd.py:253-265
+            info.ln_lkd_grad = -0.5 * tr + 0.5 * aDa + t["Ha"] * beta_grad
+        else:                                                    # optz/CalcLkd.py:104-116, 135-147
+            varK_grad = (-2.0 * t["Ha"] * beta_grad - aDa) / N
+            info.hp_varK_grad = varK_grad
+            info.ln_lkd_grad = -0.5 * (N * varK_grad / varK_scale + tr) - pn_grad * varK_grad
+        return info
+
     def calc_lkd_all(self, hp_vals, calc_lkd=True, calc_cond=False, calc_grad=False, lkd_use_adj_mtd=None):
-        """(LkdInfo, b_chofac_good) -- optz/CalcLkd.py:270-346, adjoint form only (the reference default).
+        """(LkdInfo, b_chofac_good) -- optz/CalcLkd.py:270-346.  lkd_use_adj_mtd (default: the class option, True) picks
+        the adjoint form (:149-181) or the direct one (:135-147), which also returns hp_beta_grad, hp_varK_grad and
+        ln_det_Kmat_grad; the two gradients agree to rounding.
 
         With calc_cond the 2-norm condition number of the factored matrix (and, outside precon mode, its
         hyper-parameter gradient, optz/GpHparaCon.py:161-235) is computed on the device from the factor and the
@@ -604,6 +627,7 @@ class GaussianProcess:
         eta = None if self.cond_eta_is_const else self._eta_for(hp_vals)
         self._eta_used = self._etaK if eta is None else eta
         hi = self.hp_info_optz_lkd
+        use_adj = self.lkd_use_adj_mtd if lkd_use_adj_mtd is None else lkd_use_adj_mtd
         khp = np.array([self._kern(hp_vals)[1]]) if self.kernel_has_hp else None
         if self.b_has_noisy_data:
             noise = self.calc_noise_vec(hp_vals)
@@ -626,6 +650,8 @@ class GaussianProcess:
                 if hi.has_var_fgrad:
                     g[hi.idx_var_fgrad] = o[L.OUT_DVARG]
                 info.ln_lkd_grad = g
+                if not use_adj:
+                    info = self._direct_form(hp_vals, info, float(hp_vals.varK))
             if calc_cond:
                 info.cond, info.cond_grad = self._cond_from_workspace(hp_vals, calc_grad)
                 if self.wellcond_mtd != "precon" and info.cond > self.cond_max_abs:
@@ -648,6 +674,8 @@ class GaussianProcess:
                 if hi.has_kernel:
                     g[hi.idx_kernel] = o[L.OUT_DKERN]
                 info.ln_lkd_grad = g
+                if not use_adj:
+                    info = self._direct_form(hp_vals, info, float(o[L.OUT_SIGMA2]), pn_grad)
         if calc_cond:
             info.cond, info.cond_grad = self._cond_from_workspace(hp_vals, calc_grad)
             if self.wellcond_mtd != "precon" and info.cond > self.cond_max_abs:

@@ -226,6 +226,21 @@ int gegp_quad_grad(int n, int n_g, int d, const double* X, const int32_t* grad_s
                    const double* v, int mode, double eta, int noisy, const double* varK_dev, double* out,
                    void* work, size_t work_bytes, void* stream);
 
+/* Direct (non-adjoint) likelihood form, lkd_use_adj_mtd = False (optz/CalcLkd.py:64-85, 104-116, 135-147, 349-367;
+ * eval/GpMeanFun.py:110-120; noisy data: optz/CalcLkd.py:206-207, 238-241, 253-265).  The reference forms, for every
+ * hyper-parameter hp_k with D_k = dKcov/dhp_k:  a^T D_k a,  h^T D_k a  and  tr(K^-1 D_k)  (a = K^-1 (y - H beta),
+ * h = K^-1 H) and from them hp_beta_grad, hp_varK_grad, ln_det_Kmat_grad and ln_lkd_grad.  This call produces those sums
+ * from what a preceding gegp_lml_eval(B = 1, want_grad = 1) on the same `work` left behind (factor rows, L^-T, the
+ * explicit inverse), generating D_k on the fly:
+ *   out[0 .. 3][GEGP_OUT_LEN(d)]: rows laid out as GEGP_OUT_* (GRAD + m, DKERN, and when noisy DVARK / DVARF / DVARG):
+ *       row 0: a^T D a     row 1: (a + h)^T D (a + h)     row 2: (a - h)^T D (a - h)     row 3: tr(K^-1 D)
+ *       (h^T D a = (row 1 - row 2) / 4)
+ *   out[4 * GEGP_OUT_LEN(d) + 0] = H^T K^-1 H,   out[4 * GEGP_OUT_LEN(d) + 1] = H^T a.
+ * theta, kernel, mode, eta, noisy, varK_dev must be those of that evaluation; scratch: 4 * gegp_ld(N) doubles. */
+int gegp_lml_direct_terms(int n, int n_g, int d, const double* X, const int32_t* grad_slot, const double* theta,
+                          int kernel, double kernel_hp, int mode, double eta, int noisy, const double* varK_dev,
+                          void* work, size_t work_bytes, double* scratch, double* out, void* stream);
+
 /* Instrumentation for bench.py (not on the product path): count kernel launches, and (time_gemm != 0)
  * bracket every DMMA GEMM launch with CUDA events on its stream.  gegp_profile_end synchronises the device. */
 void gegp_profile_begin(int time_gemm);

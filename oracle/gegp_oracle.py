@@ -820,3 +820,44 @@ def rescale_origin(X, fval, grad, dist_set):
     fs = (fval - fval[-1]) * s
     gs = grad * (s / c)
     return xs, fs, gs, c, s, fval[-1]
+
+
+# ----------------------------------------------------------------------------------------------
+# direct (non-adjoint) likelihood form, lkd_use_adj_mtd = False
+# ----------------------------------------------------------------------------------------------
+
+def lkd_direct(X, fval, grad, theta, mode="precon", eta=None, mask=None, kernel=None, varK=None, noise_vec=None,
+               has_var_fval=False, has_var_fgrad=False, pnlt_grad=0.0):
+    """The quantities the reference only returns with lkd_use_adj_mtd = False: (ln_lkd_grad, hp_beta_grad [1, n_hp],
+    hp_varK_grad or None, ln_det_Kmat_grad).  Noise-free (varK None): optz/CalcLkd.py:64-85 with calc_lkd_opt_varK
+    (:104-116), calc_detKmat (:349-367), calc_lkd_w_Kern_mtd_direct (:135-147) and the beta gradient of
+    eval/GpMeanFun.py:110-120.  Noisy: optz/CalcLkd.py:206-207, 238-241, 253-265."""
+    n, d = X.shape
+    if eta is None:
+        eta = nugget(n, d, mode, kernel=kernel)[1]
+    noisy = varK is not None
+    ka = all_K_w_chofac(X, theta, mode, eta, noise_vec if noisy else None, varK if noisy else 1.0, mask, kernel=kernel)
+    g = _sel(n, mask).size
+    y = make_data_vec(fval, grad)
+    N = y.size
+    H = aug_vand(n, g, d)
+    if noisy:
+        D = kcov_grad_hp_noisy(X, theta, ka.Kern, mode, eta, varK, has_var_fval, has_var_fgrad, mask, kernel=kernel)
+    else:
+        D = kerngrad_hp(X, theta, mode, eta, mask, kernel=kernel)
+    invK_H = linalg.cho_solve(ka.chofac, H)
+    term1 = np.linalg.solve(H.T @ invK_H, invK_H.T)
+    beta = term1 @ y
+    term2 = invK_H @ beta - linalg.cho_solve(ka.chofac, y)
+    beta_grad = np.einsum("ij,kjl,l->ik", term1, D, term2)
+    model_grad = H @ beta_grad
+    res = y - H @ beta
+    a = linalg.cho_solve(ka.chofac, res)
+    ln_det_grad = np.array([np.trace(linalg.cho_solve(ka.chofac, D[i])) for i in range(D.shape[0])])
+    if noisy:
+        lkd_grad = -0.5 * ln_det_grad + 0.5 * np.einsum("i,kij,j", a, D, a) + a @ model_grad
+        return lkd_grad, beta_grad, None, ln_det_grad
+    vK = max(1e-32, float(res @ a) / N)
+    varK_grad = (-2.0 * a @ model_grad - np.einsum("i,kij,j", a, D, a)) / N
+    lkd_grad = -0.5 * (N * (varK_grad / vK) + ln_det_grad) - pnlt_grad * varK_grad
+    return lkd_grad, beta_grad, varK_grad, ln_det_grad

@@ -158,3 +158,36 @@ def test_kernel_family_fit_runs_and_batched_scan_matches_single_evaluations(knam
         assert GP.hp_kernel_range[0] <= GP.hp_vals.kernel <= GP.hp_kernel_range[1]
     mu, sig = GP.eval_model(x[:5])[:2]
     assert np.max(np.abs(mu - f[:5])) < 1e-2 * (f.max() - f.min())
+
+
+DIRECT_CASES = ["direct_sqexp_d3_n20_precon", "direct_sqexp_d3_n20_base", "direct_sqexp_d2_n16_rescale_origin",
+                "direct_ratqu_d3_n20_precon", "direct_ma5f2_d3_n20_precon", "direct_sqexp_d3_n20_noisy_precon",
+                "direct_ratqu_d3_n20_noisy_base"]
+
+
+@pytest.mark.parametrize("name", DIRECT_CASES)
+def test_direct_likelihood_form_vs_reference(golden_dir, name):
+    """calc_lkd_all(lkd_use_adj_mtd=False): the direct form of optz/CalcLkd.py:64-85 / 135-147 (noise-free) and :238-241 /
+    253-265 (noisy), with hp_beta_grad (eval/GpMeanFun.py:110-120), hp_varK_grad (:104-116) and ln_det_Kmat_grad
+    (:349-367), against the live reference's values; and the adjoint default still leaves those fields None."""
+    from gpgradpy_b200.gp import GaussianProcess
+    g = _load(golden_dir, name)
+    kname, khp = _kern_of(g)
+    x, f, gr = g["x"], g["fval"], g["grad"]
+    n, d = x.shape
+    noisy = not np.isnan(float(g["varK"]))
+    GP = GaussianProcess(d, True, kname, str(g["mode"]))
+    GP.set_data(x, f, float(g["std_f"]) * np.ones(n), gr, float(g["std_g"]) * np.ones(gr.shape))
+    hp = GP.make_hp_class(theta=g["theta"], kernel=khp, varK=float(g["varK"]) if noisy else None)
+    adj, ok = GP.calc_lkd_all(hp, calc_grad=True)
+    assert ok and adj.hp_beta_grad is None and adj.ln_det_Kmat_grad is None
+    dr, ok = GP.calc_lkd_all(hp, calc_grad=True, lkd_use_adj_mtd=False)
+    assert ok
+    rel = lambda a, b: float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.max(np.abs(b)))  # noqa: E731
+    e = {"lkd_grad": rel(dr.ln_lkd_grad, g["ln_lkd_grad"]), "beta_grad": rel(dr.hp_beta_grad, g["hp_beta_grad"]),
+         "logdet_grad": rel(dr.ln_det_Kmat_grad, g["ln_det_Kmat_grad"]), "adjoint": rel(adj.ln_lkd_grad, g["ln_lkd_grad_adjoint"])}
+    if not noisy:
+        e["varK_grad"] = rel(dr.hp_varK_grad, g["hp_varK_grad"])
+    print(name, {k: f"{v:.2e}" for k, v in e.items()})
+    assert dr.hp_beta_grad.shape == g["hp_beta_grad"].shape
+    assert all(v < 1e-8 for v in e.values()), e

@@ -296,3 +296,33 @@ def test_kernel_families_noisy(golden_dir, name):
                                  mode, float(g["eta"]), g["noise_vec"], kernel=kern)
     assert np.max(np.abs(mu - g["mu"])) / np.max(np.abs(g["mu"])) < 1e-8
     assert np.max(np.abs(sig - g["sig"])) / np.max(np.abs(g["sig"])) < 1e-6
+
+
+DIRECT_CASES = ["direct_sqexp_d3_n20_precon", "direct_sqexp_d3_n20_base", "direct_sqexp_d2_n16_rescale_origin",
+                "direct_ratqu_d3_n20_precon", "direct_ma5f2_d3_n20_precon", "direct_sqexp_d3_n20_noisy_precon",
+                "direct_ratqu_d3_n20_noisy_base"]
+
+
+@pytest.mark.parametrize("name", DIRECT_CASES)
+def test_direct_likelihood_form(golden_dir, name):
+    """lkd_use_adj_mtd = False (optz/CalcLkd.py:64-85, 135-147, 238-241): ln_lkd_grad, hp_beta_grad, hp_varK_grad and
+    ln_det_Kmat_grad of the reference's direct form (oracle/make_golden_direct.py)."""
+    g = _load(golden_dir, name)
+    hp = float(g["hp_kernel"])
+    kern = (str(g["kernel"]), None if np.isnan(hp) else hp)
+    x, f, gr, mode = g["x"], g["fval"], g["grad"], str(g["mode"])
+    n, d = x.shape
+    noisy = not np.isnan(float(g["varK"]))
+    if mode == "rescale_origin":
+        x, f, gr = O.rescale_origin(x, f, gr, O.vreq_rescale_origin(n, d))[:3]
+    m = "precon" if mode == "precon" else "base"
+    if noisy:
+        nv = np.hstack((np.full(n, float(g["std_f"]) ** 2), np.full(n * d, float(g["std_g"]) ** 2)))
+        o = O.lkd_direct(x, f, gr, g["theta"], m, float(g["eta"]), kernel=kern, varK=float(g["varK"]), noise_vec=nv)
+    else:
+        o = O.lkd_direct(x, f, gr, g["theta"], m, float(g["eta"]), kernel=kern)
+    rel = lambda a, b: float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.max(np.abs(b)))  # noqa: E731
+    assert rel(o[0], g["ln_lkd_grad"]) < 1e-8 and rel(o[1], g["hp_beta_grad"]) < 1e-8 and rel(o[3], g["ln_det_Kmat_grad"]) < 1e-8
+    if not noisy:
+        assert rel(o[2], g["hp_varK_grad"]) < 1e-8
+    assert rel(g["ln_lkd_grad"], g["ln_lkd_grad_adjoint"]) < 1e-8        # the two forms of the reference agree
