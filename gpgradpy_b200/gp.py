@@ -404,6 +404,8 @@ class GaussianProcess:
             self.Rtensor_init = _DeviceRtensor(n_eval, self.dim)
         self._dev_ready = False
         self._pred = None
+        self.KernEta_chofac = None        # a model set up for the previous data cannot be evaluated any more
+        self.invKernEta_fdiff = None
         self._last_hp_vec = None
         self._last_cond = None
 
@@ -775,10 +777,9 @@ class GaussianProcess:
         hp_vec_rows: [B, n_hp] in optimiser coordinates (log10 where bvec_log_optz).  Returns a NumPy table
         [B, 9+d] laid out as GEGP_OUT_* -- identical on every rank.  This is the batched form of the loops at
         optz/GpHparaX0.py:39-45 and optz/OptzLkd.py:249-270."""
-        import torch
-        assert not self.b_has_noisy_data
         rows = np.atleast_2d(np.asarray(hp_vec_rows, dtype=float))
         hi = self.hp_info_optz_lkd
+        assert not (hi.has_var_fval or hi.has_var_fgrad), "rows with their own noise variance are evaluated one by one"
         th = rows[:, hi.idx_theta].copy()
         if self.optz_log_hp_theta:
             th = 10 ** th
@@ -788,12 +789,20 @@ class GaussianProcess:
             if hi.has_kernel and self.optz_log_hp_kernel:
                 kh = 10 ** kh
             cols.append(kh[:, None])
+        noise = None
+        if self.b_has_noisy_data:   # known noise: one vector for every row; varK is a column of the candidate table
+            vk = rows[:, hi.idx_varK].copy()
+            cols.append((10 ** vk if self.optz_log_hp_var else vk)[:, None])
+            noise = self.calc_noise_vec(self.make_hp_class(theta=th[0]))
         cand = bk.to_dev(np.hstack(cols))
         d = self.dim
+        c_k = d if self.kernel_has_hp else None
+        c_v = (d + (1 if self.kernel_has_hp else 0)) if self.b_has_noisy_data else None
 
         def eval_shard(c):
             return self._eval_rows(c[:, :d].contiguous(), want_grad=calc_grad,
-                                   khp_rows=c[:, d].cpu().numpy() if self.kernel_has_hp else None)
+                                   khp_rows=c[:, c_k].cpu().numpy() if c_k is not None else None,
+                                   varK_rows=c[:, c_v].cpu().numpy() if c_v is not None else None, noise_vec=noise)
         table = parallel.sharded_eval(eval_shard, cand, self.dist_group, width=L.out_len(self.dim))
         return table.cpu().numpy()
 
@@ -895,11 +904,36 @@ class GaussianProcess:
         else:
             raise Exception(f"Unknown lkd_optz_start_mtd: {self.lkd_optz_start_mtd}")
         hp_x0, bounds = self.get_hp_x0_lhs_median(i_optz, hp_optz_info, n_x0)
+        self._scan_stats = None
         if self.lkd_optz_start_mtd == "hp_best":
-            if self.b_has_noisy_data or self.wellcond_mtd != "precon":
+            calc_cond = self.wellcond_mtd != "precon"
+            if self._can_batch_scan(hp_optz_info):
+                # ONE batched device call for the LML of all rows; the condition number (base / rescale modes) is only
+                # needed to veto the winner, so it is computed lazily down the LML ranking: same selection as the loop
+                tab = self.calc_lkd_batch(hp_x0, calc_grad=False)
+                lml = np.where(tab[:, L.OUT_INFO] == 0, tab[:, L.OUT_LML], np.nan)
+                n_cond = 0
+                if calc_cond and np.any(np.isfinite(lml)):
+                    cond_all = np.full(n_x0, np.nan)
+                    order = [i for i in np.argsort(-np.where(np.isfinite(lml), lml, -np.inf)) if np.isfinite(lml[i])]
+                    chosen = None
+                    for i in order:
+                        info, good = self.calc_lkd_all(self.hp_vec2dataclass(hp_optz_info, hp_x0[i, :]), calc_cond=True)
+                        n_cond += 1
+                        cond_all[i] = info.cond if info.cond is not None else np.nan
+                        if good and not (cond_all[i] > 1.2 * self.cond_max):
+                            chosen = i
+                            break
+                        lml[i] = np.nan
+                    if chosen is None:      # every row is too ill-conditioned: the loop keeps the least bad one
+                        lml[:] = np.nan
+                        if np.any(np.isfinite(cond_all)):
+                            k = int(np.nanargmin(cond_all))
+                            lml[k] = tab[k, L.OUT_LML]
+                self._scan_stats = dict(batched=True, n_cond_evals=n_cond)
+            else:
                 lml = np.full(n_x0, np.nan)
                 cond_all = np.full(n_x0, np.nan)
-                calc_cond = self.wellcond_mtd != "precon"
                 for i in range(n_x0):
                     info, good = self.calc_lkd_all(self.hp_vec2dataclass(hp_optz_info, hp_x0[i, :]), calc_cond=calc_cond)
                     if good:
@@ -909,11 +943,15 @@ class GaussianProcess:
                     if np.sum(bad) == bad.size:
                         bad[np.nanargmin(cond_all)] = False
                     lml[bad] = np.nan
-            else:
-                tab = self.calc_lkd_batch(hp_x0, calc_grad=False)
-                lml = np.where(tab[:, L.OUT_INFO] == 0, tab[:, L.OUT_LML], np.nan)
+                self._scan_stats = dict(batched=False, n_cond_evals=n_x0 if calc_cond else 0)
             hp_x0 = hp_x0[np.nanargmax(lml), :][None, :]
         return hp_x0, bounds, time.time() - t0
+
+    def _can_batch_scan(self, hp_optz_info):
+        """The candidate scan runs as one batched call whenever every row shares the nugget and the noise vector: constant
+        eta, no varK penalty, and no noise variance among the optimised hyper-parameters (known noise is fine)."""
+        return self.cond_eta_is_const and (not self.lkd_varK_pnlt_use) and (not hp_optz_info.has_var_fval) \
+            and (not hp_optz_info.has_var_fgrad)
 
     # ------------------------------------------------------------------ fit (optz/GpHparaOptz.py, optz/OptzLkd.py:185-333)
     def get_init_hp_vals(self):
@@ -983,12 +1021,14 @@ class GaussianProcess:
         info = {"hp_optz_success": float(np.mean(ok)), "hp_optz_iter_mean": float(np.mean(nit)),
                 "hp_optz_iter_max": float(np.max(nit)), "hp_optz_con_good": float(np.mean(con_good)),
                 "optz_n_cho_fail": n_cho_fail, "optz_n_cond2big": n_cond2big, "optz_max_init_cond": max_init_cond}
-        cond_val = np.nan
-        if self.b_use_cond_cstr:   # final condition number of the chosen solution (:323-331)
-            best_vals = self.hp_vec2dataclass(self.hp_info_optz_lkd, best)
-            cond_val = self.calc_all_K_w_chofac(None, best_vals, calc_chofac=False, calc_cond=True,
-                                                varK=None if self.b_has_noisy_data else 1)[4]
-        return best, cond_val, info
+        return best, self._final_cond(best), info
+
+    def _final_cond(self, best):
+        """Condition number of the matrix the chosen solution factors (optz/OptzLkd.py:323-331; every mode: in precon
+        mode it is kappa of the preconditioned matrix, kernel/Kernel.py:240) -- it ends up in Kcov_cond_all."""
+        best_vals = self.hp_vec2dataclass(self.hp_info_optz_lkd, best)
+        return self.calc_all_K_w_chofac(None, best_vals, calc_chofac=False, calc_cond=True,
+                                        varK=None if self.b_has_noisy_data else 1)[4]
 
     def _can_batch_fit(self):
         """The batched objective covers the noise-free, unconstrained (precon) fit with a constant nugget."""
@@ -1047,7 +1087,7 @@ class GaussianProcess:
         info = {"hp_optz_success": float(np.mean(ok)), "hp_optz_iter_mean": float(np.mean(nit)),
                 "hp_optz_iter_max": float(np.max(nit)), "hp_optz_con_good": 1.0, "optz_n_cho_fail": 0,
                 "optz_n_cond2big": 0, "optz_max_init_cond": np.nan}
-        return best, np.nan, info
+        return best, self._final_cond(best), info
 
     def rescaling_data_w_theta_sol(self, X_scl_v1, xvec_scale_v1, hp_theta, tol_min_dist_x=1e-15):
         """base/GpWellCond.py:42-76: anisotropic re-scaling of x by sqrt(theta / geometric-mean theta), corrected so
@@ -1197,6 +1237,8 @@ class GaussianProcess:
         if calc_cond:
             self.condK = self.calc_all_K_w_chofac(None, hp, b_normlz_w_varK=True, calc_chofac=False, calc_cond=True)[4]
         good = int(self._pred.info.item()) == 0
+        if self.condK is not None and self.wellcond_mtd != "precon" and self.condK > self.cond_max_abs:
+            good = False          # the reference does not attempt the factorisation then (kernel/Kernel.py:282-283)
         self.KernEta_chofac = self._pred if good else None
         self.invKernEta_fdiff = DeviceMatrix(self._pred.alpha) if good else None
 

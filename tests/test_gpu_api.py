@@ -254,3 +254,30 @@ def test_gradient_free_gp_posterior_and_x_gradients():
         mm, sm = GP.eval_model(xs - e)[:2]
         assert np.max(np.abs((mp - mm) / (2 * eps) - dmu[:, j])) < 1e-5 * np.max(np.abs(dmu))
         assert np.max(np.abs((sp - sm) / (2 * eps) - dsig[:, j])) < 1e-4 * np.max(np.abs(dsig))
+
+
+@pytest.mark.parametrize("mode,noisy", [("rescale_origin", False), ("base", False), ("precon", True), ("base", True)])
+def test_candidate_scan_is_batched_in_every_mode(mode, noisy):
+    """Batch point A (optz/GpHparaX0.py:39-45) outside the noise-free precon case: the 40 candidate rows are evaluated
+    in ONE batched device call; in the base / rescale modes the condition number (optz/GpHparaX0.py:47-57) is only
+    computed down the LML ranking until a feasible row is found.  Same selected start point as the reference's
+    sequential loop (which this class still runs when rows do not share nugget / noise)."""
+    from gpgradpy_b200.gp import GaussianProcess
+    from oracle import gegp_oracle as O
+    n, d = 60, 3
+    x, f, g = O.synthetic_problem(n, d, 5)
+    GP = GaussianProcess(d, True, "SqExp", mode)
+    GP.init_optz_surr(3)
+    sf, sg = (1e-2, 5e-2) if noisy else (0.0, 0.0)
+    GP.set_data(x[:1], f[:1], sf * np.ones(1), g[:1], sg * np.ones((1, d)))
+    GP.set_hpara("optz", 0)
+    GP.set_data(x, f, sf * np.ones(n), g, sg * np.ones((n, d)))
+    hi = GP.hp_info_optz_lkd
+    assert GP._can_batch_scan(hi)
+    x0_b = GP.select_hp_optz_x0(1, hi)[0]
+    stats = dict(GP._scan_stats)
+    assert stats["batched"] and stats["n_cond_evals"] <= 2          # 1 batched call + at most 2 condition numbers
+    GP._can_batch_scan = lambda info: False
+    x0_s = GP.select_hp_optz_x0(1, hi)[0]
+    assert not GP._scan_stats["batched"]
+    assert np.array_equal(x0_b, x0_s)

@@ -82,6 +82,7 @@ def _make_gp(monkeypatch_obj=None):
         return torch.as_tensor(out)
 
     GP._eval_rows = fake_eval_rows
+    GP._final_cond = lambda best: np.nan     # the closing condition number is a device computation (GPU tests cover it)
     return GP
 
 
