@@ -99,3 +99,75 @@ def test_coincident_points():
         assert info2.ln_lkd is None and np.isfinite(info2.cond) and info2.cond > 1e10
     tup = GP2.calc_all_K_w_chofac(None, GP2.make_hp_class(theta=th), varK=1)
     assert (tup[3] is None) == (not ok2)
+
+
+@pytest.mark.parametrize("kname,khp", [("SqExp", None), ("Ma5f2", None), ("RatQu", 1.5)])
+def test_no_write_outside_caller_buffers_and_bit_stable_reruns(kname, khp):
+    """compute-sanitizer is closed on this GPU pool (profiles/r02/sanitizer_closed_on_pool.log), so the memcheck /
+    racecheck role is played by checks of our own: every buffer the C ABI writes (workspace, outputs, factor, posterior
+    rows) sits between canary regions that must come back untouched, the evaluation runs on a NaN-poisoned workspace, and
+    20 re-runs -- ten of them with a second evaluation in flight on another stream -- must reproduce the result bit for
+    bit (a shared-memory or cross-stream race shows up as a changed bit sooner or later)."""
+    import torch
+    from gpgradpy_b200 import backend as bk, _lib as L
+    from oracle import gegp_oracle as O
+    n, d = 100, 3
+    N = n * (d + 1)
+    x, f, g = O.synthetic_problem(n, d, 0)
+    th = O.bench_theta(d) * 3
+    y = O.make_data_vec(f, g)
+    eta = O.nugget(n, d, "precon", kernel=(kname, khp))[1]
+    lib = L.load()
+    G = 1 << 16                                                    # canary bytes on either side
+    need = int(lib.gegp_workspace_bytes(L.OP_LML_GRAD, n, n, d, 3)) + 4096
+    big = torch.full((need + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda")
+    ws = big[G:G + need]
+    ws.view(torch.float64)[:] = float("nan")
+    dev = torch.cuda.current_device()
+    old = bk._ws_cache.get(dev)
+    bk._ws_cache[dev] = ws
+    try:
+        outbig = torch.full((3 * L.out_len(d) + 64,), 7.25, dtype=torch.float64, device="cuda")
+        out = outbig[32:32 + 3 * L.out_len(d)].view(3, L.out_len(d))
+        X, Y = bk.to_dev(x), bk.to_dev(y)
+        TH = bk.to_dev(np.vstack([th, 1.3 * th, 0.6 * th]))
+        kw = dict(mode=L.MODE_PRECON, eta=eta, want_grad=True, kernel=(kname, khp), out=out)
+        bk.lml_eval(X, Y, TH, **kw)
+        torch.cuda.synchronize()
+        first = out.clone()
+        assert bool((out[:, L.OUT_INFO] == 0).all()) and bool(torch.isfinite(out).all())
+        ref = O.lkd_wo_noise(x, f, g, th, "precon", eta, kernel=(kname, khp))
+        assert abs(float(out[0, L.OUT_LML]) - ref.ln_lkd) < 1e-8 * abs(ref.ln_lkd)
+        side = torch.cuda.Stream()
+        Xb, Yb = X.clone(), Y.clone()
+        need1 = int(lib.gegp_workspace_bytes(L.OP_LML_GRAD, n, n, d, 1)) + 4096
+        ws2 = torch.empty(need1, dtype=torch.uint8, device="cuda")
+        out2 = torch.empty((1, L.out_len(d)), dtype=torch.float64, device="cuda")
+        kid, kh = bk._kern((kname, khp))
+        khp_dev = torch.full((1,), kh, dtype=torch.float64, device="cuda") if kid == L.KERNEL_RATQUAD else None
+        for rep in range(20):
+            if rep % 2:       # a second, independent evaluation in flight on another stream (its own workspace)
+                with torch.cuda.stream(side):
+                    rc = lib.gegp_lml_eval(1, TH[1:2].data_ptr(), 0, kid, bk._p(khp_dev), n, n, d, Xb.data_ptr(), 0,
+                                           Yb.data_ptr(), 0, L.MODE_PRECON, float(eta), 0, 0.0, 1, out2.data_ptr(), 0,
+                                           ws2.data_ptr(), ws2.numel(), side.cuda_stream)
+                    assert rc == 0
+            bk.lml_eval(X, Y, TH, **kw)
+            torch.cuda.synchronize()
+            assert torch.equal(out, first), rep
+            if rep % 2:
+                assert torch.equal(out2[0], first[1]), rep        # alone, in a batch, on another stream: same bits
+        # posterior rows with x-gradients and Hessians inside guarded outputs
+        st = bk.predict_setup(X, Y, th, float(first[0, L.OUT_BETA]), mode=L.MODE_PRECON, eta=eta, kernel=(kname, khp))
+        xs = np.random.default_rng(1).uniform(-2, 2, (7, d))
+        bk.predict_grad(st, xs, float(first[0, L.OUT_SIGMA2]))
+        bk.predict_hess(st, xs[0], float(first[0, L.OUT_SIGMA2]))
+        torch.cuda.synchronize()
+        assert bool((big[:G] == 0xA5).all()) and bool((big[G + need:] == 0xA5).all()), "write outside the workspace"
+        assert bool((outbig[:32] == 7.25).all()) and bool((outbig[32 + 3 * L.out_len(d):] == 7.25).all()), "write outside out"
+    finally:
+        bk._graph_cache.clear()
+        if old is not None:
+            bk._ws_cache[dev] = old
+        else:
+            bk._ws_cache.pop(dev, None)
