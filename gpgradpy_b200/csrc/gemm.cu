@@ -239,6 +239,130 @@ static int launch_cfg(const Ctx& ctx, const GemmArgs& g) {
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Panel update with K = LEAF:  C (M x N, N <= 128) = alpha * A (M x 128) * B (N x 128)^T + beta * C.
+// This is the shape of every K = 128 update beside the factorisation's chain (the block column below the next leaf
+// and the other columns of the look-ahead window get the last leaf's panel): tall, 128 wide, and so shallow that the
+// generic kernel's k-pipeline (8 k-tiles, a barrier each) is all ramp.  Here a CTA owns BM rows and ALL N columns,
+// brings its whole A strip and the whole B block into shared memory with one wave of cp.async (a single wait, a
+// single barrier) and then issues its 32 k-steps of DMMA back to back.  8 warps: BM / 16 row groups x 8 / (BM / 16)
+// column groups, 16 rows per warp.  Same k order per output element as the generic kernels (k = 0 .. 127 in steps of 4).
+// ------------------------------------------------------------------------------------------------
+constexpr int K128 = 128;
+constexpr int K128_LD = K128 + 4;   // == 4 (mod 16): conflict-free fragment loads
+
+template <int BM>
+__global__ void __launch_bounds__(256, 1)
+gemm_k128_kernel(const GemmArgs g) {
+  constexpr int RG = BM / 16;            // row groups (warps along M)
+  constexpr int CG = 8 / RG;             // column groups (warps along N)
+  constexpr int WN = 128 / CG;           // columns per warp
+  constexpr int NI = WN / 8;
+  extern __shared__ __align__(16) double smem[];
+  double* sA = smem;                     // [BM][K128_LD]
+  double* sB = smem + BM * K128_LD;      // [128][K128_LD]
+  const int zo = blockIdx.z;
+  const double* __restrict__ A = g.A + zo * g.sAo;
+  const double* __restrict__ B = g.B + zo * g.sBo;
+  double* __restrict__ C = g.C + zo * g.sCo;
+  const int m0 = blockIdx.x * BM;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lk = lane & 3;
+  // one wave of 16-byte copies: rows outside the operands are zero-filled
+  for (int e = tid; e < BM * (K128 / 2); e += 256) {
+    const int r = e >> 6, c = (e & 63) * 2;
+    const bool ok = m0 + r < g.M;
+    cp_async16(sA + r * K128_LD + c, A + (int64_t)(ok ? m0 + r : 0) * g.lda + c, ok ? 16 : 0);
+  }
+  for (int e = tid; e < 128 * (K128 / 2); e += 256) {
+    const int r = e >> 6, c = (e & 63) * 2;
+    const bool ok = r < g.N;
+    cp_async16(sB + r * K128_LD + c, B + (int64_t)(ok ? r : 0) * g.ldb + c, ok ? 16 : 0);
+  }
+  cp_async_commit();
+  const int wr = warp / CG, wc = warp % CG;
+  const int r0 = wr * 16, c0 = wc * WN;
+  if (g.cmode != C_FULL && c0 >= m0 + r0 + 16) {   // this warp's tile lies entirely above the diagonal
+    cp_async_wait<0>();
+    __syncthreads();
+    return;
+  }
+  double acc[2][NI][2];
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+  cp_async_wait<0>();
+  __syncthreads();
+  const double* a0 = sA + (r0 + lr) * K128_LD + lk;
+  const double* b0 = sB + (c0 + lr) * K128_LD + lk;
+#pragma unroll 4
+  for (int kq = 0; kq < 32; kq++) {
+    const double af0 = a0[4 * kq], af1 = a0[8 * K128_LD + 4 * kq];
+    double bf[NI];
+#pragma unroll
+    for (int j = 0; j < NI; j++) bf[j] = b0[j * 8 * K128_LD + 4 * kq];
+#pragma unroll
+    for (int j = 0; j < NI; j++) {
+      dmma884(acc[0][j][0], acc[0][j][1], af0, bf[j]);
+      dmma884(acc[1][j][0], acc[1][j][1], af1, bf[j]);
+    }
+  }
+  const bool vec_ok = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const int row = m0 + r0 + i * 8 + lr;
+    if (row >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < NI; j++) {
+      const int col = c0 + j * 8 + 2 * lk;
+      if (col >= g.N) continue;
+      double* cp = C + (int64_t)row * g.ldc + col;
+      double v0 = g.alpha * acc[i][j][0], v1 = g.alpha * acc[i][j][1];
+      const bool has1 = (col + 1 < g.N);
+      bool st0 = true, st1 = has1;
+      if (g.cmode != C_FULL) { st0 = (col <= row); st1 = has1 && (col + 1 <= row); }
+      if (g.beta != 0.0) {
+        if (st0) v0 += g.beta * cp[0];
+        if (st1) v1 += g.beta * cp[1];
+      }
+      if (st0 && st1 && vec_ok) {
+        *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
+      } else {
+        if (st0) cp[0] = v0;
+        if (st1) cp[1] = v1;
+      }
+      if (g.cmode == C_LOWER_MIRROR) {
+        if (st0 && col < row) C[(int64_t)col * g.ldc + row] = v0;
+        if (st1 && col + 1 < row) C[(int64_t)(col + 1) * g.ldc + row] = v1;
+      }
+    }
+  }
+}
+
+template <int BM>
+static int launch_k128(const Ctx& ctx, const GemmArgs& g) {
+  const size_t smem = (size_t)(BM + 128) * K128_LD * sizeof(double);
+  GEGP_SET_SMEM(gemm_k128_kernel<BM>, smem);
+  dim3 grid((g.M + BM - 1) / BM, 1, g.outer);
+  prof_gemm_begin(ctx.stream);
+  timeline_begin(ctx.stream, "gemm_k128", g.M, g.N, BM);
+  gemm_k128_kernel<BM><<<grid, 256, smem, ctx.stream>>>(g);
+  timeline_end(ctx.stream);
+  if (prof().on) prof_gemm_end(ctx.stream, gemm_useful_flops(g));
+  GEGP_CHECK_LAUNCH();
+  return 0;
+}
+
+// rows per CTA: the smallest of 16 / 32 / 64 that still gives every CTA an SM of its own (one wave), else 64
+static int gemm_k128(const Ctx& ctx, const GemmArgs& g) {
+  const long rows_total = (long)g.M * g.outer;
+  if (rows_total <= 148L * 16) return launch_k128<16>(ctx, g);
+  if (rows_total <= 148L * 32) return launch_k128<32>(ctx, g);
+  return launch_k128<64>(ctx, g);
+}
+
 static int g_tma_min_tiles = -1;
 int& tma_min_tiles() {
   if (g_tma_min_tiles < 0) g_tma_min_tiles = getenv("GEGP_BIG_TILES") ? atoi(getenv("GEGP_BIG_TILES")) : 400;
@@ -292,6 +416,13 @@ int gemm_f64(const Ctx& ctx, GemmArgs g) {
     return launch_cfg<128, 128, 64, 32, 4, false>(ctx, g);
   }
   static const int exp_cfg = getenv("GEGP_GEMM_CFG") ? atoi(getenv("GEGP_GEMM_CFG")) : 0;  // tuning experiments
+  // K = LEAF panel updates (tall, at most 128 wide): the single-wave kernel.  The choice depends on the shape of one
+  // problem only; BM (rows per CTA) only changes which CTA owns a row, not the arithmetic of an element.
+  // Only while one wave of whole-SM CTAs covers the panel (M <= 148 * 64): beyond that the problem is throughput-bound and
+  // the generic kernels, which share an SM with the bulk GEMM CTAs, are the better neighbours (measured at N = 21000).
+  if (g.b_kcont && g.K == K128 && g.N <= 128 && g.klo_mode == KLO_ZERO && g.khi_mode == KHI_K && !g.Ct && g.inner == 1 &&
+      g.M <= 148 * 64 && exp_cfg != 7)
+    return gemm_k128(ctx, g);
   if (g.b_kcont && big && exp_cfg != 9) {
     const int rc = gemm_tma_nt(ctx, g);
     if (rc <= 0) return rc;
