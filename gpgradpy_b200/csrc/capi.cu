@@ -341,7 +341,8 @@ int gegp_lml_eval(int B, const double* theta_batch, const double* varK_batch, in
     rc = launch_append_rhs(ctx, N, n, y, pinv, sC, A + (int64_t)N * L.ld, L.ld, sC);
     if (rc) return rc;
     double* D = wk + L.D;
-    rc = chol_trap(ctx, A, L.ld, sC, N + 2, N, 0, info, D, sC);
+    if (want_grad) rc = chol_trap_inverse(ctx, A, L.ld, sC, N + 2, N, info, D, sC, wk + L.U, L.ld, sC, wk + L.Kinv, L.ld, sC);
+    else rc = chol_trap(ctx, A, L.ld, sC, N + 2, N, 0, info, D, sC);
     if (rc) return rc;
     rc = launch_lml_finalize(ctx, N, A, L.ld, sC, pinv, sC, noisy, varK, W, sC, outb, outlen, info, want_grad ? 0 : d);
     if (rc) return rc;
@@ -349,10 +350,6 @@ int gegp_lml_eval(int B, const double* theta_batch, const double* varK_batch, in
     if (want_grad) {
       double* U = wk + L.U;
       double* Kinv = wk + L.Kinv;
-      rc = leaf_dinv_assemble(ctx, A, L.ld, sC, D, sC, N);
-      if (rc) return rc;
-      rc = chol_inverse(ctx, A, L.ld, sC, D, sC, U, L.ld, sC, Kinv, L.ld, sC, N);
-      if (rc) return rc;
       alpha_t = W + L.ld;
       rc = trmv_upper(ctx, U, L.ld, sC, W, sC, alpha_t, sC, N);  // U = L^-T is already there: no substitution
       if (rc) return rc;

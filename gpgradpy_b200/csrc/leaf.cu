@@ -409,6 +409,8 @@ dinv_assemble_kernel(const double* __restrict__ L, int64_t ldl, int64_t strideL,
     pair_phase2<16>(s, 0, 64, 64, kk - 64, warp, NW, lane);
     __syncthreads();
   }
+  // The upper parts of the diagonal 32-blocks are final since the leaf factorisation and may be being read by solves
+  // that run beside this kernel (it is issued while the factorisation goes on): they are not stored again.
   for (int i = warp; i < NB; i += NW) {
     const double* srow = s + i * PLD + 1;
     double* grow = Dinv + i * NB;
@@ -419,7 +421,11 @@ dinv_assemble_kernel(const double* __restrict__ L, int64_t ldl, int64_t strideL,
         if (j >= i) v.x = srow[j];
         if (j + 1 >= i) v.y = srow[j + 1];
       }
-      *reinterpret_cast<double2*>(grow + j) = v;
+      const bool same32 = i < kk && (i >> 5) == (j >> 5);   // j is even: j and j + 1 lie in the same 32-block
+      // (rows of the identity padding behind a ragged last leaf were never stored: they get their zeros below)
+      if (same32 && j >= i) continue;                // both entries already final
+      if (same32 && j + 1 >= i) grow[j] = v.x;       // (j + 1 == i: the diagonal entry is final, the one left of it is 0)
+      else *reinterpret_cast<double2*>(grow + j) = v;
     }
   }
 }

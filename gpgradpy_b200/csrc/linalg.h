@@ -79,6 +79,13 @@ int leaf_scatter_dinv(const Ctx& ctx, const double* Dinv, int64_t strideD, doubl
 // row0 (multiple of LEAF) is the global index of the first row/column; Dinv is indexed by global block.
 int chol_trap(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, int k, int row0, int* info, double* Dinv,
               int64_t strideD);
+// chol_trap followed by chol_inverse, with the triangular inverse interleaved with the factorisation: each subtree is
+// inverted on a lowest-priority stream as soon as the chain has left it, so the SMs the latency-bound chain leaves idle
+// do the inverse's GEMMs.  Same results as the two calls in sequence up to the summation order inside U (the pairs
+// follow the factorisation's tree instead of aligned power-of-two blocks).  Dinv comes back complete.
+int chol_trap_inverse(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, int k, int* info, double* Dinv,
+                      int64_t strideD, double* U, int64_t ldu, int64_t strideU, double* Kinv, int64_t ldk,
+                      int64_t strideK);
 // B (r x k) <- B * L^-T for an already factored k x k lower L (col0: global index of L's first column).
 int trsm_right_rec(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv, int64_t strideD,
                    int col0, double* B, int64_t ldb, int64_t strideB, int r, int k);

@@ -41,6 +41,58 @@ int trsm_right_rec(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL
                         k - k1);
 }
 
+// U = L^-T by levels: diagonal LEAF blocks first, then for block size bs = LEAF, 2*LEAF, ... every pair
+// (a = [s, s+bs), b = [s+bs, s+2bs)):  U_ab = -(U_aa * L_ba^T) * U_bb.  The product in parentheses is staged in the
+// upper triangle of T (the Kinv buffer, same coordinates as U_ab).  The LOWER triangle of T meanwhile collects
+// W = U^T = L^-1, so the second product is written  -(T_ab) * (W_bb)^T  with the K-contiguous lower-triangular W_bb:
+// both products are A * B^T and run on the TMA kernel; each U_ab is stored a second time, transposed, as W_ba.
+static int inverse_transposed(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv,
+                              int64_t strideD, double* U, int64_t ldu, int64_t strideU, double* T, int64_t ldt,
+                              int64_t strideT, int N) {
+  int rc = leaf_scatter_dinv(ctx, Dinv, strideD, U, ldu, strideU, T, ldt, strideT, N);
+  if (rc) return rc;
+  for (int bs = LEAF; bs < N; bs *= 2) {
+    const int npairs_full = N / (2 * bs);  // pairs whose b block is full
+    for (int pass = 0; pass < 2; pass++) {
+      // pass 0: all full pairs in one batched launch; pass 1: the ragged last pair (if any)
+      int s, bsz, inner;
+      if (pass == 0) { if (npairs_full == 0) continue; s = 0; bsz = bs; inner = npairs_full; }
+      else {
+        s = npairs_full * 2 * bs; bsz = N - s - bs; inner = 1;
+        if (bsz <= 0) continue;
+      }
+      const int64_t pstepL = (int64_t)2 * bs * (ldl + 1), pstepU = (int64_t)2 * bs * (ldu + 1),
+                    pstepT = (int64_t)2 * bs * (ldt + 1);
+      const double* Uaa = U + (int64_t)s * ldu + s;
+      const double* Lba = L + (int64_t)(s + bs) * ldl + s;
+      double* Tab = T + (int64_t)s * ldt + s + bs;
+      // T_ab (bs x bsz) = U_aa (bs x bs, upper: k >= i) * L_ba^T  -> k clipped below by m0
+      GemmArgs g1 = gemm_args(Uaa, ldu, Lba, ldl, Tab, ldt, bs, bsz, bs, 1.0, 0.0, true);
+      g1.klo_mode = KLO_M0;
+      g1.outer = ctx.batch; g1.inner = inner;
+      g1.sAo = strideU; g1.sBo = strideL; g1.sCo = strideT; g1.sAi = pstepU; g1.sBi = pstepL; g1.sCi = pstepT;
+      g1.inner_steps = true; g1.iAr = g1.iAc = g1.iBr = g1.iBc = 2 * bs;
+      rc = gemm_f64(ctx, g1);
+      if (rc) return rc;
+      // U_ab = -T_ab (bs x bsz) * W_bb^T,  W_bb = L_bb^-1 (bsz x bsz lower: element (j, k) nonzero for k <= j, read
+      // from the lower triangle of T; k clipped above by n0 + BN); the transposed copy W_ba = U_ab^T goes there too.
+      const double* Wbb = T + (int64_t)(s + bs) * ldt + s + bs;
+      double* Uab = U + (int64_t)s * ldu + s + bs;
+      double* Wba = T + (int64_t)(s + bs) * ldt + s;
+      GemmArgs g2 = gemm_args(Tab, ldt, Wbb, ldt, Uab, ldu, bs, bsz, bsz, -1.0, 0.0, true);
+      g2.khi_mode = KHI_N0;
+      g2.Ct = Wba; g2.ldct = ldt; g2.sCto = strideT; g2.sCti = pstepT;
+      g2.outer = ctx.batch; g2.inner = inner;
+      g2.sAo = strideT; g2.sBo = strideT; g2.sCo = strideU; g2.sAi = pstepT; g2.sBi = pstepT; g2.sCi = pstepU;
+      g2.inner_steps = true; g2.iAr = g2.iAc = g2.iBr = g2.iBc = 2 * bs;
+      rc = gemm_f64(ctx, g2);
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // Look-ahead.  The factorisation's critical path is the chain
 //     leaf factor (one CTA)  ->  solve of the NEXT leaf's 128-row block row + K = 128 update of its diagonal block
@@ -82,6 +134,25 @@ int la_window() {
 }
 constexpr int MAX_PIECES = 256;
 constexpr int MAX_DEV = 32;
+
+// Explicit inverse interleaved with the factorisation (chol_trap_inverse): U receives L^-T (upper), T (the Kinv buffer)
+// L^-1 (lower) and scratch.  A subtree of at most `unit_max` columns is inverted as one unit (diagonal blocks + block
+// doubling, inverse_transposed) as soon as the factorisation has left it; above that size a node X contributes
+// U_ab = -(U_aa L_ba^T) U_bb for its two children a, b: the first product as soon as a is inverted and factored rows of
+// b exist, the second once b is inverted.  Everything goes to one lowest-priority stream in post-order, so the
+// dependencies among the inverse tasks are its FIFO order.
+struct InvHook {
+  double* U; int64_t ldu, sU;
+  double* T; int64_t ldt, sT;
+  double* A0; int64_t lda, sA;        // the factor (global row/column 0)
+  double* Dinv; int64_t sD;
+  int unit_max;
+};
+// subtrees up to this many columns are inverted as one unit (env GEGP_INV_UNIT; 0 switches the interleaving off)
+int inv_unit_max() {
+  static const int v = getenv("GEGP_INV_UNIT") ? atoi(getenv("GEGP_INV_UNIT")) : 1536;
+  return v;
+}
 struct Piece { int c0, c1; cudaEvent_t done; cudaStream_t stream; bool live; };   // global column range a queued bulk GEMM writes
 struct LookAhead {
   static constexpr int NBULK = 16;
@@ -89,8 +160,8 @@ struct LookAhead {
   static constexpr int NLANE = 3;
   // bulk[depth][lane]: pieces queued at one fork are needed one after the other; the first two get streams of their
   // own with a higher priority than the rest, so that they run beside (not behind) each other and ahead of older work
-  cudaStream_t hi = nullptr, col = nullptr, late = nullptr, bulk[NBULK][NLANE] = {};
-  cudaEvent_t fork[40], ev_prep, ev_fac, ev_colupd, ev_solve, begin, end;
+  cudaStream_t hi = nullptr, col = nullptr, late = nullptr, inv = nullptr, bulk[NBULK][NLANE] = {};
+  cudaEvent_t fork[40], ev_prep, ev_fac, ev_colupd, ev_solve, ev_inv, begin, end;
   Piece piece[MAX_PIECES];
   bool colupd_pending = false;   // a K = LEAF block-column update is in flight on `col` (the next chain step reads its top rows)
   bool solve_pending = false;    // a leaf solve is in flight on `col` (bulk pieces read its rows)
@@ -116,7 +187,8 @@ struct LookAhead {
     const int mid = hip < lo ? hip + 1 : hip;
     ok = cudaStreamCreateWithPriority(&hi, cudaStreamNonBlocking, hip) == cudaSuccess &&
          cudaStreamCreateWithPriority(&col, cudaStreamNonBlocking, mid) == cudaSuccess &&
-         cudaStreamCreateWithPriority(&late, cudaStreamNonBlocking, mid) == cudaSuccess;
+         cudaStreamCreateWithPriority(&late, cudaStreamNonBlocking, mid) == cudaSuccess &&
+         cudaStreamCreateWithPriority(&inv, cudaStreamNonBlocking, lo) == cudaSuccess;
     for (int i = 0; i < NBULK && ok; i++)
       for (int j = 0; j < NLANE && ok; j++) {
         int pr = lo - (NLANE - 1 - j);               // lane 0: two levels above the lowest priority
@@ -126,7 +198,7 @@ struct LookAhead {
     auto mk = [&](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
     for (int i = 0; i < 40 && ok; i++) ok = mk(&fork[i]);
     for (int i = 0; i < MAX_PIECES && ok; i++) { ok = mk(&piece[i].done); piece[i].live = false; }
-    ok = ok && mk(&ev_prep) && mk(&ev_fac) && mk(&ev_colupd) && mk(&ev_solve) && mk(&begin) && mk(&end);
+    ok = ok && mk(&ev_prep) && mk(&ev_fac) && mk(&ev_colupd) && mk(&ev_solve) && mk(&ev_inv) && mk(&begin) && mk(&end);
     return ok;
   }
 };
@@ -207,10 +279,64 @@ int chol_node(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, in
 // same columns from different streams are serialised through their events; a piece is joined by the chain when it
 // reaches a fork or leaf that touches its columns.  The bulk pieces read panel rows from k1+w on only (never block row
 // f), all of which are produced on `col`: they wait for its last solve.
+// inverse tasks of a node (see InvHook); `chain` is the stream the factorisation's chain is on
+int inv_sync(LookAhead* la, cudaStream_t chain) {
+  // everything the factorisation has produced so far: the chain up to here and the solves on `col`
+  if (cudaEventRecord(la->ev_inv, chain) != cudaSuccess) return -1120;
+  if (cudaStreamWaitEvent(la->inv, la->ev_inv, 0) != cudaSuccess) return -1120;
+  if (la->solve_pending && cudaStreamWaitEvent(la->inv, la->ev_solve, 0) != cudaSuccess) return -1120;
+  return 0;
+}
+int inv_unit(LookAhead* la, const InvHook* h, const Ctx& chain, int row0, int k) {
+  int rc = inv_sync(la, chain.stream);
+  if (rc) return rc;
+  const Ctx ic{la->inv, chain.batch};
+  double* Ln = h->A0 + (int64_t)row0 * (h->lda + 1);
+  double* Dn = h->Dinv + (int64_t)(row0 / LEAF) * LEAF * LEAF;
+  rc = leaf_dinv_assemble(ic, Ln, h->lda, h->sA, Dn, h->sD, k);
+  if (rc) return rc;
+  return inverse_transposed(ic, Ln, h->lda, h->sA, Dn, h->sD, h->U + (int64_t)row0 * (h->ldu + 1), h->ldu, h->sU,
+                            h->T + (int64_t)row0 * (h->ldt + 1), h->ldt, h->sT, k);
+}
+// first product of the node's pair: T_ab = U_aa L_ba^T (a = [row0, row0+k1), b = the kc columns behind it), staged in
+// the upper triangle of T at the coordinates of U_ab
+int inv_pair_first(LookAhead* la, const InvHook* h, const Ctx& chain, int row0, int k1, int kc) {
+  int rc = inv_sync(la, chain.stream);
+  if (rc) return rc;
+  const Ctx ic{la->inv, chain.batch};
+  const double* Uaa = h->U + (int64_t)row0 * (h->ldu + 1);
+  const double* Lba = h->A0 + (int64_t)(row0 + k1) * h->lda + row0;
+  double* Tab = h->T + (int64_t)row0 * h->ldt + row0 + k1;
+  GemmArgs g1 = gemm_args(Uaa, h->ldu, Lba, h->lda, Tab, h->ldt, k1, kc, k1, 1.0, 0.0, true);
+  g1.klo_mode = KLO_M0;
+  g1.outer = ic.batch; g1.inner = 1;
+  g1.sAo = h->sU; g1.sBo = h->sA; g1.sCo = h->sT;
+  return gemm_f64(ic, g1);
+}
+// second product: U_ab = -T_ab W_bb^T (W_bb = L_bb^-1 from the lower triangle of T), with the transposed copy W_ba
+int inv_pair_second(LookAhead* la, const InvHook* h, const Ctx& chain, int row0, int k1, int kc) {
+  int rc = inv_sync(la, chain.stream);
+  if (rc) return rc;
+  const Ctx ic{la->inv, chain.batch};
+  const double* Tab = h->T + (int64_t)row0 * h->ldt + row0 + k1;
+  const double* Wbb = h->T + (int64_t)(row0 + k1) * (h->ldt + 1);
+  double* Uab = h->U + (int64_t)row0 * h->ldu + row0 + k1;
+  double* Wba = h->T + (int64_t)(row0 + k1) * h->ldt + row0;
+  GemmArgs g2 = gemm_args(Tab, h->ldt, Wbb, h->ldt, Uab, h->ldu, k1, kc, kc, -1.0, 0.0, true);
+  g2.khi_mode = KHI_N0;
+  g2.Ct = Wba; g2.ldct = h->ldt; g2.sCto = h->sT; g2.sCti = 0;
+  g2.outer = ic.batch; g2.inner = 1;
+  g2.sAo = h->sT; g2.sBo = h->sT; g2.sCo = h->sU;
+  return gemm_f64(ic, g2);
+}
+
 int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t lda, int64_t strideA, int m, int k,
-                 int row0, int ext, int* info, double* Dinv, int64_t strideD) {
+                 int row0, int ext, int* info, double* Dinv, int64_t strideD, const InvHook* hook = nullptr) {
   if (k <= 0) return 0;
   int rc = 0;
+  // a subtree small enough is inverted as one unit once it is factored: its descendants carry no hook
+  const bool inv_unit_here = hook && k <= hook->unit_max;
+  const InvHook* child_hook = inv_unit_here ? nullptr : hook;
   if (k <= LEAF) {
     if ((rc = la->join_columns(ctx.stream, row0, row0 + k))) return rc;
     rc = leaf_potf2_inv(ctx, A, lda, strideA, k, row0, info, Dinv + (int64_t)(row0 / LEAF) * LEAF * LEAF, strideD);
@@ -226,13 +352,14 @@ int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t ld
       if (cudaEventRecord(la->ev_solve, la->col) != cudaSuccess) return -1104;
       la->solve_pending = true;
     }
+    if (inv_unit_here) return inv_unit(la, hook, ctx, row0, k);
     return 0;
   }
   const int k1 = split_point(k);
   const int mc = m - k1, kc = k - k1;
   const int w = kc < LEAF ? kc : LEAF;
   const int ext_l = std::min(la_window(), kc + ext);   // the left child's window, in the right child's frame [0, ext_l)
-  rc = chol_node_la(ctx, la, depth + 1, A, lda, strideA, m, k1, row0, ext_l, info, Dinv, strideD);
+  rc = chol_node_la(ctx, la, depth + 1, A, lda, strideA, m, k1, row0, ext_l, info, Dinv, strideD, child_hook);
   if (rc) return rc;
   double* C = A + (int64_t)k1 * lda + k1;
   const double* P = A + (int64_t)k1 * lda;        // rows k1.., all k1 columns of the left child
@@ -316,28 +443,43 @@ int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t ld
   // the part of this node's own window that the left child's window did not reach
   if (ext > 0 && kc + ext > ext_l)
     if ((rc = queue_piece(bs, std::max(kc, ext_l), kc + ext, k1))) return rc;
-  return chol_node_la(ctx, la, depth + 1, C, lda, strideA, mc, kc, row0 + k1, ext, info, Dinv, strideD);
+  // the left child is inverted and the rows of the right child in its panel are final once the solves queued so far
+  // are done: the first product of this node's pair can start while the right child is being factored
+  if (child_hook && (rc = inv_pair_first(la, child_hook, ctx, row0, k1, kc))) return rc;
+  rc = chol_node_la(ctx, la, depth + 1, C, lda, strideA, mc, kc, row0 + k1, ext, info, Dinv, strideD, child_hook);
+  if (rc) return rc;
+  if (child_hook) return inv_pair_second(la, child_hook, ctx, row0, k1, kc);
+  if (inv_unit_here) return inv_unit(la, hook, ctx, row0, k);
+  return 0;
 }
 }  // namespace
 
-int chol_trap(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, int k, int row0, int* info, double* Dinv,
-              int64_t strideD) {
+static int chol_trap_impl(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, int k, int row0, int* info,
+                          double* Dinv, int64_t strideD, const InvHook* hook, bool* inverse_done) {
+  if (inverse_done) *inverse_done = false;
   LookAhead* la = (k > LEAF) ? la_acquire() : nullptr;
   if (!la) return chol_node(ctx, A, lda, strideA, m, k, row0, info, Dinv, strideD);
+  if (hook && (hook->unit_max < LEAF || row0 != 0)) hook = nullptr;
   for (int i = 0; i < MAX_PIECES; i++) la->piece[i].live = false;
   la->colupd_pending = la->solve_pending = false;
   int rc = 0;
   if (cudaEventRecord(la->begin, ctx.stream) != cudaSuccess) rc = -1107;
   if (!rc && (cudaStreamWaitEvent(la->hi, la->begin, 0) != cudaSuccess ||
-              cudaStreamWaitEvent(la->col, la->begin, 0) != cudaSuccess)) rc = -1108;
+              cudaStreamWaitEvent(la->col, la->begin, 0) != cudaSuccess ||
+              (hook && cudaStreamWaitEvent(la->inv, la->begin, 0) != cudaSuccess))) rc = -1108;
   if (!rc) {
     const Ctx chain{la->hi, ctx.batch};
-    rc = chol_node_la(chain, la, 0, A, lda, strideA, m, k, row0, 0, info, Dinv, strideD);
+    rc = chol_node_la(chain, la, 0, A, lda, strideA, m, k, row0, 0, info, Dinv, strideD, hook);
+    if (!rc && hook && inverse_done) *inverse_done = true;
   }
   // join everything back into the chain, then into the caller's stream (also after a failure, so that no work is left
   // un-joined inside a stream capture)
   cudaEventRecord(la->ev_solve, la->col);   // the tail of `col`: covers its last solve and column update
   cudaStreamWaitEvent(la->hi, la->ev_solve, 0);
+  if (hook) {                               // ... and the tail of the inverse stream
+    cudaEventRecord(la->ev_inv, la->inv);
+    cudaStreamWaitEvent(la->hi, la->ev_inv, 0);
+  }
   la->join_columns(la->hi, 0, 1 << 30);
   la->colupd_pending = la->solve_pending = false;
   if (cudaEventRecord(la->end, la->hi) != cudaSuccess && !rc) rc = -1109;
@@ -346,55 +488,35 @@ int chol_trap(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, in
   return rc;
 }
 
-// U = L^-T by levels: diagonal LEAF blocks first, then for block size bs = LEAF, 2*LEAF, ... every pair
-// (a = [s, s+bs), b = [s+bs, s+2bs)):  U_ab = -(U_aa * L_ba^T) * U_bb.  The product in parentheses is staged in the
-// upper triangle of T (the Kinv buffer, same coordinates as U_ab).  The LOWER triangle of T meanwhile collects
-// W = U^T = L^-1, so the second product is written  -(T_ab) * (W_bb)^T  with the K-contiguous lower-triangular W_bb:
-// both products are A * B^T and run on the TMA kernel; each U_ab is stored a second time, transposed, as W_ba.
-static int inverse_transposed(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv,
-                              int64_t strideD, double* U, int64_t ldu, int64_t strideU, double* T, int64_t ldt,
-                              int64_t strideT, int N) {
-  int rc = leaf_scatter_dinv(ctx, Dinv, strideD, U, ldu, strideU, T, ldt, strideT, N);
+int chol_trap(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, int k, int row0, int* info, double* Dinv,
+              int64_t strideD) {
+  return chol_trap_impl(ctx, A, lda, strideA, m, k, row0, info, Dinv, strideD, nullptr, nullptr);
+}
+
+int chol_inverse(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv, int64_t strideD,
+                 double* U, int64_t ldu, int64_t strideU, double* Kinv, int64_t ldk, int64_t strideK, int N);
+
+// Factorisation AND explicit inverse, interleaved (see InvHook): on return (stream order) A holds L with the solved
+// appended rows, Dinv the complete inverse-transposed diagonal blocks, U = L^-T and Kinv = (L L^T)^-1.
+int chol_trap_inverse(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, int k, int* info, double* Dinv,
+                      int64_t strideD, double* U, int64_t ldu, int64_t strideU, double* Kinv, int64_t ldk,
+                      int64_t strideK) {
+  const InvHook hook{U, ldu, strideU, Kinv, ldk, strideK, A, lda, strideA, Dinv, strideD, inv_unit_max()};
+  bool done = false;
+  int rc = chol_trap_impl(ctx, A, lda, strideA, m, k, 0, info, Dinv, strideD, inv_unit_max() >= LEAF ? &hook : nullptr, &done);
   if (rc) return rc;
-  for (int bs = LEAF; bs < N; bs *= 2) {
-    const int npairs_full = N / (2 * bs);  // pairs whose b block is full
-    for (int pass = 0; pass < 2; pass++) {
-      // pass 0: all full pairs in one batched launch; pass 1: the ragged last pair (if any)
-      int s, bsz, inner;
-      if (pass == 0) { if (npairs_full == 0) continue; s = 0; bsz = bs; inner = npairs_full; }
-      else {
-        s = npairs_full * 2 * bs; bsz = N - s - bs; inner = 1;
-        if (bsz <= 0) continue;
-      }
-      const int64_t pstepL = (int64_t)2 * bs * (ldl + 1), pstepU = (int64_t)2 * bs * (ldu + 1),
-                    pstepT = (int64_t)2 * bs * (ldt + 1);
-      const double* Uaa = U + (int64_t)s * ldu + s;
-      const double* Lba = L + (int64_t)(s + bs) * ldl + s;
-      double* Tab = T + (int64_t)s * ldt + s + bs;
-      // T_ab (bs x bsz) = U_aa (bs x bs, upper: k >= i) * L_ba^T  -> k clipped below by m0
-      GemmArgs g1 = gemm_args(Uaa, ldu, Lba, ldl, Tab, ldt, bs, bsz, bs, 1.0, 0.0, true);
-      g1.klo_mode = KLO_M0;
-      g1.outer = ctx.batch; g1.inner = inner;
-      g1.sAo = strideU; g1.sBo = strideL; g1.sCo = strideT; g1.sAi = pstepU; g1.sBi = pstepL; g1.sCi = pstepT;
-      g1.inner_steps = true; g1.iAr = g1.iAc = g1.iBr = g1.iBc = 2 * bs;
-      rc = gemm_f64(ctx, g1);
-      if (rc) return rc;
-      // U_ab = -T_ab (bs x bsz) * W_bb^T,  W_bb = L_bb^-1 (bsz x bsz lower: element (j, k) nonzero for k <= j, read
-      // from the lower triangle of T; k clipped above by n0 + BN); the transposed copy W_ba = U_ab^T goes there too.
-      const double* Wbb = T + (int64_t)(s + bs) * ldt + s + bs;
-      double* Uab = U + (int64_t)s * ldu + s + bs;
-      double* Wba = T + (int64_t)(s + bs) * ldt + s;
-      GemmArgs g2 = gemm_args(Tab, ldt, Wbb, ldt, Uab, ldu, bs, bsz, bsz, -1.0, 0.0, true);
-      g2.khi_mode = KHI_N0;
-      g2.Ct = Wba; g2.ldct = ldt; g2.sCto = strideT; g2.sCti = pstepT;
-      g2.outer = ctx.batch; g2.inner = inner;
-      g2.sAo = strideT; g2.sBo = strideT; g2.sCo = strideU; g2.sAi = pstepT; g2.sBi = pstepT; g2.sCi = pstepU;
-      g2.inner_steps = true; g2.iAr = g2.iAc = g2.iBr = g2.iBc = 2 * bs;
-      rc = gemm_f64(ctx, g2);
-      if (rc) return rc;
-    }
+  if (!done) {   // single-stream schedule or interleaving switched off: the inverse follows the factorisation
+    rc = leaf_dinv_assemble(ctx, A, lda, strideA, Dinv, strideD, k);
+    if (rc) return rc;
+    return chol_inverse(ctx, A, lda, strideA, Dinv, strideD, U, ldu, strideU, Kinv, ldk, strideK, k);
   }
-  return 0;
+  // Kinv = U * U^T, U upper: sum over k >= max(i, j); lower tiles computed, mirrored to the upper half.
+  GemmArgs g = gemm_args(U, ldu, U, ldu, Kinv, ldk, k, k, k, 1.0, 0.0, true);
+  g.klo_mode = KLO_MAXMN;
+  g.cmode = C_LOWER_MIRROR;
+  g.outer = ctx.batch; g.inner = 1;
+  g.sAo = strideU; g.sBo = strideU; g.sCo = strideK;
+  return gemm_f64(ctx, g);
 }
 
 int chol_inverse(const Ctx& ctx, const double* L, int64_t ldl, int64_t strideL, const double* Dinv, int64_t strideD,
