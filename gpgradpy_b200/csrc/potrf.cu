@@ -150,7 +150,7 @@ struct InvHook {
 };
 // subtrees up to this many columns are inverted as one unit (env GEGP_INV_UNIT; 0 switches the interleaving off)
 int inv_unit_max() {
-  static const int v = getenv("GEGP_INV_UNIT") ? atoi(getenv("GEGP_INV_UNIT")) : 1536;
+  static const int v = getenv("GEGP_INV_UNIT") ? atoi(getenv("GEGP_INV_UNIT")) : 1024;
   return v;
 }
 struct Piece { int c0, c1; cudaEvent_t done; cudaStream_t stream; bool live; };   // global column range a queued bulk GEMM writes
