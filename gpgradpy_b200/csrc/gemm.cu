@@ -416,12 +416,14 @@ int gemm_f64(const Ctx& ctx, GemmArgs g) {
     return launch_cfg<128, 128, 64, 32, 4, false>(ctx, g);
   }
   static const int exp_cfg = getenv("GEGP_GEMM_CFG") ? atoi(getenv("GEGP_GEMM_CFG")) : 0;  // tuning experiments
-  // K = LEAF panel updates (tall, at most 128 wide): the single-wave kernel.  The choice depends on the shape of one
-  // problem only; BM (rows per CTA) only changes which CTA owns a row, not the arithmetic of an element.
+  // K = LEAF panel updates (tall, at most 128 wide): the single-wave kernel; BM (rows per CTA) only changes which CTA
+  // owns a row, not the arithmetic of an element.
   // Only while one wave of whole-SM CTAs covers the panel (M <= 148 * 64): beyond that the problem is throughput-bound and
   // the generic kernels, which share an SM with the bulk GEMM CTAs, are the better neighbours (measured at N = 21000).
+  // It accumulates every element in the same k order as the generic kernels (bit-identical results, tested), which is why
+  // this choice -- like the 32 x 32 one below -- may look at the batch count.
   if (g.b_kcont && g.K == K128 && g.N <= 128 && g.klo_mode == KLO_ZERO && g.khi_mode == KHI_K && !g.Ct && g.inner == 1 &&
-      g.M <= 148 * 64 && exp_cfg != 7)
+      (long)g.M * g.outer <= 148L * 64 && exp_cfg != 7)
     return gemm_k128(ctx, g);
   if (g.b_kcont && big && exp_cfg != 9) {
     const int rc = gemm_tma_nt(ctx, g);
