@@ -450,12 +450,14 @@ int launch_build_cov(const Ctx& ctx, const Geom& gm, const double* theta, int64_
       else GEGP_SET_SMEM(build_cov_fast_kernel<false>, GEGP_MAX_DYN_SMEM);
     }
     dim3 grid((gm.n + FTB - 1) / FTB, (gm.n + FTA - 1) / FTA, ctx.batch);
+    timeline_begin(ctx.stream, "build", gm.N, lower_only);
     if (use_pvec)
       build_cov_fast_kernel<true><<<grid, BUILD_THREADS, fsmem, ctx.stream>>>(gm, theta, strideTheta, ns, pinv, strideP, mode,
                                                                             eta, out, ld, strideOut, lower_only);
     else
       build_cov_fast_kernel<false><<<grid, BUILD_THREADS, fsmem, ctx.stream>>>(gm, theta, strideTheta, ns, pinv, strideP, mode,
                                                                              eta, out, ld, strideOut, lower_only);
+    timeline_end(ctx.stream);
     GEGP_CHECK_LAUNCH();
     return 0;
   }

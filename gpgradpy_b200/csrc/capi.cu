@@ -39,13 +39,13 @@ bool timeline_on() {
   if (g_tl_state < 0) g_tl_state = getenv("GEGP_TIMELINE") ? 1 : 0;
   return g_tl_state == 1;
 }
-void timeline_begin(cudaStream_t s, const char* label, int a, int b, int c) {
+void timeline_begin(cudaStream_t s, const char* label, int a, int b, int c, double mflop) {
   if (!timeline_on()) return;
   TlMark m{};
   cudaEventCreate(&m.b);
   cudaEventCreate(&m.e);
   m.s = s;
-  snprintf(m.label, sizeof(m.label), "%s:%d:%d:%d", label, a, b, c);
+  snprintf(m.label, sizeof(m.label), "%s:%d:%d:%d:%.0f", label, a, b, c, mflop);
   cudaEventRecord(m.b, s);
   g_tl.push_back(m);
 }

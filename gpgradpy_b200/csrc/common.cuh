@@ -19,7 +19,7 @@ void prof_gemm_end(cudaStream_t s, double flops);
 // Debug timeline (env GEGP_TIMELINE=<file>): an event pair around a launch on its stream; dumped by gegp_profile_end
 // as "label stream ready_us done_us" relative to the first mark.  No cost when the variable is unset.
 bool timeline_on();
-void timeline_begin(cudaStream_t s, const char* label, int a = 0, int b = 0, int c = 0);
+void timeline_begin(cudaStream_t s, const char* label, int a = 0, int b = 0, int c = 0, double mflop = 0.0);
 void timeline_end(cudaStream_t s);
 // look-ahead (multi-stream) factorisation switch: GEGP_OPT_LOOKAHEAD / env GEGP_NO_LOOKAHEAD
 int& lookahead_enabled();

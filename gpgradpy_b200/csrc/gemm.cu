@@ -231,7 +231,7 @@ static int launch_cfg(const Ctx& ctx, const GemmArgs& g) {
   GEGP_SET_SMEM(kern, Cfg::SMEM);
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.outer * g.inner);
   prof_gemm_begin(ctx.stream);
-  timeline_begin(ctx.stream, "gemm", g.M, g.N, g.K);
+  timeline_begin(ctx.stream, BM == 32 ? "gemm32" : (BM == 64 ? (STAGES == 2 ? "gemm64s2" : "gemm64s4") : "gemm128"), g.M, g.N, g.K, timeline_on() ? gemm_useful_flops(g) * 1e-6 : 0.0);
   kern<<<grid, Cfg::THREADS, Cfg::SMEM, ctx.stream>>>(g);
   timeline_end(ctx.stream);
   if (prof().on) prof_gemm_end(ctx.stream, gemm_useful_flops(g));
@@ -347,7 +347,7 @@ static int launch_k128(const Ctx& ctx, const GemmArgs& g) {
   GEGP_SET_SMEM(gemm_k128_kernel<BM>, smem);
   dim3 grid((g.M + BM - 1) / BM, 1, g.outer);
   prof_gemm_begin(ctx.stream);
-  timeline_begin(ctx.stream, "gemm_k128", g.M, g.N, BM);
+  timeline_begin(ctx.stream, "gemm_k128", g.M, g.N, BM, timeline_on() ? gemm_useful_flops(g) * 1e-6 : 0.0);
   gemm_k128_kernel<BM><<<grid, 256, smem, ctx.stream>>>(g);
   timeline_end(ctx.stream);
   if (prof().on) prof_gemm_end(ctx.stream, gemm_useful_flops(g));

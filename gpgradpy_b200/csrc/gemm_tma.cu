@@ -298,7 +298,7 @@ static int launch_tma(const Ctx& ctx, const GemmArgs& g, uint64_t a_d0, uint64_t
   GEGP_SET_SMEM(gemm_tma_nt_kernel<Cfg>, Cfg::SMEM);
   dim3 grid((g.N + Cfg::TBN - 1) / Cfg::TBN, (g.M + Cfg::TBM - 1) / Cfg::TBM, g.outer * g.inner);
   prof_gemm_begin(ctx.stream);
-  timeline_begin(ctx.stream, "gemm_tma", g.M, g.N, g.K);
+  timeline_begin(ctx.stream, "gemm_tma", g.M, g.N, g.K, timeline_on() ? gemm_useful_flops(g) * 1e-6 : 0.0);
   gemm_tma_nt_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM, ctx.stream>>>(tmA, tmB, t);
   timeline_end(ctx.stream);
   if (prof().on) prof_gemm_end(ctx.stream, gemm_useful_flops(g));

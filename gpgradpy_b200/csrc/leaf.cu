@@ -435,7 +435,9 @@ int leaf_dinv_assemble(const Ctx& ctx, const double* L, int64_t ldl, int64_t str
   if (N <= 0) return 0;
   const int smem = NB * PLD * (int)sizeof(double);
   GEGP_SET_SMEM(dinv_assemble_kernel, smem);
+  timeline_begin(ctx.stream, "dinvasm", N);
   dinv_assemble_kernel<<<dim3((N + NB - 1) / NB, 1, ctx.batch), LT, smem, ctx.stream>>>(L, ldl, strideL, Dinv, strideD, N);
+  timeline_end(ctx.stream);
   GEGP_CHECK_LAUNCH();
   return 0;
 }
@@ -1073,7 +1075,9 @@ trmv_upper_kernel(const double* __restrict__ U, int64_t ldu, int64_t strideU, co
 int trmv_upper(const Ctx& ctx, const double* U, int64_t ldu, int64_t strideU, const double* x, int64_t strideX,
                double* y, int64_t strideY, int N) {
   if (N <= 0) return 0;
+  timeline_begin(ctx.stream, "trmv", N);
   trmv_upper_kernel<<<dim3((N + 7) / 8, 1, ctx.batch), 256, 0, ctx.stream>>>(U, ldu, strideU, x, strideX, y, strideY, N);
+  timeline_end(ctx.stream);
   GEGP_CHECK_LAUNCH();
   return 0;
 }

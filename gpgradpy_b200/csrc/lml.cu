@@ -348,6 +348,7 @@ int launch_lml_grad(const Ctx& ctx, const Geom& gm, const double* theta, int64_t
     else GEGP_SET_SMEM((lml_grad_kernel<2, true>), GEGP_MAX_DYN_SMEM);
   }
   dim3 grid((gm.n + GB - 1) / GB, gm.n, ctx.batch);
+  timeline_begin(ctx.stream, "lmlgrad", gm.N, d, quad);
 #define GEGP_LAUNCH_LML_GRAD(Q, W)                                                                                       \
   lml_grad_kernel<Q, W><<<grid, GB, smem, ctx.stream>>>(gm, theta, strideTheta, Kinv, ldk, strideK, alpha_t,             \
                                                         strideAlpha, pinv, strideP, out, strideOut, noisy, pnlt_grad,    \
@@ -356,6 +357,7 @@ int launch_lml_grad(const Ctx& ctx, const Geom& gm, const double* theta, int64_t
   else if (quad == 1) { if (wide) GEGP_LAUNCH_LML_GRAD(1, true); else GEGP_LAUNCH_LML_GRAD(1, false); }
   else { if (wide) GEGP_LAUNCH_LML_GRAD(2, true); else GEGP_LAUNCH_LML_GRAD(2, false); }
 #undef GEGP_LAUNCH_LML_GRAD
+  timeline_end(ctx.stream);
   GEGP_CHECK_LAUNCH();
   const int64_t nparts = (int64_t)grid.x * grid.y;
   const int np = 2 * d + 3;
