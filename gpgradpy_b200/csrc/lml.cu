@@ -111,10 +111,13 @@ int launch_scale_vec(const Ctx& ctx, int N, const double* a, int64_t strideA, co
 constexpr int GB = 128;
 
 // quad 0: LML gradient weights; 1: W = alpha alpha^T (Kinv not read); 2: W = the matrix passed as Kinv.
-// WIDE (d >= 8): four independent Kinv loads in flight per thread, 72 registers; otherwise the plain loop (63
-// registers, 8 CTAs per SM) -- measured: the wide form is 1.5x faster at d = 10 and 20, the narrow one at d = 5.
-template <int quad, bool WIDE>
-__global__ void __launch_bounds__(GB, WIDE ? 7 : 8)
+// WIDE (d >= 8): four independent Kinv loads in flight per thread; otherwise the plain loop -- measured: the wide form
+// is 1.5x faster at d = 10 and 20, the narrow one at d = 5.  72 registers / 7 CTAs per SM for the Gaussian kernel,
+// 80 / 6 (narrow) and 96 / 5 (wide) for the other families (ptxas -v: no spills).
+// GAUSS: the Gaussian kernel as a compile-time constant (f0 = f2 = k, f1 = f3 = -k fold into one register and the
+// alpha row disappears: no spills under the occupancy bound); false = kernel family read from gm.ktype.
+template <int quad, bool WIDE, bool GAUSS>
+__global__ void __launch_bounds__(GB, GAUSS ? 7 : (WIDE ? 5 : 6))
 lml_grad_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideTheta, const double* __restrict__ Kinv_all,
                 int64_t ldk, int64_t strideK, const double* __restrict__ alpha_all, int64_t strideAlpha,
                 const double* __restrict__ pinv_all, int64_t strideP, const double* __restrict__ out_all,
@@ -153,8 +156,8 @@ lml_grad_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideThe
   double dv = 0.0;
   RadialProfile ph;
   ph.f0 = ph.f1 = ph.f2 = ph.f3 = 0.0;
-  const int ktype = gm.ktype;
-  const double kalpha = gm.kernel_hp(z);
+  const int ktype = GAUSS ? GEGP_KERNEL_SQEXP : gm.ktype;
+  const double kalpha = GAUSS ? 0.0 : gm.kernel_hp(z);
   double ssum = 0.0;
   if (valid) {
     double e = 0.0;
@@ -227,24 +230,31 @@ lml_grad_kernel(Geom gm, const double* __restrict__ theta_all, int64_t strideThe
         const int coli = n + i * ng + sb;
         Wii = pr * pinv[coli] * (c1 * ar * alpha[coli] - c2 * kii);
       }
-      A1 += 4.0 * ui * Wi0 - 2.0 * th[i] * Wii;
-      A2 -= 4.0 * ui * rowdot;
-      t = ph.f1 * (4.0 * ri * Wi0 - 2.0 * Wii) - 8.0 * ph.f2 * (ri * rowdot);
+      if constexpr (GAUSS) {   // A0 holds S = A0 - A1 + A2, the common factor k is applied once at the end
+        A0 += -4.0 * ui * Wi0 + 2.0 * th[i] * Wii - 4.0 * ui * rowdot;
+        t = -4.0 * ri * Wi0 + 2.0 * Wii - 8.0 * ri * rowdot;
+      } else {
+        A1 += 4.0 * ui * Wi0 - 2.0 * th[i] * Wii;
+        A2 -= 4.0 * ui * rowdot;
+        t = ph.f1 * (4.0 * ri * Wi0 - 2.0 * Wii) - 8.0 * ph.f2 * (ri * rowdot);
+      }
       if (same) part[d + 2 + i] = Wii;
     }
     gs[i * GB + tid] = t;
   }
   // g_m = t_m + r_m^2 (f1 A0 + f2 A1 + f3 A2)
-  const double Sth = ph.f1 * A0 + ph.f2 * A1 + ph.f3 * A2;
+  // (Gaussian kernel: g_m = k (t_m - r_m^2 S), sum(K .* W) = k S, with S accumulated in A0)
+  const double Sth = GAUSS ? -A0 : ph.f1 * A0 + ph.f2 * A1 + ph.f3 * A2;
+  const double wk = GAUSS ? ph.f0 : 1.0;
   for (int m = 0; m < d; m++) {
     double g = 0.0;
     if (valid) {
       const double r = xa[m] - gm.X[(int64_t)b * d + m];
-      g = gs[m * GB + tid] + (r * r) * Sth;
+      g = wk * (gs[m * GB + tid] + (r * r) * Sth);
     }
     gs[m * GB + tid] = g;
   }
-  gs[d * GB + tid] = valid ? (ph.f0 * A0 + ph.f1 * A1 + ph.f2 * A2) : 0.0;
+  gs[d * GB + tid] = valid ? (GAUSS ? wk * A0 : ph.f0 * A0 + ph.f1 * A1 + ph.f2 * A2) : 0.0;
   // the kernel hyper-parameter (one block-wide sum more; only the rational-quadratic kernel has one)
   if (ktype == GEGP_KERNEL_RATQUAD) {
     double ga = 0.0;
@@ -342,20 +352,35 @@ int launch_lml_grad(const Ctx& ctx, const Geom& gm, const double* theta, int64_t
   if (quad < 0 || quad > 2) return -906;
   if (smem > (size_t)GEGP_MAX_DYN_SMEM) return -907;
   const bool wide = d >= 8;
+  const bool gauss = gm.ktype == GEGP_KERNEL_SQEXP;
   if (smem > 48 * 1024) {   // (only reached with d > 20: the wide kernels); once per device, largest size
-    if (quad == 0) GEGP_SET_SMEM((lml_grad_kernel<0, true>), GEGP_MAX_DYN_SMEM);
-    else if (quad == 1) GEGP_SET_SMEM((lml_grad_kernel<1, true>), GEGP_MAX_DYN_SMEM);
-    else GEGP_SET_SMEM((lml_grad_kernel<2, true>), GEGP_MAX_DYN_SMEM);
+    if (gauss) {
+      if (quad == 0) GEGP_SET_SMEM((lml_grad_kernel<0, true, true>), GEGP_MAX_DYN_SMEM);
+      else if (quad == 1) GEGP_SET_SMEM((lml_grad_kernel<1, true, true>), GEGP_MAX_DYN_SMEM);
+      else GEGP_SET_SMEM((lml_grad_kernel<2, true, true>), GEGP_MAX_DYN_SMEM);
+    } else {
+      if (quad == 0) GEGP_SET_SMEM((lml_grad_kernel<0, true, false>), GEGP_MAX_DYN_SMEM);
+      else if (quad == 1) GEGP_SET_SMEM((lml_grad_kernel<1, true, false>), GEGP_MAX_DYN_SMEM);
+      else GEGP_SET_SMEM((lml_grad_kernel<2, true, false>), GEGP_MAX_DYN_SMEM);
+    }
   }
   dim3 grid((gm.n + GB - 1) / GB, gm.n, ctx.batch);
   timeline_begin(ctx.stream, "lmlgrad", gm.N, d, quad);
-#define GEGP_LAUNCH_LML_GRAD(Q, W)                                                                                       \
-  lml_grad_kernel<Q, W><<<grid, GB, smem, ctx.stream>>>(gm, theta, strideTheta, Kinv, ldk, strideK, alpha_t,             \
-                                                        strideAlpha, pinv, strideP, out, strideOut, noisy, pnlt_grad,    \
-                                                        partial, stridePartial)
-  if (quad == 0) { if (wide) GEGP_LAUNCH_LML_GRAD(0, true); else GEGP_LAUNCH_LML_GRAD(0, false); }
-  else if (quad == 1) { if (wide) GEGP_LAUNCH_LML_GRAD(1, true); else GEGP_LAUNCH_LML_GRAD(1, false); }
-  else { if (wide) GEGP_LAUNCH_LML_GRAD(2, true); else GEGP_LAUNCH_LML_GRAD(2, false); }
+#define GEGP_LAUNCH_LML_GRAD(Q, W, G)                                                                                    \
+  lml_grad_kernel<Q, W, G><<<grid, GB, smem, ctx.stream>>>(gm, theta, strideTheta, Kinv, ldk, strideK, alpha_t,          \
+                                                           strideAlpha, pinv, strideP, out, strideOut, noisy, pnlt_grad, \
+                                                           partial, stridePartial)
+#define GEGP_LAUNCH_LML_GRAD_W(Q, G) do { if (wide) GEGP_LAUNCH_LML_GRAD(Q, true, G); else GEGP_LAUNCH_LML_GRAD(Q, false, G); } while (0)
+  if (gauss) {
+    if (quad == 0) GEGP_LAUNCH_LML_GRAD_W(0, true);
+    else if (quad == 1) GEGP_LAUNCH_LML_GRAD_W(1, true);
+    else GEGP_LAUNCH_LML_GRAD_W(2, true);
+  } else {
+    if (quad == 0) GEGP_LAUNCH_LML_GRAD_W(0, false);
+    else if (quad == 1) GEGP_LAUNCH_LML_GRAD_W(1, false);
+    else GEGP_LAUNCH_LML_GRAD_W(2, false);
+  }
+#undef GEGP_LAUNCH_LML_GRAD_W
 #undef GEGP_LAUNCH_LML_GRAD
   timeline_end(ctx.stream);
   GEGP_CHECK_LAUNCH();
