@@ -487,13 +487,15 @@ def run_b200(args):
 
     ph = phase_numbers(n, d, reps=3 if N < 10000 else 2)
     traffic, traffic_meta = None, None
-    for rnd in ("r02", "r01"):
+    for name in (f"r02/dominant_kernel_ncu_{args.workload}.json", "r02/dominant_kernel_ncu.json",
+                 "r01/dominant_kernel_ncu.json"):
         try:   # dram bytes of the dominant launch from the committed ncu --set full capture (per launch)
-            tm = json.load(open(os.path.join(ROOT, "profiles", rnd, "dominant_kernel_ncu.json")))
+            tm = json.load(open(os.path.join(ROOT, "profiles", name)))
             traffic, traffic_meta = tm.get("dram_bytes_per_launch"), {k: tm.get(k) for k in
                                                                       ("source", "kernel", "grid_size", "duration_us",
+                                                                       "dram_read_bytes", "dram_write_bytes",
                                                                        "algorithmic_bytes_per_launch", "algorithmic_flops_per_launch",
-                                                                       "dmma_pipe_active_pct")}
+                                                                       "dmma_pipe_active_pct", "l2_hit_pct")}
             break
         except Exception:
             continue

@@ -2,6 +2,8 @@
 
     python tools/ncu_summary.py launches <csv> [title]        -> per-kernel table on stdout
     python tools/ncu_summary.py full <name>=<file.ncu-rep> ... -> key metrics per capture (text on stdout, JSON beside)
+    python tools/ncu_summary.py dominant <file.ncu-rep> <out.json> <alg_bytes> <alg_flops> <source note>
+                                                              -> the per-launch record bench.py puts into roofline.traffic
 """
 import collections, csv, io, json, subprocess, sys
 
@@ -58,9 +60,27 @@ def full(pairs):
     return out
 
 
+def dominant(path, out_json, alg_bytes, alg_flops, note):
+    d = full([f"dominant={path}"])["dominant"]
+    val = lambda k: float(d[k]["value"].replace(",", ""))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    dram = sum(val(k) * scale[d[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    dur = val("gpu__time_duration.sum") * {"us": 1.0, "ms": 1e3, "ns": 1e-3}.get(d["gpu__time_duration.sum"]["unit"], 1.0)
+    rec = {"source": note, "kernel": d["kernel"], "grid_size": d["launch__grid_size"]["value"], "duration_us": dur,
+           "dram_bytes_per_launch": dram, "dram_read_bytes": val("dram__bytes_read.sum") * scale[d["dram__bytes_read.sum"]["unit"]],
+           "dram_write_bytes": val("dram__bytes_write.sum") * scale[d["dram__bytes_write.sum"]["unit"]],
+           "algorithmic_bytes_per_launch": float(alg_bytes), "algorithmic_flops_per_launch": float(alg_flops),
+           "dmma_pipe_active_pct": d["sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active"]["value"],
+           "l2_hit_pct": d["lts__t_sector_hit_rate.pct"]["value"]}
+    json.dump(rec, open(out_json, "w"), indent=1)
+    print(json.dumps(rec, indent=1))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], " ".join(sys.argv[3:]))
+    elif sys.argv[1] == "dominant":
+        dominant(sys.argv[2], sys.argv[3], float(sys.argv[4]), float(sys.argv[5]), " ".join(sys.argv[6:]))
     else:
         res = full(sys.argv[2:])
         json.dump(res, open("ncu_full_summary.json", "w"), indent=1)
