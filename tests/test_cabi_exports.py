@@ -86,3 +86,23 @@ def test_no_cpu_fallback_when_library_is_missing(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libgegp.so")
     with pytest.raises(RuntimeError):
         _lib.load()
+
+
+def test_integration_doc_stub_matches_the_abi():
+    """The reference-side ctypes stub shown in INTEGRATION.md binds gegp_lml_eval with the prototype of this ABI version,
+    names every exported entry point, and uses the output slots of include/gegp.h."""
+    from gpgradpy_b200 import _lib
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for name in _declared_functions():
+        assert name in doc, f"{name} is not mentioned in INTEGRATION.md"
+    m = re.search(r"_lib\.gegp_lml_eval\.argtypes = \(\[(.*?)\]\)", doc, flags=re.S)
+    assert m, "stub prototype not found"
+    stub = re.findall(r"C\.c_(\w+)", m.group(1))
+    lib = _lib.load() if os.path.exists(_lib.LIB_PATH) else None
+    assert lib is not None
+    kinds = {ctypes.c_int: "int", ctypes.c_double: "double", ctypes.c_size_t: "size_t", ctypes.c_void_p: "void_p"}
+    want = [kinds.get(t, "void_p") for t in lib.gegp_lml_eval.argtypes]   # every pointer type binds as void_p in the stub
+    assert stub == want
+    assert f"OUT_GRAD = 0, 1, 2, 4, {_lib.OUT_GRAD}" in doc
+    hdr = open(os.path.join(ROOT, "include", "gegp.h")).read()
+    assert re.search(rf"#define GEGP_OUT_GRAD\s+{_lib.OUT_GRAD}\b", hdr)
