@@ -58,7 +58,7 @@ gemm_f64_kernel(const GemmArgs g) {
   else if (g.klo_mode == KLO_N0) kb = n0;
   else if (g.klo_mode == KLO_MAXMN) kb = max(m0, n0);
   if (g.khi_mode == KHI_M0) ke = min(ke, m0 + BM);
-  else if (g.khi_mode == KHI_N0) ke = min(ke, n0 + BN);
+  else if (g.khi_mode == KHI_N0) ke = min(ke, g.khi_off + n0 + BN);
   kb = (kb / BK) * BK;
   const int ktiles = ke > kb ? (ke - kb + BK - 1) / BK : 0;
 
@@ -220,6 +220,7 @@ double gemm_useful_flops(const GemmArgs& g) {
   double f = 2.0 * g.M * (double)g.N * g.K * g.outer * g.inner;
   if (g.cmode != C_FULL) f *= 0.5 * (g.M >= g.N ? (2.0 - (double)g.N / g.M) : 1.0);
   if (g.klo_mode == KLO_MAXMN) f *= 1.0 / 3.0;  // sum_{i>=j} (N - i) / (N^2/2 * N)
+  else if (g.khi_mode == KHI_N0 && g.khi_off > 0) f *= (g.khi_off + 0.5 * g.N) / g.K;
   else if (g.klo_mode != KLO_ZERO || g.khi_mode != KHI_K) f *= 0.5;
   return f;
 }
@@ -380,7 +381,7 @@ GemmArgs gemm_args(const double* A, int64_t lda, const double* B, int64_t ldb, d
   GemmArgs g{};
   g.A = A; g.B = B; g.C = C; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
   g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.b_kcont = b_kcont;
-  g.klo_mode = KLO_ZERO; g.khi_mode = KHI_K; g.cmode = C_FULL;
+  g.klo_mode = KLO_ZERO; g.khi_mode = KHI_K; g.cmode = C_FULL; g.khi_off = 0;
   g.inner = 1; g.outer = 1;
   g.row_owner = false;
   g.inner_steps = false; g.iAr = g.iAc = g.iBr = g.iBc = 0;

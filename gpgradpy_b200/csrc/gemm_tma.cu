@@ -80,7 +80,7 @@ struct TmaGemmArgs {
   int64_t ldc, sCo, sCi;
   int M, N, K;
   double alpha, beta;
-  int klo_mode, khi_mode, cmode;
+  int klo_mode, khi_mode, cmode, khi_off;
   int inner;
   int iAr, iAc, iBr, iBc;  // inner-batch row / column steps of the operands (tensor-map coordinates)
   double* Ct;              // optional transposed second destination
@@ -128,7 +128,7 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   else if (g.klo_mode == KLO_N0) kb = n0;
   else if (g.klo_mode == KLO_MAXMN) kb = max(m0, n0);
   if (g.khi_mode == KHI_M0) ke = min(ke, m0 + TBM);
-  else if (g.khi_mode == KHI_N0) ke = min(ke, n0 + TBN);
+  else if (g.khi_mode == KHI_N0) ke = min(ke, g.khi_off + n0 + TBN);
   kb = (kb / TBK) * TBK;
   const int ktiles = ke > kb ? (ke - kb + TBK - 1) / TBK : 0;
   const bool k_down = g.klo_mode != KLO_ZERO && g.khi_mode == KHI_K;
@@ -309,7 +309,7 @@ static int launch_tma(const Ctx& ctx, const GemmArgs& g, uint64_t a_d0, uint64_t
   TmaGemmArgs t{};
   t.C = g.C; t.ldc = g.ldc; t.sCo = g.sCo; t.sCi = g.sCi;
   t.M = g.M; t.N = g.N; t.K = g.K; t.alpha = g.alpha; t.beta = g.beta;
-  t.klo_mode = g.klo_mode; t.khi_mode = g.khi_mode; t.cmode = g.cmode;
+  t.klo_mode = g.klo_mode; t.khi_mode = g.khi_mode; t.cmode = g.cmode; t.khi_off = g.khi_off;
   t.inner = g.inner; t.iAr = g.iAr; t.iAc = g.iAc; t.iBr = g.iBr; t.iBc = g.iBc;
   t.Ct = g.Ct; t.ldct = g.ldct; t.sCto = g.sCto; t.sCti = g.sCti;
   GEGP_SET_SMEM(gemm_tma_nt_kernel<Cfg>, Cfg::SMEM);

@@ -18,6 +18,8 @@ struct GemmArgs {
   double alpha, beta;     // C = alpha * A*op(B) + beta * C
   bool b_kcont;
   int klo_mode, khi_mode; // triangular-operand clipping of the k range per output tile
+  int khi_off;            // KHI_N0 only: the k range of column tile n0 ends at khi_off + n0 + BN (B is a row slice of a
+                          // lower-triangular matrix that starts khi_off rows below its first row)
   int cmode;
   // batching: z = zo*inner + zi ; pointer offset = zo*s?o + zi*s?i (elements)
   int inner;

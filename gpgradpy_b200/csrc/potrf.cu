@@ -153,6 +153,13 @@ int inv_unit_max() {
   static const int v = getenv("GEGP_INV_UNIT") ? atoi(getenv("GEGP_INV_UNIT")) : 1024;
   return v;
 }
+// Parts of K^-1 = U U^T and of the root's pair product that only need the LEFT part of the factor are issued while the
+// chain is still running (env GEGP_INV_EARLY: 0 = off, 1 = Kinv_aa only, 2 = also the root pair's first columns;
+// see inv_root_early_aa / inv_root_early_pair / finish_inverse_split)
+int inv_early_level() {
+  static const int v = getenv("GEGP_INV_EARLY") ? atoi(getenv("GEGP_INV_EARLY")) : 2;
+  return v;
+}
 struct Piece { int c0, c1; cudaEvent_t done; cudaStream_t stream; bool live; };   // global column range a queued bulk GEMM writes
 struct LookAhead {
   static constexpr int NBULK = 16;
@@ -160,8 +167,11 @@ struct LookAhead {
   static constexpr int NLANE = 3;
   // bulk[depth][lane]: pieces queued at one fork are needed one after the other; the first two get streams of their
   // own with a higher priority than the rest, so that they run beside (not behind) each other and ahead of older work
-  cudaStream_t hi = nullptr, col = nullptr, late = nullptr, inv = nullptr, bulk[NBULK][NLANE] = {};
-  cudaEvent_t fork[40], ev_prep, ev_fac, ev_colupd, ev_solve, ev_inv, begin, end;
+  cudaStream_t hi = nullptr, col = nullptr, late = nullptr, inv = nullptr, early = nullptr, bulk[NBULK][NLANE] = {};
+  cudaEvent_t fork[40], ev_prep, ev_fac, ev_colupd, ev_solve, ev_inv, ev_early, ev_fin[3], begin, end;
+  // early pieces of the explicit inverse (root node only): columns of the root's left child (0: none issued) and of the
+  // right child's left child whose share of the root's pair product has been issued early (0: none)
+  int early_k1 = 0, early_ba = 0;
   Piece piece[MAX_PIECES];
   bool colupd_pending = false;   // a K = LEAF block-column update is in flight on `col` (the next chain step reads its top rows)
   bool solve_pending = false;    // a leaf solve is in flight on `col` (bulk pieces read its rows)
@@ -188,7 +198,8 @@ struct LookAhead {
     ok = cudaStreamCreateWithPriority(&hi, cudaStreamNonBlocking, hip) == cudaSuccess &&
          cudaStreamCreateWithPriority(&col, cudaStreamNonBlocking, mid) == cudaSuccess &&
          cudaStreamCreateWithPriority(&late, cudaStreamNonBlocking, mid) == cudaSuccess &&
-         cudaStreamCreateWithPriority(&inv, cudaStreamNonBlocking, lo) == cudaSuccess;
+         cudaStreamCreateWithPriority(&inv, cudaStreamNonBlocking, lo) == cudaSuccess &&
+         cudaStreamCreateWithPriority(&early, cudaStreamNonBlocking, lo) == cudaSuccess;
     for (int i = 0; i < NBULK && ok; i++)
       for (int j = 0; j < NLANE && ok; j++) {
         int pr = lo - (NLANE - 1 - j);               // lane 0: two levels above the lowest priority
@@ -198,7 +209,8 @@ struct LookAhead {
     auto mk = [&](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
     for (int i = 0; i < 40 && ok; i++) ok = mk(&fork[i]);
     for (int i = 0; i < MAX_PIECES && ok; i++) { ok = mk(&piece[i].done); piece[i].live = false; }
-    ok = ok && mk(&ev_prep) && mk(&ev_fac) && mk(&ev_colupd) && mk(&ev_solve) && mk(&ev_inv) && mk(&begin) && mk(&end);
+    ok = ok && mk(&ev_prep) && mk(&ev_fac) && mk(&ev_colupd) && mk(&ev_solve) && mk(&ev_inv) && mk(&begin) && mk(&end) &&
+         mk(&ev_early) && mk(&ev_fin[0]) && mk(&ev_fin[1]) && mk(&ev_fin[2]);
     return ok;
   }
 };
@@ -313,25 +325,118 @@ int inv_pair_first(LookAhead* la, const InvHook* h, const Ctx& chain, int row0, 
   g1.sAo = h->sU; g1.sBo = h->sA; g1.sCo = h->sT;
   return gemm_f64(ic, g1);
 }
-// second product: U_ab = -T_ab W_bb^T (W_bb = L_bb^-1 from the lower triangle of T), with the transposed copy W_ba
-int inv_pair_second(LookAhead* la, const InvHook* h, const Ctx& chain, int row0, int k1, int kc) {
+// second product: U_ab = -T_ab W_bb^T (W_bb = L_bb^-1 from the lower triangle of T), with the transposed copy W_ba.
+// `c_from` > 0 (root only): the first c_from columns of U_ab have been produced early (inv_root_early_pair), only the
+// columns [c_from, kc) are computed -- the rows [c_from, kc) of W_bb, whose k range starts c_from columns earlier.
+// The root's W_ba is never read (the root is nobody's right child), so no transposed copy is stored then.
+int inv_pair_second(LookAhead* la, const InvHook* h, const Ctx& chain, int row0, int k1, int kc, int c_from = 0,
+                    bool store_w = true) {
   int rc = inv_sync(la, chain.stream);
   if (rc) return rc;
   const Ctx ic{la->inv, chain.batch};
   const double* Tab = h->T + (int64_t)row0 * h->ldt + row0 + k1;
-  const double* Wbb = h->T + (int64_t)(row0 + k1) * (h->ldt + 1);
-  double* Uab = h->U + (int64_t)row0 * h->ldu + row0 + k1;
-  double* Wba = h->T + (int64_t)(row0 + k1) * h->ldt + row0;
-  GemmArgs g2 = gemm_args(Tab, h->ldt, Wbb, h->ldt, Uab, h->ldu, k1, kc, kc, -1.0, 0.0, true);
+  const double* Wbb = h->T + (int64_t)(row0 + k1 + c_from) * h->ldt + row0 + k1;
+  double* Uab = h->U + (int64_t)row0 * h->ldu + row0 + k1 + c_from;
+  double* Wba = h->T + (int64_t)(row0 + k1 + c_from) * h->ldt + row0;
+  GemmArgs g2 = gemm_args(Tab, h->ldt, Wbb, h->ldt, Uab, h->ldu, k1, kc - c_from, kc, -1.0, 0.0, true);
   g2.khi_mode = KHI_N0;
-  g2.Ct = Wba; g2.ldct = h->ldt; g2.sCto = h->sT; g2.sCti = 0;
+  g2.khi_off = c_from;
+  if (store_w) { g2.Ct = Wba; g2.ldct = h->ldt; g2.sCto = h->sT; g2.sCti = 0; }
   g2.outer = ic.batch; g2.inner = 1;
   g2.sAo = h->sT; g2.sBo = h->sT; g2.sCo = h->sU;
   return gemm_f64(ic, g2);
 }
 
+// ---- early pieces of K^-1 (root node only; a = the root's left child, b = its right child with children ba, bb) ----
+// K^-1 = U U^T in blocks:  Kinv_aa = U_aa U_aa^T + U_ab U_ab^T,  Kinv_ab = U_ab U_bb^T,  Kinv_bb = U_bb U_bb^T.
+// U_aa is complete half-way down the chain, and the left spine never reads its W = L^-1 again, so the aa block of the
+// Kinv buffer is free from then on:  Kinv_aa = U_aa U_aa^T  goes to the lowest-priority stream `early` right away.
+// All tasks a piece depends on precede the event on `inv` (FIFO, post-order).
+int inv_root_early_aa(LookAhead* la, const InvHook* h, const Ctx& chain, int k1) {
+  if (cudaEventRecord(la->ev_early, la->inv) != cudaSuccess) return -1130;
+  if (cudaStreamWaitEvent(la->early, la->ev_early, 0) != cudaSuccess) return -1130;
+  const Ctx ec{la->early, chain.batch};
+  GemmArgs g = gemm_args(h->U, h->ldu, h->U, h->ldu, h->T, h->ldt, k1, k1, k1, 1.0, 0.0, true);
+  g.klo_mode = KLO_MAXMN;
+  g.cmode = C_LOWER_MIRROR;
+  g.outer = ec.batch; g.inner = 1;
+  g.sAo = h->sU; g.sBo = h->sU; g.sCo = h->sT;
+  const int rc = gemm_f64(ec, g);
+  if (!rc) la->early_k1 = k1;
+  return rc;
+}
+// Once ba is inverted (three quarters down the chain) the first kba columns of the root's pair product are final:
+//   U_a,ba = -T_a,ba U_ba,ba   (the second product restricted to the columns of ba)   and   Kinv_aa += U_a,ba U_a,ba^T.
+int inv_root_early_pair(LookAhead* la, const InvHook* h, const Ctx& chain, int k1, int kba) {
+  if (cudaEventRecord(la->ev_early, la->inv) != cudaSuccess) return -1131;
+  if (cudaStreamWaitEvent(la->early, la->ev_early, 0) != cudaSuccess) return -1131;
+  const Ctx ec{la->early, chain.batch};
+  const double* Tab = h->T + k1;
+  const double* Wbb = h->T + (int64_t)k1 * (h->ldt + 1);
+  double* Uab = h->U + k1;
+  GemmArgs g2 = gemm_args(Tab, h->ldt, Wbb, h->ldt, Uab, h->ldu, k1, kba, kba, -1.0, 0.0, true);
+  g2.khi_mode = KHI_N0;
+  g2.outer = ec.batch; g2.inner = 1;
+  g2.sAo = h->sT; g2.sBo = h->sT; g2.sCo = h->sU;
+  int rc = gemm_f64(ec, g2);
+  if (rc) return rc;
+  GemmArgs g = gemm_args(Uab, h->ldu, Uab, h->ldu, h->T, h->ldt, k1, k1, kba, 1.0, 1.0, true);
+  g.cmode = C_LOWER_MIRROR;
+  g.outer = ec.batch; g.inner = 1;
+  g.sAo = h->sU; g.sBo = h->sU; g.sCo = h->sT;
+  rc = gemm_f64(ec, g);
+  if (!rc) la->early_ba = kba;
+  return rc;
+}
+// What is left of K^-1 = U U^T after the early pieces, three independent products on three streams:
+//   Kinv_bb = U_bb U_bb^T (hi),   Kinv_ab = U_ab U_bb^T with its mirror Kinv_ba (col),
+//   Kinv_aa += U_a,x U_a,x^T over the columns x of b not yet accumulated (late).
+// Called when everything has been joined into `hi`.
+int finish_inverse_split(LookAhead* la, const InvHook* h, int batch, int N) {
+  const int k1 = la->early_k1, kc = N - k1, off = la->early_ba;
+  if (cudaEventRecord(la->ev_fin[0], la->hi) != cudaSuccess) return -1132;
+  if (cudaStreamWaitEvent(la->col, la->ev_fin[0], 0) != cudaSuccess) return -1132;
+  if (cudaStreamWaitEvent(la->late, la->ev_fin[0], 0) != cudaSuccess) return -1132;
+  const double* Ubb = h->U + (int64_t)k1 * (h->ldu + 1);
+  const double* Uab = h->U + k1;
+  int rc;
+  {  // the largest first: Kinv_ab (k1 x kc) = U_ab U_bb^T, U_bb upper: k >= column
+    const Ctx c{la->col, batch};
+    GemmArgs g = gemm_args(Uab, h->ldu, Ubb, h->ldu, h->T + k1, h->ldt, k1, kc, kc, 1.0, 0.0, true);
+    g.klo_mode = KLO_N0;
+    g.Ct = h->T + (int64_t)k1 * h->ldt; g.ldct = h->ldt; g.sCto = h->sT; g.sCti = 0;
+    g.outer = batch; g.inner = 1;
+    g.sAo = h->sU; g.sBo = h->sU; g.sCo = h->sT;
+    if ((rc = gemm_f64(c, g))) return rc;
+  }
+  {  // Kinv_aa += U_a,x U_a,x^T
+    const Ctx c{la->late, batch};
+    GemmArgs g = gemm_args(Uab + off, h->ldu, Uab + off, h->ldu, h->T, h->ldt, k1, k1, kc - off, 1.0, 1.0, true);
+    g.cmode = C_LOWER_MIRROR;
+    g.outer = batch; g.inner = 1;
+    g.sAo = h->sU; g.sBo = h->sU; g.sCo = h->sT;
+    if ((rc = gemm_f64(c, g))) return rc;
+  }
+  {  // Kinv_bb = U_bb U_bb^T
+    const Ctx c{la->hi, batch};
+    GemmArgs g = gemm_args(Ubb, h->ldu, Ubb, h->ldu, h->T + (int64_t)k1 * (h->ldt + 1), h->ldt, kc, kc, kc, 1.0, 0.0, true);
+    g.klo_mode = KLO_MAXMN;
+    g.cmode = C_LOWER_MIRROR;
+    g.outer = batch; g.inner = 1;
+    g.sAo = h->sU; g.sBo = h->sU; g.sCo = h->sT;
+    if ((rc = gemm_f64(c, g))) return rc;
+  }
+  if (cudaEventRecord(la->ev_fin[1], la->col) != cudaSuccess || cudaEventRecord(la->ev_fin[2], la->late) != cudaSuccess ||
+      cudaStreamWaitEvent(la->hi, la->ev_fin[1], 0) != cudaSuccess ||
+      cudaStreamWaitEvent(la->hi, la->ev_fin[2], 0) != cudaSuccess)
+    return -1133;
+  return 0;
+}
+
+// role: 1 = the root of a factorisation with interleaved inverse, 2 = the root's right child, 0 = any other node
 int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t lda, int64_t strideA, int m, int k,
-                 int row0, int ext, int* info, double* Dinv, int64_t strideD, const InvHook* hook = nullptr) {
+                 int row0, int ext, int* info, double* Dinv, int64_t strideD, const InvHook* hook = nullptr,
+                 int role = 0) {
   if (k <= 0) return 0;
   int rc = 0;
   // a subtree small enough is inverted as one unit once it is factored: its descendants carry no hook
@@ -445,23 +550,34 @@ int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t ld
     if ((rc = queue_piece(bs, std::max(kc, ext_l), kc + ext, k1))) return rc;
   // the left child is inverted and the rows of the right child in its panel are final once the solves queued so far
   // are done: the first product of this node's pair can start while the right child is being factored
+  const int early = child_hook ? inv_early_level() : 0;
+  // (the events of the early pieces are recorded BEFORE this node's first product is queued: they do not wait for it)
+  if (early >= 1 && role == 1 && (rc = inv_root_early_aa(la, child_hook, ctx, k1))) return rc;
+  if (early >= 2 && role == 2 && la->early_k1 > 0 && (rc = inv_root_early_pair(la, child_hook, ctx, la->early_k1, k1)))
+    return rc;
   if (child_hook && (rc = inv_pair_first(la, child_hook, ctx, row0, k1, kc))) return rc;
-  rc = chol_node_la(ctx, la, depth + 1, C, lda, strideA, mc, kc, row0 + k1, ext, info, Dinv, strideD, child_hook);
+  rc = chol_node_la(ctx, la, depth + 1, C, lda, strideA, mc, kc, row0 + k1, ext, info, Dinv, strideD, child_hook,
+                    role == 1 ? 2 : 0);
   if (rc) return rc;
-  if (child_hook) return inv_pair_second(la, child_hook, ctx, row0, k1, kc);
+  if (child_hook) {
+    if (role == 1 && la->early_k1 > 0) return inv_pair_second(la, child_hook, ctx, row0, k1, kc, la->early_ba, false);
+    return inv_pair_second(la, child_hook, ctx, row0, k1, kc);
+  }
   if (inv_unit_here) return inv_unit(la, hook, ctx, row0, k);
   return 0;
 }
 }  // namespace
 
 static int chol_trap_impl(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, int m, int k, int row0, int* info,
-                          double* Dinv, int64_t strideD, const InvHook* hook, bool* inverse_done) {
-  if (inverse_done) *inverse_done = false;
+                          double* Dinv, int64_t strideD, const InvHook* hook, int* inverse_done) {
+  // *inverse_done: 0 = nothing of the inverse has been produced, 1 = U = L^-T is complete, 2 = Kinv is complete as well
+  if (inverse_done) *inverse_done = 0;
   LookAhead* la = (k > LEAF) ? la_acquire() : nullptr;
   if (!la) return chol_node(ctx, A, lda, strideA, m, k, row0, info, Dinv, strideD);
   if (hook && (hook->unit_max < LEAF || row0 != 0)) hook = nullptr;
   for (int i = 0; i < MAX_PIECES; i++) la->piece[i].live = false;
   la->colupd_pending = la->solve_pending = false;
+  la->early_k1 = la->early_ba = 0;
   int rc = 0;
   if (cudaEventRecord(la->begin, ctx.stream) != cudaSuccess) rc = -1107;
   if (!rc && (cudaStreamWaitEvent(la->hi, la->begin, 0) != cudaSuccess ||
@@ -469,8 +585,8 @@ static int chol_trap_impl(const Ctx& ctx, double* A, int64_t lda, int64_t stride
               (hook && cudaStreamWaitEvent(la->inv, la->begin, 0) != cudaSuccess))) rc = -1108;
   if (!rc) {
     const Ctx chain{la->hi, ctx.batch};
-    rc = chol_node_la(chain, la, 0, A, lda, strideA, m, k, row0, 0, info, Dinv, strideD, hook);
-    if (!rc && hook && inverse_done) *inverse_done = true;
+    rc = chol_node_la(chain, la, 0, A, lda, strideA, m, k, row0, 0, info, Dinv, strideD, hook, hook ? 1 : 0);
+    if (!rc && hook && inverse_done) *inverse_done = 1;
   }
   // join everything back into the chain, then into the caller's stream (also after a failure, so that no work is left
   // un-joined inside a stream capture)
@@ -479,9 +595,17 @@ static int chol_trap_impl(const Ctx& ctx, double* A, int64_t lda, int64_t stride
   if (hook) {                               // ... and the tail of the inverse stream
     cudaEventRecord(la->ev_inv, la->inv);
     cudaStreamWaitEvent(la->hi, la->ev_inv, 0);
+    if (la->early_k1 > 0) {
+      cudaEventRecord(la->ev_early, la->early);
+      cudaStreamWaitEvent(la->hi, la->ev_early, 0);
+    }
   }
   la->join_columns(la->hi, 0, 1 << 30);
   la->colupd_pending = la->solve_pending = false;
+  if (!rc && hook && la->early_k1 > 0) {   // early pieces of K^-1 were issued: the rest of it, split the same way
+    rc = finish_inverse_split(la, hook, ctx.batch, k);
+    if (!rc && inverse_done) *inverse_done = 2;
+  }
   if (cudaEventRecord(la->end, la->hi) != cudaSuccess && !rc) rc = -1109;
   if (cudaStreamWaitEvent(ctx.stream, la->end, 0) != cudaSuccess && !rc) rc = -1110;
   la_release(la);
@@ -502,9 +626,10 @@ int chol_trap_inverse(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, i
                       int64_t strideD, double* U, int64_t ldu, int64_t strideU, double* Kinv, int64_t ldk,
                       int64_t strideK) {
   const InvHook hook{U, ldu, strideU, Kinv, ldk, strideK, A, lda, strideA, Dinv, strideD, inv_unit_max()};
-  bool done = false;
+  int done = 0;
   int rc = chol_trap_impl(ctx, A, lda, strideA, m, k, 0, info, Dinv, strideD, inv_unit_max() >= LEAF ? &hook : nullptr, &done);
   if (rc) return rc;
+  if (done == 2) return 0;
   if (!done) {   // single-stream schedule or interleaving switched off: the inverse follows the factorisation
     rc = leaf_dinv_assemble(ctx, A, lda, strideA, Dinv, strideD, k);
     if (rc) return rc;
