@@ -154,11 +154,15 @@ int inv_unit_max() {
   return v;
 }
 // Parts of K^-1 = U U^T and of the root's pair product that only need the LEFT part of the factor are issued while the
-// chain is still running (env GEGP_INV_EARLY: 0 = off, 1 = Kinv_aa only, 2 = also the root pair's first columns;
-// see inv_root_early_aa / inv_root_early_pair / finish_inverse_split)
-int inv_early_level() {
-  static const int v = getenv("GEGP_INV_EARLY") ? atoi(getenv("GEGP_INV_EARLY")) : 2;
-  return v;
+// chain is still running (inv_root_early_aa / inv_root_early_pair / finish_inverse_split).  Levels: 0 = off, 1 = Kinv_aa
+// only, 2 = also the root pair's first columns.  Pays where the chain leaves the machine idle (measured on B200, LML +
+// gradient: N = 5500 6.76 -> 6.60 ms; N = 11250 45.7 -> 45.9 ms and N = 21000 273.8 -> 274.7 ms, where the bulk work of
+// the factorisation already fills it), so by default it is on up to N = 8192 -- a function of the shape of one problem
+// only.  env GEGP_INV_EARLY forces a level.
+int inv_early_level(int N) {
+  static const int forced = getenv("GEGP_INV_EARLY") ? atoi(getenv("GEGP_INV_EARLY")) : -1;
+  if (forced >= 0) return forced;
+  return N <= 8192 ? 2 : 0;
 }
 struct Piece { int c0, c1; cudaEvent_t done; cudaStream_t stream; bool live; };   // global column range a queued bulk GEMM writes
 struct LookAhead {
@@ -171,7 +175,7 @@ struct LookAhead {
   cudaEvent_t fork[40], ev_prep, ev_fac, ev_colupd, ev_solve, ev_inv, ev_early, ev_fin[3], begin, end;
   // early pieces of the explicit inverse (root node only): columns of the root's left child (0: none issued) and of the
   // right child's left child whose share of the root's pair product has been issued early (0: none)
-  int early_k1 = 0, early_ba = 0;
+  int early_k1 = 0, early_ba = 0, early_n = 0;   // early_n: columns of the root
   Piece piece[MAX_PIECES];
   bool colupd_pending = false;   // a K = LEAF block-column update is in flight on `col` (the next chain step reads its top rows)
   bool solve_pending = false;    // a leaf solve is in flight on `col` (bulk pieces read its rows)
@@ -550,8 +554,9 @@ int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t ld
     if ((rc = queue_piece(bs, std::max(kc, ext_l), kc + ext, k1))) return rc;
   // the left child is inverted and the rows of the right child in its panel are final once the solves queued so far
   // are done: the first product of this node's pair can start while the right child is being factored
-  const int early = child_hook ? inv_early_level() : 0;
+  const int early = (child_hook && role != 0) ? inv_early_level(role == 1 ? k : la->early_n) : 0;
   // (the events of the early pieces are recorded BEFORE this node's first product is queued: they do not wait for it)
+  if (role == 1) la->early_n = k;
   if (early >= 1 && role == 1 && (rc = inv_root_early_aa(la, child_hook, ctx, k1))) return rc;
   if (early >= 2 && role == 2 && la->early_k1 > 0 && (rc = inv_root_early_pair(la, child_hook, ctx, la->early_k1, k1)))
     return rc;
