@@ -33,22 +33,29 @@ from .rescaling import Rescaling
 
 
 class DeviceMatrix:
-    """A matrix that lives on the GPU and turns into a NumPy array on demand (np.asarray / indexing)."""
+    """A matrix that lives on the GPU and turns into a NumPy array on demand (np.asarray / indexing).  `t` is a device
+    tensor or a zero-argument callable that produces one: the callable runs on first access, so a matrix of the
+    reference's 7-tuple that nobody reads is never built (at N = 21000 each one is 3.5 GB)."""
 
-    def __init__(self, t, symmetrize_from_lower=False):
-        self._t, self._sym, self._np = t, symmetrize_from_lower, None
+    def __init__(self, t, symmetrize_from_lower=False, shape=None):
+        self._make = t if callable(t) else None
+        self._t = None if callable(t) else t
+        self._shape = shape
+        self._sym, self._np = symmetrize_from_lower, None
 
     @property
     def tensor(self):
+        if self._t is None:
+            self._t, self._make = self._make(), None
         return self._t
 
     @property
     def shape(self):
-        return tuple(self._t.shape)
+        return tuple(self._shape) if self._t is None and self._shape is not None else tuple(self.tensor.shape)
 
     def numpy(self):
         if self._np is None:
-            a = self._t.cpu().numpy().copy()
+            a = self.tensor.cpu().numpy().copy()
             self._np = a
         return self._np
 
@@ -499,7 +506,9 @@ class GaussianProcess:
         noise = None if not np.any(noise_vec) else bk.to_dev(np.asarray(noise_vec, dtype=float) / varK)
         X, slot, ng, N = self._X_dev, self._slot_dev, self.n_grad, self.n_data
         kw = dict(n_g=ng, slot=slot, kernel=self._kern(hp_vals))
-        Kern, _ = bk.build_cov(X, theta, mode=L.MODE_BASE, eta=0.0, **kw)
+        # Only the matrix that is factored / whose condition number is asked for is built here; the other members of
+        # the tuple are built by the same kernel when (if) they are read.
+        Kern = DeviceMatrix(lambda: bk.build_cov(X, theta, mode=L.MODE_BASE, eta=0.0, **kw)[0], shape=(N, N))
         idx_etaK_argmax = None
         precon = self.wellcond_mtd == "precon"
         if precon:
@@ -507,15 +516,32 @@ class GaussianProcess:
         if self.cond_eta_is_const:
             etaK = self._etaK
         else:
-            etaK, idx_etaK_argmax = self._variable_eta(theta, noise, Kern, kernel=self._kern(hp_vals))
+            etaK, idx_etaK_argmax = self._variable_eta(theta, noise, None if precon else Kern.tensor,
+                                                       kernel=self._kern(hp_vals))
+        fac_src = pvec = None
+        need_fac = calc_chofac or calc_cond
         if precon:
-            Kt, p = bk.build_cov(X, theta, noise=noise, mode=L.MODE_PRECON, eta=etaK, varK=varK, **kw)
-            Kcor = DeviceMatrix(Kt / varK - etaK * torch.eye(N, dtype=Kt.dtype, device=Kt.device))
-            Kcov = DeviceMatrix(bk.build_cov(X, theta, noise=noise, mode=L.MODE_PRECON_COV, eta=etaK, varK=varK, **kw)[0])
-            fac_src, pvec = Kt, p[:N]
+            if need_fac:
+                fac_src, p = bk.build_cov(X, theta, noise=noise, mode=L.MODE_PRECON, eta=etaK, varK=varK, **kw)
+                pvec = p[:N]
+
+            def make_kcor(Kt=fac_src):
+                if Kt is None:
+                    Kt = bk.build_cov(X, theta, noise=noise, mode=L.MODE_PRECON, eta=etaK, varK=varK, **kw)[0]
+                out = Kt / varK
+                out.diagonal().sub_(etaK)
+                return out
+            Kcor = DeviceMatrix(make_kcor, shape=(N, N))
+            Kcov = DeviceMatrix(lambda: bk.build_cov(X, theta, noise=noise, mode=L.MODE_PRECON_COV, eta=etaK, varK=varK,
+                                                     **kw)[0], shape=(N, N))
         else:
-            Kc, _ = bk.build_cov(X, theta, noise=noise, mode=L.MODE_BASE, eta=etaK, varK=varK, **kw)
-            Kcor, Kcov, fac_src, pvec = None, DeviceMatrix(Kc), Kc, None
+            if need_fac:
+                fac_src = bk.build_cov(X, theta, noise=noise, mode=L.MODE_BASE, eta=etaK, varK=varK, **kw)[0]
+                Kcov = DeviceMatrix(fac_src)
+            else:
+                Kcov = DeviceMatrix(lambda: bk.build_cov(X, theta, noise=noise, mode=L.MODE_BASE, eta=etaK, varK=varK,
+                                                         **kw)[0], shape=(N, N))
+            Kcor = None
         condK = None
         if calc_cond:   # condition number of the matrix that is factored (kernel/Kernel.py:240,280)
             if self.cond_norm == 2:       # device Lanczos
@@ -535,13 +561,15 @@ class GaussianProcess:
             A[:, :N] = fac_src
             info, _dinv = bk.potrf(A, N, 0)
             if int(info.item()) == 0:
-                Lt = torch.tril(A[:, :N])
+                # the factor in the reference's convention, produced from the device factor when it is read
                 if precon:
-                    Kcov_chofac = (DeviceMatrix(pvec[:, None] * Lt), True)       # (P @ L, lower=True)  :252
+                    Kcov_chofac = (DeviceMatrix(lambda: torch.tril(A[:, :N]).mul_(pvec[:, None]), shape=(N, N)),
+                                   True)                                          # (P @ L, lower=True)  :252
                 else:
-                    Kcov_chofac = (DeviceMatrix(Lt.T.contiguous()), False)        # scipy default: upper     :291
+                    Kcov_chofac = (DeviceMatrix(lambda: torch.tril(A[:, :N]).T.contiguous(), shape=(N, N)),
+                                   False)                                         # scipy default: upper     :291
         self._time_chofac += time.time() - t0
-        return DeviceMatrix(Kern), Kcor, Kcov, Kcov_chofac, condK, etaK, idx_etaK_argmax
+        return Kern, Kcor, Kcov, Kcov_chofac, condK, etaK, idx_etaK_argmax
 
     def _variable_eta(self, theta, noise_div, Kern=None, kernel=None):
         """Variable nugget from the Gershgorin row sums of Kcor (precon) or of the noise-free Kern (otherwise):
