@@ -22,6 +22,7 @@ OPT_TMA_MIN_TILES = 1
 OPT_LOOKAHEAD = 2
 OPT_SMALL_TILE_MAX = 3
 OPT_CHAIN_CLUSTER = 4
+OPT_INV_EARLY = 5
 
 EXPORTS = (
     "gegp_abi_version", "gegp_set_option", "gegp_workspace_bytes", "gegp_ld", "gegp_build_cov", "gegp_cross_cov", "gegp_potrf",

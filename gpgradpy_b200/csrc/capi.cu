@@ -174,6 +174,12 @@ int gegp_set_option(int key, int value) {
     chain_cluster() = value;
     return old;
   }
+  if (key == GEGP_OPT_INV_EARLY) {
+    if (value < 0 || value > 3) return -2;
+    const int old = inv_early_option();
+    inv_early_option() = value;
+    return old;
+  }
   if (key == GEGP_OPT_LOOKAHEAD) {
     const int old = lookahead_enabled();
     lookahead_enabled() = value ? 1 : 0;

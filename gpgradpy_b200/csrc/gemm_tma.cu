@@ -15,6 +15,7 @@
 // chunk positions of the line exactly once.
 #include "linalg.h"
 #include <cuda.h>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -290,8 +291,11 @@ bool get_map(const double* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t 
   const cuuint32_t box[3] = {TBK, box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMap m;
+  static const int promo = getenv("GEGP_DBG_TMA_PROMO") ? atoi(getenv("GEGP_DBG_TMA_PROMO")) : 256;
   const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(ptr), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                    : (promo == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B),
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return false;
   cache.emplace(key, m);

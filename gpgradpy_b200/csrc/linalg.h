@@ -70,6 +70,8 @@ int leaf_chain_prep(const Ctx& ctx, const double* Lp, int64_t lda, int64_t strid
                     double* B, double* E, int kc);
 // cluster size of that step (0: automatic; 1, 2, 4) -- tuning knob, same results for every value
 int& chain_cluster();
+// early pieces of the explicit inverse (chol_trap_inverse): 0 off, 1 / 2 forced level, 3 by problem size (default)
+int& inv_early_option();
 // Diagonal blocks of the N x N buffer U <- Dinv blocks (upper triangular), diagonal blocks of W <- their transposes
 // (lower triangular); the rest of both buffers is left untouched.
 int leaf_scatter_dinv(const Ctx& ctx, const double* Dinv, int64_t strideD, double* U, int64_t ldu, int64_t strideU,

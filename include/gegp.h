@@ -91,6 +91,11 @@ int gegp_abi_version(void);
 #define GEGP_OPT_LOOKAHEAD 2       /* 0: single-stream factorisation; 1 (default): look-ahead on priority streams */
 #define GEGP_OPT_SMALL_TILE_MAX 3  /* products with at most this many 64 x 64 tiles in total use 32 x 32 tiles (36) */
 #define GEGP_OPT_CHAIN_CLUSTER 4   /* CTAs per cluster of the factorisation's chain step: 0 automatic (default), 1, 2, 4 */
+/* Pieces of K^-1 = U U^T that only need the left part of the factor are issued while the factorisation is still running
+ * (LML + gradient evaluations): 0 off, 1 the aa block only, 2 also the first columns of the root's pair product,
+ * 3 (default) level 2 up to N = 8192 and off above (a function of the shape of one problem only).  The levels differ in
+ * the summation order of K^-1 (agreement to rounding). */
+#define GEGP_OPT_INV_EARLY 5
 int gegp_set_option(int key, int value);
 
 size_t gegp_workspace_bytes(int op, int n, int n_g, int d, int arg);

@@ -1,0 +1,54 @@
+"""Reproducibility probe: the same LML(+gradient) evaluation repeated.  Prints the scalars of the result row in full
+precision and compares, per repetition, column checksums (exact, int64 wrap-around sums of the bit patterns) of the
+workspace arrays -- factor A (with the solved appended rows), Dinv, U = L^-T, Kinv -- with those of the first repetition:
+the leftmost differing column of each array localises a divergence."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from gpgradpy_b200 import backend as bk, _lib as L
+from oracle import gegp_oracle as O
+n, d = int(sys.argv[1]), int(sys.argv[2])
+grad = sys.argv[3] != "0"
+reps = int(sys.argv[4])
+N = n * (d + 1)
+x, f, g = O.synthetic_problem(n, d, 0); th = O.bench_theta(d); eta = O.nugget(n, d, "precon")[1]
+y = O.make_data_vec(f, g)
+X = bk.to_dev(x); Y = bk.to_dev(y); TH = bk.to_dev(th[None, :])
+tag = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("GEGP_"))
+lib = L.load()
+out8 = (C.c_int64 * 8)()
+assert lib.gegp_lml_layout(n, n, d, int(grad), 1, out8) == 0
+hdr, ld, per, oA, oP, oD, oU, oK = [int(v) for v in out8]
+
+def sums():
+    ws = bk._ws_cache[torch.cuda.current_device()]
+    w = ws[hdr:hdr + per * 8].view(torch.int64)
+    res = {"A": w[oA:oA + (N + 2) * ld].view(N + 2, ld).sum(dim=0),
+           "Arow": w[oA:oA + (N + 2) * ld].view(N + 2, ld).sum(dim=1),
+           "Arhs": w[oA + N * ld:oA + (N + 2) * ld].view(2, ld).sum(dim=0),
+           "D": w[oD:oD + ((N + 127) // 128) * 128 * 128].view(-1, 128 * 128).sum(dim=1)}
+    if grad:
+        res["U"] = w[oU:oU + N * ld].view(N, ld).sum(dim=0)
+        res["Kinv"] = w[oK:oK + N * ld].view(N, ld).sum(dim=0)
+    return {k: v.clone() for k, v in res.items()}
+
+first = first_s = None
+nbad = 0
+for r in range(reps):
+    out, _ = bk.lml_eval(X, Y, TH, mode=L.MODE_PRECON, eta=eta, want_grad=grad)
+    torch.cuda.synchronize()
+    o = out[0].cpu().numpy().copy()
+    s = sums()
+    if first is None:
+        first, first_s = o, s
+    same = np.array_equal(o, first)
+    diffs = []
+    for k in s:
+        bad = torch.nonzero(s[k] != first_s[k]).flatten()
+        if bad.numel():
+            diffs.append(f"{k}: {bad.numel()} differ, first {int(bad[0])} last {int(bad[-1])}")
+    nbad += (not same) or bool(diffs)
+    if r == 0 or not same or diffs:
+        print(f"[{tag}] rep {r}: same={same} lml={o[L.OUT_LML]:.15e} sigma2={o[L.OUT_SIGMA2]:.15e} beta={o[L.OUT_BETA]:.15e} "
+              f"logdet={o[L.OUT_LOGDET]:.15e} |g|={np.linalg.norm(o[L.OUT_GRAD:L.OUT_GRAD + d]):.12e} {' | '.join(diffs)}", flush=True)
+print(f"[{tag}] N={N} grad={grad}: {nbad} of {reps} repetitions differ from the first")
