@@ -426,9 +426,7 @@ int gemm_f64(const Ctx& ctx, GemmArgs g) {
   if (g.b_kcont && g.K == K128 && g.N <= 128 && g.klo_mode == KLO_ZERO && g.khi_mode == KHI_K && !g.Ct && g.inner == 1 &&
       (long)g.M * g.outer <= 148L * 64 && exp_cfg != 7)
     return gemm_k128(ctx, g);
-  static const bool dbg_inv_no_tma = getenv("GEGP_DBG_INV_NO_TMA") != nullptr;   // debug: triangular-operand products off the TMA kernel
-  const bool tri = g.klo_mode != KLO_ZERO || g.khi_mode != KHI_K;
-  if (g.b_kcont && big && exp_cfg != 9 && !(dbg_inv_no_tma && tri)) {
+  if (g.b_kcont && big && exp_cfg != 9) {
     const int rc = gemm_tma_nt(ctx, g);
     if (rc <= 0) return rc;
   }

@@ -2,11 +2,11 @@
 // (row-major, A is M x K and B is N x K, both K-contiguous -- the shape of every Cholesky trailing update,
 // of the first half of the triangular inverse and of K^-1 = U U^T).
 //
-// One CTA per 128 x 64 output tile, two CTAs per SM.  A producer warp streams [rows x 16 doubles] boxes of A and B
-// into a 4-deep shared-memory ring with cp.async.bulk.tensor (TMA, 128-byte swizzle, zero fill outside the operand),
-// signalling one mbarrier per stage; four consumer warps (64 x 32 warp tiles) wait on that barrier, feed
-// DMMA.8x8x4 from the swizzled tiles and release the stage through a second mbarrier.  There is no CTA-wide
-// barrier and no address arithmetic in the math warps, so the fp64 tensor pipe is the only busy unit.
+// One CTA per 128 x 128 output tile, ONE CTA per SM, which it has to itself (see TmaCfg).  A producer warp streams
+// [rows x 16 doubles] boxes of A and B into a 6-deep shared-memory ring with cp.async.bulk.tensor (TMA, 128-byte swizzle,
+// zero fill outside the operand), signalling one mbarrier per stage; eight consumer warps (64 x 32 warp tiles) wait on
+// that barrier, feed DMMA.8x8x4 from the swizzled tiles and release the stage through a second mbarrier.  There is no
+// CTA-wide barrier and no address arithmetic in the math warps, so the fp64 tensor pipe is the only busy unit.
 //
 // Shared-memory reads are bank-conflict free without padding: a tile row is one 128-byte line whose 16-byte
 // chunks are XOR-swizzled with (row & 7) by the TMA unit.  The k index inside a 16-wide k-tile is a summation
@@ -29,7 +29,9 @@ constexpr int TWM = 64, TWN = 32;                  // warp tile
 constexpr int TMI = TWM / 8, TNI = TWN / 8;
 
 // CTA tile TBM x TBN (multiples of the 64 x 32 warp tile), TSTAGES-deep ring, MINB CTAs per SM.
-template <int TBM_, int TBN_, int TSTAGES_, int MINB_>
+// SOLO: the CTA asks for ALL the shared memory a block may have (227 KB), so that no other CTA -- of this grid, of
+// another kernel of this library or of a foreign kernel on another stream -- can share its SM.
+template <int TBM_, int TBN_, int TSTAGES_, int MINB_, bool SOLO_>
 struct TmaCfg {
   static constexpr int TBM = TBM_, TBN = TBN_, TSTAGES = TSTAGES_, MINB = MINB_;
   static constexpr int CONSUMERS = (TBM / TWM) * (TBN / TWN);
@@ -37,13 +39,23 @@ struct TmaCfg {
   static constexpr uint32_t A_BYTES = TBM * TBK * sizeof(double);
   static constexpr uint32_t B_BYTES = TBN * TBK * sizeof(double);
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr size_t SMEM = (size_t)TSTAGES * STAGE_BYTES + 2 * TSTAGES * sizeof(uint64_t) + 1024;  // + alignment slack
+  static constexpr size_t USED = (size_t)TSTAGES * STAGE_BYTES + 2 * TSTAGES * sizeof(uint64_t) + 1024;  // + alignment slack
+  static constexpr size_t SMEM = SOLO_ ? (size_t)GEGP_MAX_DYN_SMEM : USED;
+  static_assert(USED <= (size_t)GEGP_MAX_DYN_SMEM, "ring does not fit");
 };
-// 128 x 64 tile, 4 math warps + 1 producer warp, two CTAs per SM: each CTA covers the other's ramp-up, epilogue and
-// tail, and one math warp per scheduler already issues DMMA at > 90 % of the pipe rate.  Measured on B200: 35.2 TFLOP/s
-// at 8192^3 (95 % of the DMMA issue peak; a 128 x 128 tile with 8 math warps and one CTA per SM reaches 34.2, a
-// 64 x 64 tile with four CTAs per SM is slower than the cp.async kernel on the mid-size products it would serve).
-using CfgHalf = TmaCfg<128, 64, 4, 2>;
+// WHY SOLO.  With the 128 x 64 tile / two CTAs per SM this kernel was first built with (CfgShared below; 35.2 TFLOP/s at
+// 8192^3), an evaluation was NOT reproducible whenever CTAs of this kernel shared SMs with CTAs of other kernels: beside
+// foreign cuBLAS DGEMMs on another stream 18 of 30 factorisations at N = 21000 came out wrong (a few tiles of a product,
+// up to NaN), and with this library's own inverse running beside the factorisation 3 to 5 of 24 evaluations at
+// N = 41000 / 51000 deviated by up to 1e-7 (tools/repro_probe.py; profiles/r02/repro_tma_shared_sm.log).  The cp.async
+// kernels never deviated under the same load, nor did this kernel once it had the SM to itself; tensor maps in global
+// memory, unswizzled tiles, the .shared::cta form of the copy and a producer warp that outlives the consumers did not
+// help (each tried).  The mechanism was not found -- every dependency of the ring is on an mbarrier and the protocol is
+// the textbook one -- so the kernel simply no longer shares an SM: 128 x 128 tile, 8 math warps + 1 producer warp,
+// 6 stages, the whole 227 KB.  Same k order per element as before (bit-identical results), same speed at N = 5500 and
+// 21000.  GEGP_TMA_SHARED_SM=1 brings the old configuration back (for reproducing the problem only).
+using CfgSolo = TmaCfg<128, 128, 6, 1, true>;
+using CfgShared = TmaCfg<128, 64, 4, 2, false>;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -291,11 +303,8 @@ bool get_map(const double* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t 
   const cuuint32_t box[3] = {TBK, box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMap m;
-  static const int promo = getenv("GEGP_DBG_TMA_PROMO") ? atoi(getenv("GEGP_DBG_TMA_PROMO")) : 256;
   const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(ptr), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                         promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
-                                    : (promo == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B),
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return false;
   cache.emplace(key, m);
@@ -338,7 +347,9 @@ int gemm_tma_nt(const Ctx& ctx, const GemmArgs& g) {
   const uint64_t a_d0 = (uint64_t)(inner - 1) * g.iAc + g.K, a_d1 = (uint64_t)(inner - 1) * g.iAr + g.M;
   const uint64_t b_d0 = (uint64_t)(inner - 1) * g.iBc + g.K, b_d1 = (uint64_t)(inner - 1) * g.iBr + g.N;
   if (g.K < 1 || a_d0 > (uint64_t)g.lda || b_d0 > (uint64_t)g.ldb) return 1;
-  return launch_tma<CfgHalf>(ctx, g, a_d0, a_d1, b_d0, b_d1);
+  static const bool shared_sm = getenv("GEGP_TMA_SHARED_SM") != nullptr;
+  if (shared_sm) return launch_tma<CfgShared>(ctx, g, a_d0, a_d1, b_d0, b_d1);
+  return launch_tma<CfgSolo>(ctx, g, a_d0, a_d1, b_d0, b_d1);
 }
 
 }  // namespace gegp

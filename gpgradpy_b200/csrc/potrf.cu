@@ -189,10 +189,9 @@ struct LookAhead {
   bool ok = false;
   // the chain must not touch columns [c0, c1) before every queued bulk piece that writes them has finished
   int join_columns(cudaStream_t chain, int c0, int c1) {
-    static const bool all = getenv("GEGP_DBG_JOIN_ALL") != nullptr;   // debug: ignore the column test
     for (int i = 0; i < MAX_PIECES; i++) {
       Piece& p = piece[i];
-      if (!p.live || (!all && (p.c1 <= c0 || p.c0 >= c1))) continue;
+      if (!p.live || p.c1 <= c0 || p.c0 >= c1) continue;
       if (cudaStreamWaitEvent(chain, p.done, 0) != cudaSuccess) return -1100;
       p.live = false;
     }
@@ -317,8 +316,7 @@ int inv_unit(LookAhead* la, const InvHook* h, const Ctx& chain, int row0, int k)
   const Ctx ic{la->inv, chain.batch};
   double* Ln = h->A0 + (int64_t)row0 * (h->lda + 1);
   double* Dn = h->Dinv + (int64_t)(row0 / LEAF) * LEAF * LEAF;
-  static const bool no_asm = getenv("GEGP_DBG_NO_DINVASM") != nullptr;   // debug: wrong inverse, same traffic
-  rc = no_asm ? 0 : leaf_dinv_assemble(ic, Ln, h->lda, h->sA, Dn, h->sD, k);
+  rc = leaf_dinv_assemble(ic, Ln, h->lda, h->sA, Dn, h->sD, k);
   if (rc) return rc;
   return inverse_transposed(ic, Ln, h->lda, h->sA, Dn, h->sD, h->U + (int64_t)row0 * (h->ldu + 1), h->ldu, h->sU,
                             h->T + (int64_t)row0 * (h->ldt + 1), h->ldt, h->sT, k);
@@ -521,8 +519,7 @@ int chol_node_la(const Ctx& ctx, LookAhead* la, int depth, double* A, int64_t ld
     // does not (same-stream pieces are ordered anyway)
     for (int i = 0; i < MAX_PIECES; i++) {
       const Piece& p = la->piece[i];
-      static const bool all = getenv("GEGP_DBG_JOIN_ALL") != nullptr;
-      if (p.live && p.stream != st && (all || (p.c1 > row0 + k1 + a && p.c0 < row0 + k1 + b)))
+      if (p.live && p.stream != st && p.c1 > row0 + k1 + a && p.c0 < row0 + k1 + b)
         if (cudaStreamWaitEvent(st, p.done, 0) != cudaSuccess) return -1112;
     }
     const double* Pa = P + (int64_t)a * lda + (k1 - kk);
@@ -641,11 +638,9 @@ int chol_trap_inverse(const Ctx& ctx, double* A, int64_t lda, int64_t strideA, i
                       int64_t strideD, double* U, int64_t ldu, int64_t strideU, double* Kinv, int64_t ldk,
                       int64_t strideK) {
   const InvHook hook{U, ldu, strideU, Kinv, ldk, strideK, A, lda, strideA, Dinv, strideD, inv_unit_max()};
-  // Above N = 32768 the inverse follows the factorisation instead of being interleaved with it: with the two running side
-  // by side, evaluations at N = 41000 and 51000 were NOT bit-reproducible (tools/repro_probe.py: 3 to 5 of 24 repetitions
-  // deviate, LML by up to 1e-7 relative, starting from a few perturbed rows of the factor; cause not found -- see
-  // DESIGN.md), while N <= 31000 (76 repetitions) and the sequential order at N = 51000 (24) never deviated.
-  static const int interleave_max_n = getenv("GEGP_INV_MAX_N") ? atoi(getenv("GEGP_INV_MAX_N")) : 32768;
+  // (env GEGP_INV_MAX_N: largest N with the inverse interleaved; a debugging aid -- the deviations once seen with the two
+  // side by side at N >= 41000 came from the TMA GEMM sharing SMs with other kernels, see gemm_tma.cu)
+  static const int interleave_max_n = getenv("GEGP_INV_MAX_N") ? atoi(getenv("GEGP_INV_MAX_N")) : (1 << 30);
   const bool interleave = inv_unit_max() >= LEAF && k <= interleave_max_n;
   int done = 0;
   int rc = chol_trap_impl(ctx, A, lda, strideA, m, k, 0, info, Dinv, strideD, interleave ? &hook : nullptr, &done);

@@ -193,6 +193,43 @@ def test_tma_and_cpasync_kernels_agree():
     assert (C1 - ref).abs().max().item() < 1e-12 and (C2 - ref).abs().max().item() < 1e-12
 
 
+def test_tma_gemm_beside_foreign_kernels_is_reproducible(force_tma):
+    """The TMA kernel must give the same bits whether or not other kernels run beside it.  With two CTAs of it per SM --
+    sharing the SM with whatever else was resident -- products came out wrong beside cuBLAS DGEMMs on another stream (a
+    few tiles, up to NaN in a factorisation; see csrc/gemm_tma.cu); it now takes an SM to itself."""
+    import torch
+    from gpgradpy_b200 import backend as bk
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.randn((6144, 1024), dtype=torch.float64, device="cuda", generator=g)
+    B = torch.randn((4096, 1024), dtype=torch.float64, device="cuda", generator=g)
+    C0 = torch.randn((6144, 4096), dtype=torch.float64, device="cuda", generator=g)
+    quiet = C0.clone()
+    bk.dgemm(A, B, quiet, transb=True, alpha=-1.0, beta=1.0)
+    torch.cuda.synchronize()
+    ref = C0 - A @ B.T
+    assert (quiet - ref).abs().max().item() < 1e-10
+    Fa = torch.randn((4096, 4096), dtype=torch.float64, device="cuda", generator=g)
+    Fb = torch.randn_like(Fa)
+    Fc = torch.empty_like(Fa)
+    side = torch.cuda.Stream()
+    expect = C0.clone()
+    for _step in range(4):
+        bk.dgemm(A, B, expect, transb=True, alpha=-1.0, beta=1.0)
+    torch.cuda.synchronize()
+    bad = 0
+    for _rep in range(12):
+        C = C0.clone()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _load in range(6):
+                torch.matmul(Fa, Fb, out=Fc)          # foreign load on another stream
+        for _step in range(4):                        # the product under test, beside it: C0 - 4 A B^T in four steps
+            bk.dgemm(A, B, C, transb=True, alpha=-1.0, beta=1.0)
+        torch.cuda.synchronize()
+        bad += int(not torch.equal(C, expect))
+    assert bad == 0, f"{bad} of 12 repetitions beside foreign kernels differ from the quiet result"
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 128, 1408), (100, 130, 78), (300, 128, 128)])
 def test_small_and_regular_tiles_agree_bit_for_bit(M, N, K):
     """32 x 32-tile and 64 x 64-tile cp.async kernels accumulate every output element in the same k order:

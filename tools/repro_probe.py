@@ -34,7 +34,18 @@ def sums():
 
 first = first_s = None
 nbad = 0
+# REPRO_LOAD=<n>: n foreign fp64 GEMMs (cuBLAS, 6144^3) are queued on a side stream before every evaluation, so that the
+# evaluation runs beside unrelated bulk work (tests whether a deviation needs the interleaved inverse or just a busy GPU)
+nload = int(os.environ.get("REPRO_LOAD", "0"))
+if nload:
+    side = torch.cuda.Stream()
+    Ma = torch.randn(6144, 6144, dtype=torch.float64, device="cuda"); Mb = torch.randn_like(Ma); Mc = torch.empty_like(Ma)
 for r in range(reps):
+    if nload:
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(nload):
+                torch.matmul(Ma, Mb, out=Mc)
     out, _ = bk.lml_eval(X, Y, TH, mode=L.MODE_PRECON, eta=eta, want_grad=grad)
     torch.cuda.synchronize()
     o = out[0].cpu().numpy().copy()
