@@ -499,8 +499,8 @@ def run_b200(args):
             break
         except Exception:
             continue
-    roofline = {"kernel": "fp64 DMMA.8x8x4 GEMM engine = all O(N^3) work of one evaluation (gemm_tma_nt_kernel<128,64,4,2>: "
-                          "TMA + mbarrier ring, products with >= 400 tiles of 128x128; gemm_f64_kernel<64,64,..> / <32,32,..>: "
+    roofline = {"kernel": "fp64 DMMA.8x8x4 GEMM engine = all O(N^3) work of one evaluation (gemm_tma_nt_kernel<128,128,6 stages>: "
+                          "TMA + mbarrier ring, one CTA per SM with the SM to itself, products with >= 400 tiles of 128x128; gemm_f64_kernel<64,64,..> / <32,32,..>: "
                           "cp.async ring, the smaller products and the K=128 updates beside the factorisation's chain)",
                 "bound": "tensor", "achieved": N ** 3 / ph["gemm_ms_per_eval"] * 1e-9, "peak": dmma_peak,
                 "unit": "TFLOP/s", "frac": N ** 3 / ph["gemm_ms_per_eval"] * 1e-9 / dmma_peak,

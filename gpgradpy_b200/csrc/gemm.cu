@@ -408,8 +408,9 @@ int gemm_f64(const Ctx& ctx, GemmArgs g) {
   }
   tiles_big *= g.inner;
   // Measured on B200 (d=10, n=500 and d=20, n=1000 evaluations): with fewer than ~400 tiles of 128 x 128 per problem
-  // the TMA kernel (128 x 64 tiles, 296 resident CTAs) loses more to wave quantisation than it gains over the
-  // 64 x 64 cp.async kernel; between 400 and 1000 the two are equal, above the TMA kernel wins.
+  // the TMA kernel loses more to wave quantisation than it gains over the 64 x 64 cp.async kernel; between 400 and 1000
+  // the two are equal, above the TMA kernel wins (measured with 128 x 64 tiles on 296 CTA slots; re-checked at both sizes
+  // with the 128 x 128 tiles / 148 slots the kernel has now: 150 ... 400 give the same evaluation times).
   const bool big = tiles_big >= tma_min_tiles() && g.M >= 128 && g.N >= 128;
   if (g.row_owner) {
     // in-place right multiply: one column tile must cover all of N so that a CTA only overwrites rows it alone reads

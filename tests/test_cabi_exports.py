@@ -61,6 +61,10 @@ def test_argument_checks_return_negative_codes_without_touching_the_gpu():
     assert lib.gegp_dgemm(0, 4, 4, 4, 1.0, 0, 4, 0, 4, 0.0, 0, 4, 0) == -6
     assert lib.gegp_dinv_doubles(129) == 2 * 128 * 128
     assert lib.gegp_set_option(99, 1) == -1 and lib.gegp_set_option(_lib.OPT_TMA_MIN_TILES, 0) == -2
+    # early pieces of the explicit inverse: 0 off, 1 / 2 forced level, 3 by problem size (default); returns the old value
+    assert lib.gegp_set_option(_lib.OPT_INV_EARLY, 4) == -2 and lib.gegp_set_option(_lib.OPT_INV_EARLY, -1) == -2
+    old = lib.gegp_set_option(_lib.OPT_INV_EARLY, 0)
+    assert old in (0, 1, 2, 3) and lib.gegp_set_option(_lib.OPT_INV_EARLY, old) == 0
     # condition-number / surrogate-derivative entry points
     import ctypes as C
     assert lib.gegp_symv(0, 0, 0, 0, 0, 0) == -1 and lib.gegp_symv(8, 0, 8, 0, 0, 0) == -2
