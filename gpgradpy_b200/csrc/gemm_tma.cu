@@ -31,8 +31,9 @@ constexpr int TMI = TWM / 8, TNI = TWN / 8;
 // CTA tile TBM x TBN (multiples of the 64 x 32 warp tile), TSTAGES-deep ring, MINB CTAs per SM.
 // SOLO: the CTA asks for ALL the shared memory a block may have (227 KB), so that no other CTA -- of this grid, of
 // another kernel of this library or of a foreign kernel on another stream -- can share its SM.
-template <int TBM_, int TBN_, int TSTAGES_, int MINB_, bool SOLO_>
+template <int TBM_, int TBN_, int TSTAGES_, int MINB_, bool SOLO_, bool LATE_ = false>
 struct TmaCfg {
+  static constexpr bool LATE = LATE_;   // experiment: release a ring stage one k-tile late (see CfgSharedLate)
   static constexpr int TBM = TBM_, TBN = TBN_, TSTAGES = TSTAGES_, MINB = MINB_;
   static constexpr int CONSUMERS = (TBM / TWM) * (TBN / TWN);
   static constexpr int THREADS = (CONSUMERS + 1) * 32;    // + 1 producer warp
@@ -56,6 +57,11 @@ struct TmaCfg {
 // 21000.  GEGP_TMA_SHARED_SM=1 brings the old configuration back (for reproducing the problem only).
 using CfgSolo = TmaCfg<128, 128, 6, 1, true>;
 using CfgShared = TmaCfg<128, 64, 4, 2, false>;
+// Experiment prepared for the prime suspect, not yet run: the shared configuration with every stage released
+// one k-tile LATE -- after the wait for the next stage, i.e. in program order behind every DMMA (and therefore every
+// completed shared-memory load) of the stage it releases -- instead of between the stage's last loads and the DMMAs that
+// consume them, where ptxas schedules the release otherwise.  GEGP_TMA_SHARED_SM=2 selects it.
+using CfgSharedLate = TmaCfg<128, 64, 4, 2, false, true>;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -196,6 +202,12 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   for (int kt = 0; kt < ktiles; kt++) {
     const int s = kt % TSTAGES;
     mbar_wait(bar_full + 8 * s, (kt / TSTAGES) & 1);
+    if constexpr (Cfg::LATE) {
+      if (kt > 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * ((kt - 1) % TSTAGES));
+      }
+    }
     const uint8_t* st = tiles + s * STAGE_BYTES;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
@@ -211,8 +223,10 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
         for (int j = 0; j < TNI; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+    if constexpr (!Cfg::LATE) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+    }
   }
 
   // ===== epilogue =====
@@ -347,7 +361,8 @@ int gemm_tma_nt(const Ctx& ctx, const GemmArgs& g) {
   const uint64_t a_d0 = (uint64_t)(inner - 1) * g.iAc + g.K, a_d1 = (uint64_t)(inner - 1) * g.iAr + g.M;
   const uint64_t b_d0 = (uint64_t)(inner - 1) * g.iBc + g.K, b_d1 = (uint64_t)(inner - 1) * g.iBr + g.N;
   if (g.K < 1 || a_d0 > (uint64_t)g.lda || b_d0 > (uint64_t)g.ldb) return 1;
-  static const bool shared_sm = getenv("GEGP_TMA_SHARED_SM") != nullptr;
+  static const int shared_sm = getenv("GEGP_TMA_SHARED_SM") ? atoi(getenv("GEGP_TMA_SHARED_SM")) : 0;
+  if (shared_sm == 2) return launch_tma<CfgSharedLate>(ctx, g, a_d0, a_d1, b_d0, b_d1);
   if (shared_sm) return launch_tma<CfgShared>(ctx, g, a_d0, a_d1, b_d0, b_d1);
   return launch_tma<CfgSolo>(ctx, g, a_d0, a_d1, b_d0, b_d1);
 }
