@@ -1,2 +1,8 @@
-python tools/one_eval.py 1000 50 1 2 2>&1 | tee gpurun_out/c5_lml_grad.log
-python bench.py --steps 10 --warmup 3 --no-c3 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['e2e']['value'], d['batched'])"
+# Next experiment (prepared, not yet run): does releasing a ring stage one k-tile late cure the TMA kernel's failure when it
+# shares SMs with other kernels?  (baseline GEGP_TMA_SHARED_SM=1: 18 of 30 repetitions deviate, solo config: 0.)
+for v in 1 2 0; do
+  GEGP_TMA_SHARED_SM=$v GEGP_NO_LOOKAHEAD=1 REPRO_LOAD=20 python tools/repro_probe.py 1000 20 0 30 2>&1 | tail -1
+done
+# if 2 is clean: speed of the shared configuration with the late release against the solo one
+GEGP_TMA_SHARED_SM=2 python tools/quick_probe.py 500,10 1000,20 2>&1 | tail -2
+python tools/quick_probe.py 500,10 1000,20 2>&1 | tail -2
