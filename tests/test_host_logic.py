@@ -186,3 +186,22 @@ def test_host_bookkeeping_table_vs_reference(golden_dir):
         if not ok:
             bad.append(k)
     assert not bad, bad[:10]
+
+
+def test_device_matrix_is_built_on_first_use_only():
+    """The matrices of calc_all_K_w_chofac's 7-tuple are produced when (if) somebody reads them -- kernel/Kernel.py:140-307
+    returns them all, but at N = 21000 each is 3.5 GB and the fit only ever asks for the condition number."""
+    import torch
+    from gpgradpy_b200.gp import DeviceMatrix
+    calls = []
+
+    def make():
+        calls.append(1)
+        return torch.arange(6, dtype=torch.float64).reshape(2, 3)
+
+    m = DeviceMatrix(make, shape=(2, 3))
+    assert m.shape == (2, 3) and calls == []            # the shape is known without building
+    assert np.asarray(m)[1, 2] == 5.0 and calls == [1]
+    assert m[0, 1] == 1.0 and m.tensor.shape == (2, 3) and calls == [1]   # built once, cached
+    eager = DeviceMatrix(torch.ones(2, 2, dtype=torch.float64))
+    assert eager.shape == (2, 2) and np.asarray(eager).sum() == 4.0
